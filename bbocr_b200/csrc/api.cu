@@ -1,0 +1,840 @@
+// api.cu -- the C ABI declared in include/bbocr.h and the readtext orchestration
+//   (easyocr/easyocr.py::Reader.readtext -> detect -> recognize, batch_size == 1 semantics).
+#include <thread>
+
+#include "engine.h"
+
+struct bbocr_handle : bbocr::Handle {};
+
+using namespace bbocr;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+template <typename F>
+int guarded(bbocr_handle* h, F&& f) {
+    if (!h) return BBOCR_E_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    try {
+        CUDA_CHECK(cudaSetDevice(h->device));
+        f();
+        return BBOCR_OK;
+    } catch (const Error& e) {
+        h->err = e.what();
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        h->err = "out of host memory";
+        return BBOCR_E_NOMEM;
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return BBOCR_E_ARG;
+    }
+}
+
+// host -> device through the lane's pinned staging buffer
+void* staging(Lane& lane, size_t bytes) {          // pinned H2D staging; waits for the previous copy out of it
+    if (lane.in_busy) {
+        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        lane.in_busy = false;
+    }
+    return lane.pin_in.get(bytes);
+}
+
+void upload(Lane& lane, DevBuf& dst, const void* src, size_t bytes) {
+    dst.alloc(bytes, lane.stream);
+    void* pin = staging(lane, bytes);
+    memcpy(pin, src, bytes);
+    CUDA_CHECK(cudaMemcpyAsync(dst.p, pin, bytes, cudaMemcpyHostToDevice, lane.stream));
+    lane.in_busy = true;
+}
+
+void download(Lane& lane, void* dst, const void* src_dev, size_t bytes) {
+    void* pin = lane.pin_out.get(bytes);
+    CUDA_CHECK(cudaMemcpyAsync(pin, src_dev, bytes, cudaMemcpyDeviceToHost, lane.stream));
+    CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+    lane.in_busy = false;
+    memcpy(dst, pin, bytes);
+}
+
+// One preprocessing step on host buffers: upload, run, download.
+template <typename F>
+int pp_step(bbocr_handle* h, const uint8_t* src, size_t in_bytes, uint8_t* out, size_t out_bytes, F&& run) {
+    return guarded(h, [&] {
+        ARG_CHECK(src && out && in_bytes > 0 && out_bytes > 0, "null or empty buffer");
+        Lane& lane = h->lanes[0];
+        DevBuf din, dout(out_bytes, lane.stream);
+        upload(lane, din, src, in_bytes);
+        run(lane.stream, din.as<uint8_t>(), dout.as<uint8_t>());
+        download(lane, out, dout.p, out_bytes);
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bbocr_version(void) { return "bbocr-b200 0.1 (sm_100a)"; }
+
+int bbocr_create(int device, bbocr_handle** out) {
+    if (!out) return BBOCR_E_ARG;
+    *out = nullptr;
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            fail(BBOCR_E_CUDA, "no CUDA device available (%s); libbbocr has no CPU path", cudaGetErrorString(e));
+        ARG_CHECK(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            fail(BBOCR_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                 prop.major, prop.minor);
+        std::unique_ptr<bbocr_handle> h(new bbocr_handle());
+        h->device = device;
+        h->sm_count = prop.multiProcessorCount;
+        h->lanes.resize(4);
+        for (auto& l : h->lanes) CUDA_CHECK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        // keep freed blocks in the stream-ordered pool instead of returning them to the driver after every sync
+        cudaMemPool_t pool;
+        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thresh = UINT64_MAX;
+        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        *out = h.release();
+        return BBOCR_OK;
+    } catch (const Error& e) {
+        g_create_err = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_create_err = e.what();
+        return BBOCR_E_ARG;
+    }
+}
+
+void bbocr_destroy(bbocr_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& l : h->lanes)
+        if (l.stream) cudaStreamDestroy(l.stream);
+    for (void* p : h->owned) cudaFree(p);
+    for (auto& ev : h->conv_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    delete h;
+}
+
+const char* bbocr_last_error(const bbocr_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int bbocr_load_craft(bbocr_handle* h, const bbocr_tensor* t, int n) {
+    return guarded(h, [&] { ARG_CHECK(t && n > 0, "no tensors"); load_craft(h, t, n); });
+}
+int bbocr_load_crnn(bbocr_handle* h, const bbocr_tensor* t, int n) {
+    return guarded(h, [&] { ARG_CHECK(t && n > 0, "no tensors"); load_crnn(h, t, n); });
+}
+int bbocr_set_precision(bbocr_handle* h, int prec) {
+    return guarded(h, [&] {
+        ARG_CHECK(prec == BBOCR_PREC_FP32 || prec == BBOCR_PREC_BF16, "unknown precision %d", prec);
+        h->precision = prec;
+    });
+}
+int bbocr_get_precision(const bbocr_handle* h) { return h ? h->precision : BBOCR_E_ARG; }
+
+// ---- preprocessing ---------------------------------------------------------------------------------------------------
+int bbocr_preprocess_launches_per_image(void) { return preprocess_launches_per_image(); }
+
+int bbocr_preprocess_u8(bbocr_handle* h, const uint8_t* bgr, int H, int W, int stride, int in_on_device,
+                        const bbocr_pp_params* p, uint8_t* out, int out_on_device, int* outH, int* outW) {
+    return guarded(h, [&] {
+        ARG_CHECK(bgr && p && out && outH && outW && H > 0 && W > 0 && stride >= W * 3, "bad arguments");
+        Lane& lane = h->lanes[0];
+        DevBuf din, dout;
+        const uint8_t* src = bgr;
+        if (!in_on_device) {
+            upload(lane, din, bgr, (size_t)H * stride);
+            src = din.as<uint8_t>();
+        }
+        int dH = (int)(H * (double)p->scale), dW = (int)(W * (double)p->scale);
+        ARG_CHECK(dH > 0 && dW > 0, "empty output");
+        uint8_t* dst = out;
+        if (!out_on_device) {
+            dout.alloc((size_t)dH * dW, lane.stream);
+            dst = dout.as<uint8_t>();
+        }
+        preprocess_chain_dev(h, lane.stream, src, H, W, stride, *p, dst, outH, outW);
+        if (!out_on_device) download(lane, out, dst, (size_t)dH * dW);
+        else CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+    });
+}
+
+int bbocr_pp_gray(bbocr_handle* h, const uint8_t* bgr, int H, int W, uint8_t* out) {
+    return pp_step(h, bgr, (size_t)H * W * 3, out, (size_t)H * W,
+                   [&](cudaStream_t st, const uint8_t* s, uint8_t* d) { pp_gray(h, st, s, H, W, W * 3, d); });
+}
+int bbocr_pp_resize_cubic(bbocr_handle* h, const uint8_t* src, int H, int W, int dstH, int dstW, int mode, uint8_t* out) {
+    return pp_step(h, src, (size_t)H * W, out, (size_t)dstH * dstW,
+                   [&](cudaStream_t st, const uint8_t* s, uint8_t* d) { pp_resize_cubic(h, st, s, H, W, d, dstH, dstW, mode); });
+}
+int bbocr_pp_gaussian3(bbocr_handle* h, const uint8_t* src, int H, int W, float sigma, uint8_t* out) {
+    return pp_step(h, src, (size_t)H * W, out, (size_t)H * W,
+                   [&](cudaStream_t st, const uint8_t* s, uint8_t* d) { pp_gaussian3(h, st, s, d, H, W, sigma, nullptr); });
+}
+static int tone_step(bbocr_handle* h, const uint8_t* src, int H, int W, float contrast, float brightness, uint8_t* out) {
+    return pp_step(h, src, (size_t)H * W, out, (size_t)H * W, [&](cudaStream_t st, const uint8_t* s, uint8_t* d) {
+        DevBuf small(8 + 256, st);
+        unsigned long long* sum = small.as<unsigned long long>();
+        uint8_t* lut = small.as<uint8_t>() + 8;
+        pp_sum(h, st, s, (int64_t)H * W, sum);
+        pp_tone_lut(h, st, sum, (int64_t)H * W, contrast, brightness, lut);
+        pp_apply_lut(h, st, s, d, (int64_t)H * W, lut);
+    });
+}
+int bbocr_pp_contrast(bbocr_handle* h, const uint8_t* src, int H, int W, float factor, uint8_t* out) {
+    return tone_step(h, src, H, W, factor, 0.f, out);
+}
+int bbocr_pp_brightness(bbocr_handle* h, const uint8_t* src, int H, int W, float factor, uint8_t* out) {
+    return tone_step(h, src, H, W, 0.f, factor, out);
+}
+int bbocr_pp_clahe(bbocr_handle* h, const uint8_t* src, int H, int W, float clip, uint8_t* out) {
+    return pp_step(h, src, (size_t)H * W, out, (size_t)H * W, [&](cudaStream_t st, const uint8_t* s, uint8_t* d) {
+        DevBuf small(64 * 256 * 4 + 64 * 256, st);
+        unsigned int* hist = small.as<unsigned int>();
+        uint8_t* luts = small.as<uint8_t>() + 64 * 256 * 4;
+        pp_clahe_luts(h, st, s, H, W, clip, nullptr, hist, luts);
+        pp_clahe_apply(h, st, s, d, H, W, nullptr, luts);
+    });
+}
+int bbocr_pp_unsharp(bbocr_handle* h, const uint8_t* src, int H, int W, int percent, int threshold, uint8_t* out) {
+    return pp_step(h, src, (size_t)H * W, out, (size_t)H * W, [&](cudaStream_t st, const uint8_t* s, uint8_t* d) {
+        pp_unsharp(h, st, s, d, H, W, percent, threshold, nullptr, nullptr);
+    });
+}
+int bbocr_pp_adaptive_threshold(bbocr_handle* h, const uint8_t* src, int H, int W, int method, int inv, int block,
+                                float delta, uint8_t* out) {
+    return pp_step(h, src, (size_t)H * W, out, (size_t)H * W, [&](cudaStream_t st, const uint8_t* s, uint8_t* d) {
+        pp_adaptive_threshold(h, st, s, d, H, W, method, inv, block, delta);
+    });
+}
+int bbocr_pp_deskew(bbocr_handle* h, const uint8_t* src, int H, int W, float max_deg, uint8_t* out, float* angle_out) {
+    return pp_step(h, src, (size_t)H * W, out, (size_t)H * W, [&](cudaStream_t st, const uint8_t* s, uint8_t* d) {
+        float a = pp_deskew(h, st, s, d, H, W, max_deg);
+        if (angle_out) *angle_out = a;
+    });
+}
+
+// ---- detector ---------------------------------------------------------------------------------------------------------
+int bbocr_craft_forward(bbocr_handle* h, const uint8_t* img, int H, int W, int on_device, int canvas_size,
+                        double mag_ratio, float* score_text, float* score_link, int* mapH, int* mapW, double* ratio) {
+    return guarded(h, [&] {
+        ARG_CHECK(H > 0 && W > 0 && canvas_size >= 32, "bad geometry");
+        CanvasGeom g = canvas_geom(H, W, canvas_size, mag_ratio);
+        if (mapH) *mapH = g.H32 / 2;
+        if (mapW) *mapW = g.W32 / 2;
+        if (ratio) *ratio = g.ratio;
+        if (!score_text || !score_link) return;          // size query
+        ARG_CHECK(img, "null image");
+        Lane& lane = h->lanes[0];
+        DevBuf din;
+        const uint8_t* src = img;
+        if (!on_device) { upload(lane, din, img, (size_t)H * W * 3); src = din.as<uint8_t>(); }
+        size_t n = (size_t)(g.H32 / 2) * (g.W32 / 2);
+        DevBuf maps(n * 8, lane.stream);
+        craft_forward_dev(h, lane.stream, src, g, maps.as<float>(), maps.as<float>() + n);
+        std::vector<float> tmp(n * 2);
+        download(lane, tmp.data(), maps.p, n * 8);
+        memcpy(score_text, tmp.data(), n * 4);
+        memcpy(score_link, tmp.data() + n, n * 4);
+    });
+}
+
+int bbocr_det_boxes(bbocr_handle* h, const float* textmap, const float* linkmap, int mapH, int mapW,
+                    double text_threshold, double link_threshold, double low_text, float* boxes, int cap, int* n) {
+    return guarded(h, [&] {
+        ARG_CHECK(textmap && linkmap && boxes && n && mapH > 0 && mapW > 0, "bad arguments");
+        Lane& lane = h->lanes[0];
+        size_t np = (size_t)mapH * mapW;
+        DevBuf dt, dl;
+        upload(lane, dt, textmap, np * 4);
+        CUDA_CHECK(cudaStreamSynchronize(lane.stream));      // pin_in is reused by the next upload
+        upload(lane, dl, linkmap, np * 4);
+        DetComponents dc;
+        det_components_dev(h, lane, dt.as<float>(), dl.as<float>(), mapH, mapW, (float)text_threshold,
+                           (float)link_threshold, (float)low_text, dc);
+        std::vector<float> b;
+        boxes_from_components(dc, mapH, mapW, b);
+        int nb = (int)b.size() / 8;
+        ARG_CHECK(nb <= cap, "box capacity %d too small for %d boxes", cap, nb);
+        memcpy(boxes, b.data(), b.size() * 4);
+        *n = nb;
+    });
+}
+
+int bbocr_min_area_box(const int32_t* xy, int npoints, float* out8) {
+    if (!xy || !out8 || npoints <= 0) return BBOCR_E_ARG;
+    try {
+        min_area_box(xy, npoints, out8);
+    } catch (...) {
+        return BBOCR_E_ARG;
+    }
+    return BBOCR_OK;
+}
+
+int bbocr_dbg_convex_hull(const int32_t* xy, int n, int clockwise, int32_t* out, int* nout) {
+    std::vector<int> hull;
+    debug_convex_hull(xy, n, clockwise, hull);
+    for (size_t i = 0; i < hull.size(); ++i) out[i] = hull[i];
+    *nout = (int)hull.size();
+    return 0;
+}
+
+int bbocr_group_boxes(const float* boxes, int n, double ratio, const bbocr_group_params* p, int32_t* hlist, int* nh,
+                      double* flist, int* nf, int cap) {
+    if (!p || !hlist || !nh || !flist || !nf || n < 0 || (n > 0 && !boxes)) return BBOCR_E_ARG;
+    try {
+        std::vector<int32_t> hl;
+        std::vector<double> fl;
+        group_boxes(boxes, n, ratio, *p, hl, fl);
+        if ((int)hl.size() / 4 > cap || (int)fl.size() / 8 > cap) return BBOCR_E_ARG;
+        memcpy(hlist, hl.data(), hl.size() * 4);
+        memcpy(flist, fl.data(), fl.size() * 8);
+        *nh = (int)hl.size() / 4;
+        *nf = (int)fl.size() / 8;
+    } catch (...) {
+        return BBOCR_E_ARG;
+    }
+    return BBOCR_OK;
+}
+
+void bbocr_default_params(bbocr_params* p) {
+    if (!p) return;
+    p->min_size = 20;
+    p->canvas_size = 2560;
+    p->contrast_ths = 0.1;
+    p->adjust_contrast = 0.5;
+    p->text_threshold = 0.7;
+    p->low_text = 0.4;
+    p->link_threshold = 0.4;
+    p->mag_ratio = 1.0;
+    p->slope_ths = 0.1;
+    p->ycenter_ths = 0.5;
+    p->height_ths = 0.5;
+    p->width_ths = 0.5;
+    p->add_margin = 0.1;
+    p->ignore = nullptr;
+}
+
+}  // extern "C"
+
+// ======================================================================================================================
+// recognition orchestration
+// ======================================================================================================================
+namespace {
+
+struct CropJob {
+    CropDesc d;
+    bool is_free = false;
+    double box[8];          // result box (clamped ints for horizontal boxes, the free quad otherwise)
+    bool tall = false;
+};
+
+// utils.get_image_list geometry for one horizontal box [xmin,xmax,ymin,ymax]
+bool horizontal_job(const int32_t* b, int H, int W, CropJob& j) {
+    int x_min = std::max(0, b[0]), x_max = std::min(b[1], W), y_min = std::max(0, b[2]), y_max = std::min(b[3], H);
+    int width = x_max - x_min, height = y_max - y_min;
+    if (width <= 0 || height <= 0) fail(BBOCR_E_ARG, "degenerate text box %dx%d (upstream raises here as well)", width, height);
+    j.d.x0 = x_min; j.d.y0 = y_min; j.d.w = width; j.d.h = height;
+    j.d.free_idx = -1;
+    j.is_free = false;
+    double q[8] = {(double)x_min, (double)y_min, (double)x_max, (double)y_min, (double)x_max, (double)y_max, (double)x_min, (double)y_max};
+    memcpy(j.box, q, sizeof q);
+    return true;
+}
+
+// calculate_ratio + compute_ratio_and_resize + AlignCollate geometry; returns false when upstream skips the box
+bool finish_geometry(CropJob& j) {
+    const int width = j.d.w, height = j.d.h;
+    double ratio = (double)width / (double)height;
+    double cr = ratio < 1.0 ? 1.0 / ratio : ratio;                 // calculate_ratio
+    int new_width = (int)(64 * cr);
+    if (new_width == 0) return false;
+    if (ratio < 1.0) { j.d.ow = 64; j.d.oh = (int)(64 * cr); j.tall = true; }
+    else { j.d.ow = (int)(64 * ratio); j.d.oh = 64; j.tall = false; }
+    double max_ratio = std::max(cr, 1.0);
+    j.d.model_w = (int)std::ceil(std::ceil(max_ratio)) * 64;
+    // AlignCollate: ratio = w / float(h); resized_w = min(ceil(64 * ratio), imgW)
+    double r2 = (double)j.d.ow / (double)j.d.oh;
+    int rw = (int)std::ceil(64 * r2);
+    j.d.resized_w = rw > j.d.model_w ? j.d.model_w : rw;
+    if (j.d.oh == 64 && j.d.resized_w == j.d.ow) j.tall = false;    // identity resize
+    return true;
+}
+
+// np.percentile(img, q) (method='linear') from a 256-bin histogram, replicating NumPy's float64 arithmetic
+double percentile_from_hist(const unsigned int* hist, int64_t n, double q100) {
+    double q = q100 / 100.0;
+    double vi = (double)n * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;
+    double prev_f = std::floor(vi);
+    int64_t prev = (int64_t)prev_f, next = prev + 1;
+    double gamma = vi - prev_f;
+    prev = std::min<int64_t>(std::max<int64_t>(prev, 0), n - 1);
+    next = std::min<int64_t>(std::max<int64_t>(next, 0), n - 1);
+    auto value_at = [&](int64_t k) {
+        int64_t c = 0;
+        for (int v = 0; v < 256; ++v) {
+            c += hist[v];
+            if (k < c) return (double)v;
+        }
+        return 255.0;
+    };
+    double a = value_at(prev), b = value_at(next);
+    double diff = b - a;
+    double r = a + diff * gamma;
+    if (gamma >= 0.5) r = b - diff * (1 - gamma);
+    return r;
+}
+
+struct Recognized {
+    std::vector<int32_t> text;
+    double conf = 0;
+};
+
+// custom_mean over the max probabilities of the non-blank timesteps (float32 running product, float64 pow)
+double confidence_of(const float* prob, const int32_t* idx, int T) {
+    float prod = 1.f;
+    int cnt = 0;
+    for (int t = 0; t < T; ++t)
+        if (idx[t] != 0) { prod = prod * prob[t]; ++cnt; }
+    if (cnt == 0) return 0.0;
+    return std::pow((double)prod, 2.0 / std::sqrt((double)cnt));
+}
+
+// One pass of AlignCollate -> CRNN -> decode over `jobs` whose (possibly contrast-adjusted) crops live in `crops`.
+void recognize_pass(Handle* h, Lane& lane, std::vector<CropJob>& jobs, const std::vector<int>& which, const uint8_t* crops,
+                    size_t crops_bytes, const uint8_t* ignore_dev, std::vector<Recognized>& out) {
+    cudaStream_t st = lane.stream;
+    const int n = (int)which.size();
+    out.assign(n, Recognized());
+    if (n == 0) return;
+    // aligned buffer: tall crops are Pillow-resized to 64 rows, the rest alias the crop buffer
+    size_t aligned_extra = 0, scratch_max = 0;
+    for (int i : which)
+        if (jobs[i].tall) {
+            aligned_extra += (size_t)64 * jobs[i].d.resized_w;
+            scratch_max = std::max(scratch_max, (size_t)jobs[i].d.oh * std::max(jobs[i].d.resized_w, jobs[i].d.ow));
+        }
+    DevBuf aligned_buf(crops_bytes + aligned_extra + 16, st), pil_scratch(scratch_max + 16, st);
+    CUDA_CHECK(cudaMemcpyAsync(aligned_buf.p, crops, crops_bytes, cudaMemcpyDeviceToDevice, st));
+    size_t acur = crops_bytes;
+    // buckets by model width, in first-appearance order
+    std::vector<int> bucket_w, bucket_n;
+    std::vector<CropDesc> descs(n);
+    for (int k = 0; k < n; ++k) {
+        CropJob& j = jobs[which[k]];
+        if (j.tall) {
+            pil_resize_bicubic_dev(h, st, aligned_buf.as<uint8_t>() + j.d.off, j.d.oh, j.d.ow,
+                                   aligned_buf.as<uint8_t>() + acur, 64, j.d.resized_w, pil_scratch.as<uint8_t>());
+            j.d.aoff = (int)acur;
+            acur += (size_t)64 * j.d.resized_w;
+        } else {
+            j.d.aoff = j.d.off;
+        }
+        int b = -1;
+        for (size_t q = 0; q < bucket_w.size(); ++q)
+            if (bucket_w[q] == j.d.model_w) b = (int)q;
+        if (b < 0) { b = (int)bucket_w.size(); bucket_w.push_back(j.d.model_w); bucket_n.push_back(0); }
+        j.d.slot = bucket_n[b]++;
+        j.d.bucket_off = b;                                       // bucket index for now
+    }
+    std::vector<size_t> bucket_off(bucket_w.size());
+    size_t in_floats = 0, logit_floats = 0, step_elems = 0;
+    std::vector<size_t> logit_off(bucket_w.size()), step_off(bucket_w.size());
+    const int C = h->crnn.num_class;
+    int max_w = 0;
+    for (size_t q = 0; q < bucket_w.size(); ++q) {
+        bucket_off[q] = in_floats;
+        in_floats += (size_t)bucket_n[q] * 64 * bucket_w[q];
+        int T = bucket_w[q] / 4 - 1;
+        logit_off[q] = logit_floats;
+        logit_floats += (size_t)bucket_n[q] * T * C;
+        step_off[q] = step_elems;
+        step_elems += (size_t)bucket_n[q] * T;
+        max_w = std::max(max_w, bucket_w[q]);
+    }
+    std::vector<int> job_bucket(n);
+    for (int k = 0; k < n; ++k) {
+        CropJob& j = jobs[which[k]];
+        job_bucket[k] = j.d.bucket_off;
+        j.d.bucket_off = (int)bucket_off[job_bucket[k]];
+        descs[k] = j.d;
+    }
+    DevBuf ddesc, inputs(in_floats * 4, st), logits(logit_floats * 4, st);
+    upload(lane, ddesc, descs.data(), descs.size() * sizeof(CropDesc));
+    crops_to_input_dev(h, st, aligned_buf.as<uint8_t>(), ddesc.as<CropDesc>(), n, max_w, inputs.as<float>());
+    // decode outputs: [text_idx | step_idx] int32 (step_elems each), text_len (n), step_prob float
+    DevBuf dec((step_elems * 3 + (size_t)n) * 4, st);
+    int32_t* text_idx = dec.as<int32_t>();
+    int32_t* step_idx = text_idx + step_elems;
+    float* step_prob = reinterpret_cast<float*>(step_idx + step_elems);
+    int32_t* text_len = reinterpret_cast<int32_t*>(step_prob + step_elems);
+    std::vector<size_t> len_off(bucket_w.size());
+    size_t lo = 0;
+    for (size_t q = 0; q < bucket_w.size(); ++q) {
+        int T = bucket_w[q] / 4 - 1;
+        crnn_forward_dev(h, st, inputs.as<float>() + bucket_off[q], bucket_n[q], bucket_w[q], logits.as<float>() + logit_off[q]);
+        ctc_decode_dev(h, st, logits.as<float>() + logit_off[q], bucket_n[q], T, C, ignore_dev, text_idx + step_off[q],
+                       text_len + lo, step_prob + step_off[q], step_idx + step_off[q]);
+        len_off[q] = lo;
+        lo += bucket_n[q];
+    }
+    std::vector<int32_t> hdec(step_elems * 3 + n);
+    download(lane, hdec.data(), dec.p, hdec.size() * 4);
+    const int32_t* h_text = hdec.data();
+    const int32_t* h_sidx = h_text + step_elems;
+    const float* h_prob = reinterpret_cast<const float*>(h_sidx + step_elems);
+    const int32_t* h_len = reinterpret_cast<const int32_t*>(h_prob + step_elems);
+    for (int k = 0; k < n; ++k) {
+        const CropJob& j = jobs[which[k]];
+        int q = job_bucket[k], T = bucket_w[q] / 4 - 1;
+        size_t so = step_off[q] + (size_t)j.d.slot * T;
+        int len = h_len[len_off[q] + j.d.slot];
+        out[k].text.assign(h_text + so, h_text + so + len);
+        out[k].conf = confidence_of(h_prob + so, h_sidx + so, T);
+    }
+}
+
+// Reader.readtext for one page on one lane
+bbocr_results* readtext_page(Handle* h, Lane& lane, const bbocr_image& img, const bbocr_params& p) {
+    cudaStream_t st = lane.stream;
+    ARG_CHECK(img.color && img.H > 0 && img.W > 0, "bad image");
+    if (!h->craft_loaded || !h->crnn_loaded) fail(BBOCR_E_STATE, "weights not loaded");
+    const int H = img.H, W = img.W;
+    DevBuf dcolor, dgray, dignore;
+    const uint8_t* color = img.color;
+    const uint8_t* gray = img.gray;
+    if (!img.on_device) {
+        size_t cb = (size_t)H * W * 3, gb = img.gray ? (size_t)H * W : 0;
+        uint8_t* pin = (uint8_t*)staging(lane, cb + gb);
+        memcpy(pin, img.color, cb);
+        if (gb) memcpy(pin + cb, img.gray, gb);
+        dcolor.alloc(cb + gb, st);
+        CUDA_CHECK(cudaMemcpyAsync(dcolor.p, pin, cb + gb, cudaMemcpyHostToDevice, st));
+        lane.in_busy = true;
+        color = dcolor.as<uint8_t>();
+        gray = gb ? dcolor.as<uint8_t>() + cb : nullptr;
+    }
+    if (!gray) {                                      // reformat_input: cv2.cvtColor(image, COLOR_BGR2GRAY)
+        dgray.alloc((size_t)H * W, st);
+        pp_gray(h, st, color, H, W, W * 3, dgray.as<uint8_t>());
+        gray = dgray.as<uint8_t>();
+    }
+    const uint8_t* ignore_dev = nullptr;
+    if (p.ignore) {
+        upload(lane, dignore, p.ignore, h->crnn.num_class);
+        ignore_dev = dignore.as<uint8_t>();
+    }
+    // ---- detect -------------------------------------------------------------------------------------------------
+    CanvasGeom g = canvas_geom(H, W, p.canvas_size, p.mag_ratio);
+    const int mh = g.H32 / 2, mw = g.W32 / 2;
+    DevBuf maps((size_t)mh * mw * 8, st);
+    float* text = maps.as<float>();
+    float* link = text + (size_t)mh * mw;
+    craft_forward_dev(h, st, color, g, text, link);
+    DetComponents dc;
+    det_components_dev(h, lane, text, link, mh, mw, (float)p.text_threshold, (float)p.link_threshold, (float)p.low_text, dc);
+    maps.release();
+    std::vector<float> boxes;
+    boxes_from_components(dc, mh, mw, boxes);
+    bbocr_group_params gp{p.slope_ths, p.ycenter_ths, p.height_ths, p.width_ths, p.add_margin, p.min_size};
+    std::vector<int32_t> hlist;
+    std::vector<double> flist;
+    group_boxes(boxes.data(), (int)boxes.size() / 8, g.ratio, gp, hlist, flist);
+    // ---- recognize (batch_size == 1 semantics: every box has its own max_width) -------------------------------------
+    std::vector<CropJob> jobs;
+    std::vector<double> mats;
+    size_t scratch_bytes = 0;
+    for (size_t i = 0; i + 4 <= hlist.size(); i += 4) {
+        CropJob j;
+        horizontal_job(&hlist[i], H, W, j);
+        if (finish_geometry(j)) jobs.push_back(j);
+    }
+    for (size_t i = 0; i + 8 <= flist.size(); i += 8) {
+        CropJob j;
+        int mwid, mhei;
+        double M[9];
+        free_box_transform(&flist[i], &mwid, &mhei, M);
+        if (mwid <= 0 || mhei <= 0) fail(BBOCR_E_ARG, "degenerate free-form box");
+        j.is_free = true;
+        memcpy(j.box, &flist[i], 64);
+        j.d.free_idx = (int)mats.size() / 9;
+        mats.insert(mats.end(), M, M + 9);
+        j.d.x0 = (int)scratch_bytes; j.d.y0 = 0; j.d.w = mwid; j.d.h = mhei;
+        scratch_bytes += (size_t)mwid * mhei;
+        if (finish_geometry(j)) jobs.push_back(j);
+    }
+    const int n = (int)jobs.size();
+    bbocr_results* r = new bbocr_results();
+    memset(r, 0, sizeof *r);
+    r->n_components = dc.n_labels;
+    std::vector<Recognized> final_rec(n);
+    if (n > 0) {
+        size_t crops_bytes = 0;
+        for (auto& j : jobs) { j.d.off = (int)crops_bytes; crops_bytes += (size_t)j.d.ow * j.d.oh; }
+        std::vector<CropDesc> descs(n);
+        for (int i = 0; i < n; ++i) descs[i] = jobs[i].d;
+        DevBuf ddesc, dmats, dscratch(scratch_bytes + 16, st), dcrops(crops_bytes + 16, st);
+        upload(lane, ddesc, descs.data(), descs.size() * sizeof(CropDesc));
+        if (!mats.empty()) {
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            upload(lane, dmats, mats.data(), mats.size() * 8);
+        }
+        crops_dev(h, st, gray, H, W, ddesc.as<CropDesc>(), n, descs.data(), dmats.as<double>(), dscratch.as<uint8_t>(),
+                  dcrops.as<uint8_t>());
+        CUDA_CHECK(cudaStreamSynchronize(st));             // pin_in (descs) is reused below
+        std::vector<int> all(n);
+        for (int i = 0; i < n; ++i) all[i] = i;
+        std::vector<Recognized> rec1;
+        recognize_pass(h, lane, jobs, all, dcrops.as<uint8_t>(), crops_bytes, ignore_dev, rec1);
+        r->n_crops = n;
+        std::vector<int> low;
+        for (int i = 0; i < n; ++i)
+            if (rec1[i].conf < p.contrast_ths) low.push_back(i);
+        final_rec = rec1;
+        if (!low.empty()) {
+            // second round: adjust_contrast_grey(target = adjust_contrast) on the low-confidence crops
+            const int nl = (int)low.size();
+            std::vector<CropDesc> ldesc(nl);
+            for (int k = 0; k < nl; ++k) ldesc[k] = jobs[low[k]].d;
+            DevBuf dl, dhist((size_t)nl * 256 * 4, st), dadj(crops_bytes + 16, st);
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            upload(lane, dl, ldesc.data(), ldesc.size() * sizeof(CropDesc));
+            crop_hist_dev(h, st, dcrops.as<uint8_t>(), dl.as<CropDesc>(), nl, dhist.as<unsigned int>());
+            std::vector<unsigned int> hist((size_t)nl * 256);
+            download(lane, hist.data(), dhist.p, hist.size() * 4);
+            std::vector<double> lowv(nl), ratio(nl);
+            std::vector<int> apply(nl);
+            for (int k = 0; k < nl; ++k) {
+                int64_t np = (int64_t)ldesc[k].ow * ldesc[k].oh;
+                double high = percentile_from_hist(&hist[(size_t)k * 256], np, 90.0);
+                double lo = percentile_from_hist(&hist[(size_t)k * 256], np, 10.0);
+                double contrast = (high - lo) / std::max(10.0, high + lo);
+                apply[k] = contrast < p.adjust_contrast;
+                lowv[k] = lo;
+                ratio[k] = 200.0 / std::max(10.0, high - lo);
+            }
+            std::vector<uint8_t> packed((size_t)nl * 20);
+            DevBuf dpar;
+            std::vector<double> par((size_t)nl * 2);
+            memcpy(par.data(), lowv.data(), nl * 8);
+            memcpy(par.data() + nl, ratio.data(), nl * 8);
+            upload(lane, dpar, par.data(), par.size() * 8);
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            DevBuf dapply;
+            upload(lane, dapply, apply.data(), (size_t)nl * 4);
+            crop_contrast_dev(h, st, dcrops.as<uint8_t>(), dl.as<CropDesc>(), nl, dpar.as<double>(), dpar.as<double>() + nl,
+                              dapply.as<int>(), dadj.as<uint8_t>());
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            std::vector<Recognized> rec2;
+            recognize_pass(h, lane, jobs, low, dadj.as<uint8_t>(), crops_bytes, ignore_dev, rec2);
+            r->n_crops += nl;
+            for (int k = 0; k < nl; ++k)
+                if (!(rec1[low[k]].conf > rec2[k].conf)) final_rec[low[k]] = rec2[k];
+        }
+    }
+    // ---- assemble (horizontal boxes in group order, then free boxes) ----------------------------------------------
+    r->n = n;
+    r->box = new double[(size_t)std::max(n, 1) * 8];
+    r->is_free = new uint8_t[std::max(n, 1)];
+    r->text_off = new int32_t[n + 1];
+    r->conf = new double[std::max(n, 1)];
+    size_t total = 0;
+    for (auto& f : final_rec) total += f.text.size();
+    r->text_idx = new int32_t[std::max<size_t>(total, 1)];
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+        memcpy(r->box + (size_t)i * 8, jobs[i].box, 64);
+        r->is_free[i] = jobs[i].is_free;
+        r->text_off[i] = (int32_t)off;
+        memcpy(r->text_idx + off, final_rec[i].text.data(), final_rec[i].text.size() * 4);
+        off += final_rec[i].text.size();
+        r->conf[i] = final_rec[i].conf;
+    }
+    r->text_off[n] = (int32_t)off;
+    return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+void bbocr_results_free(bbocr_results* r) {
+    if (!r) return;
+    delete[] r->box;
+    delete[] r->is_free;
+    delete[] r->text_off;
+    delete[] r->text_idx;
+    delete[] r->conf;
+    delete r;
+}
+
+int bbocr_readtext(bbocr_handle* h, const bbocr_image* img, const bbocr_params* p, bbocr_results** out) {
+    return guarded(h, [&] {
+        ARG_CHECK(img && out, "null argument");
+        bbocr_params dp;
+        if (!p) { bbocr_default_params(&dp); p = &dp; }
+        *out = readtext_page(h, h->lanes[0], *img, *p);
+    });
+}
+
+int bbocr_readtext_batch(bbocr_handle* h, int n, const bbocr_image* imgs, const bbocr_params* p, bbocr_results** out) {
+    return guarded(h, [&] {
+        ARG_CHECK(n >= 0 && (n == 0 || (imgs && out)), "null argument");
+        bbocr_params dp;
+        if (!p) { bbocr_default_params(&dp); p = &dp; }
+        for (int i = 0; i < n; ++i) out[i] = nullptr;
+        // pages are independent: each lane (stream + pinned staging + host thread) takes pages off a shared counter
+        const int nl = std::min<int>((int)h->lanes.size(), std::max(n, 1));
+        std::atomic<int> next{0};
+        std::vector<std::string> errs(nl);
+        std::vector<int> codes(nl, 0);
+        std::vector<std::thread> threads;
+        for (int l = 0; l < nl; ++l)
+            threads.emplace_back([&, l] {
+                try {
+                    CUDA_CHECK(cudaSetDevice(h->device));
+                    for (int i; (i = next.fetch_add(1)) < n;) out[i] = readtext_page(h, h->lanes[l], imgs[i], *p);
+                } catch (const Error& e) {
+                    errs[l] = e.what();
+                    codes[l] = e.code;
+                    next.store(n);
+                } catch (const std::exception& e) {
+                    errs[l] = e.what();
+                    codes[l] = BBOCR_E_ARG;
+                    next.store(n);
+                }
+            });
+        for (auto& t : threads) t.join();
+        for (int l = 0; l < nl; ++l)
+            if (codes[l]) {
+                for (int i = 0; i < n; ++i) { bbocr_results_free(out[i]); out[i] = nullptr; }
+                throw Error(codes[l], errs[l]);
+            }
+    });
+}
+
+// single-stage recogniser entry points (parity-test surface)
+int bbocr_crop_horizontal(bbocr_handle* h, const uint8_t* gray, int H, int W, const int32_t box[4], uint8_t* out, int cap,
+                          int* outH, int* outW, int* model_w) {
+    return guarded(h, [&] {
+        ARG_CHECK(gray && box && out && outH && outW && model_w && H > 0 && W > 0, "bad arguments");
+        Lane& lane = h->lanes[0];
+        CropJob j;
+        horizontal_job(box, H, W, j);
+        if (!finish_geometry(j)) { *outW = *outH = 0; *model_w = 0; return; }
+        ARG_CHECK(j.d.ow * j.d.oh <= cap, "crop buffer too small");
+        j.d.off = 0;
+        DevBuf dg, dd, dc((size_t)j.d.ow * j.d.oh + 16, lane.stream);
+        upload(lane, dg, gray, (size_t)H * W);
+        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        upload(lane, dd, &j.d, sizeof(CropDesc));
+        crops_dev(h, lane.stream, dg.as<uint8_t>(), H, W, dd.as<CropDesc>(), 1, &j.d, nullptr, nullptr, dc.as<uint8_t>());
+        download(lane, out, dc.p, (size_t)j.d.ow * j.d.oh);
+        *outW = j.d.ow; *outH = j.d.oh; *model_w = j.d.model_w;
+    });
+}
+
+int bbocr_crop_free(bbocr_handle* h, const uint8_t* gray, int H, int W, const double quad[8], uint8_t* out, int cap,
+                    int* outH, int* outW, int* model_w) {
+    return guarded(h, [&] {
+        ARG_CHECK(gray && quad && out && outH && outW && model_w && H > 0 && W > 0, "bad arguments");
+        Lane& lane = h->lanes[0];
+        CropJob j;
+        int mwid, mhei;
+        double M[9];
+        free_box_transform(quad, &mwid, &mhei, M);
+        ARG_CHECK(mwid > 0 && mhei > 0, "degenerate free-form box");
+        j.d.free_idx = 0; j.d.x0 = 0; j.d.y0 = 0; j.d.w = mwid; j.d.h = mhei;
+        if (!finish_geometry(j)) { *outW = *outH = 0; *model_w = 0; return; }
+        ARG_CHECK(j.d.ow * j.d.oh <= cap, "crop buffer too small");
+        j.d.off = 0;
+        DevBuf dg, dd, dm, ds((size_t)mwid * mhei + 16, lane.stream), dc((size_t)j.d.ow * j.d.oh + 16, lane.stream);
+        upload(lane, dg, gray, (size_t)H * W);
+        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        upload(lane, dd, &j.d, sizeof(CropDesc));
+        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        upload(lane, dm, M, 72);
+        crops_dev(h, lane.stream, dg.as<uint8_t>(), H, W, dd.as<CropDesc>(), 1, &j.d, dm.as<double>(), ds.as<uint8_t>(),
+                  dc.as<uint8_t>());
+        download(lane, out, dc.p, (size_t)j.d.ow * j.d.oh);
+        *outW = j.d.ow; *outH = j.d.oh; *model_w = j.d.model_w;
+    });
+}
+
+int bbocr_crnn_forward(bbocr_handle* h, const float* x, int N, int Wm, float* logits) {
+    return guarded(h, [&] {
+        ARG_CHECK(x && logits && N > 0 && Wm >= 64 && Wm % 64 == 0, "bad arguments");
+        Lane& lane = h->lanes[0];
+        const int T = Wm / 4 - 1, C = h->crnn.num_class;
+        DevBuf dx, dl((size_t)N * T * C * 4, lane.stream);
+        upload(lane, dx, x, (size_t)N * 64 * Wm * 4);
+        crnn_forward_dev(h, lane.stream, dx.as<float>(), N, Wm, dl.as<float>());
+        download(lane, logits, dl.p, (size_t)N * T * C * 4);
+    });
+}
+
+int bbocr_ctc_decode(bbocr_handle* h, const float* logits, int N, int T, int C, const uint8_t* ignore, int32_t* text_idx,
+                     int32_t* text_len, double* conf) {
+    return guarded(h, [&] {
+        ARG_CHECK(logits && text_idx && text_len && conf && N > 0 && T > 0 && C > 1, "bad arguments");
+        Lane& lane = h->lanes[0];
+        cudaStream_t st = lane.stream;
+        DevBuf dlg, dig;
+        upload(lane, dlg, logits, (size_t)N * T * C * 4);
+        if (ignore) {
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            upload(lane, dig, ignore, C);
+        }
+        size_t se = (size_t)N * T;
+        DevBuf dec((se * 3 + N) * 4, st);
+        int32_t* d_text = dec.as<int32_t>();
+        int32_t* d_sidx = d_text + se;
+        float* d_prob = reinterpret_cast<float*>(d_sidx + se);
+        int32_t* d_len = reinterpret_cast<int32_t*>(d_prob + se);
+        ctc_decode_dev(h, st, dlg.as<float>(), N, T, C, ignore ? dig.as<uint8_t>() : nullptr, d_text, d_len, d_prob, d_sidx);
+        std::vector<int32_t> hd(se * 3 + N);
+        download(lane, hd.data(), dec.p, hd.size() * 4);
+        memcpy(text_idx, hd.data(), se * 4);
+        memcpy(text_len, hd.data() + se * 3, (size_t)N * 4);
+        const float* prob = reinterpret_cast<const float*>(hd.data() + se * 2);
+        for (int i = 0; i < N; ++i) conf[i] = confidence_of(prob + (size_t)i * T, hd.data() + se + (size_t)i * T, T);
+    });
+}
+
+int64_t bbocr_launch_count(const bbocr_handle* h) { return h ? h->launches.load() : 0; }
+void bbocr_reset_launch_count(bbocr_handle* h) {
+    if (h) h->launches.store(0);
+}
+int bbocr_enable_conv_timing(bbocr_handle* h, int on) {
+    return guarded(h, [&] { h->conv_timing = on != 0; });
+}
+int bbocr_conv_stats(bbocr_handle* h, double* ms, int64_t* launches, double* flops) {
+    return guarded(h, [&] {
+        CUDA_CHECK(cudaDeviceSynchronize());
+        std::lock_guard<std::mutex> g(h->stat_mu);
+        double total = 0;
+        for (auto& ev : h->conv_events) {
+            float t = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&t, ev.first, ev.second));
+            total += t;
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
+        h->conv_events.clear();
+        if (ms) *ms = total;
+        if (launches) *launches = h->conv_launches;
+        if (flops) *flops = h->conv_flops;
+        h->conv_launches = 0;
+        h->conv_flops = 0;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// common.cuh -- shared plumbing for libbbocr.so (handle, error propagation, stream-ordered buffers, launch counting)
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/bbocr.h"
+
+namespace bbocr {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] inline void fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Error(code, buf);
+}
+
+#define CUDA_CHECK(expr)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            ::bbocr::fail(BBOCR_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define ARG_CHECK(cond, ...)                                   \
+    do {                                                       \
+        if (!(cond)) ::bbocr::fail(BBOCR_E_ARG, __VA_ARGS__);  \
+    } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Stream-ordered device buffer (cudaMallocAsync pool: no device-wide sync on alloc/free).
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(size_t n, cudaStream_t st) { alloc(n, st); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), s(o.s) { o.p = nullptr; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; s = o.s; o.p = nullptr; }
+        return *this;
+    }
+    void alloc(size_t n, cudaStream_t st) {
+        release();
+        s = st;
+        bytes = n ? n : 16;
+        CUDA_CHECK(cudaMallocAsync(&p, bytes, s));
+    }
+    void release() {
+        if (p) { cudaFreeAsync(p, s); p = nullptr; }
+    }
+    ~DevBuf() { release(); }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Pinned host staging buffer that grows on demand (one per lane; reused across pages).
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* get(size_t n) {
+        if (n > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = n + n / 4 + 4096;
+            CUDA_CHECK(cudaMallocHost(&p, cap));
+        }
+        return p;
+    }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+
+// ---- activation tensors: NHWC, element type float (FP32 mode) or __nv_bfloat16 (BF16 mode) --------------------------
+struct Act {
+    void* p = nullptr;
+    int N = 0, H = 0, W = 0, C = 0;
+    int64_t elems() const { return (int64_t)N * H * W * C; }
+};
+
+// Convolution parameters after load-time folding (BatchNorm -> per-channel scale/bias applied in the epilogue).
+struct ConvW {
+    int cin = 0, cout = 0, kh = 0, kw = 0, pad = 0, dil = 1;
+    int cout_pad = 0;                 // cout rounded up to 16 (BF16 weight rows)
+    float* w_f32 = nullptr;           // [kh*kw][cin][cout]          (FP32 path; cout contiguous)
+    __nv_bfloat16* w_bf16 = nullptr;  // [kh*kw][cout_pad][cin]      (tcgen05 path; K-major rows)
+    float* scale = nullptr;           // [cout_pad]
+    float* bias = nullptr;            // [cout_pad]
+};
+
+struct LstmW {                        // one BidirectionalLSTM block (easyocr/model/modules.py)
+    ConvW in_proj;                    // 256 -> 2048 : [fwd i,f,g,o | bwd i,f,g,o], bias = b_ih + b_hh
+    float* w_hh = nullptr;            // [2][256 (k)][1024 (gate row)]  FP32, k-major for coalesced reads
+    ConvW linear;                     // 512 -> 256
+};
+
+struct Handle;
+void count_launch(Handle* h, int n = 1);
+
+}  // namespace bbocr

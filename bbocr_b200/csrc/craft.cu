@@ -1,0 +1,141 @@
+// craft.cu -- detector front half: easyocr/detection.py::test_net up to the score maps.
+//   resize_aspect_ratio (easyocr/imgproc.py) -> normalizeMeanVariance -> CRAFT.forward (easyocr/craft.py,
+//   easyocr/model/modules.py::vgg16_bn).   SURVEY.md §8a B2-B4.
+#include "engine.h"
+#include "resize.cuh"
+
+namespace bbocr {
+
+CanvasGeom canvas_geom(int H, int W, int canvas_size, double mag_ratio) {
+    CanvasGeom g;
+    g.H = H; g.W = W;
+    double target = mag_ratio * std::max(H, W);          // Python float arithmetic
+    if (target > canvas_size) target = canvas_size;
+    g.ratio = target / std::max(H, W);
+    g.th = (int)(H * g.ratio);
+    g.tw = (int)(W * g.ratio);
+    g.H32 = g.th % 32 ? g.th + (32 - g.th % 32) : g.th;
+    g.W32 = g.tw % 32 ? g.tw + (32 - g.tw % 32) : g.tw;
+    return g;
+}
+
+__global__ void k_resize_bilinear_u8(const uint8_t* __restrict__ src, int sH, int sW, int sstride, int C,
+                                     uint8_t* __restrict__ dst, int dH, int dW, double scale_x, double scale_y) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dW * C) return;
+    int px = x / C, c = x - px * C;
+    dst[(int64_t)y * dW * C + x] = bilinear_u8_px(src, sH, sW, sstride, C, c, px, y, scale_x, scale_y);
+}
+
+void resize_bilinear_u8(Handle* h, cudaStream_t st, const uint8_t* src, int sH, int sW, int sstride, int C, uint8_t* dst,
+                        int dH, int dW) {
+    double scale_x = 1.0 / ((double)dW / sW), scale_y = 1.0 / ((double)dH / sH);
+    k_resize_bilinear_u8<<<dim3(cdiv(dW * C, 256), dH), 256, 0, st>>>(src, sH, sW, sstride, C, dst, dH, dW, scale_x, scale_y);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// canvas: zero-padded (H32 x W32) float image, then (x - mean*255) / (std*255) per channel; 4th lane = 0
+__global__ void k_canvas(const uint8_t* __restrict__ img, int th, int tw, float* __restrict__ out, int H32, int W32,
+                         float m0, float m1, float m2, float s0, float s1, float s2) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W32) return;
+    float r = 0.f, g = 0.f, b = 0.f;
+    if (y < th && x < tw) {
+        const uint8_t* p = img + ((int64_t)y * tw + x) * 3;
+        r = p[0]; g = p[1]; b = p[2];
+    }
+    float4 o;
+    o.x = __fdiv_rn(__fsub_rn(r, m0), s0);
+    o.y = __fdiv_rn(__fsub_rn(g, m1), s1);
+    o.z = __fdiv_rn(__fsub_rn(b, m2), s2);
+    o.w = 0.f;
+    reinterpret_cast<float4*>(out)[(int64_t)y * W32 + x] = o;
+}
+
+void craft_forward_dev(Handle* h, cudaStream_t st, const uint8_t* img_dev, const CanvasGeom& g, float* text, float* link) {
+    if (!h->craft_loaded) fail(BBOCR_E_STATE, "CRAFT weights not loaded (bbocr_load_craft)");
+    const CraftW& w = h->craft;
+    const int H = g.H32, W = g.W32;
+    DevBuf resized;
+    const uint8_t* src = img_dev;
+    if (g.th != g.H || g.tw != g.W) {
+        resized.alloc((size_t)g.th * g.tw * 3, st);
+        resize_bilinear_u8(h, st, img_dev, g.H, g.W, g.W * 3, 3, resized.as<uint8_t>(), g.th, g.tw);
+        src = resized.as<uint8_t>();
+    }
+    DevBuf canvas((size_t)H * W * 16, st);
+    const float m0 = (float)(0.485 * 255.0), m1 = (float)(0.456 * 255.0), m2 = (float)(0.406 * 255.0);
+    const float s0 = (float)(0.229 * 255.0), s1 = (float)(0.224 * 255.0), s2 = (float)(0.225 * 255.0);
+    k_canvas<<<dim3(cdiv(W, 256), H), 256, 0, st>>>(src, g.th, g.tw, canvas.as<float>(), H, W, m0, m1, m2, s0, s1, s2);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+
+    const Act none;
+    auto conv = [&](const ConvW& cw, const Act& a, const Act& b, DevBuf& buf, int flags) {
+        Act o = act_alloc(h, st, buf, a.N, a.H + 2 * cw.pad - cw.dil * (cw.kh - 1), a.W + 2 * cw.pad - cw.dil * (cw.kw - 1), cw.cout);
+        conv_forward(h, st, cw, a, b, o, flags);
+        return o;
+    };
+    auto pool2 = [&](const Act& a, DevBuf& buf) {
+        Act o = act_alloc(h, st, buf, a.N, a.H / 2, a.W / 2, a.C);
+        maxpool(h, st, a, o, 2, 2, 2, 2, 0, 0);
+        return o;
+    };
+    auto up2 = [&](const Act& a, DevBuf& buf) {
+        Act o = act_alloc(h, st, buf, a.N, a.H * 2, a.W * 2, a.C);
+        upsample2x(h, st, a, o);
+        return o;
+    };
+    const int R = CONV_RELU;
+    DevBuf b0, b1, b_r22, b_r32, b_r43, b_r53;
+    // slice1
+    Act a = act_alloc(h, st, b0, 1, H, W, 64);
+    conv_first(h, st, w.c1_1, canvas.as<float>(), 1, H, W, 4, a, R);
+    canvas.release();
+    a = conv(w.c1_2, a, none, b1, R);
+    a = pool2(a, b0);
+    a = conv(w.c2_1, a, none, b1, R);
+    Act r22 = conv(w.c2_2, a, none, b_r22, R);        // in-place ReLU of slice2[12] rectifies the aliased tap
+    // slice2
+    a = pool2(r22, b0);
+    a = conv(w.c3_1, a, none, b1, R);
+    Act r32 = conv(w.c3_2, a, none, b_r32, R);
+    // slice3
+    a = conv(w.c3_3, r32, none, b0, R);
+    a = pool2(a, b1);
+    a = conv(w.c4_1, a, none, b0, R);
+    Act r43 = conv(w.c4_2, a, none, b_r43, R);
+    // slice4
+    a = conv(w.c4_3, r43, none, b0, R);
+    a = pool2(a, b1);
+    a = conv(w.c5_1, a, none, b0, R);
+    Act r53 = conv(w.c5_2, a, none, b_r53, 0);        // followed by MaxPool, not ReLU: stays the raw BN output
+    // slice5
+    a = act_alloc(h, st, b0, 1, r53.H, r53.W, 512);
+    maxpool(h, st, r53, a, 3, 3, 1, 1, 1, 1);
+    a = conv(w.fc6, a, none, b1, 0);
+    Act fc7 = conv(w.fc7, a, none, b0, 0);
+    // decoder
+    a = conv(w.up1a, fc7, r53, b1, R);
+    a = conv(w.up1b, a, none, b0, R);
+    b_r53.release();
+    a = up2(a, b1);
+    a = conv(w.up2a, a, r43, b0, R);
+    a = conv(w.up2b, a, none, b1, R);
+    b_r43.release();
+    a = up2(a, b0);
+    a = conv(w.up3a, a, r32, b1, R);
+    a = conv(w.up3b, a, none, b0, R);
+    b_r32.release();
+    a = up2(a, b1);
+    a = conv(w.up4a, a, r22, b0, R);
+    a = conv(w.up4b, a, none, b1, R);
+    b_r22.release();
+    a = conv(w.cls0, a, none, b0, R);
+    a = conv(w.cls1, a, none, b1, R);
+    a = conv(w.cls2, a, none, b0, R);
+    cls_tail(h, st, w.cls3, w.cls4, a, text, link);
+}
+
+}  // namespace bbocr

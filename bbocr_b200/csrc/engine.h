@@ -1,0 +1,152 @@
+// engine.h -- internal interfaces between the translation units of libbbocr.so
+#pragma once
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "common.cuh"
+
+namespace bbocr {
+
+struct CraftW {
+    ConvW c1_1, c1_2, c2_1, c2_2, c3_1, c3_2, c3_3, c4_1, c4_2, c4_3, c5_1, c5_2, fc6, fc7;
+    ConvW up1a, up1b, up2a, up2b, up3a, up3b, up4a, up4b, cls0, cls1, cls2, cls3, cls4;
+};
+struct CrnnW {
+    ConvW c0, c1, c2, c3, c4, c5, c6;
+    LstmW l0, l1;
+    ConvW pred;
+    int num_class = 97;
+};
+
+struct Lane {                       // one in-flight page: a stream + its pinned staging
+    cudaStream_t stream = nullptr;
+    PinnedBuf pin_in, pin_out;
+    bool in_busy = false;           // an async H2D copy out of pin_in may still be in flight
+};
+
+struct Handle {
+    int device = 0;
+    int sm_count = 148;
+    int precision = BBOCR_PREC_FP32;
+    std::string err;
+    std::mutex mu;                  // one public call at a time per handle (Reader is shared between threads:
+                                    // batch_processor_enhanced.py:215-216 + enhanced_extractor.py:97-98)
+    std::atomic<int64_t> launches{0};
+    bool craft_loaded = false, crnn_loaded = false;
+    CraftW craft;
+    CrnnW crnn;
+    std::vector<void*> owned;       // weight allocations
+    std::vector<Lane> lanes;
+    // dominant-kernel instrumentation (bench.py roofline): CUDA events around every implicit-GEMM conv launch
+    bool conv_timing = false;
+    std::mutex stat_mu;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
+    double conv_flops = 0;
+    int64_t conv_launches = 0;
+};
+
+inline void count_launch(Handle* h, int n) { h->launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- preprocess.cu ---------------------------------------------------------------------------------------------------
+void pp_gray(Handle*, cudaStream_t, const uint8_t* bgr, int H, int W, int stride, uint8_t* out);
+void pp_resize_cubic(Handle*, cudaStream_t, const uint8_t* src, int sH, int sW, uint8_t* dst, int dH, int dW, int mode);
+void pp_gaussian3(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int H, int W, float sigma,
+                  unsigned long long* sum_out);
+void pp_sum(Handle*, cudaStream_t, const uint8_t* src, int64_t n, unsigned long long* sum);
+void pp_tone_lut(Handle*, cudaStream_t, const unsigned long long* sum, int64_t npix, float contrast, float brightness,
+                 uint8_t* lut);
+void pp_apply_lut(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int64_t n, const uint8_t* lut);
+void pp_clahe_luts(Handle*, cudaStream_t, const uint8_t* src, int H, int W, float clip, const uint8_t* tone,
+                   unsigned int* hist, uint8_t* luts);
+void pp_clahe_apply(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int H, int W, const uint8_t* tone,
+                    const uint8_t* luts);
+void pp_unsharp(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int H, int W, int percent, int threshold,
+                const uint8_t* tone, const uint8_t* clahe_luts);
+void pp_adaptive_threshold(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int H, int W, int method, int inv,
+                           int block, float delta);
+void preprocess_chain_dev(Handle*, cudaStream_t, const uint8_t* bgr, int H, int W, int stride, const bbocr_pp_params&,
+                          uint8_t* out, int* outH, int* outW);
+int preprocess_launches_per_image();
+float pp_deskew(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int H, int W, float max_deg);
+
+// ---- nn.cu : layer kernels (NHWC; T = float | __nv_bfloat16 chosen by Handle::precision) ------------------------------
+enum ConvFlags { CONV_RELU = 1, CONV_OUT_F32 = 2 };
+// out = epilogue(conv(concat_channels(in1, in2)))   in2 may be empty (C == 0).  'same' geometry unless pad says otherwise.
+void conv_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags);
+// cin in {1,3(stored 4)} direct convolution from an FP32 NHWC tensor (canvas / crop batch)
+void conv_first(Handle*, cudaStream_t, const ConvW&, const float* in, int N, int H, int W, int cstride, Act& out,
+                int flags);
+void maxpool(Handle*, cudaStream_t, const Act& in, Act& out, int kh, int kw, int sh, int sw, int ph, int pw);
+void upsample2x(Handle*, cudaStream_t, const Act& in, Act& out);          // bilinear, align_corners=False
+void mean_rows(Handle*, cudaStream_t, const Act& in, Act& out);           // AdaptiveAvgPool2d((None,1)) after permute
+void cls_tail(Handle*, cudaStream_t, const ConvW& c3, const ConvW& c4, const Act& in, float* text, float* link);
+void lstm_recurrence(Handle*, cudaStream_t, const float* gates_in, const float* w_hh, int B, int T, Act& out);
+size_t act_elem_size(const Handle*);
+Act act_alloc(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C, bool force_f32 = false);
+
+// ---- conv_tc.cu : tcgen05 implicit GEMM ------------------------------------------------------------------------------
+bool conv_tc_supported(const ConvW&, const Act& in1, const Act& in2);
+void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags);
+
+// ---- weights.cu ------------------------------------------------------------------------------------------------------
+void load_craft(Handle*, const bbocr_tensor* t, int n);
+void load_crnn(Handle*, const bbocr_tensor* t, int n);
+
+// ---- craft.cu --------------------------------------------------------------------------------------------------------
+struct CanvasGeom {
+    int H, W;            // source image
+    int th, tw;          // after resize_aspect_ratio
+    int H32, W32;        // padded canvas
+    double ratio;
+};
+CanvasGeom canvas_geom(int H, int W, int canvas_size, double mag_ratio);
+// img_dev: HxWx3 u8 device.  text/link: device float maps (H32/2 x W32/2)
+void craft_forward_dev(Handle*, cudaStream_t, const uint8_t* img_dev, const CanvasGeom&, float* text, float* link);
+void resize_bilinear_u8(Handle*, cudaStream_t, const uint8_t* src, int sH, int sW, int sstride, int C, uint8_t* dst,
+                        int dH, int dW);
+
+// ---- postproc.cu + boxes.cpp -----------------------------------------------------------------------------------------
+struct DetComponents {             // kept components of one page, host side
+    int n_labels = 0;              // all foreground components (OpenCV nLabels - 1)
+    std::vector<int> comp_x, comp_y, comp_w, comp_h, comp_area;
+    std::vector<int> row_off;      // per kept comp: offset into row_min/row_max (comp_h entries each)
+    std::vector<int> row_min, row_max;   // per source row: min/max x of (component minus link-only) pixels; min > max = empty
+};
+void det_components_dev(Handle*, Lane&, const float* text, const float* link, int mh, int mw, float text_threshold,
+                        float link_threshold, float low_text, DetComponents& out);
+void boxes_from_components(const DetComponents&, int mh, int mw, std::vector<float>& boxes /*n*8*/);
+void min_area_box(const int32_t* xy, int n, float* out8);
+void debug_convex_hull(const int32_t* xy, int n, int clockwise, std::vector<int>& hull);
+void group_boxes(const float* boxes, int n, double ratio, const bbocr_group_params& p, std::vector<int32_t>& hlist,
+                 std::vector<double>& flist);
+void free_box_transform(const double* quad, int* max_w, int* max_h, double* Minv);
+
+// ---- recog.cu --------------------------------------------------------------------------------------------------------
+struct CropDesc {                  // one crop job (device-visible POD)
+    int x0, y0, w, h;              // horizontal: source rect in the gray page.  free-form: x0 = scratch offset of the
+                                   // warped patch (w x h), y0 unused
+    int ow, oh;                    // compute_ratio_and_resize output size
+    int model_w;                   // ceil(ratio)*64
+    int off;                       // byte offset of the (oh x ow) crop in the packed crop buffer
+    int aoff;                      // byte offset of the AlignCollate'd (64 x resized_w) crop (== off for wide crops)
+    int resized_w;                 // AlignCollate resized width (<= model_w)
+    int slot, bucket_off;          // slot inside its width bucket / float offset of the bucket's input tensor
+    int free_idx;                  // >= 0 : free-form box (index into the 3x3 warp matrices), else -1
+};
+void crops_dev(Handle*, cudaStream_t, const uint8_t* gray, int H, int W, const CropDesc* descs_dev, int n,
+               const CropDesc* descs_host, const double* warp_dev, uint8_t* scratch, uint8_t* crops);
+void crop_hist_dev(Handle*, cudaStream_t, const uint8_t* crops, const CropDesc* descs_dev, int n, unsigned int* hist);
+void crop_contrast_dev(Handle*, cudaStream_t, const uint8_t* crops, const CropDesc* descs_dev, int n, const double* low,
+                       const double* ratio, const int* apply, uint8_t* out);
+void pil_resize_bicubic_dev(Handle*, cudaStream_t, const uint8_t* src, int sH, int sW, uint8_t* dst, int dH, int dW,
+                            uint8_t* scratch);
+void crops_to_input_dev(Handle*, cudaStream_t, const uint8_t* aligned, const CropDesc* descs_dev, int n, int max_model_w,
+                        float* inputs);
+void crnn_forward_dev(Handle*, cudaStream_t, const float* x, int N, int Wm, float* logits);
+void ctc_decode_dev(Handle*, cudaStream_t, const float* logits, int N, int T, int C, const uint8_t* ignore_dev,
+                    int32_t* text_idx, int32_t* text_len, float* step_prob, int32_t* step_idx);
+
+}  // namespace bbocr

@@ -1,0 +1,480 @@
+// nn.cu -- layer kernels shared by the CRAFT detector and the CRNN recogniser (NHWC activations).
+//   * k_conv_generic : CUDA-core FP32-accumulate implicit GEMM (the <=1e-3 parity mode, and the fall-back for the few
+//                      layer shapes the tcgen05 kernel in conv_tc.cu does not take: tiny Cin/Cout heads)
+//   * k_conv_first   : direct convolution for Cin in {1,3} (CRNN conv0 / CRAFT conv1_1 reading the FP32 canvas)
+//   * pooling, bilinear x2 up-sampling, row mean, fused classification tail, BiLSTM recurrence
+// Upstream semantics: easyocr/craft.py, easyocr/model/modules.py, easyocr/model/vgg_model.py.
+#include "engine.h"
+
+namespace bbocr {
+
+size_t act_elem_size(const Handle* h) { return h->precision == BBOCR_PREC_BF16 ? 2 : 4; }
+
+Act act_alloc(Handle* h, cudaStream_t st, DevBuf& buf, int N, int H, int W, int C, bool force_f32) {
+    Act a;
+    a.N = N; a.H = H; a.W = W; a.C = C;
+    size_t es = force_f32 ? 4 : act_elem_size(h);
+    buf.alloc((size_t)a.elems() * es + 256, st);
+    a.p = buf.p;
+    return a;
+}
+
+__device__ __forceinline__ void load4(const float* p, float v[4]) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float v[4]) {
+    uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x), b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+__device__ __forceinline__ void store4(float* p, const float v[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float v[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+}
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// generic implicit-GEMM convolution, 64x64x16 tiles, 256 threads x (4x4) micro-tiles, FP32 accumulation
+// ------------------------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) k_conv_generic(const TI* __restrict__ in1, int C1, const TI* __restrict__ in2,
+                                                     int C2, TO* __restrict__ out, int N, int H, int W, int OH, int OW,
+                                                     const float* __restrict__ w, const float* __restrict__ scale,
+                                                     const float* __restrict__ bias, int cout, int cout_pad, int kh,
+                                                     int kw, int pad, int dil, int relu) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t M = (int64_t)N * OH * OW;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int a_row = tid >> 2, a_k = (tid & 3) * 4;
+    const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+    const int64_t m = m0 + a_row;
+    const bool mvalid = m < M;
+    int n_img = 0, oy = 0, ox = 0;
+    if (mvalid) {
+        n_img = (int)(m / ((int64_t)OH * OW));
+        int r = (int)(m - (int64_t)n_img * OH * OW);
+        oy = r / OW;
+        ox = r - oy * OW;
+    }
+    const int cin = C1 + C2;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int tap = 0; tap < kh * kw; ++tap) {
+        const int ky = tap / kw, kx = tap - ky * kw;
+        const int iy = oy - pad + ky * dil, ix = ox - pad + kx * dil;
+        const bool ok = mvalid && iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const int64_t pix = ((int64_t)n_img * H + iy) * W + ix;
+        for (int c0 = 0; c0 < cin; c0 += BK) {
+            float av[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ok) {
+                int c = c0 + a_k;
+                if (c < C1) load4(in1 + pix * C1 + c, av);
+                else load4(in2 + pix * C2 + (c - C1), av);
+            }
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + b_n < cout_pad)
+                bv = __ldg(reinterpret_cast<const float4*>(w + ((int64_t)tap * cin + c0 + b_k) * cout_pad + n0 + b_n));
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) As[a_k + i][a_row] = av[i];
+            *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = bv;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BK; ++k) {
+                float a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+                float4 bb = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                b[0] = bb.x; b[1] = bb.y; b[2] = bb.z; b[3] = bb.w;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t mm = m0 + ty * 4 + i;
+        if (mm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n < cout) {
+                float v = fmaf(acc[i][j], __ldg(scale + n), __ldg(bias + n));
+                if (relu) v = fmaxf(v, 0.f);
+                st1(out + mm * cout + n, v);
+            }
+        }
+    }
+}
+
+static void conv_generic(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags) {
+    const bool bf = h->precision == BBOCR_PREC_BF16;
+    const bool out_f32 = !bf || (flags & CONV_OUT_F32);
+    int64_t M = (int64_t)out.N * out.H * out.W;
+    dim3 grd((unsigned)cdiv64(M, 64), cdiv(cw.cout, 64));
+    int relu = (flags & CONV_RELU) ? 1 : 0;
+#define LAUNCH(TI, TO)                                                                                            \
+    k_conv_generic<TI, TO><<<grd, 256, 0, st>>>((const TI*)in1.p, in1.C, (const TI*)in2.p, in2.C, (TO*)out.p, out.N, \
+                                                in1.H, in1.W, out.H, out.W, cw.w_f32, cw.scale, cw.bias, cw.cout,   \
+                                                cw.cout_pad, cw.kh, cw.kw, cw.pad, cw.dil, relu)
+    if (!bf) LAUNCH(float, float);
+    else if (out_f32) LAUNCH(__nv_bfloat16, float);
+    else LAUNCH(__nv_bfloat16, __nv_bfloat16);
+#undef LAUNCH
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags) {
+    ARG_CHECK(in1.C + in2.C == cw.cin, "conv: channel mismatch (%d+%d vs %d)", in1.C, in2.C, cw.cin);
+    ARG_CHECK(in1.C % 16 == 0 && in2.C % 16 == 0, "conv: channel segments must be multiples of 16");
+    ARG_CHECK(out.C == cw.cout, "conv: output channel mismatch");
+    ARG_CHECK(out.H == in1.H + 2 * cw.pad - cw.dil * (cw.kh - 1) && out.W == in1.W + 2 * cw.pad - cw.dil * (cw.kw - 1),
+              "conv: output geometry mismatch");
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->conv_timing) {
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        CUDA_CHECK(cudaEventRecord(e0, st));
+    }
+    if (h->precision == BBOCR_PREC_BF16 && conv_tc_supported(cw, in1, in2)) conv_tc_forward(h, st, cw, in1, in2, out, flags);
+    else conv_generic(h, st, cw, in1, in2, out, flags);
+    if (h->conv_timing) {
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        std::lock_guard<std::mutex> g(h->stat_mu);
+        h->conv_events.emplace_back(e0, e1);
+        h->conv_flops += 2.0 * (double)out.N * out.H * out.W * cw.cout * cw.cin * cw.kh * cw.kw;
+        h->conv_launches += 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// direct convolution for Cin in {1,3}: one thread per output pixel, all COUT channels in registers
+// ------------------------------------------------------------------------------------------------------------------
+template <int COUT, typename TO>
+__global__ void __launch_bounds__(128) k_conv_first(const float* __restrict__ in, int N, int H, int W, int cs, int cin,
+                                                   const float* __restrict__ w /*[9][cin][cout_pad]*/,
+                                                   int cout_pad, const float* __restrict__ scale,
+                                                   const float* __restrict__ bias, TO* __restrict__ out, int relu) {
+    __shared__ float sw[9 * 3 * COUT];
+    __shared__ float ss[COUT], sb[COUT];
+    for (int i = threadIdx.x; i < 9 * cin * COUT; i += blockDim.x) {
+        int t = i / COUT, c = i - t * COUT;
+        sw[i] = w[(int64_t)t * cout_pad + c];
+    }
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) { ss[i] = scale[i]; sb[i] = bias[i]; }
+    __syncthreads();
+    int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t M = (int64_t)N * H * W;
+    if (m >= M) return;
+    int n_img = (int)(m / ((int64_t)H * W));
+    int r = (int)(m - (int64_t)n_img * H * W);
+    int oy = r / W, ox = r - oy * W;
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+        int iy = oy - 1 + ky;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            int ix = ox - 1 + kx;
+            if (ix < 0 || ix >= W) continue;
+            const float* p = in + (((int64_t)n_img * H + iy) * W + ix) * cs;
+            for (int ci = 0; ci < cin; ++ci) {
+                float v = __ldg(p + ci);
+                const float* wr = sw + ((ky * 3 + kx) * cin + ci) * COUT;
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+            }
+        }
+    }
+    TO* o = out + m * COUT;
+#pragma unroll
+    for (int c = 0; c < COUT; c += 4) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = fmaf(acc[c + j], ss[c + j], sb[c + j]);
+            if (relu) v[j] = fmaxf(v[j], 0.f);
+        }
+        store4(o + c, v);
+    }
+}
+
+void conv_first(Handle* h, cudaStream_t st, const ConvW& cw, const float* in, int N, int H, int W, int cstride, Act& out,
+                int flags) {
+    ARG_CHECK(cw.kh == 3 && cw.kw == 3 && cw.pad == 1 && cw.dil == 1 && cw.cin <= 3, "conv_first: unsupported shape");
+    ARG_CHECK(cw.cout == 32 || cw.cout == 64, "conv_first: cout must be 32 or 64");
+    int64_t M = (int64_t)N * H * W;
+    unsigned grd = (unsigned)cdiv64(M, 128);
+    int relu = (flags & CONV_RELU) ? 1 : 0;
+    const bool bf = h->precision == BBOCR_PREC_BF16;
+#define LAUNCH(CO, TO) \
+    k_conv_first<CO, TO><<<grd, 128, 0, st>>>(in, N, H, W, cstride, cw.cin, cw.w_f32, cw.cout_pad, cw.scale, cw.bias, (TO*)out.p, relu)
+    if (cw.cout == 64) { if (bf) LAUNCH(64, __nv_bfloat16); else LAUNCH(64, float); }
+    else { if (bf) LAUNCH(32, __nv_bfloat16); else LAUNCH(32, float); }
+#undef LAUNCH
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// max pooling (-inf padding), 4 channels per thread
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_maxpool(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C, int OH, int OW,
+                          int kh, int kw, int sh, int sw, int ph, int pw) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int C4 = C >> 2;
+    int64_t total = (int64_t)N * OH * OW * C4;
+    if (idx >= total) return;
+    int c = (int)(idx % C4) * 4;
+    int64_t p = idx / C4;
+    int ox = (int)(p % OW);
+    p /= OW;
+    int oy = (int)(p % OH);
+    int n = (int)(p / OH);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int ky = 0; ky < kh; ++ky) {
+        int iy = oy * sh - ph + ky;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < kw; ++kx) {
+            int ix = ox * sw - pw + kx;
+            if (ix < 0 || ix >= W) continue;
+            float v[4];
+            load4(in + (((int64_t)n * H + iy) * W + ix) * C + c, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], v[j]);
+        }
+    }
+    store4(out + (((int64_t)n * OH + oy) * OW + ox) * C + c, best);
+}
+
+void maxpool(Handle* h, cudaStream_t st, const Act& in, Act& out, int kh, int kw, int sh, int sw, int ph, int pw) {
+    ARG_CHECK(in.C % 4 == 0 && out.C == in.C, "maxpool: channels");
+    int64_t total = (int64_t)out.N * out.H * out.W * (in.C / 4);
+    unsigned grd = (unsigned)cdiv64(total, 256);
+    if (h->precision == BBOCR_PREC_BF16)
+        k_maxpool<<<grd, 256, 0, st>>>((const __nv_bfloat16*)in.p, (__nv_bfloat16*)out.p, in.N, in.H, in.W, in.C, out.H,
+                                       out.W, kh, kw, sh, sw, ph, pw);
+    else
+        k_maxpool<<<grd, 256, 0, st>>>((const float*)in.p, (float*)out.p, in.N, in.H, in.W, in.C, out.H, out.W, kh, kw,
+                                       sh, sw, ph, pw);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// F.interpolate(mode='bilinear', align_corners=False) to exactly twice the size (general in/out ratio kept)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_upsample(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C, int OH, int OW,
+                           float sy, float sx) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int C4 = C >> 2;
+    int64_t total = (int64_t)N * OH * OW * C4;
+    if (idx >= total) return;
+    int c = (int)(idx % C4) * 4;
+    int64_t p = idx / C4;
+    int ox = (int)(p % OW);
+    p /= OW;
+    int oy = (int)(p % OH);
+    int n = (int)(p / OH);
+    float fy = fmaxf(sy * ((float)oy + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)ox + 0.5f) - 0.5f, 0.f);
+    int y0 = (int)fy, x0 = (int)fx;
+    int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    float a[4], b[4], cc[4], d[4], o[4];
+    const T* base = in + (int64_t)n * H * W * C + c;
+    load4(base + ((int64_t)y0 * W + x0) * C, a);
+    load4(base + ((int64_t)y0 * W + x1) * C, b);
+    load4(base + ((int64_t)y1 * W + x0) * C, cc);
+    load4(base + ((int64_t)y1 * W + x1) * C, d);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = hy * (hx * a[j] + lx * b[j]) + ly * (hx * cc[j] + lx * d[j]);
+    store4(out + (((int64_t)n * OH + oy) * OW + ox) * C + c, o);
+}
+
+void upsample2x(Handle* h, cudaStream_t st, const Act& in, Act& out) {
+    ARG_CHECK(in.C % 4 == 0 && out.C == in.C, "upsample: channels");
+    int64_t total = (int64_t)out.N * out.H * out.W * (in.C / 4);
+    unsigned grd = (unsigned)cdiv64(total, 256);
+    float sy = (float)in.H / (float)out.H, sx = (float)in.W / (float)out.W;
+    if (h->precision == BBOCR_PREC_BF16)
+        k_upsample<<<grd, 256, 0, st>>>((const __nv_bfloat16*)in.p, (__nv_bfloat16*)out.p, in.N, in.H, in.W, in.C, out.H,
+                                        out.W, sy, sx);
+    else
+        k_upsample<<<grd, 256, 0, st>>>((const float*)in.p, (float*)out.p, in.N, in.H, in.W, in.C, out.H, out.W, sy, sx);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// AdaptiveAvgPool2d((None,1)) on the permuted feature map: mean over the H rows -> [N][1][W][C]
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_mean_rows(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)N * W * C;
+    if (idx >= total) return;
+    int c = (int)(idx % C);
+    int64_t p = idx / C;
+    int x = (int)(p % W);
+    int n = (int)(p / W);
+    float s = 0.f;
+    for (int y = 0; y < H; ++y) s += to_f(in[(((int64_t)n * H + y) * W + x) * C + c]);
+    st1(out + idx, s / (float)H);
+}
+
+void mean_rows(Handle* h, cudaStream_t st, const Act& in, Act& out) {
+    int64_t total = (int64_t)in.N * in.W * in.C;
+    unsigned grd = (unsigned)cdiv64(total, 256);
+    if (h->precision == BBOCR_PREC_BF16)
+        k_mean_rows<<<grd, 256, 0, st>>>((const __nv_bfloat16*)in.p, (__nv_bfloat16*)out.p, in.N, in.H, in.W, in.C);
+    else
+        k_mean_rows<<<grd, 256, 0, st>>>((const float*)in.p, (float*)out.p, in.N, in.H, in.W, in.C);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// conv_cls tail: 1x1 16->16 + ReLU, 1x1 16->2, split into the text and link maps (y.permute(0,2,3,1)[...,0/1])
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_cls_tail(const T* __restrict__ in, int64_t M, const float* __restrict__ w3, int cp3,
+                           const float* __restrict__ b3, const float* __restrict__ w4, int cp4,
+                           const float* __restrict__ b4, float* __restrict__ text, float* __restrict__ link) {
+    __shared__ float s3[16 * 16], sb3[16], s4[16 * 2], sb4[2];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s3[i] = w3[(i / 16) * cp3 + (i % 16)];     // [cin][cout]
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) s4[i] = w4[(i / 2) * cp4 + (i % 2)];
+    if (threadIdx.x < 16) sb3[threadIdx.x] = b3[threadIdx.x];
+    if (threadIdx.x < 2) sb4[threadIdx.x] = b4[threadIdx.x];
+    __syncthreads();
+    int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float x[16], y[16];
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) load4(in + m * 16 + c, x + c);
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a = fmaf(x[c], s3[c * 16 + o], a);
+        y[o] = fmaxf(a + sb3[o], 0.f);
+    }
+    float t = 0.f, l = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        t = fmaf(y[c], s4[c * 2], t);
+        l = fmaf(y[c], s4[c * 2 + 1], l);
+    }
+    text[m] = t + sb4[0];
+    link[m] = l + sb4[1];
+}
+
+void cls_tail(Handle* h, cudaStream_t st, const ConvW& c3, const ConvW& c4, const Act& in, float* text, float* link) {
+    ARG_CHECK(in.C == 16 && c3.cin == 16 && c3.cout == 16 && c4.cin == 16 && c4.cout == 2, "cls_tail: shapes");
+    int64_t M = (int64_t)in.N * in.H * in.W;
+    unsigned grd = (unsigned)cdiv64(M, 256);
+    // scale is 1 for these bias-only convolutions; bias holds the conv bias
+    if (h->precision == BBOCR_PREC_BF16)
+        k_cls_tail<<<grd, 256, 0, st>>>((const __nv_bfloat16*)in.p, M, c3.w_f32, c3.cout_pad, c3.bias, c4.w_f32,
+                                        c4.cout_pad, c4.bias, text, link);
+    else
+        k_cls_tail<<<grd, 256, 0, st>>>((const float*)in.p, M, c3.w_f32, c3.cout_pad, c3.bias, c4.w_f32, c4.cout_pad,
+                                        c4.bias, text, link);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// BiLSTM recurrence (nn.LSTM(256,256,bidirectional), gate order i,f,g,o; h0=c0=0).
+//   gates_in : [B][T][2048] FP32 = x_t W_ih^T + b_ih + b_hh for [fwd | bwd]        (input projection GEMM)
+//   w_hh     : [2][256 k][1024 rows] FP32 (k-major so that the 256 threads read consecutive rows)
+//   out      : [B][T][512] = [h_fwd(t) | h_bwd(t)]
+// One CTA = NB crops x one direction, persistent over all T steps; thread j owns hidden unit j of every crop.
+// ------------------------------------------------------------------------------------------------------------------
+template <int NB, typename TO>
+__global__ void __launch_bounds__(256) k_lstm(const float* __restrict__ gates_in, const float* __restrict__ w_hh,
+                                             TO* __restrict__ out, int B, int T) {
+    __shared__ float hs[2][NB][256];
+    const int j = threadIdx.x, dir = blockIdx.y, b0 = blockIdx.x * NB;
+    const float* wd = w_hh + (int64_t)dir * 256 * 1024;
+    float c[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { c[b] = 0.f; hs[0][b][j] = 0.f; }
+    __syncthreads();
+    int cur = 0;
+    for (int s = 0; s < T; ++s) {
+        const int t = dir ? T - 1 - s : s;
+        float acc[NB][4];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (b0 + b < B) {
+                const float* g = gates_in + ((int64_t)(b0 + b) * T + t) * 2048 + dir * 1024 + j;
+                acc[b][0] = __ldg(g); acc[b][1] = __ldg(g + 256); acc[b][2] = __ldg(g + 512); acc[b][3] = __ldg(g + 768);
+            } else {
+                acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f;
+            }
+        }
+#pragma unroll 4
+        for (int k = 0; k < 256; ++k) {
+            const float* wr = wd + (int64_t)k * 1024 + j;
+            float w0 = __ldg(wr), w1 = __ldg(wr + 256), w2 = __ldg(wr + 512), w3 = __ldg(wr + 768);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                float hv = hs[cur][b][k];
+                acc[b][0] = fmaf(w0, hv, acc[b][0]);
+                acc[b][1] = fmaf(w1, hv, acc[b][1]);
+                acc[b][2] = fmaf(w2, hv, acc[b][2]);
+                acc[b][3] = fmaf(w3, hv, acc[b][3]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float ig = 1.f / (1.f + expf(-acc[b][0]));
+            float fg = 1.f / (1.f + expf(-acc[b][1]));
+            float gg = tanhf(acc[b][2]);
+            float og = 1.f / (1.f + expf(-acc[b][3]));
+            c[b] = fg * c[b] + ig * gg;
+            float hv = og * tanhf(c[b]);
+            hs[cur ^ 1][b][j] = hv;
+            if (b0 + b < B) st1(out + ((int64_t)(b0 + b) * T + t) * 512 + dir * 256 + j, hv);
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+void lstm_recurrence(Handle* h, cudaStream_t st, const float* gates_in, const float* w_hh, int B, int T, Act& out) {
+    constexpr int NB = 4;
+    dim3 grd(cdiv(B, NB), 2);
+    if (h->precision == BBOCR_PREC_BF16)
+        k_lstm<NB, __nv_bfloat16><<<grd, 256, 0, st>>>(gates_in, w_hh, (__nv_bfloat16*)out.p, B, T);
+    else
+        k_lstm<NB, float><<<grd, 256, 0, st>>>(gates_in, w_hh, (float*)out.p, B, T);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace bbocr

@@ -1,0 +1,669 @@
+// preprocess.cu -- stage 1 of the OCR path: the OpenCV/Pillow chain of
+//   /root/reference/pipeline_demo/ocr_testing/preprocessing/image_preprocessor.py:17-160
+// as bit-exact integer / unfused-FP32 CUDA kernels (HBM-bound byte work: coalesced, vectorised where alignment allows,
+// shared-memory tiles for the stencils).  Float expressions that OpenCV/Pillow evaluate without FMA contraction use
+// __fmul_rn/__fadd_rn so nvcc cannot fuse them.
+#include "engine.h"
+
+namespace bbocr {
+
+// ------------------------------------------------------------------------------------------------------------------
+// A2  cv2.cvtColor(BGR2GRAY): (B*3735 + G*19235 + R*9798 + 16384) >> 15          image_preprocessor.py:25-30
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) {
+    return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
+}
+
+// contiguous rows: thread handles 16 pixels = 3 x 16-byte loads -> 1 x 16-byte store
+__global__ void k_gray_packed(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t npix) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t p0 = t * 16;
+    if (p0 + 16 <= npix) {
+        const uint4* s = reinterpret_cast<const uint4*>(src + p0 * 3);
+        uint4 a = __ldg(s), b = __ldg(s + 1), c = __ldg(s + 2);
+        uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {          // 4 pixels = 12 bytes = 3 words
+            uint32_t w0 = w[q * 3], w1 = w[q * 3 + 1], w2 = w[q * 3 + 2];
+            uint32_t g0 = gray_of(w0 & 255, (w0 >> 8) & 255, (w0 >> 16) & 255);
+            uint32_t g1 = gray_of(w0 >> 24, w1 & 255, (w1 >> 8) & 255);
+            uint32_t g2 = gray_of((w1 >> 16) & 255, w1 >> 24, w2 & 255);
+            uint32_t g3 = gray_of((w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24);
+            o[q] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+        }
+        *reinterpret_cast<uint4*>(dst + p0) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int64_t p = p0; p < npix; ++p)
+            dst[p] = (uint8_t)gray_of(src[p * 3], src[p * 3 + 1], src[p * 3 + 2]);
+    }
+}
+
+__global__ void k_gray_strided(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ dst, int H, int W) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < W) {
+        const uint8_t* s = src + (int64_t)y * stride + x * 3;
+        dst[(int64_t)y * W + x] = (uint8_t)gray_of(s[0], s[1], s[2]);
+    }
+}
+
+void pp_gray(Handle* h, cudaStream_t st, const uint8_t* bgr, int H, int W, int stride, uint8_t* out) {
+    int64_t npix = (int64_t)H * W;
+    if (stride == W * 3 && ((uintptr_t)bgr % 16 == 0) && ((uintptr_t)out % 16 == 0)) {
+        int64_t threads = cdiv64(npix, 16);
+        k_gray_packed<<<(unsigned)cdiv64(threads, 256), 256, 0, st>>>(bgr, out, npix);
+    } else {
+        k_gray_strided<<<dim3(cdiv(W, 256), H), 256, 0, st>>>(bgr, stride, out, H, W);
+    }
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A3  cv2.resize(INTER_CUBIC), u8 x1                                                   image_preprocessor.py:125-132
+// Coefficient tables are built on the host exactly as OpenCV builds them (double coordinate, float32 Keys cubic
+// A=-0.75, rint(c*2048) shorts); the kernel does the int32 horizontal pass and the float32 vertical pass.
+// ------------------------------------------------------------------------------------------------------------------
+static void cubic_coeffs(float x, float* c) {
+    const float A = -0.75f;
+    c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+    c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+    c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+struct CubicAxis {
+    std::vector<int32_t> idx;     // [n][4] clamped source indices
+    std::vector<int32_t> ci;      // [n][4] rint(c*2048)
+    std::vector<float> cf;        // [n][4] raw float coefficients (T2) or ci * 2^-22 (T1 vertical)
+};
+
+static CubicAxis cubic_axis(int src, int dst, bool vertical_t1) {
+    CubicAxis a;
+    a.idx.resize((size_t)dst * 4);
+    a.ci.resize((size_t)dst * 4);
+    a.cf.resize((size_t)dst * 4);
+    double inv_scale = (double)dst / src;
+    double scale = 1.0 / inv_scale;
+    const float s22 = 1.f / (2048.f * 2048.f);
+    for (int d = 0; d < dst; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        float c[4];
+        cubic_coeffs(f, c);
+        for (int k = 0; k < 4; ++k) {
+            int j = s - 1 + k;
+            j = j < 0 ? 0 : (j > src - 1 ? src - 1 : j);
+            a.idx[d * 4 + k] = j;
+            int q = (int)lrintf(c[k] * 2048.f);
+            a.ci[d * 4 + k] = q;
+            a.cf[d * 4 + k] = vertical_t1 ? (float)q * s22 : c[k];
+        }
+    }
+    return a;
+}
+
+// mode 0 (T1): H_k = sum_j p*ax (int32); out = rint(S0*b0 + (S1*b1 + (S2*b2 + S3*b3))) unfused float32;
+//              the last dst_w % 8 columns use OpenCV's scalar tail (sum S_k*beta_k + 2^21) >> 22.
+// mode 1 (T2): float32 real-arithmetic cubic, sequential unfused accumulation (oracle/preprocess_np.py resize_cubic T2)
+__global__ void k_resize_cubic(const uint8_t* __restrict__ src, int sH, int sW, uint8_t* __restrict__ dst, int dH,
+                               int dW, const int32_t* __restrict__ xidx, const int32_t* __restrict__ xci,
+                               const float* __restrict__ xcf, const int32_t* __restrict__ yidx,
+                               const int32_t* __restrict__ yci, const float* __restrict__ ycf, int mode) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dW || y >= dH) return;
+    int4 xi = __ldg(reinterpret_cast<const int4*>(xidx) + x);
+    int4 yi = __ldg(reinterpret_cast<const int4*>(yidx) + y);
+    const uint8_t* r0 = src + (int64_t)yi.x * sW;
+    const uint8_t* r1 = src + (int64_t)yi.y * sW;
+    const uint8_t* r2 = src + (int64_t)yi.z * sW;
+    const uint8_t* r3 = src + (int64_t)yi.w * sW;
+    uint8_t o;
+    if (mode == 0) {
+        int4 ax = __ldg(reinterpret_cast<const int4*>(xci) + x);
+        int S0 = r0[xi.x] * ax.x + r0[xi.y] * ax.y + r0[xi.z] * ax.z + r0[xi.w] * ax.w;
+        int S1 = r1[xi.x] * ax.x + r1[xi.y] * ax.y + r1[xi.z] * ax.z + r1[xi.w] * ax.w;
+        int S2 = r2[xi.x] * ax.x + r2[xi.y] * ax.y + r2[xi.z] * ax.z + r2[xi.w] * ax.w;
+        int S3 = r3[xi.x] * ax.x + r3[xi.y] * ax.y + r3[xi.z] * ax.z + r3[xi.w] * ax.w;
+        if (x < (dW / 8) * 8) {
+            float4 b = __ldg(reinterpret_cast<const float4*>(ycf) + y);
+            float acc = __fmul_rn((float)S3, b.w);
+            acc = __fadd_rn(__fmul_rn((float)S2, b.z), acc);
+            acc = __fadd_rn(__fmul_rn((float)S1, b.y), acc);
+            acc = __fadd_rn(__fmul_rn((float)S0, b.x), acc);
+            int v = __float2int_rn(acc);
+            o = (uint8_t)min(max(v, 0), 255);
+        } else {
+            int4 by = __ldg(reinterpret_cast<const int4*>(yci) + y);
+            int v = (S0 * by.x + S1 * by.y + S2 * by.z + S3 * by.w + (1 << 21)) >> 22;
+            o = (uint8_t)min(max(v, 0), 255);
+        }
+    } else {
+        float4 cx = __ldg(reinterpret_cast<const float4*>(xcf) + x);
+        float4 cy = __ldg(reinterpret_cast<const float4*>(ycf) + y);
+        auto hrow = [&](const uint8_t* r) {
+            float a = __fmul_rn((float)r[xi.x], cx.x);
+            a = __fadd_rn(a, __fmul_rn((float)r[xi.y], cx.y));
+            a = __fadd_rn(a, __fmul_rn((float)r[xi.z], cx.z));
+            a = __fadd_rn(a, __fmul_rn((float)r[xi.w], cx.w));
+            return a;
+        };
+        float a = __fmul_rn(hrow(r0), cy.x);
+        a = __fadd_rn(a, __fmul_rn(hrow(r1), cy.y));
+        a = __fadd_rn(a, __fmul_rn(hrow(r2), cy.z));
+        a = __fadd_rn(a, __fmul_rn(hrow(r3), cy.w));
+        int v = __float2int_rn(a);
+        o = (uint8_t)min(max(v, 0), 255);
+    }
+    dst[(int64_t)y * dW + x] = o;
+}
+
+struct CubicTables {
+    DevBuf buf;
+    int32_t *xidx, *xci, *yidx, *yci;
+    float *xcf, *ycf;
+};
+
+static void upload_cubic_tables(cudaStream_t st, int sH, int sW, int dH, int dW, int mode, CubicTables& t) {
+    CubicAxis ax = cubic_axis(sW, dW, false), ay = cubic_axis(sH, dH, mode == 0);
+    size_t nx = (size_t)dW * 4, ny = (size_t)dH * 4;
+    std::vector<int32_t> host((nx + ny) * 3);
+    memcpy(&host[0], ax.idx.data(), nx * 4);
+    memcpy(&host[nx], ax.ci.data(), nx * 4);
+    memcpy(&host[2 * nx], ax.cf.data(), nx * 4);
+    memcpy(&host[3 * nx], ay.idx.data(), ny * 4);
+    memcpy(&host[3 * nx + ny], ay.ci.data(), ny * 4);
+    memcpy(&host[3 * nx + 2 * ny], ay.cf.data(), ny * 4);
+    t.buf.alloc(host.size() * 4, st);
+    CUDA_CHECK(cudaMemcpyAsync(t.buf.p, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));     // host vector goes out of scope (pageable copy is staged, but be explicit)
+    int32_t* b = t.buf.as<int32_t>();
+    t.xidx = b; t.xci = b + nx; t.xcf = reinterpret_cast<float*>(b + 2 * nx);
+    t.yidx = b + 3 * nx; t.yci = b + 3 * nx + ny; t.ycf = reinterpret_cast<float*>(b + 3 * nx + 2 * ny);
+}
+
+void pp_resize_cubic(Handle* h, cudaStream_t st, const uint8_t* src, int sH, int sW, uint8_t* dst, int dH, int dW,
+                     int mode) {
+    CubicTables t;
+    upload_cubic_tables(st, sH, sW, dH, dW, mode, t);
+    dim3 blk(64, 4), grd(cdiv(dW, 64), cdiv(dH, 4));
+    k_resize_cubic<<<grd, blk, 0, st>>>(src, sH, sW, dst, dH, dW, t.xidx, t.xci, t.xcf, t.yidx, t.yci, t.ycf, mode);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A4  cv2.GaussianBlur((3,3), sigma): fixed-point [k0,k1,k0]/256 both ways, BORDER_REFLECT_101, one rounding
+//     (v + 2^15) >> 16.  Optionally accumulates the global pixel sum of the OUTPUT (Pillow Contrast's mean).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+__global__ void k_gaussian3(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, int k0, int k1,
+                            unsigned long long* __restrict__ sum_out) {
+    __shared__ uint8_t tile[18][128 + 2 + 2];           // 16 rows + halo; 128 cols + halo (+pad)
+    const int bx = blockIdx.x * 128, by = blockIdx.y * 16;
+    for (int i = threadIdx.x; i < 18 * 130; i += blockDim.x) {
+        int ty = i / 130, tx = i % 130;
+        int gy = reflect101(by + ty - 1, H), gx = reflect101(bx + tx - 1, W);
+        tile[ty][tx] = src[(int64_t)gy * W + gx];
+    }
+    __syncthreads();
+    unsigned int local = 0;
+    for (int i = threadIdx.x; i < 16 * 128; i += blockDim.x) {
+        int ty = i / 128, tx = i % 128;
+        int gy = by + ty, gx = bx + tx;
+        if (gy < H && gx < W) {
+            int h0 = tile[ty][tx] * k0 + tile[ty][tx + 1] * k1 + tile[ty][tx + 2] * k0;
+            int h1 = tile[ty + 1][tx] * k0 + tile[ty + 1][tx + 1] * k1 + tile[ty + 1][tx + 2] * k0;
+            int h2 = tile[ty + 2][tx] * k0 + tile[ty + 2][tx + 1] * k1 + tile[ty + 2][tx + 2] * k0;
+            int v = (h0 * k0 + h1 * k1 + h2 * k0 + (1 << 15)) >> 16;
+            dst[(int64_t)gy * W + gx] = (uint8_t)v;
+            local += v;
+        }
+    }
+    if (sum_out) {
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        __shared__ unsigned int wsum[8];
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long s = 0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += wsum[i];
+            atomicAdd(sum_out, s);
+        }
+    }
+}
+
+void gaussian3_kernel_q8(float sigma, int* k0, int* k1) {
+    // OpenCV getGaussianKernelBitExact -> 8-bit fixed point; centre tap absorbs the rounding residue
+    double e = exp(-1.0 / (2.0 * (double)sigma * sigma));
+    double norm = 1.0 + 2.0 * e;
+    int q0 = (int)lrint(e / norm * 256.0), q1 = (int)lrint(1.0 / norm * 256.0);
+    q1 += 256 - (2 * q0 + q1);
+    *k0 = q0;
+    *k1 = q1;
+}
+
+void pp_gaussian3(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, int H, int W, float sigma,
+                  unsigned long long* sum_out) {
+    int k0, k1;
+    gaussian3_kernel_q8(sigma, &k0, &k1);
+    k_gaussian3<<<dim3(cdiv(W, 128), cdiv(H, 16)), 256, 0, st>>>(src, dst, H, W, k0, k1, sum_out);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A5/A6  Pillow ImageEnhance.Contrast / Brightness = ImagingBlend extrapolation: a 256-entry byte LUT.
+//   contrast: t = m + f*(p - m), m = int(mean + 0.5);  brightness: t = 0 + f*(p - 0);  out = t<=0 ? 0 : t>=255 ? 255 : (u8)t
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t pil_blend_px(int base, int p, float f) {
+    float t = __fadd_rn((float)base, __fmul_rn(f, (float)(p - base)));
+    if (f >= 0.f && f <= 1.f) return (uint8_t)t;
+    return t <= 0.f ? 0 : (t >= 255.f ? 255 : (uint8_t)t);
+}
+
+__global__ void k_sum_u8(const uint8_t* __restrict__ src, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long local = 0;
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
+    for (; i + 16 <= n; i += stride) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) local += __dp4a(w[q], 0x01010101u, 0u);
+    }
+    if (i < n && i + 16 > n)
+        for (int64_t j = i; j < n; ++j) local += src[j];
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, local);
+}
+
+// lut = brightness(contrast(p)); either factor may be disabled with f <= 0 (identity)
+__global__ void k_build_tone_lut(const unsigned long long* __restrict__ sum, double npix, float contrast,
+                                 float brightness, uint8_t* __restrict__ lut) {
+    int p = threadIdx.x;
+    int v = p;
+    if (contrast > 0.f) {
+        int m = (int)((double)(*sum) / npix + 0.5);
+        v = pil_blend_px(m, v, contrast);
+    }
+    if (brightness > 0.f) v = pil_blend_px(0, v, brightness);
+    lut[p] = (uint8_t)v;
+}
+
+__global__ void k_apply_lut(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t n,
+                            const uint8_t* __restrict__ lut) {
+    __shared__ uint8_t s[256];
+    s[threadIdx.x & 255] = lut[threadIdx.x & 255];
+    __syncthreads();
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i + 16 <= n) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            w[q] = s[w[q] & 255] | (s[(w[q] >> 8) & 255] << 8) | (s[(w[q] >> 16) & 255] << 16) | (s[w[q] >> 24] << 24);
+        *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        for (int64_t j = i; j < n; ++j) dst[j] = s[src[j]];
+    }
+}
+
+void pp_sum(Handle* h, cudaStream_t st, const uint8_t* src, int64_t n, unsigned long long* sum) {
+    CUDA_CHECK(cudaMemsetAsync(sum, 0, 8, st));
+    int blocks = (int)std::min<int64_t>(cdiv64(n, 256 * 16), 148 * 8);
+    k_sum_u8<<<blocks, 256, 0, st>>>(src, n, sum);
+    count_launch(h);
+}
+
+void pp_tone_lut(Handle* h, cudaStream_t st, const unsigned long long* sum, int64_t npix, float contrast,
+                 float brightness, uint8_t* lut) {
+    k_build_tone_lut<<<1, 256, 0, st>>>(sum, (double)npix, contrast, brightness, lut);
+    count_launch(h);
+}
+
+void pp_apply_lut(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, int64_t n, const uint8_t* lut) {
+    k_apply_lut<<<(unsigned)cdiv64(cdiv64(n, 16), 256), 256, 0, st>>>(src, dst, n, lut);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A7  cv2.createCLAHE(clip, (8,8)).apply                                              image_preprocessor.py:48-56
+// ------------------------------------------------------------------------------------------------------------------
+// Histogram of every tile of the (reflect-101 padded) image, pixels optionally mapped through a tone LUT first.
+// grid = (8 tiles x, 8 tiles y, row chunks); block = 256 threads over a chunk of the tile's rows.
+__global__ void k_clahe_hist(const uint8_t* __restrict__ src, int H, int W, int tw, int th, int rows_per_chunk,
+                             const uint8_t* __restrict__ tone, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[256];
+    __shared__ uint8_t stone[256];
+    sh[threadIdx.x] = 0;
+    stone[threadIdx.x] = tone ? tone[threadIdx.x] : (uint8_t)threadIdx.x;
+    __syncthreads();
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int y0 = blockIdx.z * rows_per_chunk, y1 = min(th, y0 + rows_per_chunk);
+    const int n = (y1 - y0) * tw;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int yy = y0 + i / tw, xx = i % tw;
+        int gy = reflect101(ty * th + yy, H), gx = reflect101(tx * tw + xx, W);
+        atomicAdd(&sh[stone[src[(int64_t)gy * W + gx]]], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[(ty * 8 + tx) * 256 + threadIdx.x], sh[threadIdx.x]);
+}
+
+// One block per tile: clip, redistribute, cumulative sum, scale -> LUT.
+__global__ void k_clahe_lut(const unsigned int* __restrict__ hist, int clip, float lut_scale, uint8_t* __restrict__ luts) {
+    __shared__ int sh[256];
+    __shared__ int red[256];
+    const int t = threadIdx.x;
+    int v = (int)hist[blockIdx.x * 256 + t];
+    if (clip > 0) {
+        red[t] = max(v - clip, 0);
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (t < o) red[t] += red[t + o];
+            __syncthreads();
+        }
+        int excess = red[0];
+        v = min(v, clip) + excess / 256;
+        int r = excess % 256;
+        if (r > 0) {
+            int step = max(256 / r, 1);
+            if (t % step == 0 && t / step < r) v += 1;
+        }
+    }
+    sh[t] = v;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {          // Hillis-Steele inclusive scan
+        int add = t >= o ? sh[t - o] : 0;
+        __syncthreads();
+        sh[t] += add;
+        __syncthreads();
+    }
+    int q = __float2int_rn(__fmul_rn((float)sh[t], lut_scale));
+    luts[blockIdx.x * 256 + t] = (uint8_t)min(max(q, 0), 255);
+}
+
+struct ClaheGeom {
+    int tw, th;
+    float inv_tw, inv_th;
+};
+
+__device__ __forceinline__ uint8_t clahe_px(const uint8_t* __restrict__ luts, int v, int x, int y, ClaheGeom g) {
+    float txf = __fsub_rn(__fmul_rn((float)x, g.inv_tw), 0.5f);
+    int tx1 = (int)floorf(txf);
+    float xa = __fsub_rn(txf, (float)tx1), xa1 = __fsub_rn(1.0f, xa);
+    int tx2 = min(tx1 + 1, 7);
+    tx1 = max(tx1, 0);
+    float tyf = __fsub_rn(__fmul_rn((float)y, g.inv_th), 0.5f);
+    int ty1 = (int)floorf(tyf);
+    float ya = __fsub_rn(tyf, (float)ty1), ya1 = __fsub_rn(1.0f, ya);
+    int ty2 = min(ty1 + 1, 7);
+    ty1 = max(ty1, 0);
+    float a = (float)luts[((ty1 * 8 + tx1) << 8) + v], b = (float)luts[((ty1 * 8 + tx2) << 8) + v];
+    float c = (float)luts[((ty2 * 8 + tx1) << 8) + v], d = (float)luts[((ty2 * 8 + tx2) << 8) + v];
+    float top = __fadd_rn(__fmul_rn(a, xa1), __fmul_rn(b, xa));
+    float bot = __fadd_rn(__fmul_rn(c, xa1), __fmul_rn(d, xa));
+    float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+    int q = __float2int_rn(res);
+    return (uint8_t)min(max(q, 0), 255);
+}
+
+__global__ void k_clahe_apply(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, ClaheGeom g,
+                              const uint8_t* __restrict__ tone, const uint8_t* __restrict__ luts_g) {
+    extern __shared__ uint8_t smem[];
+    uint8_t* luts = smem;                 // 64*256
+    uint8_t* stone = smem + 64 * 256;     // 256
+    for (int i = threadIdx.x; i < 64 * 256 / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(luts)[i] = __ldg(reinterpret_cast<const uint4*>(luts_g) + i);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) stone[i] = tone ? tone[i] : (uint8_t)i;
+    __syncthreads();
+    int y = blockIdx.y;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+        int v = stone[src[(int64_t)y * W + x]];
+        dst[(int64_t)y * W + x] = clahe_px(luts, v, x, y, g);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A8  Pillow UnsharpMask(radius=1.0, percent, threshold): GaussianBlur(1.0) = 3 horizontal + 3 vertical passes of the
+//     radius-0.25 extended box blur (c*ww + (l+r)*fw + 2^23) >> 24 with per-pass edge replication, then
+//     out = |in-blur| > thr ? clip8(in + (in-blur)*percent/100) : in.
+// Fused with the CLAHE application (tone LUT -> CLAHE LUT blend -> unsharp) when `luts_g` != nullptr so the chain
+// reads its input once and writes its output once.
+// ------------------------------------------------------------------------------------------------------------------
+#define US_T 32
+#define US_H 3
+#define US_S (US_T + 2 * US_H)      // 38
+
+__global__ void k_unsharp(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, unsigned ww,
+                          unsigned fw, int percent, int threshold, ClaheGeom g, const uint8_t* __restrict__ tone,
+                          const uint8_t* __restrict__ luts_g) {
+    __shared__ uint8_t a[US_S][US_S + 2], b[US_S][US_S + 2], orig[US_T][US_T];
+    const int bx = blockIdx.x * US_T - US_H, by = blockIdx.y * US_T - US_H;
+    for (int i = threadIdx.x; i < US_S * US_S; i += blockDim.x) {
+        int ty = i / US_S, tx = i % US_S;
+        int gy = by + ty, gx = bx + tx;
+        uint8_t v = 0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            v = src[(int64_t)gy * W + gx];
+            if (luts_g) {
+                if (tone) v = tone[v];
+                v = clahe_px(luts_g, v, gx, gy, g);
+            }
+        }
+        a[ty][tx] = v;
+        if (ty >= US_H && ty < US_H + US_T && tx >= US_H && tx < US_H + US_T) orig[ty - US_H][tx - US_H] = v;
+    }
+    __syncthreads();
+    // tile-coordinate clamps that implement image-border replication
+    const int cx0 = max(0, -bx), cx1 = min(US_S - 1, W - 1 - bx);
+    const int cy0 = max(0, -by), cy1 = min(US_S - 1, H - 1 - by);
+    uint8_t(*in)[US_S + 2] = a;
+    uint8_t(*out)[US_S + 2] = b;
+    for (int pass = 0; pass < 6; ++pass) {
+        for (int i = threadIdx.x; i < US_S * US_S; i += blockDim.x) {
+            int ty = i / US_S, tx = i % US_S;
+            unsigned c = in[ty][tx], l, r;
+            if (pass < 3) {
+                l = in[ty][min(max(tx - 1, cx0), cx1)];
+                r = in[ty][min(max(tx + 1, cx0), cx1)];
+            } else {
+                l = in[min(max(ty - 1, cy0), cy1)][tx];
+                r = in[min(max(ty + 1, cy0), cy1)][tx];
+            }
+            out[ty][tx] = (uint8_t)((c * ww + (l + r) * fw + (1u << 23)) >> 24);
+        }
+        __syncthreads();
+        uint8_t(*t)[US_S + 2] = in; in = out; out = t;
+    }
+    for (int i = threadIdx.x; i < US_T * US_T; i += blockDim.x) {
+        int ty = i / US_T, tx = i % US_T;
+        int gy = by + US_H + ty, gx = bx + US_H + tx;
+        if (gy < H && gx < W) {
+            int s = orig[ty][tx], bl = in[ty + US_H][tx + US_H];
+            int d = s - bl, o = s;
+            if (abs(d) > threshold) o = min(max(s + d * percent / 100, 0), 255);
+            dst[(int64_t)gy * W + gx] = (uint8_t)o;
+        }
+    }
+}
+
+static void pil_box_params(float radius_sigma, unsigned* ww, unsigned* fw) {
+    // Pillow BoxBlur.c: _gaussian_blur_radius (all float) then ImagingLineBoxBlur8 weights
+    float sigma2 = radius_sigma * radius_sigma / 3;
+    float L = (float)sqrt(12.0 * sigma2 + 1.0);
+    float l = (float)floor((L - 1.0) / 2.0);
+    float a = (2 * l + 1) * (l * (l + 1) - 3 * sigma2);
+    a /= 6 * (sigma2 - (l + 1) * (l + 1));
+    float fr = l + a;
+    int radius = (int)fr;
+    if (radius != 0) fail(BBOCR_E_UNSUPPORTED, "unsharp: only box radius < 1 (UnsharpMask radius=1.0) is implemented");
+    *ww = (unsigned)((float)(1 << 24) / (fr * 2 + 1));
+    *fw = ((1u << 24) - (radius * 2 + 1) * (*ww)) / 2;
+}
+
+static ClaheGeom clahe_geom(int H, int W) {
+    int pw = (W % 8) ? W + 8 - W % 8 : W, ph = (H % 8) ? H + 8 - H % 8 : H;
+    ClaheGeom g;
+    g.tw = pw / 8;
+    g.th = ph / 8;
+    g.inv_tw = 1.0f / g.tw;
+    g.inv_th = 1.0f / g.th;
+    return g;
+}
+
+// builds the 64 tile LUTs for `src` seen through the optional tone LUT
+void pp_clahe_luts(Handle* h, cudaStream_t st, const uint8_t* src, int H, int W, float clip_limit, const uint8_t* tone,
+                   unsigned int* hist /*64*256*/, uint8_t* luts /*64*256*/) {
+    ClaheGeom g = clahe_geom(H, W);
+    CUDA_CHECK(cudaMemsetAsync(hist, 0, 64 * 256 * 4, st));
+    int rows_per_chunk = std::max(1, 8192 / g.tw);
+    k_clahe_hist<<<dim3(8, 8, cdiv(g.th, rows_per_chunk)), 256, 0, st>>>(src, H, W, g.tw, g.th, rows_per_chunk, tone, hist);
+    int area = g.tw * g.th, clip = 0;
+    if (clip_limit > 0.0f) {
+        clip = (int)((double)clip_limit * area / 256);     // static_cast<int>(clipLimit_ * tileSizeTotal / histSize), clipLimit_ double
+        clip = std::max(clip, 1);
+    }
+    float lut_scale = 255.0f / (float)area;
+    k_clahe_lut<<<64, 256, 0, st>>>(hist, clip, lut_scale, luts);
+    count_launch(h, 2);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void pp_clahe_apply(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, int H, int W, const uint8_t* tone,
+                    const uint8_t* luts) {
+    ClaheGeom g = clahe_geom(H, W);
+    k_clahe_apply<<<dim3(cdiv(W, 1024), H), 256, 64 * 256 + 256, st>>>(src, dst, H, W, g, tone, luts);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void pp_unsharp(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, int H, int W, int percent, int threshold,
+                const uint8_t* tone, const uint8_t* clahe_luts) {
+    unsigned ww, fw;
+    pil_box_params(1.0f, &ww, &fw);
+    ClaheGeom g = clahe_geom(H, W);
+    k_unsharp<<<dim3(cdiv(W, US_T), cdiv(H, US_T)), 256, 0, st>>>(src, dst, H, W, ww, fw, percent, threshold, g, tone,
+                                                                  clahe_luts);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A10  cv2.adaptiveThreshold (BORDER_REPLICATE).  GAUSSIAN_C: float32 separable blur, rint -> u8 mean;
+//      MEAN_C: exact integer box sum, rint(sum / block^2) in double.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_at_rows(const uint8_t* __restrict__ src, int H, int W, int block, const float* __restrict__ k,
+                          float* __restrict__ outf, int* __restrict__ outi) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const uint8_t* row = src + (int64_t)y * W;
+    int r = block / 2;
+    if (outf) {
+        float acc = 0.f;
+        for (int i = 0; i < block; ++i) {
+            int xx = min(max(x - r + i, 0), W - 1);
+            acc = __fadd_rn(acc, __fmul_rn((float)row[xx], k[i]));
+        }
+        outf[(int64_t)y * W + x] = acc;
+    } else {
+        int acc = 0;
+        for (int i = 0; i < block; ++i) acc += row[min(max(x - r + i, 0), W - 1)];
+        outi[(int64_t)y * W + x] = acc;
+    }
+}
+
+__global__ void k_at_cols(const uint8_t* __restrict__ src, const float* __restrict__ inf, const int* __restrict__ ini,
+                          int H, int W, int block, const float* __restrict__ k, int inv, int idelta,
+                          uint8_t* __restrict__ dst) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    int r = block / 2, mean;
+    if (inf) {
+        float acc = 0.f;
+        for (int i = 0; i < block; ++i) {
+            int yy = min(max(y - r + i, 0), H - 1);
+            acc = __fadd_rn(acc, __fmul_rn(inf[(int64_t)yy * W + x], k[i]));
+        }
+        mean = min(max(__float2int_rn(acc), 0), 255);
+    } else {
+        int acc = 0;
+        for (int i = 0; i < block; ++i) acc += ini[(int64_t)min(max(y - r + i, 0), H - 1) * W + x];
+        mean = min(max(__double2int_rn((double)acc * (1.0 / ((double)block * block))), 0), 255);
+    }
+    int d = (int)src[(int64_t)y * W + x] - mean;
+    dst[(int64_t)y * W + x] = inv ? (d <= -idelta ? 255 : 0) : (d > -idelta ? 255 : 0);
+}
+
+void pp_adaptive_threshold(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, int H, int W, int method,
+                           int inv, int block, float delta) {
+    ARG_CHECK(block % 2 == 1 && block > 1 && block <= 255, "adaptiveThreshold: block must be odd, 3..255");
+    DevBuf tmp((size_t)H * W * 4, st), kbuf(256 * 4, st);
+    if (method == 1) {
+        double sigma = ((block - 1) * 0.5 - 1) * 0.3 + 0.8;
+        std::vector<double> kd(block);
+        double s = 0;
+        for (int i = 0; i < block; ++i) {
+            double x = i - (block - 1) * 0.5;
+            kd[i] = exp(-(x * x) / (2.0 * sigma * sigma));
+            s += kd[i];
+        }
+        std::vector<float> kf(block);
+        for (int i = 0; i < block; ++i) kf[i] = (float)(kd[i] / s);
+        CUDA_CHECK(cudaMemcpyAsync(kbuf.p, kf.data(), block * 4, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    int idelta = inv ? (int)floor((double)delta) : (int)ceil((double)delta);
+    dim3 grd(cdiv(W, 256), H);
+    k_at_rows<<<grd, 256, 0, st>>>(src, H, W, block, kbuf.as<float>(), method == 1 ? tmp.as<float>() : nullptr,
+                                   method == 1 ? nullptr : tmp.as<int>());
+    k_at_cols<<<grd, 256, 0, st>>>(src, method == 1 ? tmp.as<float>() : nullptr, method == 1 ? nullptr : tmp.as<int>(), H,
+                                   W, block, kbuf.as<float>(), inv, idelta, dst);
+    count_launch(h, 2);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A11  preprocess_for_book_cover minus file I/O, all on one stream; device in, device out.
+//   launches: gray, resize, gaussian(+sum), tone LUT, CLAHE hist, CLAHE lut, fused CLAHE-apply+unsharp  (7)
+// ------------------------------------------------------------------------------------------------------------------
+int preprocess_launches_per_image() { return 7; }
+
+void preprocess_chain_dev(Handle* h, cudaStream_t st, const uint8_t* bgr, int H, int W, int stride,
+                          const bbocr_pp_params& p, uint8_t* out, int* outH, int* outW) {
+    ARG_CHECK(H > 0 && W > 0 && p.scale > 0, "preprocess: bad geometry");
+    int dH = (int)(H * (double)p.scale), dW = (int)(W * (double)p.scale);     // int(h * scale_factor) in Python doubles
+    ARG_CHECK(dH > 0 && dW > 0, "preprocess: empty output");
+    int64_t n = (int64_t)dH * dW;
+    DevBuf gray((size_t)H * W, st), resized((size_t)n, st), blurred((size_t)n, st);
+    DevBuf small(8 + 256 + 64 * 256 * 4 + 64 * 256, st);
+    unsigned long long* sum = small.as<unsigned long long>();
+    uint8_t* tone = small.as<uint8_t>() + 8;
+    unsigned int* hist = reinterpret_cast<unsigned int*>(small.as<uint8_t>() + 8 + 256);
+    uint8_t* luts = small.as<uint8_t>() + 8 + 256 + 64 * 256 * 4;
+    pp_gray(h, st, bgr, H, W, stride, gray.as<uint8_t>());
+    pp_resize_cubic(h, st, gray.as<uint8_t>(), H, W, resized.as<uint8_t>(), dH, dW, p.resize_mode);
+    CUDA_CHECK(cudaMemsetAsync(sum, 0, 8, st));
+    pp_gaussian3(h, st, resized.as<uint8_t>(), blurred.as<uint8_t>(), dH, dW, p.sigma, sum);
+    pp_tone_lut(h, st, sum, n, p.contrast, p.brightness, tone);
+    pp_clahe_luts(h, st, blurred.as<uint8_t>(), dH, dW, p.clahe_clip, tone, hist, luts);
+    pp_unsharp(h, st, blurred.as<uint8_t>(), out, dH, dW, p.sharpen_percent, 3, tone, luts);
+    *outH = dH;
+    *outW = dW;
+}
+
+float pp_deskew(Handle*, cudaStream_t, const uint8_t*, uint8_t*, int, int, float) {
+    fail(BBOCR_E_UNSUPPORTED, "deskew: not implemented yet");
+}
+
+}  // namespace bbocr

@@ -1,0 +1,355 @@
+// recog.cu -- crop / recognise / decode:
+//   utils.get_image_list + compute_ratio_and_resize (cv2 INTER_LINEAR u8), four_point_transform (warpPerspective),
+//   recognition.AlignCollate + NormalizePAD (Pillow BICUBIC for tall crops, (x/255-0.5)/0.5, replicate right pad),
+//   adjust_contrast_grey, vgg_model.Model.forward, softmax / greedy CTC / custom_mean.
+#include "engine.h"
+#include "resize.cuh"
+
+namespace bbocr {
+
+// ------------------------------------------------------------------------------------------------------------------
+// crops: one launch for all boxes of a page.  grid = (x chunks, rows, boxes)
+// ------------------------------------------------------------------------------------------------------------------
+// cv2.warpPerspective(INTER_LINEAR, BORDER_CONSTANT 0) sample: fixed-point 5-bit sub-pixel, 15-bit weights
+__device__ __forceinline__ uint8_t warp_px(const uint8_t* __restrict__ src, int H, int W, const double* __restrict__ M,
+                                           int x, int y) {
+    // OpenCV evaluates X0 at the start of each 32-wide block and adds M[0]*x1 inside it (WarpPerspectiveInvoker)
+    const int xb = x & ~31, x1 = x - xb;
+    double X0 = M[0] * xb + M[1] * y + M[2];
+    double Y0 = M[3] * xb + M[4] * y + M[5];
+    double W0 = M[6] * xb + M[7] * y + M[8];
+    double Wd = W0 + M[6] * x1;
+    Wd = Wd ? 32.0 / Wd : 0;
+    double fX = fmax((double)INT_MIN, fmin((double)INT_MAX, (X0 + M[0] * x1) * Wd));
+    double fY = fmax((double)INT_MIN, fmin((double)INT_MAX, (Y0 + M[3] * x1) * Wd));
+    int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+    int sx = X >> 5, sy = Y >> 5;
+    sx = max(-32768, min(32767, sx));
+    sy = max(-32768, min(32767, sy));
+    int ax = X & 31, ay = Y & 31;
+    int w00 = (32 - ay) * (32 - ax) * 32, w01 = (32 - ay) * ax * 32, w10 = ay * (32 - ax) * 32, w11 = ay * ax * 32;
+    auto px = [&](int yy, int xx) -> int {
+        return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (int)src[(int64_t)yy * W + xx] : 0;
+    };
+    int v = px(sy, sx) * w00 + px(sy, sx + 1) * w01 + px(sy + 1, sx) * w10 + px(sy + 1, sx + 1) * w11;
+    return (uint8_t)((v + (1 << 14)) >> 15);
+}
+
+// stage A (free boxes only): warpPerspective into a scratch rectangle (desc.w x desc.h at desc.x0 = scratch offset)
+__global__ void k_warp(const uint8_t* __restrict__ gray, int H, int W, const CropDesc* __restrict__ descs,
+                       const double* __restrict__ mats, uint8_t* __restrict__ scratch) {
+    const CropDesc d = descs[blockIdx.z];
+    if (d.free_idx < 0) return;
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= d.w || y >= d.h) return;
+    scratch[(int64_t)d.x0 + (int64_t)y * d.w + x] = warp_px(gray, H, W, mats + d.free_idx * 9, x, y);
+}
+
+// stage B: compute_ratio_and_resize (cv2.resize INTER_LINEAR) of the source rectangle into the packed crop buffer
+__global__ void k_crop_resize(const uint8_t* __restrict__ gray, int W, const uint8_t* __restrict__ scratch,
+                              const CropDesc* __restrict__ descs, uint8_t* __restrict__ crops) {
+    const CropDesc d = descs[blockIdx.z];
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= d.ow || y >= d.oh) return;
+    const uint8_t* src;
+    int stride;
+    if (d.free_idx >= 0) { src = scratch + d.x0; stride = d.w; }
+    else { src = gray + (int64_t)d.y0 * W + d.x0; stride = W; }
+    double scale_x = 1.0 / ((double)d.ow / d.w), scale_y = 1.0 / ((double)d.oh / d.h);
+    crops[(int64_t)d.off + (int64_t)y * d.ow + x] = bilinear_u8_px(src, d.h, d.w, stride, 1, 0, x, y, scale_x, scale_y);
+}
+
+void crops_dev(Handle* h, cudaStream_t st, const uint8_t* gray, int H, int W, const CropDesc* descs_dev, int n,
+               const CropDesc* descs_host, const double* warp_dev, uint8_t* scratch, uint8_t* crops) {
+    if (n == 0) return;
+    int max_ow = 1, max_oh = 1, max_w = 0, max_h = 0;
+    for (int i = 0; i < n; ++i) {
+        max_ow = std::max(max_ow, descs_host[i].ow);
+        max_oh = std::max(max_oh, descs_host[i].oh);
+        if (descs_host[i].free_idx >= 0) { max_w = std::max(max_w, descs_host[i].w); max_h = std::max(max_h, descs_host[i].h); }
+    }
+    if (max_w > 0) {
+        k_warp<<<dim3(cdiv(max_w, 128), max_h, n), 128, 0, st>>>(gray, H, W, descs_dev, warp_dev, scratch);
+        count_launch(h);
+    }
+    k_crop_resize<<<dim3(cdiv(max_ow, 128), max_oh, n), 128, 0, st>>>(gray, W, scratch, descs_dev, crops);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// adjust_contrast_grey: per-crop 256-bin histogram on the device; the two percentiles (np.percentile, linear) and
+// the ratio are O(256) host arithmetic in float64 exactly as NumPy does them; the remap is a device kernel.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_crop_hist(const uint8_t* __restrict__ crops, const CropDesc* __restrict__ descs,
+                            unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[256];
+    const CropDesc d = descs[blockIdx.x];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int n = d.ow * d.oh;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&sh[crops[(int64_t)d.off + i]], 1u);
+    __syncthreads();
+    hist[blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
+}
+
+// img = clip((int(img) - low + 25) * ratio, 0, 255).astype(u8) in float64 ; apply[i] == 0 leaves the crop unchanged
+__global__ void k_crop_contrast(const uint8_t* __restrict__ crops, const CropDesc* __restrict__ descs,
+                                const double* __restrict__ low, const double* __restrict__ ratio,
+                                const int* __restrict__ apply, uint8_t* __restrict__ out) {
+    const CropDesc d = descs[blockIdx.y];
+    const int n = d.ow * d.oh;
+    const double lo = low[blockIdx.y], r = ratio[blockIdx.y];
+    const int ap = apply[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint8_t v = crops[(int64_t)d.off + i];
+        if (ap) {
+            double t = ((double)(int)v - lo + 25.0) * r;
+            t = fmax(0.0, fmin(255.0, t));
+            v = (uint8_t)t;
+        }
+        out[(int64_t)d.off + i] = v;
+    }
+}
+
+void crop_hist_dev(Handle* h, cudaStream_t st, const uint8_t* crops, const CropDesc* descs_dev, int n, unsigned int* hist) {
+    if (n == 0) return;
+    k_crop_hist<<<n, 256, 0, st>>>(crops, descs_dev, hist);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void crop_contrast_dev(Handle* h, cudaStream_t st, const uint8_t* crops, const CropDesc* descs_dev, int n,
+                       const double* low, const double* ratio, const int* apply, uint8_t* out) {
+    if (n == 0) return;
+    k_crop_contrast<<<dim3(8, n), 256, 0, st>>>(crops, descs_dev, low, ratio, apply, out);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Pillow Image.resize(BICUBIC) for mode L (ImagingResample 8bpc): integer coefficient tables come from the host
+// (computed in double exactly as Pillow's precompute_coeffs / normalize_coeffs_8bpc), horizontal then vertical pass.
+// Only tall crops (h > w) take this path; everything else is an identity resize.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_pil_pass(const uint8_t* __restrict__ src, int sW, int sH, uint8_t* __restrict__ dst, int dW, int dH,
+                           const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, int vertical) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dW || y >= dH) return;
+    int o = vertical ? y : x;
+    int lo = bounds[o * 2], cnt = bounds[o * 2 + 1];
+    const int* k = kk + o * ksize;
+    int ss = 1 << 21;
+    for (int i = 0; i < cnt; ++i) {
+        int v = vertical ? src[(int64_t)(lo + i) * sW + x] : src[(int64_t)y * sW + lo + i];
+        ss += v * k[i];
+    }
+    ss >>= 22;
+    dst[(int64_t)y * dW + x] = (uint8_t)min(max(ss, 0), 255);
+}
+
+static double pil_bicubic(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+
+static int pil_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk) {
+    double scale = (double)in_size / out_size, filterscale = scale;
+    if (filterscale < 1.0) filterscale = 1.0;
+    double support = 2.0 * filterscale;
+    int ksize = (int)ceil(support) * 2 + 1;
+    bounds.assign((size_t)out_size * 2, 0);
+    kk.assign((size_t)out_size * ksize, 0);
+    std::vector<double> k(ksize);
+    for (int xx = 0; xx < out_size; ++xx) {
+        double center = 0.0 + (xx + 0.5) * scale, ww = 0.0, ss = 1.0 / filterscale;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        for (int x = 0; x < xmax; ++x) {
+            double w = pil_bicubic((x + xmin - center + 0.5) * ss);
+            k[x] = w;
+            ww += w;
+        }
+        for (int x = 0; x < xmax; ++x) {
+            if (ww != 0.0) k[x] /= ww;
+            kk[(size_t)xx * ksize + x] = k[x] < 0 ? (int)(-0.5 + k[x] * (1 << 22)) : (int)(0.5 + k[x] * (1 << 22));
+        }
+        bounds[xx * 2] = xmin;
+        bounds[xx * 2 + 1] = xmax;
+    }
+    return ksize;
+}
+
+// src (sH x sW) -> dst (dH x dW); scratch must hold sH*dW bytes
+void pil_resize_bicubic_dev(Handle* h, cudaStream_t st, const uint8_t* src, int sH, int sW, uint8_t* dst, int dH, int dW,
+                            uint8_t* scratch) {
+    std::vector<int> bx, kx, by, ky;
+    int ksx = pil_coeffs(sW, dW, bx, kx), ksy = pil_coeffs(sH, dH, by, ky);
+    std::vector<int> all;
+    all.insert(all.end(), bx.begin(), bx.end());
+    all.insert(all.end(), kx.begin(), kx.end());
+    all.insert(all.end(), by.begin(), by.end());
+    all.insert(all.end(), ky.begin(), ky.end());
+    DevBuf tab(all.size() * 4, st);
+    CUDA_CHECK(cudaMemcpyAsync(tab.p, all.data(), all.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    int* t = tab.as<int>();
+    const uint8_t* hsrc = src;
+    if (dW != sW) {
+        k_pil_pass<<<dim3(cdiv(dW, 64), sH), 64, 0, st>>>(src, sW, sH, scratch, dW, sH, t, t + bx.size(), ksx, 0);
+        count_launch(h);
+        hsrc = scratch;
+    }
+    if (dH != sH) {
+        k_pil_pass<<<dim3(cdiv(dW, 64), dH), 64, 0, st>>>(hsrc, dW, sH, dst, dW, dH, t + bx.size() + kx.size(),
+                                                         t + bx.size() + kx.size() + by.size(), ksy, 1);
+        count_launch(h);
+    } else {
+        CUDA_CHECK(cudaMemcpyAsync(dst, hsrc, (size_t)dW * dH, cudaMemcpyDeviceToDevice, st));
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// NormalizePAD: ToTensor (/255), sub 0.5, div 0.5; right-pad to model_w by replicating the last column.
+// aligned crops are 64 rows x resized_w columns at desc.aoff
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_crops_to_input(const uint8_t* __restrict__ aligned, const CropDesc* __restrict__ descs,
+                                 float* __restrict__ inputs) {
+    const CropDesc d = descs[blockIdx.z];
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= d.model_w) return;
+    int sx = min(x, d.resized_w - 1);
+    float v = (float)aligned[(int64_t)d.aoff + (int64_t)y * d.resized_w + sx];
+    v = __fdiv_rn(v, 255.f);
+    v = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+    inputs[(int64_t)d.bucket_off + ((int64_t)d.slot * 64 + y) * d.model_w + x] = v;
+}
+
+void crops_to_input_dev(Handle* h, cudaStream_t st, const uint8_t* aligned, const CropDesc* descs_dev, int n, int max_model_w,
+                        float* inputs) {
+    if (n == 0) return;
+    k_crops_to_input<<<dim3(cdiv(max_model_w, 128), 64, n), 128, 0, st>>>(aligned, descs_dev, inputs);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// vgg_model.Model.forward on a bucket of N crops of identical model width Wm.  x: [N][64][Wm] FP32 (device)
+// ------------------------------------------------------------------------------------------------------------------
+void crnn_forward_dev(Handle* h, cudaStream_t st, const float* x, int N, int Wm, float* logits) {
+    if (!h->crnn_loaded) fail(BBOCR_E_STATE, "CRNN weights not loaded (bbocr_load_crnn)");
+    ARG_CHECK(N > 0 && Wm >= 64 && Wm % 4 == 0, "crnn: bad batch geometry (N=%d, W=%d)", N, Wm);
+    const CrnnW& w = h->crnn;
+    const Act none;
+    const int R = CONV_RELU;
+    DevBuf b0, b1, b2;
+    auto conv = [&](const ConvW& cw, const Act& a, DevBuf& buf, int flags) {
+        Act o = act_alloc(h, st, buf, a.N, a.H + 2 * cw.pad - cw.dil * (cw.kh - 1), a.W + 2 * cw.pad - cw.dil * (cw.kw - 1),
+                          cw.cout, (flags & CONV_OUT_F32) != 0);
+        conv_forward(h, st, cw, a, none, o, flags);
+        return o;
+    };
+    auto pool = [&](const Act& a, DevBuf& buf, int kh, int kw) {
+        Act o = act_alloc(h, st, buf, a.N, a.H / kh, a.W / kw, a.C);
+        maxpool(h, st, a, o, kh, kw, kh, kw, 0, 0);
+        return o;
+    };
+    Act a = act_alloc(h, st, b0, N, 64, Wm, 32);
+    conv_first(h, st, w.c0, x, N, 64, Wm, 1, a, R);
+    a = pool(a, b1, 2, 2);               // 32 x Wm/2
+    a = conv(w.c1, a, b0, R);
+    a = pool(a, b1, 2, 2);               // 16 x Wm/4
+    a = conv(w.c2, a, b0, R);
+    a = conv(w.c3, a, b1, R);
+    a = pool(a, b0, 2, 1);               // 8 x Wm/4
+    a = conv(w.c4, a, b1, R);
+    a = conv(w.c5, a, b0, R);
+    a = pool(a, b1, 2, 1);               // 4 x Wm/4
+    a = conv(w.c6, a, b0, R);            // 3 x (Wm/4 - 1)
+    const int T = a.W;
+    Act seq = act_alloc(h, st, b1, N, 1, T, 256);
+    mean_rows(h, st, a, seq);
+    for (int layer = 0; layer < 2; ++layer) {
+        const LstmW& l = layer == 0 ? w.l0 : w.l1;
+        Act gates = conv(l.in_proj, seq, b0, CONV_OUT_F32);          // [N][1][T][2048] FP32
+        Act hcat = act_alloc(h, st, b2, N, 1, T, 512);
+        lstm_recurrence(h, st, (const float*)gates.p, l.w_hh, N, T, hcat);
+        seq = conv(l.linear, hcat, b1, 0);                           // [N][1][T][256]
+    }
+    Act out;
+    out.N = N; out.H = 1; out.W = T; out.C = w.num_class; out.p = logits;
+    conv_forward(h, st, w.pred, seq, none, out, CONV_OUT_F32);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// recognizer_predict (greedy) + CTCLabelConverter.decode_greedy + the inputs of custom_mean: one warp per crop.
+//   p = softmax(logits); p[ignore] = 0; p /= sum(p); idx = argmax; keep t where idx[t] != idx[t-1] and idx[t] != 0;
+//   confidence inputs = max p at every t with idx[t] != 0 (product taken here in float32, left to right per lane chunk)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_ctc_decode(const float* __restrict__ logits, int N, int T, int C, const uint8_t* __restrict__ ignore,
+                             int32_t* __restrict__ text_idx, int32_t* __restrict__ text_len,
+                             float* __restrict__ step_prob, int32_t* __restrict__ step_idx) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= N) return;
+    const float* lg = logits + (int64_t)warp * T * C;
+    // pass 1: per-timestep argmax / max probability, one timestep at a time with the 32 lanes over the classes
+    for (int t = 0; t < T; ++t) {
+        const float* row = lg + (int64_t)t * C;
+        float mx = -INFINITY;
+        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum_all = 0.f, sum_kept = 0.f, best = -1.f;
+        int besti = INT_MAX;
+        for (int c = lane; c < C; c += 32) {
+            float e = expf(row[c] - mx);
+            sum_all += e;
+            bool ig = ignore && ignore[c];
+            if (!ig) sum_kept += e;
+            float v = ig ? 0.f : e;
+            if (v > best) { best = v; besti = c; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            sum_all += __shfl_xor_sync(0xffffffffu, sum_all, o);
+            sum_kept += __shfl_xor_sync(0xffffffffu, sum_kept, o);
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) {
+            // softmax prob = e/sum_all ; renormalised by the kept mass sum_kept/sum_all
+            float p = (best / sum_all) / (sum_kept / sum_all);
+            step_prob[(int64_t)warp * T + t] = p;
+            step_idx[(int64_t)warp * T + t] = besti;
+        }
+    }
+    __syncwarp();
+    // pass 2: CTC collapse, 32 timesteps per iteration with ballot compaction
+    int count = 0;
+    for (int base = 0; base < T; base += 32) {
+        int t = base + lane;
+        int cur = t < T ? step_idx[(int64_t)warp * T + t] : 0;
+        int prev = (t > 0 && t < T) ? step_idx[(int64_t)warp * T + t - 1] : -1;
+        bool keep = t < T && cur != prev && cur != 0;
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) text_idx[(int64_t)warp * T + count + __popc(m & ((1u << lane) - 1u))] = cur;
+        count += __popc(m);
+    }
+    if (lane == 0) text_len[warp] = count;
+}
+
+void ctc_decode_dev(Handle* h, cudaStream_t st, const float* logits, int N, int T, int C, const uint8_t* ignore_dev,
+                    int32_t* text_idx, int32_t* text_len, float* step_prob, int32_t* step_idx) {
+    if (N == 0) return;
+    k_ctc_decode<<<cdiv(N * 32, 128), 128, 0, st>>>(logits, N, T, C, ignore_dev, text_idx, text_len, step_prob, step_idx);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace bbocr
