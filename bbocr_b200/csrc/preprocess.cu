@@ -570,10 +570,11 @@ __global__ void k_at_rows(const uint8_t* __restrict__ src, int H, int W, int blo
     const uint8_t* row = src + (int64_t)y * W;
     int r = block / 2;
     if (outf) {
-        float acc = 0.f;
-        for (int i = 0; i < block; ++i) {
+        // generic float row filter with fused multiply-add: s = p0*k0; s = fma(p_i, k_i, s)
+        float acc = __fmul_rn((float)row[min(max(x - r, 0), W - 1)], k[0]);
+        for (int i = 1; i < block; ++i) {
             int xx = min(max(x - r + i, 0), W - 1);
-            acc = __fadd_rn(acc, __fmul_rn((float)row[xx], k[i]));
+            acc = __fmaf_rn((float)row[xx], k[i], acc);
         }
         outf[(int64_t)y * W + x] = acc;
     } else {
@@ -590,10 +591,11 @@ __global__ void k_at_cols(const uint8_t* __restrict__ src, const float* __restri
     if (x >= W) return;
     int r = block / 2, mean;
     if (inf) {
-        float acc = 0.f;
-        for (int i = 0; i < block; ++i) {
-            int yy = min(max(y - r + i, 0), H - 1);
-            acc = __fadd_rn(acc, __fmul_rn(inf[(int64_t)yy * W + x], k[i]));
+        // symmetric float column filter: s = c*k_c; s = fma(r_{+j} + r_{-j}, k_j, s)
+        float acc = __fmul_rn(inf[(int64_t)y * W + x], k[r]);
+        for (int j = 1; j <= r; ++j) {
+            int ya = min(y + j, H - 1), yb = max(y - j, 0);
+            acc = __fmaf_rn(__fadd_rn(inf[(int64_t)ya * W + x], inf[(int64_t)yb * W + x]), k[r + j], acc);
         }
         mean = min(max(__float2int_rn(acc), 0), 255);
     } else {

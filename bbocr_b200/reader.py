@@ -1,0 +1,208 @@
+"""EasyOCR-compatible `Reader` backed by libbbocr.so (hand-written sm_100a kernels).
+
+Mirrors the surface BB-OCR uses:
+    pipeline_demo/extractor/enhanced_extractor.py:153   easyocr.Reader(["en"], gpu=use_gpu)
+    pipeline_demo/extractor/enhanced_extractor.py:520   reader.readtext(path, paragraph=False, batch_size=1, workers=0)
+    pipeline_components/img_to_json/ocr_testing/ocr_engines/test_easyocr.py:20-23,50-53   for (bbox, text, prob) in result
+Same names, argument meaning, result format `(box, text, confidence)` and error behaviour (ordinary Python
+exceptions; the caller swallows them).  There is no CPU fallback: constructing a Reader without a B200 raises.
+"""
+from __future__ import annotations
+
+import os
+import threading
+
+import cv2
+import numpy as np
+
+from . import _lib, weights
+
+# easyocr/config.py : recognition_models['gen2']['english_g2']
+SYMBOLS = "0123456789!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~ €"
+CHARACTERS = SYMBOLS + "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz"
+
+
+def reformat_input(image):
+    """easyocr/utils.py::reformat_input -> (img HxWx3 as fed to the detector, img_cv_grey HxW).  Host-side decode;
+    JPEG/PNG decoding stays on the host."""
+    if isinstance(image, str):
+        img_cv_grey = cv2.imread(image, cv2.IMREAD_GRAYSCALE)
+        bgr = cv2.imread(os.path.expanduser(image), cv2.IMREAD_COLOR)
+        if bgr is None or img_cv_grey is None:
+            raise ValueError(f"Invalid input: could not read {image}")
+        img = cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB)          # upstream: skimage.io.imread (RGB)
+    elif isinstance(image, bytes):
+        nparr = np.frombuffer(image, np.uint8)
+        img = cv2.imdecode(nparr, cv2.IMREAD_COLOR)
+        if img is None:
+            raise ValueError("Invalid input: undecodable bytes")
+        img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+        img_cv_grey = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+    elif isinstance(image, np.ndarray):
+        if image.ndim == 2:
+            img_cv_grey = image
+            img = cv2.cvtColor(image, cv2.COLOR_GRAY2BGR)
+        elif image.ndim == 3 and image.shape[2] == 1:
+            img_cv_grey = np.squeeze(image)
+            img = cv2.cvtColor(img_cv_grey, cv2.COLOR_GRAY2BGR)
+        elif image.ndim == 3 and image.shape[2] == 3:
+            img = image
+            img_cv_grey = None                                # derived on the device: BGR2GRAY fixed-point formula
+        elif image.ndim == 3 and image.shape[2] == 4:
+            img = cv2.cvtColor(image[:, :, :3], cv2.COLOR_RGB2BGR)
+            img_cv_grey = None
+        else:
+            raise ValueError("Invalid input type. Supporting format = string(file path or url), bytes, numpy array")
+    else:
+        raise ValueError("Invalid input type. Supporting format = string(file path or url), bytes, numpy array")
+    if img.dtype != np.uint8:
+        raise ValueError("Invalid input: image must be uint8")
+    return img, img_cv_grey
+
+
+class Reader:
+    """easyocr.Reader(['en']) drop-in.  Unknown keyword arguments are accepted and ignored like upstream's optional ones."""
+
+    def __init__(self, lang_list=("en",), gpu=True, model_storage_directory=None, user_network_directory=None,
+                 detect_network="craft", recog_network="standard", download_enabled=True, detector=True,
+                 recognizer=True, verbose=True, quantize=True, cudnn_benchmark=False, *, precision="bf16",
+                 craft_state=None, crnn_state=None, **_ignored):
+        if list(lang_list) != ["en"]:
+            raise ValueError(f"{list(lang_list)} is not supported (only ['en'] / english_g2)")
+        if detect_network != "craft":
+            raise ValueError("only detect_network='craft' is supported")
+        device = 0
+        if isinstance(gpu, str) and gpu.startswith("cuda:"):
+            device = int(gpu.split(":")[1])
+        elif isinstance(gpu, int) and not isinstance(gpu, bool):
+            device = gpu
+        elif os.environ.get("LOCAL_RANK") is not None:
+            device = int(os.environ["LOCAL_RANK"])
+        self.device = f"cuda:{device}"
+        self._h = _lib.Handle(device)                         # raises without a B200: no CPU path
+        self._lock = threading.Lock()
+        self.character = CHARACTERS
+        self.lang_char = CHARACTERS                            # en_char.txt + symbols cover the whole english_g2 alphabet
+        self.model_lang = "english"
+        craft_path, crnn_path = weights.find_checkpoints(model_storage_directory)
+        if craft_state is None:
+            craft_state = weights.load_pth(craft_path) if craft_path else weights.calibrated_craft_state()
+        if crnn_state is None:
+            crnn_state = weights.load_pth(crnn_path) if crnn_path else weights.calibrated_crnn_state()
+        self.weights_source = {"craft": craft_path or "seeded-random+probe", "crnn": crnn_path or "seeded-random+probe"}
+        if verbose and not (craft_path and crnn_path):
+            print("bbocr_b200: genuine EasyOCR checkpoints not found; using the seeded synthetic weights "
+                  "(bbocr_b200/weights.py)")
+        self._h.load_craft(craft_state)
+        self._h.load_crnn(crnn_state)
+        self.set_precision(precision)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def set_precision(self, precision: str):
+        self._h.set_precision({"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision])
+        self.precision = precision
+
+    def _params(self, kw, allowlist=None, blocklist=None):
+        p = self._h.default_params()
+        for k in ("min_size", "canvas_size", "contrast_ths", "adjust_contrast", "text_threshold", "low_text",
+                  "link_threshold", "mag_ratio", "slope_ths", "ycenter_ths", "height_ths", "width_ths", "add_margin"):
+            if k in kw and kw[k] is not None:
+                setattr(p, k, kw[k])
+        ignore = None
+        if allowlist:
+            ign = set(self.character) - set(allowlist)
+        elif blocklist:
+            ign = set(blocklist)
+        else:
+            ign = set(self.character) - set(self.lang_char)
+        if ign:
+            ignore = np.zeros(len(self.character) + 1, np.uint8)
+            for ch in ign:
+                if ch in self.character:
+                    ignore[self.character.index(ch) + 1] = 1
+            p.ignore = ignore.ctypes.data
+        return p, ignore
+
+    def _format(self, raw, detail=1, output_format="standard"):
+        out = []
+        for box, is_free, idx, conf in raw:
+            text = "".join(self.character[i - 1] for i in idx)
+            if is_free:
+                b = [[float(x), float(y)] for x, y in box]
+            else:
+                b = [[int(x), int(y)] for x, y in box]
+            out.append((b, text, conf))
+        if detail == 0:
+            return [item[1] for item in out]
+        if output_format == "dict":
+            return [{"boxes": item[0], "text": item[1], "confident": item[2]} for item in out]
+        return out
+
+    @staticmethod
+    def _check_unsupported(decoder, rotation_info, paragraph):
+        if decoder != "greedy":
+            raise NotImplementedError("only decoder='greedy' is implemented (SURVEY.md §8f-3)")
+        if rotation_info:
+            raise NotImplementedError("rotation_info is not implemented (SURVEY.md §8f-3)")
+        if paragraph:
+            raise NotImplementedError("paragraph=True is not implemented (SURVEY.md §8f-3)")
+
+    def readtext(self, image, decoder="greedy", beamWidth=5, batch_size=1, workers=0, allowlist=None, blocklist=None,
+                 detail=1, rotation_info=None, paragraph=False, min_size=20, contrast_ths=0.1, adjust_contrast=0.5,
+                 filter_ths=0.003, text_threshold=0.7, low_text=0.4, link_threshold=0.4, canvas_size=2560, mag_ratio=1.0,
+                 slope_ths=0.1, ycenter_ths=0.5, height_ths=0.5, width_ths=0.5, y_ths=0.5, x_ths=1.0, add_margin=0.1,
+                 threshold=0.2, bbox_min_score=0.2, bbox_min_size=3, max_candidates=0, output_format="standard"):
+        """Reader.readtext (easyocr/easyocr.py).  Returns [(box, text, confidence), ...] in upstream order."""
+        return self.readtext_batched([image], decoder=decoder, allowlist=allowlist, blocklist=blocklist, detail=detail,
+                                     rotation_info=rotation_info, paragraph=paragraph, min_size=min_size,
+                                     contrast_ths=contrast_ths, adjust_contrast=adjust_contrast,
+                                     text_threshold=text_threshold, low_text=low_text, link_threshold=link_threshold,
+                                     canvas_size=canvas_size, mag_ratio=mag_ratio, slope_ths=slope_ths,
+                                     ycenter_ths=ycenter_ths, height_ths=height_ths, width_ths=width_ths,
+                                     add_margin=add_margin, output_format=output_format)[0]
+
+    def readtext_batched(self, images, decoder="greedy", allowlist=None, blocklist=None, detail=1, rotation_info=None,
+                         paragraph=False, output_format="standard", return_stats=False, **kw):
+        """Batched extension: independent pages pipelined over the handle's CUDA streams; per-page semantics are exactly
+        those of readtext(batch_size=1)."""
+        self._check_unsupported(decoder, rotation_info, paragraph)
+        p, keep = self._params(kw, allowlist, blocklist)
+        pages = []
+        for im in images:
+            img, grey = reformat_input(im)
+            pages.append((np.ascontiguousarray(img), None if grey is None else np.ascontiguousarray(grey),
+                          img.shape[0], img.shape[1]))
+        with self._lock:
+            raw = self._h.readtext_raw(pages, p)
+        res = [self._format(r, detail, output_format) for r, _ in raw]
+        if return_stats:
+            return res, [s for _, s in raw]
+        return res
+
+    def readtext_device(self, color_ptrs, H, W, **kw):
+        """Pages already resident in HBM: `color_ptrs` are raw device pointers to HxWx3 u8 images."""
+        p, keep = self._params(kw)
+        with self._lock:
+            raw = self._h.readtext_raw([(ptr, None, H, W) for ptr in color_ptrs], p, on_device=True)
+        return [self._format(r) for r, _ in raw], [s for _, s in raw]
+
+    # stage boundaries (upstream signatures, reduced to the arguments that change arithmetic)
+    def detect(self, img, min_size=20, text_threshold=0.7, low_text=0.4, link_threshold=0.4, canvas_size=2560,
+               mag_ratio=1.0, slope_ths=0.1, ycenter_ths=0.5, height_ths=0.5, width_ths=0.5, add_margin=0.1,
+               reformat=True, **_ignored):
+        """Reader.detect -> ([horizontal_list], [free_list])"""
+        if reformat:
+            img, _ = reformat_input(img)
+        with self._lock:
+            text, link, ratio = self._h.craft_forward(img, canvas_size, mag_ratio)
+            boxes = self._h.det_boxes(text, link, text_threshold, link_threshold, low_text)
+        hl, fl = _lib.group_boxes(boxes, ratio, slope_ths, ycenter_ths, height_ths, width_ths, add_margin, min_size)
+        return [[list(map(int, b)) for b in hl]], [[[[float(x), float(y)] for x, y in q] for q in fl]]
+
+    def score_maps(self, img, canvas_size=2560, mag_ratio=1.0):
+        with self._lock:
+            return self._h.craft_forward(img, canvas_size, mag_ratio)
+
+    @property
+    def handle(self):
+        return self._h

@@ -115,6 +115,20 @@ def random_crnn_state(seed: int = 4321, num_class: int = 97, hidden: int = 256) 
     return sd
 
 
+def calibrated_crnn_state(seed: int = 4321):
+    """Random recogniser with its Prediction read-out fitted on synthetic lines (tools/fit_crnn_probe.py)."""
+    sd = random_crnn_state(seed)
+    p = os.path.join(_DATA, "crnn_probe.npz")
+    if os.path.exists(p):
+        z = np.load(p)
+        if int(z["seed"]) == seed:
+            for k in z.files:
+                if k != "seed":
+                    assert sd[k].shape == z[k].shape, k
+                    sd[k] = z[k].astype(np.float32)
+    return sd
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 
 def find_checkpoints(model_storage_directory: str | None = None):

@@ -1,0 +1,86 @@
+"""GPU: stage-1 kernels through the C ABI vs the NumPy oracle (bit-exact) and the reference fixtures."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from bbocr_b200 import synth
+from bbocr_b200.preprocess import ImagePreprocessor, preprocess_array, pp_params, CURRENT, LEGACY
+from oracle import preprocess_np as P
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rnd(seed, h, w, c=None):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, (h, w) if c is None else (h, w, c)).astype(np.uint8)
+
+
+SIZES = [(1, 1), (7, 5), (16, 16), (97, 131), (240, 320), (203, 517), (600, 801)]
+
+
+@pytest.mark.parametrize("hw", SIZES)
+def test_steps_bit_exact(handle, hw):
+    h, w = hw
+    g = rnd(h * 7 + w, h, w)
+    bgr = rnd(h * 11 + w, h, w, 3)
+    assert np.array_equal(handle.pp_gray(bgr), P.bgr2gray(bgr))
+    for s in (3.0, 5.0):
+        assert np.array_equal(handle.pp_gaussian3(g, s), P.gaussian_blur3(g, s))
+    for f in (1.9, 1.3, 0.5):
+        assert np.array_equal(handle.pp_contrast(g, f), P.pil_contrast(g, f))
+    assert np.array_equal(handle.pp_brightness(g, 1.2), P.pil_brightness(g, 1.2))
+    if h >= 8 and w >= 8:
+        for cl in (2.0, 2.5):
+            assert np.array_equal(handle.pp_clahe(g, cl), P.clahe(g, cl))
+    for pc in (20, 30):
+        assert np.array_equal(handle.pp_unsharp(g, pc, 3), P.pil_unsharp(g, 1.0, pc, 3))
+    dh, dw = int(h * 1.5), int(w * 1.5)
+    for mode, name in ((0, "T1"), (1, "T2")):
+        assert np.array_equal(handle.pp_resize_cubic(g, dh, dw, mode), P.resize_cubic(g, dw, dh, name))
+    if h >= 2 and w >= 2:
+        assert np.array_equal(handle.pp_adaptive_threshold(g, 1, False, 11, 2.0), P.adaptive_threshold(g, 255, "gaussian", False, 11, 2))
+        assert np.array_equal(handle.pp_adaptive_threshold(g, 0, True, 35, 10.0), P.adaptive_threshold(g, 255, "mean", True, 35, 10))
+        assert np.array_equal(handle.pp_adaptive_threshold(g, 1, True, 31, 5.0), P.adaptive_threshold(g, 255, "gaussian", True, 31, 5))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "preprocess_*.npz"))))
+def test_chain_matches_reference_fixtures(handle, path):
+    z = np.load(path)
+    for name, cfg in (("current", CURRENT), ("legacy", LEGACY)):
+        got = preprocess_array(z["bgr"], cfg, 0)
+        assert np.array_equal(got, z[f"ref_{name}_ippoff"]), (path, name)     # the reference's own output, cv2.ipp off
+        got2 = preprocess_array(z["bgr"], cfg, 1)
+        d = np.abs(got2.astype(int) - z[f"ref_{name}_ippon"].astype(int))
+        assert (d > 0).mean() < 2e-3 and d.max() <= 8
+
+
+def test_fluent_interface_mirrors_reference(handle):
+    bgr = synth.phone_photo(3003, 403, 302)
+    pp = ImagePreprocessor().load_array(bgr)
+    pp.to_grayscale().resize(scale_factor=1.5).denoise(strength=3).increase_contrast(1.9).increase_brightness(1.2)
+    pp.clahe(clip_limit=2.5).sharpen(amount=0.3)
+    want, stages = P.preprocess_chain(bgr, P.CURRENT, "T1", return_stages=True)
+    assert np.array_equal(pp.get_image(), want)
+    assert pp.get_steps_applied() == P.steps_list(P.CURRENT)
+    assert np.array_equal(preprocess_array(bgr, CURRENT, 0), want)            # fused chain == step-by-step
+    with pytest.raises(ValueError):
+        ImagePreprocessor().to_grayscale()
+    with pytest.raises(ValueError):
+        ImagePreprocessor().load_image("/nonexistent/file.png")
+
+
+def test_full_size_phone_photo(handle):
+    """BASELINE config 3 size (4032x3024): bit-exact against the oracle on one photo, plus size-independent properties."""
+    bgr = synth.phone_photo(3001)
+    got = preprocess_array(bgr, CURRENT, 0)
+    assert got.shape == (4536, 6048)
+    want = P.preprocess_chain(bgr, P.CURRENT, "T1")
+    assert np.array_equal(got, want)
+    # idempotence of the tone LUT on a constant image and determinism of repeated launches
+    assert np.array_equal(preprocess_array(bgr, CURRENT, 0), got)
+    flat = np.full((3024, 4032, 3), 127, np.uint8)
+    out = preprocess_array(flat, CURRENT, 0)
+    assert out.min() == out.max()

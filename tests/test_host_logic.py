@@ -1,0 +1,129 @@
+"""CPU: host-side logic of the product (no CUDA calls): export table, box geometry vs cv2 / the oracle, sharding."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import easyocr_restated as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    hdr = open(os.path.join(ROOT, "include", "bbocr.h")).read()
+    declared = set(re.findall(r"\b(bbocr_[a-z0-9_]+)\s*\(", hdr))
+    L = lib_built.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+    assert declared == set(lib_built.SYMBOLS)
+    assert b"sm_100a" in L.bbocr_version()
+
+
+def test_no_cpu_fallback_without_gpu(lib_built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(lib_built.BbocrError):
+        lib_built.Handle(0)
+    import bbocr_b200
+    with pytest.raises(lib_built.BbocrError):
+        bbocr_b200.Reader(["en"], verbose=False)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "bbocr_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_min_area_box_matches_cv2(lib_built):
+    rng = np.random.default_rng(0)
+    for it in range(1500):
+        kind = it % 3
+        if kind == 0:
+            h, w = int(rng.integers(3, 40)), int(rng.integers(3, 120))
+            m = np.zeros((h, w), np.uint8)
+            for _ in range(int(rng.integers(1, 6))):
+                cv2.ellipse(m, (int(rng.integers(0, w)), int(rng.integers(0, h))),
+                            (int(rng.integers(1, w)), int(rng.integers(1, h))), float(rng.uniform(0, 180)), 0, 360, 255, -1)
+            pts = np.roll(np.array(np.where(m != 0)), 1, axis=0).transpose().reshape(-1, 2)
+            if len(pts) == 0:
+                continue
+        elif kind == 1:
+            pts = rng.integers(0, 60, (int(rng.integers(1, 40)), 2))
+        else:
+            t = rng.integers(0, 30, int(rng.integers(1, 10)))
+            pts = np.stack([t * int(rng.integers(0, 3)), t * int(rng.integers(0, 3))], 1)
+        pts = np.ascontiguousarray(pts, np.int32)
+        ref = cv2.boxPoints(cv2.minAreaRect(pts))
+        got = lib_built.min_area_box(pts)
+        assert np.array_equal(ref.view(np.uint32), got.view(np.uint32)), (kind, pts.tolist())
+
+
+def test_group_boxes_matches_oracle(lib_built):
+    rng = np.random.default_rng(1)
+    for it in range(300):
+        n = int(rng.integers(0, 40))
+        boxes = []
+        for _ in range(n):
+            cx, cy = rng.uniform(20, 600), rng.uniform(20, 400)
+            w, h = rng.uniform(5, 150), rng.uniform(4, 40)
+            ang = rng.choice([0, 0, 0, rng.uniform(-25, 25)])
+            r = cv2.boxPoints(((cx, cy), (w, h), float(ang)))
+            r = np.roll(r, 4 - r.sum(1).argmin(), 0)
+            if rng.random() < 0.5:
+                r = np.round(r)
+            boxes.append(r.astype(np.float32))
+        ratio = float(rng.choice([1.0, 0.8, 2560 / 3000]))
+        polys = E.boxes_to_polys_int([b.copy() for b in boxes], ratio)
+        hl, fl = E.group_text_box(polys, 0.1, 0.5, 0.5, 0.5, 0.1, True)
+        hl, fl = E.filter_min_size(hl, fl, 20)
+        arr = np.array(boxes, np.float32).reshape(-1, 8) if n else np.zeros((0, 8), np.float32)
+        mh, mf = lib_built.group_boxes(arr, ratio)
+        assert [list(map(int, a)) for a in hl] == mh.tolist()
+        assert len(fl) == len(mf) and all(np.array_equal(np.array(a, np.float64), b) for a, b in zip(fl, mf))
+
+
+def test_sharding_is_a_partition():
+    from bbocr_b200 import sharding
+    for world in (1, 2, 4, 8):
+        parts = [sharding.shard_round_robin(37, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(37))
+        costs = [1280 * 960 if i % 2 else 1920 * 1440 for i in range(37)]
+        parts = [sharding.shard_by_cost(costs, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(37))
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(costs)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import torch.distributed as dist
+from bbocr_b200 import sharding
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%d" %% int(os.environ["PORT"]),
+                        rank=int(os.environ["RANK"]), world_size=2)
+mine = sharding.shard_by_cost([3, 1, 4, 1, 5, 9, 2, 6], dist.get_rank(), 2)
+counts = sharding.gather_counts(len(mine))
+assert sum(counts) == 8, counts
+dist.barrier()
+print("ok", dist.get_rank(), mine, counts)
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % ROOT)
+    port = 29500 + os.getpid() % 2000
+    procs = [subprocess.Popen([sys.executable, str(script)], env={**os.environ, "RANK": str(r), "PORT": str(port)},
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)

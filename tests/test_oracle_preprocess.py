@@ -1,0 +1,79 @@
+"""CPU: pin the NumPy preprocessing oracle against cv2 / Pillow and the reference's golden outputs."""
+import glob
+import os
+
+import cv2
+import numpy as np
+import pytest
+from PIL import Image, ImageEnhance, ImageFilter
+
+from oracle import preprocess_np as P
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def smooth(rng, h, w):
+    a = rng.integers(0, 256, (h // 8 + 2, w // 8 + 2)).astype(np.float32)
+    a = cv2.resize(a, (w, h), interpolation=cv2.INTER_CUBIC) + rng.normal(0, 12, (h, w))
+    return np.clip(a, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("hw", [(97, 131), (240, 320), (203, 517), (64, 64)])
+def test_steps_match_cv2_and_pillow(hw):
+    rng = np.random.default_rng(hw[0] * 1000 + hw[1])
+    h, w = hw
+    bgr = np.stack([smooth(rng, h, w) for _ in range(3)], -1)
+    g = smooth(rng, h, w)
+    pil = Image.fromarray(g)
+    assert np.array_equal(P.bgr2gray(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    ipp = cv2.ipp.useIPP()
+    try:
+        cv2.ipp.setUseIPP(False)
+        ref = cv2.resize(g, (int(w * 1.5), int(h * 1.5)), interpolation=cv2.INTER_CUBIC)
+    finally:
+        cv2.ipp.setUseIPP(ipp)
+    assert np.array_equal(P.resize_scale(g, 1.5, "T1"), ref)
+    for s in (3, 5):
+        assert np.array_equal(P.gaussian_blur3(g, s), cv2.GaussianBlur(g, (3, 3), s))
+    for f in (1.9, 1.3):
+        assert np.array_equal(P.pil_contrast(g, f), np.array(ImageEnhance.Contrast(pil).enhance(f)))
+    assert np.array_equal(P.pil_brightness(g, 1.2), np.array(ImageEnhance.Brightness(pil).enhance(1.2)))
+    for cl in (2.0, 2.5):
+        assert np.array_equal(P.clahe(g, cl), cv2.createCLAHE(clipLimit=cl, tileGridSize=(8, 8)).apply(g))
+    for pc in (20, 30):
+        assert np.array_equal(P.pil_unsharp(g, 1.0, pc, 3),
+                              np.array(pil.filter(ImageFilter.UnsharpMask(radius=1.0, percent=pc, threshold=3))))
+    # GAUSSIAN_C: cv2's float filter rounds its scalar tail columns differently -> pixel-count tolerance
+    d = P.adaptive_threshold(g, 255, "gaussian", False, 11, 2) != \
+        cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_GAUSSIAN_C, cv2.THRESH_BINARY, 11, 2)
+    assert d.mean() < 2e-4
+    assert np.array_equal(P.adaptive_threshold(g, 255, "mean", True, 35, 10),
+                          cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY_INV, 35, 10))
+    d = P.adaptive_threshold(g, 255, "gaussian", True, 31, 5) != \
+        cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_GAUSSIAN_C, cv2.THRESH_BINARY_INV, 31, 5)
+    assert d.mean() < 2e-4
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "preprocess_*.npz"))))
+def test_chain_matches_reference_fixtures(path):
+    """Fixtures = the reference's own preprocess_for_book_cover (current + legacy constants) run by make_golden.py."""
+    z = np.load(path)
+    for name, params in (("current", P.CURRENT), ("legacy", P.LEGACY)):
+        t1 = P.preprocess_chain(z["bgr"], params, "T1")
+        assert np.array_equal(t1, z[f"ref_{name}_ippoff"]), (path, name)
+        # IPP-enabled x86 wheels: real-arithmetic cubic; tolerance-checked (pixel count and amplitude)
+        t2 = P.preprocess_chain(z["bgr"], params, "T2")
+        ref = z[f"ref_{name}_ippon"]
+        d = np.abs(t2.astype(int) - ref.astype(int))
+        assert (d > 0).mean() < 2e-3 and d.max() <= 8, (path, name, (d > 0).mean(), d.max())
+    if "golden_legacy" in z.files:
+        # the PNG recorded by the reference author reproduces with the IPP-on reference to <= 4 px
+        assert (z["golden_legacy"] != z["ref_legacy_ippon"]).sum() <= 4
+        d = np.abs(P.preprocess_chain(z["bgr"], P.LEGACY, "T2").astype(int) - z["golden_legacy"].astype(int))
+        assert (d > 0).mean() < 2e-3 and d.max() <= 8
+
+
+def test_step_strings():
+    assert P.steps_list(P.CURRENT) == ["original", "grayscale", "resize(scale_factor=1.5)", "denoise(strength=3)",
+                                       "increase_contrast(factor=1.9)", "increase_brightness(factor=1.2)",
+                                       "clahe(clip_limit=2.5)", "sharpen(amount=0.3)"]
