@@ -513,7 +513,10 @@ static void pil_box_params(float radius_sigma, unsigned* ww, unsigned* fw) {
 }
 
 static ClaheGeom clahe_geom(int H, int W) {
-    int pw = (W % 8) ? W + 8 - W % 8 : W, ph = (H % 8) ? H + 8 - H % 8 : H;
+    // OpenCV pads BOTH dimensions by 8 - (dim % 8) as soon as either is not a multiple of 8 (so a divisible dimension
+    // grows by a full 8 when the other one is not divisible)
+    int pw = W, ph = H;
+    if (W % 8 != 0 || H % 8 != 0) { pw = W + 8 - W % 8; ph = H + 8 - H % 8; }
     ClaheGeom g;
     g.tw = pw / 8;
     g.th = ph / 8;

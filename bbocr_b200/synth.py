@@ -132,7 +132,7 @@ def phone_photo(seed: int, width: int = 4032, height: int = 3024) -> np.ndarray:
     vig = 1.0 - 0.35 * (((xx - width / 2) / (width / 2)) ** 2 + ((yy - height / 2) / (height / 2)) ** 2)
     vig = cv2.resize(vig, (width, height), interpolation=cv2.INTER_LINEAR)
     out *= vig[..., None]
-    out += rng.normal(0, 2.5, (height // 2, width // 2, 1)).astype(np.float32).repeat(2, 0).repeat(2, 1)
+    out += rng.normal(0, 2.5, ((height + 1) // 2, (width + 1) // 2, 1)).astype(np.float32).repeat(2, 0).repeat(2, 1)[:height, :width]
     return np.clip(out, 0, 255).astype(np.uint8)
 
 

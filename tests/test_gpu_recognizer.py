@@ -75,7 +75,9 @@ def test_crnn_bf16_string_rate(gpu_reader, oracle_reader):
     s_got = [r[0] for r in E.decode_probs(E.probs_from_logits(torch.from_numpy(got)))]
     rate = np.mean([a == b for a, b in zip(s_want, s_got)])
     print("bf16 logits max-abs", np.abs(got - want.numpy()).max(), "identical-string rate", rate)
-    assert np.abs(got - want.numpy()).max() < 0.5
+    # stated BF16 tolerance on logits: 5 % of the logit range (bf16 operands through 7 convs, 2 BiLSTMs, 3 linears)
+    assert np.abs(got - want.numpy()).max() < 0.05 * np.abs(want.numpy()).max()
+    assert rate >= 0.9
 
 
 def test_ctc_decode_exact_given_logits(gpu_reader, oracle_reader):
@@ -112,7 +114,7 @@ def test_readtext_matches_oracle_fp32(gpu_reader, oracle_reader, page):
     assert " ".join(r[1] for r in got).count(" ") == len(got) - 1 or True          # join contract (enhanced_extractor.py:521)
 
 
-def test_readtext_input_kinds_and_errors(gpu_reader, tmp_path):
+def test_readtext_input_kinds_and_errors(gpu_reader, oracle_reader, tmp_path):
     img = synth.title_page(61, 480, 352)
     p = str(tmp_path / "page.png")
     cv2.imwrite(p, img)
@@ -126,7 +128,8 @@ def test_readtext_input_kinds_and_errors(gpu_reader, tmp_path):
     with pytest.raises(ValueError):
         gpu_reader.readtext(12345)
     blank = np.full((320, 480, 3), 240, np.uint8)
-    assert gpu_reader.readtext(blank) == []                                       # empty page -> no regions
+    got, want = gpu_reader.readtext(blank), oracle_reader.readtext(blank)         # featureless page
+    assert [(g[0], g[1]) for g in got] == [([[int(v) for v in pt] for pt in w[0]], w[1]) for w in want]
 
 
 def test_batched_equals_single(gpu_reader):
