@@ -287,6 +287,42 @@ int bbocr_dbg_convex_hull(const int32_t* xy, int n, int clockwise, int32_t* out,
     return 0;
 }
 
+// test hook (not part of include/bbocr.h): one convolution on host FP32 NHWC data in the handle's precision mode.
+// force_generic != 0 routes BF16 mode through the CUDA-core kernel so the tcgen05 kernel can be compared against it.
+int bbocr_dbg_conv(bbocr_handle* h, const float* in1, int C1, const float* in2, int C2, int N, int H, int W, const float* w,
+                   const float* bias, int cout, int kh, int kw, int pad, int dil, int relu, int force_generic, float* out) {
+    return guarded(h, [&] {
+        Lane& lane = h->lanes[0];
+        cudaStream_t st = lane.stream;
+        ConvW cw = make_conv_raw(h, w, bias, cout, C1 + C2, kh, kw, pad, dil);
+        Act a1, a2, o;
+        DevBuf f1, f2, b1, b2, bo, fo;
+        int64_t n1 = (int64_t)N * H * W * C1, n2 = (int64_t)N * H * W * C2;
+        upload(lane, f1, in1, n1 * 4);
+        a1 = act_alloc(h, st, b1, N, H, W, C1);
+        act_from_f32(h, st, f1.as<float>(), a1.p, n1);
+        if (C2 > 0) {
+            upload(lane, f2, in2, n2 * 4);
+            a2 = act_alloc(h, st, b2, N, H, W, C2);
+            act_from_f32(h, st, f2.as<float>(), a2.p, n2);
+        }
+        int OH = H + 2 * pad - dil * (kh - 1), OW = W + 2 * pad - dil * (kw - 1);
+        o = act_alloc(h, st, bo, N, OH, OW, cout);
+        h->force_generic_conv = force_generic != 0;
+        try {
+            conv_forward(h, st, cw, a1, a2, o, relu ? CONV_RELU : 0);
+        } catch (...) {
+            h->force_generic_conv = false;
+            throw;
+        }
+        h->force_generic_conv = false;
+        int64_t no = (int64_t)N * OH * OW * cout;
+        fo.alloc(no * 4, st);
+        act_to_f32(h, st, o.p, fo.as<float>(), no);
+        download(lane, out, fo.p, no * 4);
+    });
+}
+
 int bbocr_group_boxes(const float* boxes, int n, double ratio, const bbocr_group_params* p, int32_t* hlist, int* nh,
                       double* flist, int* nf, int cap) {
     if (!p || !hlist || !nh || !flist || !nf || n < 0 || (n > 0 && !boxes)) return BBOCR_E_ARG;

@@ -1,8 +1,382 @@
-// conv_tc.cu -- tcgen05 implicit-GEMM convolution (placeholder until the TMA/UMMA kernel lands in this file)
+// conv_tc.cu -- implicit-GEMM convolution on the 5th-generation tensor cores (sm_100a):
+//     D[128 pixels x BN channels] (FP32, TMEM)  +=  A[128 x BK] (bf16, smem)  x  B[BN x BK]^T (bf16, smem)
+// for every filter tap and every BK-channel block.  No im2col buffer exists anywhere: the A tile of tap (ky,kx) is
+// fetched by ONE TMA tiled load of the (BK ch x TW x TH x 1) box at spatial offset (kx*dil - pad, ky*dil - pad) of the NHWC
+// activation tensor; TMA's out-of-bounds zero fill IS the convolution's zero padding.  1x1 convolutions / Linear layers
+// use a flat 2-D view (channels x pixels).  Channel concatenation (U-Net skips) is two tensor maps walked back to back.
+//
+//   warp 0 : TMA producer (one lane)      -> full[stage]   (mbarrier expect_tx / complete_tx)
+//   warp 1 : tcgen05.mma issuer (one lane)-> empty[stage]  (tcgen05.commit), accum barrier after the last k-block
+//   warp 2 : TMEM allocate / free
+//   warps 4-7 : epilogue: tcgen05.ld 32x32b -> folded-BN scale/bias (+ReLU) -> bf16 / fp32 NHWC stores
+//
+// Operand tiles are the canonical K-major SWIZZLE_128B (BK = 64) / SWIZZLE_64B (BK = 32) layouts that the TMA box
+// produces directly; the UMMA shared-memory descriptors walk them in 32-byte (UMMA_K = 16) steps.
+#include <cuda.h>
+
 #include "engine.h"
+
 namespace bbocr {
-bool conv_tc_supported(const ConvW&, const Act&, const Act&) { return false; }
-void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act&, const Act&, Act&, int) {
-    fail(BBOCR_E_UNSUPPORTED, "tcgen05 convolution not built");
+
+namespace {
+
+constexpr int BM = 128;
+
+struct TcParams {
+    int C1, C2;                 // channels of the two input segments (C2 may be 0)
+    int taps_w, taps;           // kw, kh*kw
+    int pad, dil;
+    int TW, TH, tiles_x, tiles_y;
+    int OH, OW, NIMG;
+    int flat;                   // 1: 1x1 conv over a flat [pixels][channels] view
+    int64_t M;                  // total output pixels
+    int cout, BN;
+    int relu, out_f32;
+    void* out;
+    const float* scale;
+    const float* bias;
+    int stages;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(=1)<<16 | SBO>>4<<32 |
+// version(=1)<<46 | layout<<61 ; SWIZZLE_128B = 2 (8 rows x 128 B atoms, SBO = 1024), SWIZZLE_64B = 4 (SBO = 512)
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    constexpr uint64_t layout = (BK == 64) ? 2 : 4;
+    constexpr uint64_t sbo = (BK == 64) ? 1024 : 512;
+    return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BK>
+__global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtensorMap tmA1,
+                                                 const __grid_constant__ CUtensorMap tmA2,
+                                                 const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[8], empty_bar[8], accum_bar;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = BM * BK * 2;
+    const int B_BYTES = p.BN * BK * 2;
+    const int STAGE_BYTES = A_BYTES + B_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    const int n0 = blockIdx.y * p.BN;
+    int img = 0, x0 = 0, y0 = 0;
+    int64_t m0 = 0;
+    if (p.flat) {
+        m0 = (int64_t)blockIdx.x * BM;
+    } else {
+        int t = blockIdx.x;
+        int tx = t % p.tiles_x;
+        t /= p.tiles_x;
+        int ty = t % p.tiles_y;
+        img = t / p.tiles_y;
+        x0 = tx * p.TW;
+        y0 = ty * p.TH;
+    }
+    const int kb1 = p.C1 / BK, kb2 = p.C2 / BK;
+    const int total = p.taps * (kb1 + kb2);
+    uint32_t ncols = 32;
+    while ((int)ncols < p.BN) ncols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer ----------------
+        int it = 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+            const int ky = tap / p.taps_w, kx = tap - ky * p.taps_w;
+            const int cx = x0 - p.pad + kx * p.dil, cy = y0 - p.pad + ky * p.dil;
+            for (int kb = 0; kb < kb1 + kb2; ++kb, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+                uint8_t* sb = sa + A_BYTES;
+                mbar_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
+                const bool second = kb >= kb1;
+                const CUtensorMap* tma = second ? &tmA2 : &tmA1;
+                const int c0 = (second ? kb - kb1 : kb) * BK;
+                if (p.flat) tma_load_2d(sa, tma, &full_bar[s], c0, (int)m0);
+                else tma_load_4d(sa, tma, &full_bar[s], c0, cx, cy, img);
+                tma_load_3d(sb, &tmB, &full_bar[s], kb * BK, n0, tap);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer ----------------
+        // instruction descriptor: D = F32 (1<<4), A = B = BF16 (1<<7, 1<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int it = 0; it < total; ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+            const uint64_t adesc = umma_desc<BK>(sa), bdesc = umma_desc<BK>(sa + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)        // +32 bytes (2 x 16 B units) per UMMA_K = 16 step inside the swizzle atom
+                umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&accum_bar);
+    } else if (warp >= 4) {
+        // ---------------- epilogue ----------------
+        mbar_wait(&accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int wq = warp & 3;
+        const int r = wq * 32 + lane;
+        int64_t pix = -1;
+        if (p.flat) {
+            if (m0 + r < p.M) pix = m0 + r;
+        } else {
+            int hl = r / p.TW, wl = r - hl * p.TW;
+            int y = y0 + hl, x = x0 + wl;
+            if (y < p.OH && x < p.OW) pix = ((int64_t)img * p.OH + y) * p.OW + x;
+        }
+        const uint32_t trow = tmem_acc + ((uint32_t)(wq * 32) << 16);
+        for (int c = 0; c < p.BN; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c, v);
+            if (pix < 0) continue;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                int n = n0 + c + j;
+                float a = __uint_as_float(v[j]);
+                float sc = __ldg(p.scale + n), bi = __ldg(p.bias + n);      // scale/bias are padded to cout_pad
+                a = fmaf(a, sc, bi);
+                f[j] = p.relu ? fmaxf(a, 0.f) : a;
+            }
+            const int nbase = n0 + c;
+            if (p.out_f32) {
+                float* o = reinterpret_cast<float*>(p.out) + pix * p.cout + nbase;
+                if ((p.cout & 3) == 0 && nbase + 16 <= p.cout) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                } else {
+                    for (int j = 0; j < 16; ++j)
+                        if (nbase + j < p.cout) o[j] = f[j];
+                }
+            } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout + nbase;
+                if ((p.cout & 7) == 0 && nbase + 16 <= p.cout) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                        w[j] = *reinterpret_cast<uint32_t*>(&t);
+                    }
+                    *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                } else {
+                    for (int j = 0; j < 16; ++j)
+                        if (nbase + j < p.cout) o[j] = __float2bfloat16_rn(f[j]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(ncols) : "memory");
+    }
+}
+
+// ---- host side: tensor maps --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    });
+    if (!fn) fail(BBOCR_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    return fn;
+}
+
+CUtensorMap make_map(void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int bk) {
+    CUtensorMap m;
+    cuuint64_t gd[5];
+    cuuint64_t gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+    CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) fail(BBOCR_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rank %d", (int)r, rank);
+    return m;
+}
+
+int pick_bk(const ConvW& cw, const Act& in1, const Act& in2) {
+    if (in1.C % 64 == 0 && in2.C % 64 == 0) return 64;
+    if (in1.C % 32 == 0 && in2.C % 32 == 0) return 32;
+    return 0;
+}
+
+}  // namespace
+
+bool conv_tc_supported(const ConvW& cw, const Act& in1, const Act& in2) {
+    if (pick_bk(cw, in1, in2) == 0) return false;
+    if (cw.cout_pad > 128 && cw.cout_pad % 128 != 0) return false;
+    if (!cw.w_bf16) return false;
+    const bool flat = cw.kh == 1 && cw.kw == 1 && cw.pad == 0;
+    if (!flat && in1.H < 4) return false;
+    if ((int64_t)in1.N * in1.H * in1.W > (1ll << 31) - 256) return false;
+    return true;
+}
+
+void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags) {
+    const int bk = pick_bk(cw, in1, in2);
+    TcParams p;
+    p.C1 = in1.C; p.C2 = in2.C;
+    p.taps_w = cw.kw; p.taps = cw.kh * cw.kw;
+    p.pad = cw.pad; p.dil = cw.dil;
+    p.OH = out.H; p.OW = out.W; p.NIMG = out.N;
+    p.M = (int64_t)out.N * out.H * out.W;
+    p.flat = (cw.kh == 1 && cw.kw == 1 && cw.pad == 0) ? 1 : 0;
+    p.cout = cw.cout;
+    p.BN = cw.cout_pad <= 128 ? cw.cout_pad : 128;
+    p.relu = (flags & CONV_RELU) ? 1 : 0;
+    p.out_f32 = (flags & CONV_OUT_F32) ? 1 : 0;
+    p.out = out.p;
+    p.scale = cw.scale;
+    p.bias = cw.bias;
+    if (p.flat) { p.TW = 128; p.TH = 1; p.tiles_x = p.tiles_y = 1; }
+    else if (out.H >= 8) { p.TW = 16; p.TH = 8; }
+    else { p.TW = 32; p.TH = 4; }
+    unsigned grid_x;
+    if (p.flat) grid_x = (unsigned)cdiv64(p.M, BM);
+    else {
+        p.tiles_x = cdiv(out.W, p.TW);
+        p.tiles_y = cdiv(out.H, p.TH);
+        grid_x = (unsigned)((int64_t)p.tiles_x * p.tiles_y * out.N);
+    }
+    const int stage_bytes = BM * bk * 2 + p.BN * bk * 2;
+    p.stages = std::min(6, std::max(2, (100 * 1024) / stage_bytes));       // <= ~100 KB so that two CTAs share an SM
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+
+    auto act_map = [&](const Act& a) {
+        if (p.flat) {
+            uint64_t dims[2] = {(uint64_t)a.C, (uint64_t)((int64_t)a.N * a.H * a.W)};
+            uint64_t str[1] = {(uint64_t)a.C * 2};
+            uint32_t box[2] = {(uint32_t)bk, (uint32_t)BM};
+            return make_map(a.p, 2, dims, str, box, bk);
+        }
+        uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+        uint64_t str[3] = {(uint64_t)a.C * 2, (uint64_t)a.W * a.C * 2, (uint64_t)a.H * a.W * a.C * 2};
+        uint32_t box[4] = {(uint32_t)bk, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        return make_map(a.p, 4, dims, str, box, bk);
+    };
+    CUtensorMap mA1 = act_map(in1);
+    CUtensorMap mA2 = in2.C > 0 ? act_map(in2) : mA1;
+    uint64_t wd[3] = {(uint64_t)cw.cin, (uint64_t)cw.cout_pad, (uint64_t)p.taps};
+    uint64_t ws[2] = {(uint64_t)cw.cin * 2, (uint64_t)cw.cout_pad * cw.cin * 2};
+    uint32_t wb[3] = {(uint32_t)bk, (uint32_t)p.BN, 1};
+    CUtensorMap mB = make_map(cw.w_bf16, 3, wd, ws, wb, bk);
+
+    dim3 grd(grid_x, cw.cout_pad / p.BN);
+    if (!h->tc_attr_set) {          // per device (one handle = one device)
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        h->tc_attr_set = true;
+    }
+    if (bk == 64) k_conv_tc<64><<<grd, 256, smem, st>>>(mA1, mA2, mB, p);
+    else k_conv_tc<32><<<grd, 256, smem, st>>>(mA1, mA2, mB, p);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 }  // namespace bbocr

@@ -42,6 +42,8 @@ struct Handle {
     std::vector<Lane> lanes;
     // dominant-kernel instrumentation (bench.py roofline): CUDA events around every implicit-GEMM conv launch
     bool conv_timing = false;
+    bool force_generic_conv = false; // test hook: route BF16-mode convolutions through the CUDA-core kernel
+    bool tc_attr_set = false;
     std::mutex stat_mu;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
     double conv_flops = 0;
@@ -84,6 +86,8 @@ void upsample2x(Handle*, cudaStream_t, const Act& in, Act& out);          // bil
 void mean_rows(Handle*, cudaStream_t, const Act& in, Act& out);           // AdaptiveAvgPool2d((None,1)) after permute
 void cls_tail(Handle*, cudaStream_t, const ConvW& c3, const ConvW& c4, const Act& in, float* text, float* link);
 void lstm_recurrence(Handle*, cudaStream_t, const float* gates_in, const float* w_hh, int B, int T, Act& out);
+void act_from_f32(Handle*, cudaStream_t, const float* in, void* out, int64_t n);
+void act_to_f32(Handle*, cudaStream_t, const void* in, float* out, int64_t n);
 size_t act_elem_size(const Handle*);
 Act act_alloc(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C, bool force_f32 = false);
 
@@ -94,6 +98,7 @@ void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const 
 // ---- weights.cu ------------------------------------------------------------------------------------------------------
 void load_craft(Handle*, const bbocr_tensor* t, int n);
 void load_crnn(Handle*, const bbocr_tensor* t, int n);
+ConvW make_conv_raw(Handle*, const float* w, const float* bias, int cout, int cin, int kh, int kw, int pad, int dil);
 
 // ---- craft.cu --------------------------------------------------------------------------------------------------------
 struct CanvasGeom {

@@ -157,7 +157,7 @@ void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, c
         CUDA_CHECK(cudaEventCreate(&e1));
         CUDA_CHECK(cudaEventRecord(e0, st));
     }
-    if (h->precision == BBOCR_PREC_BF16 && conv_tc_supported(cw, in1, in2)) conv_tc_forward(h, st, cw, in1, in2, out, flags);
+    if (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && conv_tc_supported(cw, in1, in2)) conv_tc_forward(h, st, cw, in1, in2, out, flags);
     else conv_generic(h, st, cw, in1, in2, out, flags);
     if (h->conv_timing) {
         CUDA_CHECK(cudaEventRecord(e1, st));
@@ -475,6 +475,30 @@ void lstm_recurrence(Handle* h, cudaStream_t st, const float* gates_in, const fl
         k_lstm<NB, float><<<grd, 256, 0, st>>>(gates_in, w_hh, (float*)out.p, B, T);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
+}
+
+// ---- dtype conversion between host-facing FP32 buffers and the activation dtype of the current precision mode -------
+template <typename T>
+__global__ void k_from_f32(const float* __restrict__ in, T* __restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st1(out + i, in[i]);
+}
+template <typename T>
+__global__ void k_to_f32(const T* __restrict__ in, float* __restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = to_f(in[i]);
+}
+void act_from_f32(Handle* h, cudaStream_t st, const float* in, void* out, int64_t n) {
+    unsigned g = (unsigned)cdiv64(n, 256);
+    if (h->precision == BBOCR_PREC_BF16) k_from_f32<<<g, 256, 0, st>>>(in, (__nv_bfloat16*)out, n);
+    else k_from_f32<<<g, 256, 0, st>>>(in, (float*)out, n);
+    count_launch(h);
+}
+void act_to_f32(Handle* h, cudaStream_t st, const void* in, float* out, int64_t n) {
+    unsigned g = (unsigned)cdiv64(n, 256);
+    if (h->precision == BBOCR_PREC_BF16) k_to_f32<<<g, 256, 0, st>>>((const __nv_bfloat16*)in, out, n);
+    else k_to_f32<<<g, 256, 0, st>>>((const float*)in, out, n);
+    count_launch(h);
 }
 
 }  // namespace bbocr

@@ -143,6 +143,16 @@ LstmW make_lstm(Handle* h, const Dict& d, const std::string& p) {
 
 }  // namespace
 
+// test hook: a bias-only convolution from raw PyTorch-layout arrays
+ConvW make_conv_raw(Handle* h, const float* w, const float* bias, int cout, int cin, int kh, int kw, int pad, int dil) {
+    bbocr_tensor t[2];
+    t[0].name = "c.weight"; t[0].data = w; t[0].ndim = 4;
+    t[0].shape[0] = cout; t[0].shape[1] = cin; t[0].shape[2] = kh; t[0].shape[3] = kw;
+    t[1].name = "c.bias"; t[1].data = bias; t[1].ndim = 1; t[1].shape[0] = cout;
+    Dict d(t, bias ? 2 : 1);
+    return make_conv(h, d, "c", "", pad, dil);
+}
+
 void load_craft(Handle* h, const bbocr_tensor* t, int n) {
     Dict d(t, n);
     CraftW& c = h->craft;
