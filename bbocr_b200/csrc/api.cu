@@ -506,23 +506,31 @@ void recognize_pass(Handle* h, Lane& lane, std::vector<CropJob>& jobs, const std
     DevBuf ddesc, inputs(in_floats * 4, st), logits(logit_floats * 4, st);
     upload(lane, ddesc, descs.data(), descs.size() * sizeof(CropDesc));
     crops_to_input_dev(h, st, aligned_buf.as<uint8_t>(), ddesc.as<CropDesc>(), n, max_w, inputs.as<float>());
-    // decode outputs: [text_idx | step_idx] int32 (step_elems each), text_len (n), step_prob float
-    DevBuf dec((step_elems * 3 + (size_t)n) * 4, st);
+    // feature extractor per width bucket -> one flat [rows][256] sequence tensor; sequence k = (bucket, slot)
+    const int rows = (int)step_elems;
+    DevBuf seq((size_t)rows * 256 * act_elem_size(h) + 256, st);
+    std::vector<SeqDesc> seqs;
+    std::vector<int> seq_of_bucket_slot0(bucket_w.size());
+    for (size_t q = 0; q < bucket_w.size(); ++q) {
+        int T = bucket_w[q] / 4 - 1;
+        crnn_features_dev(h, st, inputs.as<float>() + bucket_off[q], bucket_n[q], bucket_w[q], seq.p, (int)step_off[q]);
+        seq_of_bucket_slot0[q] = (int)seqs.size();
+        for (int sl = 0; sl < bucket_n[q]; ++sl) seqs.push_back(SeqDesc{(int)step_off[q] + sl * T, T});
+    }
+    // recurrent half + Prediction once over all crops, then greedy CTC over all rows
+    crnn_sequence_dev(h, lane, seq.p, rows, seqs, logits.as<float>());
+    const int n_seq = (int)seqs.size();
+    DevBuf dseq;
+    upload(lane, dseq, seqs.data(), seqs.size() * sizeof(SeqDesc));
+    // decode outputs: text_idx | step_idx (int32, rows each) | step_prob (float, rows) | text_len (n_seq)
+    DevBuf dec((step_elems * 3 + (size_t)n_seq) * 4, st);
     int32_t* text_idx = dec.as<int32_t>();
     int32_t* step_idx = text_idx + step_elems;
     float* step_prob = reinterpret_cast<float*>(step_idx + step_elems);
     int32_t* text_len = reinterpret_cast<int32_t*>(step_prob + step_elems);
-    std::vector<size_t> len_off(bucket_w.size());
-    size_t lo = 0;
-    for (size_t q = 0; q < bucket_w.size(); ++q) {
-        int T = bucket_w[q] / 4 - 1;
-        crnn_forward_dev(h, st, inputs.as<float>() + bucket_off[q], bucket_n[q], bucket_w[q], logits.as<float>() + logit_off[q]);
-        ctc_decode_dev(h, st, logits.as<float>() + logit_off[q], bucket_n[q], T, C, ignore_dev, text_idx + step_off[q],
-                       text_len + lo, step_prob + step_off[q], step_idx + step_off[q]);
-        len_off[q] = lo;
-        lo += bucket_n[q];
-    }
-    std::vector<int32_t> hdec(step_elems * 3 + n);
+    ctc_decode_dev(h, st, logits.as<float>(), rows, C, ignore_dev, dseq.as<SeqDesc>(), n_seq, text_idx, text_len, step_prob,
+                   step_idx);
+    std::vector<int32_t> hdec(step_elems * 3 + n_seq);
     download(lane, hdec.data(), dec.p, hdec.size() * 4);
     const int32_t* h_text = hdec.data();
     const int32_t* h_sidx = h_text + step_elems;
@@ -532,7 +540,7 @@ void recognize_pass(Handle* h, Lane& lane, std::vector<CropJob>& jobs, const std
         const CropJob& j = jobs[which[k]];
         int q = job_bucket[k], T = bucket_w[q] / 4 - 1;
         size_t so = step_off[q] + (size_t)j.d.slot * T;
-        int len = h_len[len_off[q] + j.d.slot];
+        int len = h_len[seq_of_bucket_slot0[q] + j.d.slot];
         out[k].text.assign(h_text + so, h_text + so + len);
         out[k].conf = confidence_of(h_prob + so, h_sidx + so, T);
     }
@@ -812,7 +820,7 @@ int bbocr_crnn_forward(bbocr_handle* h, const float* x, int N, int Wm, float* lo
         const int T = Wm / 4 - 1, C = h->crnn.num_class;
         DevBuf dx, dl((size_t)N * T * C * 4, lane.stream);
         upload(lane, dx, x, (size_t)N * 64 * Wm * 4);
-        crnn_forward_dev(h, lane.stream, dx.as<float>(), N, Wm, dl.as<float>());
+        crnn_forward_dev(h, lane, dx.as<float>(), N, Wm, dl.as<float>());
         download(lane, logits, dl.p, (size_t)N * T * C * 4);
     });
 }
@@ -835,7 +843,13 @@ int bbocr_ctc_decode(bbocr_handle* h, const float* logits, int N, int T, int C, 
         int32_t* d_sidx = d_text + se;
         float* d_prob = reinterpret_cast<float*>(d_sidx + se);
         int32_t* d_len = reinterpret_cast<int32_t*>(d_prob + se);
-        ctc_decode_dev(h, st, dlg.as<float>(), N, T, C, ignore ? dig.as<uint8_t>() : nullptr, d_text, d_len, d_prob, d_sidx);
+        std::vector<SeqDesc> seqs(N);
+        for (int i = 0; i < N; ++i) { seqs[i].row0 = i * T; seqs[i].T = T; }
+        DevBuf dseq;
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        upload(lane, dseq, seqs.data(), seqs.size() * sizeof(SeqDesc));
+        ctc_decode_dev(h, st, dlg.as<float>(), N * T, C, ignore ? dig.as<uint8_t>() : nullptr, dseq.as<SeqDesc>(), N, d_text,
+                       d_len, d_prob, d_sidx);
         std::vector<int32_t> hd(se * 3 + N);
         download(lane, hd.data(), dec.p, hd.size() * 4);
         memcpy(text_idx, hd.data(), se * 4);

@@ -85,7 +85,7 @@ void maxpool(Handle*, cudaStream_t, const Act& in, Act& out, int kh, int kw, int
 void upsample2x(Handle*, cudaStream_t, const Act& in, Act& out);          // bilinear, align_corners=False
 void mean_rows(Handle*, cudaStream_t, const Act& in, Act& out);           // AdaptiveAvgPool2d((None,1)) after permute
 void cls_tail(Handle*, cudaStream_t, const ConvW& c3, const ConvW& c4, const Act& in, float* text, float* link);
-void lstm_recurrence(Handle*, cudaStream_t, const float* gates_in, const float* w_hh, int B, int T, Act& out);
+
 void act_from_f32(Handle*, cudaStream_t, const float* in, void* out, int64_t n);
 void act_to_f32(Handle*, cudaStream_t, const void* in, float* out, int64_t n);
 size_t act_elem_size(const Handle*);
@@ -150,8 +150,20 @@ void pil_resize_bicubic_dev(Handle*, cudaStream_t, const uint8_t* src, int sH, i
                             uint8_t* scratch);
 void crops_to_input_dev(Handle*, cudaStream_t, const uint8_t* aligned, const CropDesc* descs_dev, int n, int max_model_w,
                         float* inputs);
-void crnn_forward_dev(Handle*, cudaStream_t, const float* x, int N, int Wm, float* logits);
-void ctc_decode_dev(Handle*, cudaStream_t, const float* logits, int N, int T, int C, const uint8_t* ignore_dev,
-                    int32_t* text_idx, int32_t* text_len, float* step_prob, int32_t* step_idx);
+struct SeqDesc {                   // one crop's feature sequence inside the flat [rows][channels] tensors
+    int row0, T;
+};
+// conv stack + row mean of one width bucket: x [N][64][Wm] FP32 -> seq rows [row0, row0 + N*(Wm/4-1)) of `seq` ([rows][256])
+void crnn_features_dev(Handle*, cudaStream_t, const float* x, int N, int Wm, void* seq, int row0);
+// both BiLSTM blocks + Prediction over all sequences at once: seq [rows][256] -> logits [rows][num_class] FP32
+void crnn_sequence_dev(Handle*, Lane&, void* seq, int rows, const std::vector<SeqDesc>& seqs, float* logits);
+void crnn_forward_dev(Handle*, Lane&, const float* x, int N, int Wm, float* logits);
+void lstm_sequences(Handle*, Lane&, const float* gates_in, const float* w_hh, const SeqDesc* seqs_host, int n_seq,
+                    const SeqDesc* seqs_dev, const int* groups_dev, int n_groups, void* out);
+int lstm_group_size();
+// greedy CTC over all rows: per-row argmax / renormalised max probability, then per-sequence collapse
+void ctc_decode_dev(Handle*, cudaStream_t, const float* logits, int rows, int C, const uint8_t* ignore_dev,
+                    const SeqDesc* seqs_dev, int n_seq, int32_t* text_idx /*[rows]*/, int32_t* text_len /*[n_seq]*/,
+                    float* step_prob /*[rows]*/, int32_t* step_idx /*[rows]*/);
 
 }  // namespace bbocr

@@ -1,0 +1,167 @@
+// lstm.cu -- BiLSTM recurrence of the CRNN (easyocr/model/modules.py::BidirectionalLSTM, nn.LSTM(256, 256,
+// bidirectional=True); gate order i,f,g,o; h0 = c0 = 0).  SURVEY.md §8a B11, §7.3-6.
+//
+// The recurrence is a chain of T dependent 256x1024 mat-vecs per crop and direction: latency-bound, and W_hh
+// (1 MiB in FP32) does not fit one SM.  One thread-block CLUSTER of 8 CTAs therefore owns one (group of NB crops,
+// direction): CTA r keeps the 128 gate columns of hidden units [32r, 32r+32) resident in its shared memory (128 KiB)
+// for the whole sequence, every step each CTA computes its 32 units for all NB crops, and the new hidden state is
+// exchanged through distributed shared memory (one 128-float block per peer) followed by one cluster barrier.
+// The input projections x_t W_ih^T + b_ih + b_hh for all time steps come from one tensor-core GEMM (conv_tc.cu).
+//
+//   gates_in : [rows][2048] FP32, row = seq.row0 + t, columns [fwd i,f,g,o | bwd i,f,g,o]
+//   w_hh     : [2][256 k][1024] FP32 (k-major)
+//   out      : [rows][512] = [h_fwd(t) | h_bwd(t)]   (activation dtype of the precision mode)
+#include <cooperative_groups.h>
+
+#include "engine.h"
+
+namespace cg = cooperative_groups;
+
+namespace bbocr {
+
+namespace {
+
+constexpr int NB = 4;            // crops per cluster
+constexpr int CL = 8;            // CTAs per cluster
+constexpr int UNITS = 32;        // hidden units per CTA
+constexpr int COLS = 4 * UNITS;  // gate columns per CTA
+
+__device__ __forceinline__ void st_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename TO>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
+    k_lstm_cluster(const float* __restrict__ gates_in, const float* __restrict__ w_hh, TO* __restrict__ out,
+                   const SeqDesc* __restrict__ seqs, const int* __restrict__ groups /*[n_groups][NB], -1 = empty*/) {
+    extern __shared__ __align__(16) float lsm[];
+    float* Ws = lsm;                               // [256][COLS]
+    float* hbuf = Ws + 256 * COLS;                 // [2][NB][256]
+    float* part = hbuf + 2 * NB * 256;             // [2][COLS][NB]
+    float* hstage = part + 2 * COLS * NB;          // [NB][UNITS]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();
+    const int group = blockIdx.x / CL, dir = blockIdx.y;
+    const int tid = threadIdx.x;
+
+    // resident weight slice: Ws[k][g*32 + u] = W_hh[dir][k][g*256 + 32r + u]
+    const float* wd = w_hh + (size_t)dir * 256 * 1024;
+    for (int i = tid; i < 256 * COLS; i += 256) {
+        int k = i / COLS, c = i - k * COLS;
+        int g = c >> 5, u = c & 31;
+        Ws[i] = __ldg(wd + (size_t)k * 1024 + g * 256 + UNITS * r + u);
+    }
+    for (int i = tid; i < 2 * NB * 256; i += 256) hbuf[i] = 0.f;
+
+    // phase-2 role: thread (b, u) for tid < NB*32
+    const int pb = tid >> 5, pu = tid & 31;
+    int row0 = 0, T = 0;
+    if (tid < NB * UNITS) {
+        int s = groups[group * NB + pb];
+        if (s >= 0) { row0 = seqs[s].row0; T = seqs[s].T; }
+    }
+    int Tmax = T;
+    for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
+    __shared__ int s_tmax[8];
+    if ((tid & 31) == 0) s_tmax[tid >> 5] = Tmax;
+    __syncthreads();
+    Tmax = 0;
+    for (int i = 0; i < NB; ++i) Tmax = max(Tmax, s_tmax[i]);
+    float cstate = 0.f;
+    cluster.sync();                                 // every CTA's hbuf is zeroed before any peer writes into it
+
+    const int c = tid & (COLS - 1), half = tid >> 7;
+    int cur = 0;
+    for (int s = 0; s < Tmax; ++s) {
+        // prefetch this step's input projections (latency hidden behind the mat-vec)
+        float gin[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool active = tid < NB * UNITS && s < T;
+        const int t = dir ? T - 1 - s : s;
+        if (active) {
+            const float* g = gates_in + (size_t)(row0 + t) * 2048 + dir * 1024 + UNITS * r + pu;
+            gin[0] = __ldg(g); gin[1] = __ldg(g + 256); gin[2] = __ldg(g + 512); gin[3] = __ldg(g + 768);
+        }
+        // phase 1: partial mat-vec over this thread's half of k for gate column c, all NB crops
+        float acc[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+        const float* hb = hbuf + cur * NB * 256;
+        const int k0 = half * 128;
+#pragma unroll 2
+        for (int k = k0; k < k0 + 128; k += 4) {
+            float w0 = Ws[(k + 0) * COLS + c], w1 = Ws[(k + 1) * COLS + c], w2 = Ws[(k + 2) * COLS + c], w3 = Ws[(k + 3) * COLS + c];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                float4 hv = *reinterpret_cast<const float4*>(hb + b * 256 + k);
+                acc[b] = fmaf(w0, hv.x, acc[b]);
+                acc[b] = fmaf(w1, hv.y, acc[b]);
+                acc[b] = fmaf(w2, hv.z, acc[b]);
+                acc[b] = fmaf(w3, hv.w, acc[b]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) part[(half * COLS + c) * NB + b] = acc[b];
+        __syncthreads();
+        // phase 2: gates, cell and hidden state of unit pu for crop pb
+        if (tid < NB * UNITS) {
+            float hv = 0.f;
+            if (active) {
+                float pre[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    pre[g] = gin[g] + part[(g * UNITS + pu) * NB + pb] + part[(COLS + g * UNITS + pu) * NB + pb];
+                float ig = 1.f / (1.f + expf(-pre[0]));
+                float fg = 1.f / (1.f + expf(-pre[1]));
+                float gg = tanhf(pre[2]);
+                float og = 1.f / (1.f + expf(-pre[3]));
+                cstate = fg * cstate + ig * gg;
+                hv = og * tanhf(cstate);
+                st_out(out + (size_t)(row0 + t) * 512 + dir * 256 + UNITS * r + pu, hv);
+            }
+            hstage[pb * UNITS + pu] = hv;
+        }
+        __syncthreads();
+        // phase 3: warp q pushes this CTA's NB x 32 block into peer q's next-step buffer (distributed shared memory)
+        {
+            const int q = tid >> 5, l = tid & 31;
+            float* remote = cluster.map_shared_rank(hbuf, q) + (cur ^ 1) * NB * 256;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) remote[b * 256 + UNITS * r + l] = hstage[b * UNITS + l];
+        }
+        cluster.sync();
+        cur ^= 1;
+    }
+}
+
+}  // namespace
+
+// seqs: device array of n_seq descriptors; the host copy is used to form groups of NB sequences of similar length
+void lstm_sequences(Handle* h, Lane& lane, const float* gates_in, const float* w_hh, const SeqDesc* seqs_host, int n_seq,
+                    const SeqDesc* seqs_dev, const int* groups_dev, int n_groups, void* out) {
+    cudaStream_t st = lane.stream;
+    if (n_seq == 0) return;
+    const size_t smem = (size_t)(256 * COLS + 2 * NB * 256 + 2 * COLS * NB + NB * UNITS) * sizeof(float);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CL * n_groups, 2);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (h->precision == BBOCR_PREC_BF16) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_lstm_cluster<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_lstm_cluster<__nv_bfloat16>, gates_in, w_hh, (__nv_bfloat16*)out, seqs_dev, groups_dev));
+    } else {
+        CUDA_CHECK(cudaFuncSetAttribute(k_lstm_cluster<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_lstm_cluster<float>, gates_in, w_hh, (float*)out, seqs_dev, groups_dev));
+    }
+    count_launch(h);
+}
+
+int lstm_group_size() { return NB; }
+
+}  // namespace bbocr

@@ -407,75 +407,6 @@ void cls_tail(Handle* h, cudaStream_t st, const ConvW& c3, const ConvW& c4, cons
     CUDA_CHECK(cudaGetLastError());
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// BiLSTM recurrence (nn.LSTM(256,256,bidirectional), gate order i,f,g,o; h0=c0=0).
-//   gates_in : [B][T][2048] FP32 = x_t W_ih^T + b_ih + b_hh for [fwd | bwd]        (input projection GEMM)
-//   w_hh     : [2][256 k][1024 rows] FP32 (k-major so that the 256 threads read consecutive rows)
-//   out      : [B][T][512] = [h_fwd(t) | h_bwd(t)]
-// One CTA = NB crops x one direction, persistent over all T steps; thread j owns hidden unit j of every crop.
-// ------------------------------------------------------------------------------------------------------------------
-template <int NB, typename TO>
-__global__ void __launch_bounds__(256) k_lstm(const float* __restrict__ gates_in, const float* __restrict__ w_hh,
-                                             TO* __restrict__ out, int B, int T) {
-    __shared__ float hs[2][NB][256];
-    const int j = threadIdx.x, dir = blockIdx.y, b0 = blockIdx.x * NB;
-    const float* wd = w_hh + (int64_t)dir * 256 * 1024;
-    float c[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) { c[b] = 0.f; hs[0][b][j] = 0.f; }
-    __syncthreads();
-    int cur = 0;
-    for (int s = 0; s < T; ++s) {
-        const int t = dir ? T - 1 - s : s;
-        float acc[NB][4];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            if (b0 + b < B) {
-                const float* g = gates_in + ((int64_t)(b0 + b) * T + t) * 2048 + dir * 1024 + j;
-                acc[b][0] = __ldg(g); acc[b][1] = __ldg(g + 256); acc[b][2] = __ldg(g + 512); acc[b][3] = __ldg(g + 768);
-            } else {
-                acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f;
-            }
-        }
-#pragma unroll 4
-        for (int k = 0; k < 256; ++k) {
-            const float* wr = wd + (int64_t)k * 1024 + j;
-            float w0 = __ldg(wr), w1 = __ldg(wr + 256), w2 = __ldg(wr + 512), w3 = __ldg(wr + 768);
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                float hv = hs[cur][b][k];
-                acc[b][0] = fmaf(w0, hv, acc[b][0]);
-                acc[b][1] = fmaf(w1, hv, acc[b][1]);
-                acc[b][2] = fmaf(w2, hv, acc[b][2]);
-                acc[b][3] = fmaf(w3, hv, acc[b][3]);
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            float ig = 1.f / (1.f + expf(-acc[b][0]));
-            float fg = 1.f / (1.f + expf(-acc[b][1]));
-            float gg = tanhf(acc[b][2]);
-            float og = 1.f / (1.f + expf(-acc[b][3]));
-            c[b] = fg * c[b] + ig * gg;
-            float hv = og * tanhf(c[b]);
-            hs[cur ^ 1][b][j] = hv;
-            if (b0 + b < B) st1(out + ((int64_t)(b0 + b) * T + t) * 512 + dir * 256 + j, hv);
-        }
-        __syncthreads();
-        cur ^= 1;
-    }
-}
-
-void lstm_recurrence(Handle* h, cudaStream_t st, const float* gates_in, const float* w_hh, int B, int T, Act& out) {
-    constexpr int NB = 4;
-    dim3 grd(cdiv(B, NB), 2);
-    if (h->precision == BBOCR_PREC_BF16)
-        k_lstm<NB, __nv_bfloat16><<<grd, 256, 0, st>>>(gates_in, w_hh, (__nv_bfloat16*)out.p, B, T);
-    else
-        k_lstm<NB, float><<<grd, 256, 0, st>>>(gates_in, w_hh, (float*)out.p, B, T);
-    count_launch(h);
-    CUDA_CHECK(cudaGetLastError());
-}
 
 // ---- dtype conversion between host-facing FP32 buffers and the activation dtype of the current precision mode -------
 template <typename T>

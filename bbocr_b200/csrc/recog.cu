@@ -241,18 +241,20 @@ void crops_to_input_dev(Handle* h, cudaStream_t st, const uint8_t* aligned, cons
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// vgg_model.Model.forward on a bucket of N crops of identical model width Wm.  x: [N][64][Wm] FP32 (device)
+// vgg_model.Model.forward, split at the sequence boundary so that the recurrent half runs ONCE per page over the crops
+// of every width bucket:
+//   crnn_features_dev : VGG feature extractor + AdaptiveAvgPool of one bucket (N crops of identical model width Wm)
+//   crnn_sequence_dev : 2 x (input-projection GEMM -> clustered BiLSTM recurrence -> Linear) + Prediction, all crops
 // ------------------------------------------------------------------------------------------------------------------
-void crnn_forward_dev(Handle* h, cudaStream_t st, const float* x, int N, int Wm, float* logits) {
+void crnn_features_dev(Handle* h, cudaStream_t st, const float* x, int N, int Wm, void* seq, int row0) {
     if (!h->crnn_loaded) fail(BBOCR_E_STATE, "CRNN weights not loaded (bbocr_load_crnn)");
     ARG_CHECK(N > 0 && Wm >= 64 && Wm % 4 == 0, "crnn: bad batch geometry (N=%d, W=%d)", N, Wm);
     const CrnnW& w = h->crnn;
     const Act none;
     const int R = CONV_RELU;
-    DevBuf b0, b1, b2;
+    DevBuf b0, b1;
     auto conv = [&](const ConvW& cw, const Act& a, DevBuf& buf, int flags) {
-        Act o = act_alloc(h, st, buf, a.N, a.H + 2 * cw.pad - cw.dil * (cw.kh - 1), a.W + 2 * cw.pad - cw.dil * (cw.kw - 1),
-                          cw.cout, (flags & CONV_OUT_F32) != 0);
+        Act o = act_alloc(h, st, buf, a.N, a.H + 2 * cw.pad - cw.dil * (cw.kh - 1), a.W + 2 * cw.pad - cw.dil * (cw.kw - 1), cw.cout);
         conv_forward(h, st, cw, a, none, o, flags);
         return o;
     };
@@ -273,82 +275,126 @@ void crnn_forward_dev(Handle* h, cudaStream_t st, const float* x, int N, int Wm,
     a = conv(w.c5, a, b0, R);
     a = pool(a, b1, 2, 1);               // 4 x Wm/4
     a = conv(w.c6, a, b0, R);            // 3 x (Wm/4 - 1)
-    const int T = a.W;
-    Act seq = act_alloc(h, st, b1, N, 1, T, 256);
-    mean_rows(h, st, a, seq);
+    Act s;
+    s.N = N; s.H = 1; s.W = a.W; s.C = 256;
+    s.p = (uint8_t*)seq + (size_t)row0 * 256 * act_elem_size(h);
+    mean_rows(h, st, a, s);
+}
+
+void crnn_sequence_dev(Handle* h, Lane& lane, void* seq, int rows, const std::vector<SeqDesc>& seqs, float* logits) {
+    cudaStream_t st = lane.stream;
+    const CrnnW& w = h->crnn;
+    const Act none;
+    const int n_seq = (int)seqs.size();
+    if (rows == 0 || n_seq == 0) return;
+    // groups of NB sequences of similar length (longest first) -> one cluster each per direction
+    const int NBg = lstm_group_size();
+    std::vector<int> order(n_seq);
+    for (int i = 0; i < n_seq; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return seqs[a].T > seqs[b].T; });
+    const int n_groups = cdiv(n_seq, NBg);
+    std::vector<int> meta((size_t)n_seq * 2 + (size_t)n_groups * NBg, -1);
+    for (int i = 0; i < n_seq; ++i) { meta[2 * i] = seqs[i].row0; meta[2 * i + 1] = seqs[i].T; }
+    for (int i = 0; i < n_seq; ++i) meta[(size_t)n_seq * 2 + i] = order[i];
+    DevBuf dmeta(meta.size() * 4, st);
+    {
+        if (lane.in_busy) { CUDA_CHECK(cudaStreamSynchronize(st)); lane.in_busy = false; }
+        void* pin = lane.pin_in.get(meta.size() * 4);
+        memcpy(pin, meta.data(), meta.size() * 4);
+        CUDA_CHECK(cudaMemcpyAsync(dmeta.p, pin, meta.size() * 4, cudaMemcpyHostToDevice, st));
+        lane.in_busy = true;
+    }
+    const SeqDesc* seqs_dev = dmeta.as<SeqDesc>();
+    const int* groups_dev = dmeta.as<int>() + (size_t)n_seq * 2;
+
+    DevBuf bg, bh, bs[2];
+    Act cur;
+    cur.N = 1; cur.H = 1; cur.W = rows; cur.C = 256; cur.p = seq;
     for (int layer = 0; layer < 2; ++layer) {
         const LstmW& l = layer == 0 ? w.l0 : w.l1;
-        Act gates = conv(l.in_proj, seq, b0, CONV_OUT_F32);          // [N][1][T][2048] FP32
-        Act hcat = act_alloc(h, st, b2, N, 1, T, 512);
-        lstm_recurrence(h, st, (const float*)gates.p, l.w_hh, N, T, hcat);
-        seq = conv(l.linear, hcat, b1, 0);                           // [N][1][T][256]
+        Act gates = act_alloc(h, st, bg, 1, 1, rows, 2048, true);               // FP32 input projections, all time steps
+        conv_forward(h, st, l.in_proj, cur, none, gates, CONV_OUT_F32);
+        Act hcat = act_alloc(h, st, bh, 1, 1, rows, 512);
+        lstm_sequences(h, lane, (const float*)gates.p, l.w_hh, seqs.data(), n_seq, seqs_dev, groups_dev, n_groups, hcat.p);
+        Act nxt = act_alloc(h, st, bs[layer], 1, 1, rows, 256);
+        conv_forward(h, st, l.linear, hcat, none, nxt, 0);
+        cur = nxt;
     }
     Act out;
-    out.N = N; out.H = 1; out.W = T; out.C = w.num_class; out.p = logits;
-    conv_forward(h, st, w.pred, seq, none, out, CONV_OUT_F32);
+    out.N = 1; out.H = 1; out.W = rows; out.C = w.num_class; out.p = logits;
+    conv_forward(h, st, w.pred, cur, none, out, CONV_OUT_F32);
+}
+
+void crnn_forward_dev(Handle* h, Lane& lane, const float* x, int N, int Wm, float* logits) {
+    const int T = Wm / 4 - 1, rows = N * T;
+    DevBuf seq((size_t)rows * 256 * act_elem_size(h) + 256, lane.stream);
+    crnn_features_dev(h, lane.stream, x, N, Wm, seq.p, 0);
+    std::vector<SeqDesc> seqs(N);
+    for (int i = 0; i < N; ++i) { seqs[i].row0 = i * T; seqs[i].T = T; }
+    crnn_sequence_dev(h, lane, seq.p, rows, seqs, logits);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// recognizer_predict (greedy) + CTCLabelConverter.decode_greedy + the inputs of custom_mean: one warp per crop.
-//   p = softmax(logits); p[ignore] = 0; p /= sum(p); idx = argmax; keep t where idx[t] != idx[t-1] and idx[t] != 0;
-//   confidence inputs = max p at every t with idx[t] != 0 (product taken here in float32, left to right per lane chunk)
+// recognizer_predict (greedy) + CTCLabelConverter.decode_greedy + the inputs of custom_mean.
+//   k_row_argmax  : one warp per time step: p = softmax(logits); p[ignore] = 0; p /= sum(p); (argmax, max p)
+//   k_ctc_collapse: one warp per crop: keep t where idx[t] != idx[t-1] and idx[t] != 0 (ballot compaction)
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void k_ctc_decode(const float* __restrict__ logits, int N, int T, int C, const uint8_t* __restrict__ ignore,
-                             int32_t* __restrict__ text_idx, int32_t* __restrict__ text_len,
+__global__ void k_row_argmax(const float* __restrict__ logits, int rows, int C, const uint8_t* __restrict__ ignore,
                              float* __restrict__ step_prob, int32_t* __restrict__ step_idx) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= N) return;
-    const float* lg = logits + (int64_t)warp * T * C;
-    // pass 1: per-timestep argmax / max probability, one timestep at a time with the 32 lanes over the classes
-    for (int t = 0; t < T; ++t) {
-        const float* row = lg + (int64_t)t * C;
-        float mx = -INFINITY;
-        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float sum_all = 0.f, sum_kept = 0.f, best = -1.f;
-        int besti = INT_MAX;
-        for (int c = lane; c < C; c += 32) {
-            float e = expf(row[c] - mx);
-            sum_all += e;
-            bool ig = ignore && ignore[c];
-            if (!ig) sum_kept += e;
-            float v = ig ? 0.f : e;
-            if (v > best) { best = v; besti = c; }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            sum_all += __shfl_xor_sync(0xffffffffu, sum_all, o);
-            sum_kept += __shfl_xor_sync(0xffffffffu, sum_kept, o);
-            float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
-        }
-        if (lane == 0) {
-            // softmax prob = e/sum_all ; renormalised by the kept mass sum_kept/sum_all
-            float p = (best / sum_all) / (sum_kept / sum_all);
-            step_prob[(int64_t)warp * T + t] = p;
-            step_idx[(int64_t)warp * T + t] = besti;
-        }
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* lg = logits + (int64_t)row * C;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lg[c]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum_all = 0.f, sum_kept = 0.f, best = -1.f;
+    int besti = INT_MAX;
+    for (int c = lane; c < C; c += 32) {
+        float e = expf(lg[c] - mx);
+        sum_all += e;
+        bool ig = ignore && ignore[c];
+        if (!ig) sum_kept += e;
+        float v = ig ? 0.f : e;
+        if (v > best) { best = v; besti = c; }
     }
-    __syncwarp();
-    // pass 2: CTC collapse, 32 timesteps per iteration with ballot compaction
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_all += __shfl_xor_sync(0xffffffffu, sum_all, o);
+        sum_kept += __shfl_xor_sync(0xffffffffu, sum_kept, o);
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    if (lane == 0) {
+        step_prob[row] = (best / sum_all) / (sum_kept / sum_all);
+        step_idx[row] = besti;
+    }
+}
+
+__global__ void k_ctc_collapse(const int32_t* __restrict__ step_idx, const SeqDesc* __restrict__ seqs, int n_seq,
+                               int32_t* __restrict__ text_idx, int32_t* __restrict__ text_len) {
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= n_seq) return;
+    const int row0 = seqs[s].row0, T = seqs[s].T;
     int count = 0;
     for (int base = 0; base < T; base += 32) {
         int t = base + lane;
-        int cur = t < T ? step_idx[(int64_t)warp * T + t] : 0;
-        int prev = (t > 0 && t < T) ? step_idx[(int64_t)warp * T + t - 1] : -1;
+        int cur = t < T ? step_idx[row0 + t] : 0;
+        int prev = (t > 0 && t < T) ? step_idx[row0 + t - 1] : -1;
         bool keep = t < T && cur != prev && cur != 0;
         unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) text_idx[(int64_t)warp * T + count + __popc(m & ((1u << lane) - 1u))] = cur;
+        if (keep) text_idx[row0 + count + __popc(m & ((1u << lane) - 1u))] = cur;
         count += __popc(m);
     }
-    if (lane == 0) text_len[warp] = count;
+    if (lane == 0) text_len[s] = count;
 }
 
-void ctc_decode_dev(Handle* h, cudaStream_t st, const float* logits, int N, int T, int C, const uint8_t* ignore_dev,
-                    int32_t* text_idx, int32_t* text_len, float* step_prob, int32_t* step_idx) {
-    if (N == 0) return;
-    k_ctc_decode<<<cdiv(N * 32, 128), 128, 0, st>>>(logits, N, T, C, ignore_dev, text_idx, text_len, step_prob, step_idx);
-    count_launch(h);
+void ctc_decode_dev(Handle* h, cudaStream_t st, const float* logits, int rows, int C, const uint8_t* ignore_dev,
+                    const SeqDesc* seqs_dev, int n_seq, int32_t* text_idx, int32_t* text_len, float* step_prob,
+                    int32_t* step_idx) {
+    if (rows == 0 || n_seq == 0) return;
+    k_row_argmax<<<cdiv(rows * 32, 256), 256, 0, st>>>(logits, rows, C, ignore_dev, step_prob, step_idx);
+    k_ctc_collapse<<<cdiv(n_seq * 32, 128), 128, 0, st>>>(step_idx, seqs_dev, n_seq, text_idx, text_len);
+    count_launch(h, 2);
     CUDA_CHECK(cudaGetLastError());
 }
 
