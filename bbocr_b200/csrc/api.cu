@@ -8,9 +8,21 @@ struct bbocr_handle : bbocr::Handle {};
 
 using namespace bbocr;
 
+#include <chrono>
+
 namespace {
 
 thread_local std::string g_create_err;
+
+struct StageTimer {        // wall-clock per readtext stage (includes the stream waits): bbocr_dbg_stage_ms
+    Handle* h; int idx; std::chrono::steady_clock::time_point t0;
+    StageTimer(Handle* hh, int i) : h(hh), idx(i), t0(std::chrono::steady_clock::now()) {}
+    ~StageTimer() {
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        std::lock_guard<std::mutex> g(h->stat_mu);
+        h->stage_ms[idx] += ms;
+    }
+};
 
 template <typename F>
 int guarded(bbocr_handle* h, F&& f) {
@@ -95,13 +107,33 @@ int bbocr_create(int device, bbocr_handle** out) {
         std::unique_ptr<bbocr_handle> h(new bbocr_handle());
         h->device = device;
         h->sm_count = prop.multiProcessorCount;
-        h->lanes.resize(4);
+        {
+            const char* e = getenv("BBOCR_LANES");        // pages in flight per handle (streams + host threads)
+            int nl = e ? atoi(e) : 8;
+            h->lanes.resize(std::min(std::max(nl, 1), 32));
+        }
         for (auto& l : h->lanes) CUDA_CHECK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         // keep freed blocks in the stream-ordered pool instead of returning them to the driver after every sync
         cudaMemPool_t pool;
         CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t thresh = UINT64_MAX;
         CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        {
+            // Reserve the working set up front: growing the pool later means cudaMalloc-class calls that serialise
+            // every lane.  180 GB of HBM3e per GPU; the default reservation covers 8 pages of 1920x1440 in flight.
+            const char* e = getenv("BBOCR_POOL_GB");
+            double gb = e ? atof(e) : 16.0;
+            size_t free_b = 0, total_b = 0;
+            CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+            size_t want = std::min((size_t)(gb * (1ull << 30)), free_b / 2);
+            if (want > 0) {
+                void* p = nullptr;
+                cudaStream_t s0 = h->lanes[0].stream;
+                if (cudaMallocAsync(&p, want, s0) == cudaSuccess) cudaFreeAsync(p, s0);
+                else cudaGetLastError();
+                CUDA_CHECK(cudaStreamSynchronize(s0));
+            }
+        }
         *out = h.release();
         return BBOCR_OK;
     } catch (const Error& e) {
@@ -577,15 +609,18 @@ bbocr_results* readtext_page(Handle* h, Lane& lane, const bbocr_image& img, cons
         ignore_dev = dignore.as<uint8_t>();
     }
     // ---- detect -------------------------------------------------------------------------------------------------
+    std::unique_ptr<StageTimer> tm(new StageTimer(h, 0));
     CanvasGeom g = canvas_geom(H, W, p.canvas_size, p.mag_ratio);
     const int mh = g.H32 / 2, mw = g.W32 / 2;
     DevBuf maps((size_t)mh * mw * 8, st);
     float* text = maps.as<float>();
     float* link = text + (size_t)mh * mw;
     craft_forward_dev(h, st, color, g, text, link);
+    tm.reset(new StageTimer(h, 1));
     DetComponents dc;
     det_components_dev(h, lane, text, link, mh, mw, (float)p.text_threshold, (float)p.link_threshold, (float)p.low_text, dc);
     maps.release();
+    tm.reset(new StageTimer(h, 2));
     std::vector<float> boxes;
     boxes_from_components(dc, mh, mw, boxes);
     bbocr_group_params gp{p.slope_ths, p.ycenter_ths, p.height_ths, p.width_ths, p.add_margin, p.min_size};
@@ -636,6 +671,7 @@ bbocr_results* readtext_page(Handle* h, Lane& lane, const bbocr_image& img, cons
         CUDA_CHECK(cudaStreamSynchronize(st));             // pin_in (descs) is reused below
         std::vector<int> all(n);
         for (int i = 0; i < n; ++i) all[i] = i;
+        tm.reset(new StageTimer(h, 3));
         std::vector<Recognized> rec1;
         recognize_pass(h, lane, jobs, all, dcrops.as<uint8_t>(), crops_bytes, ignore_dev, rec1);
         r->n_crops = n;
@@ -643,6 +679,7 @@ bbocr_results* readtext_page(Handle* h, Lane& lane, const bbocr_image& img, cons
         for (int i = 0; i < n; ++i)
             if (rec1[i].conf < p.contrast_ths) low.push_back(i);
         final_rec = rec1;
+        tm.reset(new StageTimer(h, 4));
         if (!low.empty()) {
             // second round: adjust_contrast_grey(target = adjust_contrast) on the low-confidence crops
             const int nl = (int)low.size();
@@ -684,6 +721,7 @@ bbocr_results* readtext_page(Handle* h, Lane& lane, const bbocr_image& img, cons
                 if (!(rec1[low[k]].conf > rec2[k].conf)) final_rec[low[k]] = rec2[k];
         }
     }
+    tm.reset();
     // ---- assemble (horizontal boxes in group order, then free boxes) ----------------------------------------------
     r->n = n;
     r->box = new double[(size_t)std::max(n, 1) * 8];
@@ -857,6 +895,15 @@ int bbocr_ctc_decode(bbocr_handle* h, const float* logits, int N, int T, int C, 
         const float* prob = reinterpret_cast<const float*>(hd.data() + se * 2);
         for (int i = 0; i < N; ++i) conf[i] = confidence_of(prob + (size_t)i * T, hd.data() + se + (size_t)i * T, T);
     });
+}
+
+// test/diagnostic hook: cumulative wall-clock ms per readtext stage [craft enqueue, det (waits for CRAFT), boxes+crops,
+// recognise pass 1, pass 2]; resets on read
+int bbocr_dbg_stage_ms(bbocr_handle* h, double* out5) {
+    if (!h || !out5) return BBOCR_E_ARG;
+    std::lock_guard<std::mutex> g(h->stat_mu);
+    for (int i = 0; i < 5; ++i) { out5[i] = h->stage_ms[i]; h->stage_ms[i] = 0; }
+    return 0;
 }
 
 int64_t bbocr_launch_count(const bbocr_handle* h) { return h ? h->launches.load() : 0; }

@@ -47,6 +47,7 @@ struct Handle {
     std::mutex stat_mu;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
     double conv_flops = 0;
+    double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t conv_launches = 0;
 };
 

@@ -21,10 +21,11 @@ namespace bbocr {
 
 namespace {
 
-constexpr int NB = 4;            // crops per cluster
+constexpr int NB = 8;            // crops per cluster (phase 2 maps one thread to each (crop, unit) pair: NB * 32 = 256)
 constexpr int CL = 8;            // CTAs per cluster
 constexpr int UNITS = 32;        // hidden units per CTA
 constexpr int COLS = 4 * UNITS;  // gate columns per CTA
+constexpr int KPARTS = 8;        // k-split of the 256-long dot products: one warp per 32-wide k range
 
 __device__ __forceinline__ void st_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
@@ -36,8 +37,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
     extern __shared__ __align__(16) float lsm[];
     float* Ws = lsm;                               // [256][COLS]
     float* hbuf = Ws + 256 * COLS;                 // [2][NB][256]
-    float* part = hbuf + 2 * NB * 256;             // [2][COLS][NB]
-    float* hstage = part + 2 * COLS * NB;          // [NB][UNITS]
+    float* part = hbuf + 2 * NB * 256;             // [KPARTS][NB][COLS]
+    float* hstage = part + KPARTS * COLS * NB;     // [NB][UNITS]
     cg::cluster_group cluster = cg::this_cluster();
     const int r = (int)cluster.block_rank();
     const int group = blockIdx.x / CL, dir = blockIdx.y;
@@ -55,7 +56,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
     // phase-2 role: thread (b, u) for tid < NB*32
     const int pb = tid >> 5, pu = tid & 31;
     int row0 = 0, T = 0;
-    if (tid < NB * UNITS) {
+    {
         int s = groups[group * NB + pb];
         if (s >= 0) { row0 = seqs[s].row0; T = seqs[s].T; }
     }
@@ -69,46 +70,60 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
     float cstate = 0.f;
     cluster.sync();                                 // every CTA's hbuf is zeroed before any peer writes into it
 
-    const int c = tid & (COLS - 1), half = tid >> 7;
+    // phase-1 role: warp kp owns k in [32 kp, 32 kp + 32); lane cgp owns gate columns [4 cgp, 4 cgp + 4).  All lanes of a
+    // warp read the same h values (shared-memory broadcast) and consecutive 16-byte weight vectors (conflict-free).
+    const int kp = tid >> 5, cgp = tid & 31;
     int cur = 0;
     for (int s = 0; s < Tmax; ++s) {
         // prefetch this step's input projections (latency hidden behind the mat-vec)
         float gin[4] = {0.f, 0.f, 0.f, 0.f};
-        const bool active = tid < NB * UNITS && s < T;
+        const bool active = s < T;
         const int t = dir ? T - 1 - s : s;
         if (active) {
             const float* g = gates_in + (size_t)(row0 + t) * 2048 + dir * 1024 + UNITS * r + pu;
             gin[0] = __ldg(g); gin[1] = __ldg(g + 256); gin[2] = __ldg(g + 512); gin[3] = __ldg(g + 768);
         }
-        // phase 1: partial mat-vec over this thread's half of k for gate column c, all NB crops
-        float acc[NB];
+        float acc[NB][4];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+        for (int b = 0; b < NB; ++b) acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f;
         const float* hb = hbuf + cur * NB * 256;
-        const int k0 = half * 128;
+        const int k0 = kp * 32;
 #pragma unroll 2
-        for (int k = k0; k < k0 + 128; k += 4) {
-            float w0 = Ws[(k + 0) * COLS + c], w1 = Ws[(k + 1) * COLS + c], w2 = Ws[(k + 2) * COLS + c], w3 = Ws[(k + 3) * COLS + c];
+        for (int k = k0; k < k0 + 32; k += 4) {
+            float4 w0 = *reinterpret_cast<const float4*>(Ws + (k + 0) * COLS + 4 * cgp);
+            float4 w1 = *reinterpret_cast<const float4*>(Ws + (k + 1) * COLS + 4 * cgp);
+            float4 w2 = *reinterpret_cast<const float4*>(Ws + (k + 2) * COLS + 4 * cgp);
+            float4 w3 = *reinterpret_cast<const float4*>(Ws + (k + 3) * COLS + 4 * cgp);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 float4 hv = *reinterpret_cast<const float4*>(hb + b * 256 + k);
-                acc[b] = fmaf(w0, hv.x, acc[b]);
-                acc[b] = fmaf(w1, hv.y, acc[b]);
-                acc[b] = fmaf(w2, hv.z, acc[b]);
-                acc[b] = fmaf(w3, hv.w, acc[b]);
+                acc[b][0] = fmaf(w0.x, hv.x, acc[b][0]); acc[b][1] = fmaf(w0.y, hv.x, acc[b][1]);
+                acc[b][2] = fmaf(w0.z, hv.x, acc[b][2]); acc[b][3] = fmaf(w0.w, hv.x, acc[b][3]);
+                acc[b][0] = fmaf(w1.x, hv.y, acc[b][0]); acc[b][1] = fmaf(w1.y, hv.y, acc[b][1]);
+                acc[b][2] = fmaf(w1.z, hv.y, acc[b][2]); acc[b][3] = fmaf(w1.w, hv.y, acc[b][3]);
+                acc[b][0] = fmaf(w2.x, hv.z, acc[b][0]); acc[b][1] = fmaf(w2.y, hv.z, acc[b][1]);
+                acc[b][2] = fmaf(w2.z, hv.z, acc[b][2]); acc[b][3] = fmaf(w2.w, hv.z, acc[b][3]);
+                acc[b][0] = fmaf(w3.x, hv.w, acc[b][0]); acc[b][1] = fmaf(w3.y, hv.w, acc[b][1]);
+                acc[b][2] = fmaf(w3.z, hv.w, acc[b][2]); acc[b][3] = fmaf(w3.w, hv.w, acc[b][3]);
             }
         }
+        // partial sums: part[kp][b][col] (column fastest: conflict-free 16-byte stores and phase-2 loads)
 #pragma unroll
-        for (int b = 0; b < NB; ++b) part[(half * COLS + c) * NB + b] = acc[b];
+        for (int b = 0; b < NB; ++b)
+            *reinterpret_cast<float4*>(part + ((kp * NB + b) * COLS + 4 * cgp)) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
         __syncthreads();
         // phase 2: gates, cell and hidden state of unit pu for crop pb
-        if (tid < NB * UNITS) {
+        {
             float hv = 0.f;
             if (active) {
                 float pre[4];
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    pre[g] = gin[g] + part[(g * UNITS + pu) * NB + pb] + part[(COLS + g * UNITS + pu) * NB + pb];
+                for (int g = 0; g < 4; ++g) {
+                    float a = gin[g];
+#pragma unroll
+                    for (int q = 0; q < KPARTS; ++q) a += part[(q * NB + pb) * COLS + g * UNITS + pu];
+                    pre[g] = a;
+                }
                 float ig = 1.f / (1.f + expf(-pre[0]));
                 float fg = 1.f / (1.f + expf(-pre[1]));
                 float gg = tanhf(pre[2]);
@@ -139,7 +154,7 @@ void lstm_sequences(Handle* h, Lane& lane, const float* gates_in, const float* w
                     const SeqDesc* seqs_dev, const int* groups_dev, int n_groups, void* out) {
     cudaStream_t st = lane.stream;
     if (n_seq == 0) return;
-    const size_t smem = (size_t)(256 * COLS + 2 * NB * 256 + 2 * COLS * NB + NB * UNITS) * sizeof(float);
+    const size_t smem = (size_t)(256 * COLS + 2 * NB * 256 + KPARTS * COLS * NB + NB * UNITS) * sizeof(float);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CL * n_groups, 2);
     cfg.blockDim = dim3(256);
