@@ -345,7 +345,8 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
         grid_x = (unsigned)((int64_t)p.tiles_x * p.tiles_y * out.N);
     }
     const int stage_bytes = BM * bk * 2 + p.BN * bk * 2;
-    p.stages = std::min(6, std::max(2, (100 * 1024) / stage_bytes));       // <= ~100 KB so that two CTAs share an SM
+    static const int smem_budget_kb = getenv("BBOCR_TC_SMEM_KB") ? atoi(getenv("BBOCR_TC_SMEM_KB")) : 56;
+    p.stages = std::min(6, std::max(2, (smem_budget_kb * 1024) / stage_bytes));   // budget per CTA: several CTAs share an SM
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
 
     auto act_map = [&](const Act& a) {

@@ -667,8 +667,96 @@ void preprocess_chain_dev(Handle* h, cudaStream_t st, const uint8_t* bgr, int H,
     *outW = dW;
 }
 
-float pp_deskew(Handle*, cudaStream_t, const uint8_t*, uint8_t*, int, int, float) {
-    fail(BBOCR_E_UNSUPPORTED, "deskew: not implemented yet");
+// ------------------------------------------------------------------------------------------------------------------
+// A15  deskew -- NOT in the reference (only promised in prose); defined by this repository as
+//   1. ink mask = adaptiveThreshold(GAUSSIAN_C, BINARY_INV, 31, 5)
+//   2. for theta_i = -max + 0.1*i degrees: projection profile of the ink pixels of every row / even columns,
+//      bin = floor((y-cy)*cos - (x-cx)*sin) + R0 ; score_i = sum(bin_count^2) ; theta = first arg-max
+//   3. out(x,y) = bilinear sample (float64, replicate border) of src at (cx + c*dx - s*dy, cy + s*dx + c*dy)
+// float64 everywhere with the operation order of oracle/preprocess_np.py::deskew (no FMA contraction).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_deskew_hist(const uint8_t* __restrict__ fg, int H, int W, const double* __restrict__ cs, int n_ang, int NR,
+                              int R0, double cx, double cy, unsigned int* __restrict__ bins) {
+    int x = (blockIdx.x * blockDim.x + threadIdx.x) * 2, y = blockIdx.y;      // every row, even columns
+    if (x >= W || y >= H || !fg[(int64_t)y * W + x]) return;
+    const double dx = (double)x - cx, dy = (double)y - cy;
+    for (int i = 0; i < n_ang; ++i) {
+        double v = __dsub_rn(__dmul_rn(dy, cs[2 * i]), __dmul_rn(dx, cs[2 * i + 1]));
+        int r = (int)floor(v) + R0;
+        r = min(max(r, 0), NR - 1);
+        atomicAdd(&bins[(int64_t)i * NR + r], 1u);
+    }
+}
+
+__global__ void k_deskew_score(const unsigned int* __restrict__ bins, int NR, unsigned long long* __restrict__ score) {
+    unsigned long long acc = 0;
+    for (int r = threadIdx.x; r < NR; r += blockDim.x) {
+        unsigned long long c = bins[(int64_t)blockIdx.x * NR + r];
+        acc += c * c;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    __shared__ unsigned long long ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += ws[i];
+        score[blockIdx.x] = t;
+    }
+}
+
+__global__ void k_rotate_bilinear(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, double c,
+                                  double s, double cx, double cy) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const double dx = (double)x - cx, dy = (double)y - cy;
+    double sx = __dadd_rn(__dsub_rn(__dmul_rn(c, dx), __dmul_rn(s, dy)), cx);
+    double sy = __dadd_rn(__dadd_rn(__dmul_rn(s, dx), __dmul_rn(c, dy)), cy);
+    double fx0 = floor(sx), fy0 = floor(sy);
+    double fx = __dsub_rn(sx, fx0), fy = __dsub_rn(sy, fy0);
+    int x0 = (int)fx0, y0 = (int)fy0;
+    int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
+    int ya = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
+    double p00 = src[(int64_t)ya * W + xa], p01 = src[(int64_t)ya * W + xb];
+    double p10 = src[(int64_t)yb * W + xa], p11 = src[(int64_t)yb * W + xb];
+    double gx = __dsub_rn(1.0, fx), gy = __dsub_rn(1.0, fy);
+    double top = __dadd_rn(__dmul_rn(gx, p00), __dmul_rn(fx, p01));
+    double bot = __dadd_rn(__dmul_rn(gx, p10), __dmul_rn(fx, p11));
+    double v = __dadd_rn(__dmul_rn(gy, top), __dmul_rn(fy, bot));
+    int q = __double2int_rn(v);
+    dst[(int64_t)y * W + x] = (uint8_t)min(max(q, 0), 255);
+}
+
+float pp_deskew(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, int H, int W, float max_deg) {
+    ARG_CHECK(max_deg >= 0.f && max_deg <= 45.f, "deskew: max_deg out of range");
+    const int half = (int)lrint((double)max_deg / 0.1);
+    const int n_ang = 2 * half + 1;
+    const int NR = (int)ceil(sqrt((double)H * H + (double)W * W)) + 3, R0 = NR / 2;
+    const double cx = (W - 1) * 0.5, cy = (H - 1) * 0.5;
+    std::vector<double> cs((size_t)n_ang * 2), deg(n_ang);
+    for (int i = 0; i < n_ang; ++i) {
+        deg[i] = (double)(i - half) * 0.1;
+        double rad = deg[i] * 3.141592653589793 / 180.0;
+        cs[2 * i] = cos(rad);
+        cs[2 * i + 1] = sin(rad);
+    }
+    DevBuf fg((size_t)H * W, st), dcs(cs.size() * 8, st), bins((size_t)n_ang * NR * 4, st), score((size_t)n_ang * 8, st);
+    pp_adaptive_threshold(h, st, src, fg.as<uint8_t>(), H, W, 1, 1, 31, 5.0f);
+    CUDA_CHECK(cudaMemcpyAsync(dcs.p, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemsetAsync(bins.p, 0, (size_t)n_ang * NR * 4, st));
+    k_deskew_hist<<<dim3(cdiv(cdiv(W, 2), 128), H), 128, 0, st>>>(fg.as<uint8_t>(), H, W, dcs.as<double>(), n_ang, NR, R0,
+                                                                       cx, cy, bins.as<unsigned int>());
+    k_deskew_score<<<n_ang, 256, 0, st>>>(bins.as<unsigned int>(), NR, score.as<unsigned long long>());
+    std::vector<unsigned long long> hs(n_ang);
+    CUDA_CHECK(cudaMemcpyAsync(hs.data(), score.p, (size_t)n_ang * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    int best = 0;
+    for (int i = 1; i < n_ang; ++i)
+        if (hs[i] > hs[best]) best = i;
+    k_rotate_bilinear<<<dim3(cdiv(W, 256), H), 256, 0, st>>>(src, dst, H, W, cs[2 * best], cs[2 * best + 1], cx, cy);
+    count_launch(h, 3);
+    CUDA_CHECK(cudaGetLastError());
+    return (float)deg[best];
 }
 
 }  // namespace bbocr

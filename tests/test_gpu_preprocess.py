@@ -84,3 +84,17 @@ def test_full_size_phone_photo(handle):
     flat = np.full((3024, 4032, 3), 127, np.uint8)
     out = preprocess_array(flat, CURRENT, 0)
     assert out.min() == out.max()
+
+
+def test_deskew_matches_oracle_and_recovers_angle(handle):
+    """Deskew is defined by this repository (not in the reference): CUDA == NumPy definition, and a page rotated by a
+    known angle is brought back."""
+    import cv2
+    page = cv2.cvtColor(synth.title_page(5, 640, 480), cv2.COLOR_RGB2GRAY)
+    for ang in (-3.0, 2.2, 0.7):
+        M = cv2.getRotationMatrix2D((319.5, 239.5), -ang, 1.0)
+        rot = cv2.warpAffine(page, M, (640, 480), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+        want, wa = P.deskew(rot, 5.0)
+        got, ga = handle.pp_deskew(rot, 5.0)
+        assert abs(ga - float(wa)) < 1e-6 and abs(ga - ang) <= 0.15
+        assert np.array_equal(got, want)
