@@ -161,7 +161,10 @@ void crnn_sequence_dev(Handle*, Lane&, void* seq, int rows, const std::vector<Se
 void crnn_forward_dev(Handle*, Lane&, const float* x, int N, int Wm, float* logits);
 void lstm_sequences(Handle*, Lane&, const float* gates_in, const float* w_hh, const SeqDesc* seqs_host, int n_seq,
                     const SeqDesc* seqs_dev, const int* groups_dev, int n_groups, void* out);
-int lstm_group_size();
+int lstm_group_size(const Handle*);
+void lstm_sequences_tc(Handle*, Lane&, const float* gates_in, const float* w_hh, int n_seq, const SeqDesc* seqs_dev,
+                       const int* groups_dev, int n_groups, void* out);
+int lstm_tc_group_size();
 // greedy CTC over all rows: per-row argmax / renormalised max probability, then per-sequence collapse
 void ctc_decode_dev(Handle*, cudaStream_t, const float* logits, int rows, int C, const uint8_t* ignore_dev,
                     const SeqDesc* seqs_dev, int n_seq, int32_t* text_idx /*[rows]*/, int32_t* text_len /*[n_seq]*/,

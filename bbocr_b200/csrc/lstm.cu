@@ -154,6 +154,10 @@ void lstm_sequences(Handle* h, Lane& lane, const float* gates_in, const float* w
                     const SeqDesc* seqs_dev, const int* groups_dev, int n_groups, void* out) {
     cudaStream_t st = lane.stream;
     if (n_seq == 0) return;
+    if (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv) {      // throughput mode: mat-vec on the tensor cores
+        lstm_sequences_tc(h, lane, gates_in, w_hh, n_seq, seqs_dev, groups_dev, n_groups, out);
+        return;
+    }
     const size_t smem = (size_t)(256 * COLS + 2 * NB * 256 + KPARTS * COLS * NB + NB * UNITS) * sizeof(float);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CL * n_groups, 2);
@@ -177,6 +181,8 @@ void lstm_sequences(Handle* h, Lane& lane, const float* gates_in, const float* w
     count_launch(h);
 }
 
-int lstm_group_size() { return NB; }
+int lstm_group_size(const Handle* h) {
+    return (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv) ? lstm_tc_group_size() : NB;
+}
 
 }  // namespace bbocr

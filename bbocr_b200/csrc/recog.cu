@@ -288,7 +288,7 @@ void crnn_sequence_dev(Handle* h, Lane& lane, void* seq, int rows, const std::ve
     const int n_seq = (int)seqs.size();
     if (rows == 0 || n_seq == 0) return;
     // groups of NB sequences of similar length (longest first) -> one cluster each per direction
-    const int NBg = lstm_group_size();
+    const int NBg = lstm_group_size(h);
     std::vector<int> order(n_seq);
     for (int i = 0; i < n_seq; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return seqs[a].T > seqs[b].T; });
