@@ -5,10 +5,12 @@
 // activation tensor; TMA's out-of-bounds zero fill IS the convolution's zero padding.  1x1 convolutions / Linear layers
 // use a flat 2-D view (channels x pixels).  Channel concatenation (U-Net skips) is two tensor maps walked back to back.
 //
-//   warp 0 : TMA producer (one lane)      -> full[stage]   (mbarrier expect_tx / complete_tx)
-//   warp 1 : tcgen05.mma issuer (one lane)-> empty[stage]  (tcgen05.commit), accum barrier after the last k-block
-//   warp 2 : TMEM allocate / free
-//   warps 4-7 : epilogue: tcgen05.ld 32x32b -> folded-BN scale/bias (+ReLU) -> bf16 / fp32 NHWC stores
+// Persistent CTAs (static round-robin over output tiles) with warp roles
+//   warp 0    : TMA producer (one lane)       -> full[stage]   (mbarrier expect_tx / complete_tx)
+//   warp 1    : tcgen05.mma issuer (one lane) -> empty[stage]  (tcgen05.commit); tfull[acc] after a tile's last k-block
+//   warp 2    : TMEM allocate / free (2 accumulator stages of BN columns: tile i+1 accumulates while tile i drains)
+//   warps 4-7 : epilogue: tcgen05.ld 32x32b -> folded-BN scale/bias (+ReLU) -> optional fused 2x2 / 2x1 max-pool by
+//               warp shuffles -> bf16 / fp32 NHWC stores -> tempty[acc]
 //
 // Operand tiles are the canonical K-major SWIZZLE_128B (BK = 64) / SWIZZLE_64B (BK = 32) layouts that the TMA box
 // produces directly; the UMMA shared-memory descriptors walk them in 32-byte (UMMA_K = 16) steps.
@@ -30,9 +32,13 @@ struct TcParams {
     int OH, OW, NIMG;
     int flat;                   // 1: 1x1 conv over a flat [pixels][channels] view
     int64_t M;                  // total output pixels
-    int cout, BN;
+    int cout, BN, n_tiles;      // n_tiles = cout_pad / BN
+    int m_tiles, total_tiles;
     int relu, out_f32;
-    void* out;
+    int pool;                   // 0 none, 1 = MaxPool2d(2,2), 2 = MaxPool2d((2,1),(2,1))  (tile must be 16 wide)
+    int write_full;             // store the un-pooled tensor as well (skip connections)
+    void* out;                  // un-pooled output [N][OH][OW][cout]
+    void* out2;                 // pooled output    [N][OH/2][OW/(pool==1?2:1)][cout]
     const float* scale;
     const float* bias;
     int stages;
@@ -45,6 +51,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -114,42 +123,78 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+struct TileCoord {
+    int n0, img, x0, y0;
+    int64_t m0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
+    TileCoord t;
+    const int mt = tile / p.n_tiles;
+    t.n0 = (tile - mt * p.n_tiles) * p.BN;        // N tiles of one M tile run on neighbouring CTAs: the A tile is shared in L2
+    t.img = 0; t.x0 = 0; t.y0 = 0; t.m0 = 0;
+    if (p.flat) {
+        t.m0 = (int64_t)mt * BM;
+    } else {
+        int q = mt;
+        int tx = q % p.tiles_x;
+        q /= p.tiles_x;
+        int ty = q % p.tiles_y;
+        t.img = q / p.tiles_y;
+        t.x0 = tx * p.TW;
+        t.y0 = ty * p.TH;
+    }
+    return t;
+}
+
+template <typename TO>
+__device__ __forceinline__ void store16(TO* o, const float* f, int nbase, int cout);
+template <>
+__device__ __forceinline__ void store16<float>(float* o, const float* f, int nbase, int cout) {
+    if ((cout & 3) == 0 && nbase + 16 <= cout) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+        for (int j = 0; j < 16; ++j)
+            if (nbase + j < cout) o[j] = f[j];
+    }
+}
+template <>
+__device__ __forceinline__ void store16<__nv_bfloat16>(__nv_bfloat16* o, const float* f, int nbase, int cout) {
+    if ((cout & 7) == 0 && nbase + 16 <= cout) {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+        for (int j = 0; j < 16; ++j)
+            if (nbase + j < cout) o[j] = __float2bfloat16_rn(f[j]);
+    }
+}
+
 template <int BK>
 __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtensorMap tmA1,
                                                  const __grid_constant__ CUtensorMap tmA2,
                                                  const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[8], empty_bar[8], accum_bar;
+    __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int A_BYTES = BM * BK * 2;
     const int B_BYTES = p.BN * BK * 2;
     const int STAGE_BYTES = A_BYTES + B_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // tile coordinates
-    const int n0 = blockIdx.y * p.BN;
-    int img = 0, x0 = 0, y0 = 0;
-    int64_t m0 = 0;
-    if (p.flat) {
-        m0 = (int64_t)blockIdx.x * BM;
-    } else {
-        int t = blockIdx.x;
-        int tx = t % p.tiles_x;
-        t /= p.tiles_x;
-        int ty = t % p.tiles_y;
-        img = t / p.tiles_y;
-        x0 = tx * p.TW;
-        y0 = ty * p.TH;
-    }
     const int kb1 = p.C1 / BK, kb2 = p.C2 / BK;
-    const int total = p.taps * (kb1 + kb2);
+    const int kiters = p.taps * (kb1 + kb2);
     uint32_t ncols = 32;
-    while ((int)ncols < p.BN) ncols <<= 1;
+    while ((int)ncols < 2 * p.BN) ncols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&accum_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -164,106 +209,122 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_acc = tmem_slot;
+    const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0 && lane == 0) {
         // ---------------- TMA producer ----------------
         int it = 0;
-        for (int tap = 0; tap < p.taps; ++tap) {
-            const int ky = tap / p.taps_w, kx = tap - ky * p.taps_w;
-            const int cx = x0 - p.pad + kx * p.dil, cy = y0 - p.pad + ky * p.dil;
-            for (int kb = 0; kb < kb1 + kb2; ++kb, ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (it / p.stages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-                uint8_t* sb = sa + A_BYTES;
-                mbar_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
-                const bool second = kb >= kb1;
-                const CUtensorMap* tma = second ? &tmA2 : &tmA1;
-                const int c0 = (second ? kb - kb1 : kb) * BK;
-                if (p.flat) tma_load_2d(sa, tma, &full_bar[s], c0, (int)m0);
-                else tma_load_4d(sa, tma, &full_bar[s], c0, cx, cy, img);
-                tma_load_3d(sb, &tmB, &full_bar[s], kb * BK, n0, tap);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord tc = tile_coord(p, tile);
+            for (int tap = 0; tap < p.taps; ++tap) {
+                const int ky = tap / p.taps_w, kx = tap - ky * p.taps_w;
+                const int cx = tc.x0 - p.pad + kx * p.dil, cy = tc.y0 - p.pad + ky * p.dil;
+                for (int kb = 0; kb < kb1 + kb2; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
+                    const bool second = kb >= kb1;
+                    const CUtensorMap* tma = second ? &tmA2 : &tmA1;
+                    const int c0 = (second ? kb - kb1 : kb) * BK;
+                    if (p.flat) tma_load_2d(sa, tma, &full_bar[s], c0, (int)tc.m0);
+                    else tma_load_4d(sa, tma, &full_bar[s], c0, cx, cy, tc.img);
+                    tma_load_3d(sb, &tmB, &full_bar[s], kb * BK, tc.n0, tap);
+                }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ---------------- MMA issuer ----------------
         // instruction descriptor: D = F32 (1<<4), A = B = BF16 (1<<7, 1<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        for (int it = 0; it < total; ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
-            mbar_wait(&full_bar[s], ph);
+        int it = 0, ti = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+            const int as = ti & 1;
+            const uint32_t aph = (ti >> 1) & 1;
+            mbar_wait(&tempty_bar[as], aph ^ 1);                 // the epilogue has drained this accumulator stage
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-            const uint64_t adesc = umma_desc<BK>(sa), bdesc = umma_desc<BK>(sa + A_BYTES);
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.BN);
+            for (int k = 0; k < kiters; ++k, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint64_t adesc = umma_desc<BK>(sa), bdesc = umma_desc<BK>(sa + A_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)        // +32 bytes (2 x 16 B units) per UMMA_K = 16 step inside the swizzle atom
-                umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&empty_bar[s]);
+                for (int kk = 0; kk < BK / 16; ++kk)      // +32 bytes (2 x 16 B units) per UMMA_K = 16 step inside the swizzle atom
+                    umma_bf16(tmem_acc, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&tfull_bar[as]);
         }
-        umma_commit(&accum_bar);
     } else if (warp >= 4) {
         // ---------------- epilogue ----------------
-        mbar_wait(&accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int wq = warp & 3;
         const int r = wq * 32 + lane;
-        int64_t pix = -1;
-        if (p.flat) {
-            if (m0 + r < p.M) pix = m0 + r;
-        } else {
-            int hl = r / p.TW, wl = r - hl * p.TW;
-            int y = y0 + hl, x = x0 + wl;
-            if (y < p.OH && x < p.OW) pix = ((int64_t)img * p.OH + y) * p.OW + x;
-        }
-        const uint32_t trow = tmem_acc + ((uint32_t)(wq * 32) << 16);
-        for (int c = 0; c < p.BN; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + c, v);
-            if (pix < 0) continue;
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                int n = n0 + c + j;
-                float a = __uint_as_float(v[j]);
-                float sc = __ldg(p.scale + n), bi = __ldg(p.bias + n);      // scale/bias are padded to cout_pad
-                a = fmaf(a, sc, bi);
-                f[j] = p.relu ? fmaxf(a, 0.f) : a;
-            }
-            const int nbase = n0 + c;
-            if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(p.out) + pix * p.cout + nbase;
-                if ((p.cout & 3) == 0 && nbase + 16 <= p.cout) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                } else {
-                    for (int j = 0; j < 16; ++j)
-                        if (nbase + j < p.cout) o[j] = f[j];
-                }
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+            const TileCoord tc = tile_coord(p, tile);
+            const int as = ti & 1;
+            const uint32_t aph = (ti >> 1) & 1;
+            mbar_wait(&tfull_bar[as], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int64_t pix = -1, pix2 = -1;
+            if (p.flat) {
+                if (tc.m0 + r < p.M) pix = tc.m0 + r;
             } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout + nbase;
-                if ((p.cout & 7) == 0 && nbase + 16 <= p.cout) {
-                    uint32_t w[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                        w[j] = *reinterpret_cast<uint32_t*>(&t);
-                    }
-                    *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
-                    *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-                } else {
-                    for (int j = 0; j < 16; ++j)
-                        if (nbase + j < p.cout) o[j] = __float2bfloat16_rn(f[j]);
+                const int hl = r / p.TW, wl = r - hl * p.TW;
+                const int y = tc.y0 + hl, x = tc.x0 + wl;
+                if (y < p.OH && x < p.OW) pix = ((int64_t)tc.img * p.OH + y) * p.OW + x;
+                if (p.pool) {
+                    // TW == 16: lane = (hl & 1) * 16 + wl ; the 2x2 (2x1) window lives in lanes {l, l^1, l^16, l^17} ({l, l^16})
+                    const int POH = p.OH >> 1, POW = p.pool == 1 ? p.OW >> 1 : p.OW;
+                    const int py = y >> 1, px = p.pool == 1 ? x >> 1 : x;
+                    const bool writer = (lane & 16) == 0 && (p.pool == 2 || (lane & 1) == 0);
+                    if (writer && py < POH && px < POW) pix2 = ((int64_t)tc.img * POH + py) * POW + px;
                 }
             }
+            const uint32_t trow = tmem_base + (uint32_t)(as * p.BN) + ((uint32_t)(wq * 32) << 16);
+            for (int c = 0; c < p.BN; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + c, v);
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = tc.n0 + c + j;
+                    float a = fmaf(__uint_as_float(v[j]), __ldg(p.scale + n), __ldg(p.bias + n));   // padded to cout_pad
+                    f[j] = p.relu ? fmaxf(a, 0.f) : a;
+                }
+                const int nbase = tc.n0 + c;
+                if (pix >= 0 && (!p.pool || p.write_full)) {
+                    if (p.out_f32) store16(reinterpret_cast<float*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
+                    else store16(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
+                }
+                if (p.pool) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float m = f[j];
+                        if (p.pool == 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                        f[j] = m;
+                    }
+                    if (pix2 >= 0) {
+                        if (p.out_f32) store16(reinterpret_cast<float*>(p.out2) + pix2 * p.cout + nbase, f, nbase, p.cout);
+                        else store16(reinterpret_cast<__nv_bfloat16*>(p.out2) + pix2 * p.cout + nbase, f, nbase, p.cout);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(ncols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
 
@@ -318,7 +379,10 @@ bool conv_tc_supported(const ConvW& cw, const Act& in1, const Act& in2) {
     return true;
 }
 
-void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags) {
+// pooled: optional second output (fused MaxPool2d(2,2) when flags & CONV_POOL22, MaxPool2d((2,1)) when CONV_POOL21);
+// out.p may be null together with a pooled output when only the pooled tensor is needed.
+void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags,
+                     Act* pooled) {
     const int bk = pick_bk(cw, in1, in2);
     TcParams p;
     p.C1 = in1.C; p.C2 = in2.C;
@@ -329,24 +393,37 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     p.flat = (cw.kh == 1 && cw.kw == 1 && cw.pad == 0) ? 1 : 0;
     p.cout = cw.cout;
     p.BN = cw.cout_pad <= 128 ? cw.cout_pad : 128;
+    p.n_tiles = cw.cout_pad / p.BN;
     p.relu = (flags & CONV_RELU) ? 1 : 0;
     p.out_f32 = (flags & CONV_OUT_F32) ? 1 : 0;
     p.out = out.p;
+    p.out2 = nullptr;
+    p.pool = 0;
+    p.write_full = 1;
     p.scale = cw.scale;
     p.bias = cw.bias;
     if (p.flat) { p.TW = 128; p.TH = 1; p.tiles_x = p.tiles_y = 1; }
     else if (out.H >= 8) { p.TW = 16; p.TH = 8; }
     else { p.TW = 32; p.TH = 4; }
-    unsigned grid_x;
-    if (p.flat) grid_x = (unsigned)cdiv64(p.M, BM);
+    if (pooled) {
+        ARG_CHECK(!p.flat && p.TW == 16, "fused pooling needs the 16x8 spatial tile");
+        p.pool = (flags & CONV_POOL22) ? 1 : 2;
+        ARG_CHECK(out.H % 2 == 0 && (p.pool == 2 || out.W % 2 == 0), "fused pooling needs even output dimensions");
+        ARG_CHECK(pooled->H == out.H / 2 && pooled->W == (p.pool == 1 ? out.W / 2 : out.W) && pooled->C == out.C, "pooled geometry");
+        p.out2 = pooled->p;
+        p.write_full = out.p != nullptr;
+    }
+    if (p.flat) p.m_tiles = (int)cdiv64(p.M, BM);
     else {
         p.tiles_x = cdiv(out.W, p.TW);
         p.tiles_y = cdiv(out.H, p.TH);
-        grid_x = (unsigned)((int64_t)p.tiles_x * p.tiles_y * out.N);
+        p.m_tiles = p.tiles_x * p.tiles_y * out.N;
     }
+    p.total_tiles = p.m_tiles * p.n_tiles;
     const int stage_bytes = BM * bk * 2 + p.BN * bk * 2;
-    static const int smem_budget_kb = getenv("BBOCR_TC_SMEM_KB") ? atoi(getenv("BBOCR_TC_SMEM_KB")) : 56;
-    p.stages = std::min(6, std::max(2, (smem_budget_kb * 1024) / stage_bytes));   // budget per CTA: several CTAs share an SM
+    static const int smem_budget_kb = getenv("BBOCR_TC_SMEM_KB") ? atoi(getenv("BBOCR_TC_SMEM_KB")) : 100;
+    static const int ctas_per_sm = getenv("BBOCR_TC_CTAS") ? atoi(getenv("BBOCR_TC_CTAS")) : 2;
+    p.stages = std::min(8, std::max(2, (smem_budget_kb * 1024) / stage_bytes));
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
 
     auto act_map = [&](const Act& a) {
@@ -368,14 +445,15 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     uint32_t wb[3] = {(uint32_t)bk, (uint32_t)p.BN, 1};
     CUtensorMap mB = make_map(cw.w_bf16, 3, wd, ws, wb, bk);
 
-    dim3 grd(grid_x, cw.cout_pad / p.BN);
+    // persistent grid: a multiple of the SM count (148 on B200), never more CTAs than tiles
+    const unsigned grid = (unsigned)std::min<int64_t>(p.total_tiles, (int64_t)h->sm_count * ctas_per_sm);
     if (!h->tc_attr_set) {          // per device (one handle = one device)
         CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         h->tc_attr_set = true;
     }
-    if (bk == 64) k_conv_tc<64><<<grd, 256, smem, st>>>(mA1, mA2, mB, p);
-    else k_conv_tc<32><<<grd, 256, smem, st>>>(mA1, mA2, mB, p);
+    if (bk == 64) k_conv_tc<64><<<grid, 256, smem, st>>>(mA1, mA2, mB, p);
+    else k_conv_tc<32><<<grid, 256, smem, st>>>(mA1, mA2, mB, p);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 }

@@ -87,28 +87,36 @@ void craft_forward_dev(Handle* h, cudaStream_t st, const uint8_t* img_dev, const
         upsample2x(h, st, a, o);
         return o;
     };
+    // conv + ReLU + MaxPool2d(2,2) in one launch; keep_full also materialises the un-pooled tensor (skip connection)
+    auto conv_pool = [&](const ConvW& cw, const Act& a, DevBuf* full_buf, DevBuf& pool_buf, Act* full_out) {
+        Act full;
+        full.N = a.N; full.H = a.H; full.W = a.W; full.C = cw.cout; full.p = nullptr;
+        if (full_buf) full = act_alloc(h, st, *full_buf, a.N, a.H, a.W, cw.cout);
+        Act pooled = act_alloc(h, st, pool_buf, a.N, a.H / 2, a.W / 2, cw.cout);
+        conv_forward(h, st, cw, a, none, full, CONV_RELU | CONV_POOL22, &pooled);
+        if (full_out) *full_out = full;
+        return pooled;
+    };
     const int R = CONV_RELU;
     DevBuf b0, b1, b_r22, b_r32, b_r43, b_r53;
     // slice1
     Act a = act_alloc(h, st, b0, 1, H, W, 64);
     conv_first(h, st, w.c1_1, canvas.as<float>(), 1, H, W, 4, a, R);
     canvas.release();
-    a = conv(w.c1_2, a, none, b1, R);
-    a = pool2(a, b0);
-    a = conv(w.c2_1, a, none, b1, R);
-    Act r22 = conv(w.c2_2, a, none, b_r22, R);        // in-place ReLU of slice2[12] rectifies the aliased tap
+    a = conv_pool(w.c1_2, a, nullptr, b1, nullptr);
+    a = conv(w.c2_1, a, none, b0, R);
+    Act r22;                                          // in-place ReLU of slice2[12] rectifies the aliased tap
+    a = conv_pool(w.c2_2, a, &b_r22, b1, &r22);       // slice2 starts with the pool
     // slice2
-    a = pool2(r22, b0);
-    a = conv(w.c3_1, a, none, b1, R);
+    a = conv(w.c3_1, a, none, b0, R);
+    std::swap(b0, b1);
     Act r32 = conv(w.c3_2, a, none, b_r32, R);
     // slice3
-    a = conv(w.c3_3, r32, none, b0, R);
-    a = pool2(a, b1);
+    a = conv_pool(w.c3_3, r32, nullptr, b1, nullptr);
     a = conv(w.c4_1, a, none, b0, R);
     Act r43 = conv(w.c4_2, a, none, b_r43, R);
     // slice4
-    a = conv(w.c4_3, r43, none, b0, R);
-    a = pool2(a, b1);
+    a = conv_pool(w.c4_3, r43, nullptr, b1, nullptr);
     a = conv(w.c5_1, a, none, b0, R);
     Act r53 = conv(w.c5_2, a, none, b_r53, 0);        // followed by MaxPool, not ReLU: stays the raw BN output
     // slice5

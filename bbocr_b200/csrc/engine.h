@@ -76,9 +76,12 @@ int preprocess_launches_per_image();
 float pp_deskew(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int H, int W, float max_deg);
 
 // ---- nn.cu : layer kernels (NHWC; T = float | __nv_bfloat16 chosen by Handle::precision) ------------------------------
-enum ConvFlags { CONV_RELU = 1, CONV_OUT_F32 = 2 };
+enum ConvFlags { CONV_RELU = 1, CONV_OUT_F32 = 2, CONV_POOL22 = 4, CONV_POOL21 = 8 };
 // out = epilogue(conv(concat_channels(in1, in2)))   in2 may be empty (C == 0).  'same' geometry unless pad says otherwise.
-void conv_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags);
+// `pooled` (optional): also produce MaxPool2d(2,2) [CONV_POOL22] / MaxPool2d((2,1)) [CONV_POOL21] of the output; out.p may
+// then be null when only the pooled tensor is needed.
+void conv_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags,
+                  Act* pooled = nullptr);
 // cin in {1,3(stored 4)} direct convolution from an FP32 NHWC tensor (canvas / crop batch)
 void conv_first(Handle*, cudaStream_t, const ConvW&, const float* in, int N, int H, int W, int cstride, Act& out,
                 int flags);
@@ -94,7 +97,7 @@ Act act_alloc(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C, bo
 
 // ---- conv_tc.cu : tcgen05 implicit GEMM ------------------------------------------------------------------------------
 bool conv_tc_supported(const ConvW&, const Act& in1, const Act& in2);
-void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags);
+void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled);
 
 // ---- weights.cu ------------------------------------------------------------------------------------------------------
 void load_craft(Handle*, const bbocr_tensor* t, int n);

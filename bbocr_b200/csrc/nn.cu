@@ -145,7 +145,8 @@ static void conv_generic(Handle* h, cudaStream_t st, const ConvW& cw, const Act&
     CUDA_CHECK(cudaGetLastError());
 }
 
-void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags) {
+void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags,
+                  Act* pooled) {
     ARG_CHECK(in1.C + in2.C == cw.cin, "conv: channel mismatch (%d+%d vs %d)", in1.C, in2.C, cw.cin);
     ARG_CHECK(in1.C % 16 == 0 && in2.C % 16 == 0, "conv: channel segments must be multiples of 16");
     ARG_CHECK(out.C == cw.cout, "conv: output channel mismatch");
@@ -157,8 +158,23 @@ void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, c
         CUDA_CHECK(cudaEventCreate(&e1));
         CUDA_CHECK(cudaEventRecord(e0, st));
     }
-    if (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && conv_tc_supported(cw, in1, in2)) conv_tc_forward(h, st, cw, in1, in2, out, flags);
-    else conv_generic(h, st, cw, in1, in2, out, flags);
+    const bool tc = h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && conv_tc_supported(cw, in1, in2);
+    if (tc && (!pooled || (out.H >= 8 && out.H % 2 == 0 && ((flags & CONV_POOL21) || out.W % 2 == 0)))) {
+        conv_tc_forward(h, st, cw, in1, in2, out, flags, pooled);       // max-pool fused into the epilogue
+    } else {
+        DevBuf tmp;
+        Act full = out;
+        if (pooled && !full.p) {                                        // caller only wants the pooled tensor
+            bool f32 = (flags & CONV_OUT_F32) != 0;
+            full = act_alloc(h, st, tmp, out.N, out.H, out.W, out.C, f32);
+        }
+        if (tc) conv_tc_forward(h, st, cw, in1, in2, full, flags, nullptr);
+        else conv_generic(h, st, cw, in1, in2, full, flags);
+        if (pooled) {
+            if (flags & CONV_POOL22) maxpool(h, st, full, *pooled, 2, 2, 2, 2, 0, 0);
+            else maxpool(h, st, full, *pooled, 2, 1, 2, 1, 0, 0);
+        }
+    }
     if (h->conv_timing) {
         CUDA_CHECK(cudaEventRecord(e1, st));
         std::lock_guard<std::mutex> g(h->stat_mu);

@@ -263,18 +263,23 @@ void crnn_features_dev(Handle* h, cudaStream_t st, const float* x, int N, int Wm
         maxpool(h, st, a, o, kh, kw, kh, kw, 0, 0);
         return o;
     };
+    // conv + ReLU + max-pool in one launch (the pool runs in the tcgen05 kernel's epilogue)
+    auto conv_pool = [&](const ConvW& cw, const Act& a, DevBuf& buf, int kh, int kw) {
+        Act full;
+        full.N = a.N; full.H = a.H; full.W = a.W; full.C = cw.cout; full.p = nullptr;
+        Act pooled = act_alloc(h, st, buf, a.N, a.H / kh, a.W / kw, cw.cout);
+        conv_forward(h, st, cw, a, none, full, R | (kw == 2 ? CONV_POOL22 : CONV_POOL21), &pooled);
+        return pooled;
+    };
     Act a = act_alloc(h, st, b0, N, 64, Wm, 32);
     conv_first(h, st, w.c0, x, N, 64, Wm, 1, a, R);
     a = pool(a, b1, 2, 2);               // 32 x Wm/2
-    a = conv(w.c1, a, b0, R);
-    a = pool(a, b1, 2, 2);               // 16 x Wm/4
-    a = conv(w.c2, a, b0, R);
-    a = conv(w.c3, a, b1, R);
-    a = pool(a, b0, 2, 1);               // 8 x Wm/4
+    a = conv_pool(w.c1, a, b0, 2, 2);    // 16 x Wm/4
+    a = conv(w.c2, a, b1, R);
+    a = conv_pool(w.c3, a, b0, 2, 1);    // 8 x Wm/4
     a = conv(w.c4, a, b1, R);
-    a = conv(w.c5, a, b0, R);
-    a = pool(a, b1, 2, 1);               // 4 x Wm/4
-    a = conv(w.c6, a, b0, R);            // 3 x (Wm/4 - 1)
+    a = conv_pool(w.c5, a, b0, 2, 1);    // 4 x Wm/4
+    a = conv(w.c6, a, b1, R);            // 3 x (Wm/4 - 1)
     Act s;
     s.N = N; s.H = 1; s.W = a.W; s.C = 256;
     s.p = (uint8_t*)seq + (size_t)row0 * 256 * act_elem_size(h);
