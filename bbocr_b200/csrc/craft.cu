@@ -53,6 +53,42 @@ __global__ void k_canvas(const uint8_t* __restrict__ img, int th, int tw, float*
     reinterpret_cast<float4*>(out)[(int64_t)y * W32 + x] = o;
 }
 
+// BF16 path: normalise + gather the 3x3x3 neighbourhood of every canvas pixel into 32 bf16 channels (tap*3 + c; 27..31 = 0),
+// so that conv1_1 runs as a K = 32 GEMM on the tensor cores.  Outside the canvas = conv zero padding; inside the canvas
+// but outside the image = the normalised zero pixel (resize_aspect_ratio pads before normalizeMeanVariance).
+__global__ void k_im2col_rgb(const uint8_t* __restrict__ img, int th, int tw, __nv_bfloat16* __restrict__ out, int H32, int W32,
+                             float m0, float m1, float m2, float s0, float s1, float s2) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W32) return;
+    const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+    uint32_t w[16];
+    float v[32];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+        const bool in_canvas = yy >= 0 && yy < H32 && xx >= 0 && xx < W32;
+        const bool in_img = in_canvas && yy < th && xx < tw;
+        const uint8_t* p = img + ((int64_t)yy * tw + xx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float px = in_img ? (float)p[c] : 0.f;
+            v[t * 3 + c] = in_canvas ? __fdiv_rn(__fsub_rn(px, mean[c]), sd[c]) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int i = 27; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + ((int64_t)y * W32 + x) * 32);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    o[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    o[3] = make_uint4(w[12], w[13], w[14], w[15]);
+}
+
 void craft_forward_dev(Handle* h, cudaStream_t st, const uint8_t* img_dev, const CanvasGeom& g, float* text, float* link) {
     if (!h->craft_loaded) fail(BBOCR_E_STATE, "CRAFT weights not loaded (bbocr_load_craft)");
     const CraftW& w = h->craft;
@@ -64,10 +100,17 @@ void craft_forward_dev(Handle* h, cudaStream_t st, const uint8_t* img_dev, const
         resize_bilinear_u8(h, st, img_dev, g.H, g.W, g.W * 3, 3, resized.as<uint8_t>(), g.th, g.tw);
         src = resized.as<uint8_t>();
     }
-    DevBuf canvas((size_t)H * W * 16, st);
     const float m0 = (float)(0.485 * 255.0), m1 = (float)(0.456 * 255.0), m2 = (float)(0.406 * 255.0);
     const float s0 = (float)(0.229 * 255.0), s1 = (float)(0.224 * 255.0), s2 = (float)(0.225 * 255.0);
-    k_canvas<<<dim3(cdiv(W, 256), H), 256, 0, st>>>(src, g.th, g.tw, canvas.as<float>(), H, W, m0, m1, m2, s0, s1, s2);
+    const bool tc_first = h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv;
+    DevBuf canvas;
+    if (tc_first) {
+        canvas.alloc((size_t)H * W * 64, st);
+        k_im2col_rgb<<<dim3(cdiv(W, 128), H), 128, 0, st>>>(src, g.th, g.tw, canvas.as<__nv_bfloat16>(), H, W, m0, m1, m2, s0, s1, s2);
+    } else {
+        canvas.alloc((size_t)H * W * 16, st);
+        k_canvas<<<dim3(cdiv(W, 256), H), 256, 0, st>>>(src, g.th, g.tw, canvas.as<float>(), H, W, m0, m1, m2, s0, s1, s2);
+    }
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 
@@ -101,7 +144,13 @@ void craft_forward_dev(Handle* h, cudaStream_t st, const uint8_t* img_dev, const
     DevBuf b0, b1, b_r22, b_r32, b_r43, b_r53;
     // slice1
     Act a = act_alloc(h, st, b0, 1, H, W, 64);
-    conv_first(h, st, w.c1_1, canvas.as<float>(), 1, H, W, 4, a, R);
+    if (tc_first) {
+        Act x32;
+        x32.N = 1; x32.H = H; x32.W = W; x32.C = 32; x32.p = canvas.p;
+        conv_forward(h, st, w.c1_1_tc, x32, none, a, R);
+    } else {
+        conv_first(h, st, w.c1_1, canvas.as<float>(), 1, H, W, 4, a, R);
+    }
     canvas.release();
     a = conv_pool(w.c1_2, a, nullptr, b1, nullptr);
     a = conv(w.c2_1, a, none, b0, R);

@@ -11,6 +11,7 @@
 namespace bbocr {
 
 struct CraftW {
+    ConvW c1_1_tc;      // conv1_1 as a 1x1 convolution over the 32-channel gathered neighbourhood (tensor-core path)
     ConvW c1_1, c1_2, c2_1, c2_2, c3_1, c3_2, c3_3, c4_1, c4_2, c4_3, c5_1, c5_2, fc6, fc7;
     ConvW up1a, up1b, up2a, up2b, up3a, up3b, up4a, up4b, cls0, cls1, cls2, cls3, cls4;
 };

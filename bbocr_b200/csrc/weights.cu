@@ -178,6 +178,25 @@ void load_craft(Handle* h, const bbocr_tensor* t, int n) {
     c.cls3 = make_conv(h, d, "conv_cls.6", "", 0, 1);
     c.cls4 = make_conv(h, d, "conv_cls.8", "", 0, 1);
     ARG_CHECK(c.c1_1.cin == 3 && c.c1_1.cout == 64 && c.cls4.cout == 2, "CRAFT: unexpected shapes");
+    {
+        // conv1_1 for the tensor-core path: the 3x3x3 neighbourhood is gathered into 32 channels (27 + 5 zeros) by
+        // k_im2col_rgb, which turns the layer into a 1x1 convolution with Cin = 32: W32[o][tap*3 + c] = w[o][c][tap]
+        const bbocr_tensor* w = d.get("basenet.slice1.0.weight");
+        std::vector<__nv_bfloat16> wb((size_t)64 * 32, __float2bfloat16(0.f));
+        std::vector<float> wf((size_t)32 * 64, 0.f);
+        for (int o = 0; o < 64; ++o)
+            for (int ci = 0; ci < 3; ++ci)
+                for (int t = 0; t < 9; ++t) {
+                    float v = w->data[((int64_t)o * 3 + ci) * 9 + t];
+                    wb[(size_t)o * 32 + t * 3 + ci] = __float2bfloat16(v);
+                    wf[(size_t)(t * 3 + ci) * 64 + o] = v;
+                }
+        ConvW e = c.c1_1;
+        e.cin = 32; e.kh = e.kw = 1; e.pad = 0; e.dil = 1;
+        e.w_bf16 = to_device(h, wb);
+        e.w_f32 = to_device(h, wf);
+        c.c1_1_tc = e;
+    }
     h->craft_loaded = true;
 }
 
