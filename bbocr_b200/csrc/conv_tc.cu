@@ -369,6 +369,10 @@ int pick_bk(const ConvW& cw, const Act& in1, const Act& in2) {
 
 }  // namespace
 
+CUtensorMap tc_make_map(void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int bk) {
+    return make_map(base, rank, dims, strides_bytes, box, bk);
+}
+
 bool conv_tc_supported(const ConvW& cw, const Act& in1, const Act& in2) {
     if (pick_bk(cw, in1, in2) == 0) return false;
     if (cw.cout_pad > 128 && cw.cout_pad % 128 != 0) return false;
@@ -392,7 +396,8 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     p.M = (int64_t)out.N * out.H * out.W;
     p.flat = (cw.kh == 1 && cw.kw == 1 && cw.pad == 0) ? 1 : 0;
     p.cout = cw.cout;
-    p.BN = cw.cout_pad <= 128 ? cw.cout_pad : 128;
+    static const int bn_max = getenv("BBOCR_TC_BN") ? atoi(getenv("BBOCR_TC_BN")) : 256;
+    p.BN = cw.cout_pad <= 128 ? cw.cout_pad : ((bn_max >= 256 && cw.cout_pad % 256 == 0) ? 256 : 128);
     p.n_tiles = cw.cout_pad / p.BN;
     p.relu = (flags & CONV_RELU) ? 1 : 0;
     p.out_f32 = (flags & CONV_OUT_F32) ? 1 : 0;
@@ -423,7 +428,7 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     const int stage_bytes = BM * bk * 2 + p.BN * bk * 2;
     static const int smem_budget_kb = getenv("BBOCR_TC_SMEM_KB") ? atoi(getenv("BBOCR_TC_SMEM_KB")) : 100;
     static const int ctas_per_sm = getenv("BBOCR_TC_CTAS") ? atoi(getenv("BBOCR_TC_CTAS")) : 2;
-    p.stages = std::min(8, std::max(2, (smem_budget_kb * 1024) / stage_bytes));
+    p.stages = std::min(8, std::max(2, ((p.BN > 128 ? 200 : smem_budget_kb) * 1024) / stage_bytes));
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
 
     auto act_map = [&](const Act& a) {
@@ -446,10 +451,10 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     CUtensorMap mB = make_map(cw.w_bf16, 3, wd, ws, wb, bk);
 
     // persistent grid: a multiple of the SM count (148 on B200), never more CTAs than tiles
-    const unsigned grid = (unsigned)std::min<int64_t>(p.total_tiles, (int64_t)h->sm_count * ctas_per_sm);
+    const unsigned grid = (unsigned)std::min<int64_t>(p.total_tiles, (int64_t)h->sm_count * (p.BN > 128 ? 1 : ctas_per_sm));
     if (!h->tc_attr_set) {          // per device (one handle = one device)
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         h->tc_attr_set = true;
     }
     if (bk == 64) k_conv_tc<64><<<grid, 256, smem, st>>>(mA1, mA2, mB, p);

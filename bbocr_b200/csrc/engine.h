@@ -44,7 +44,7 @@ struct Handle {
     // dominant-kernel instrumentation (bench.py roofline): CUDA events around every implicit-GEMM conv launch
     bool conv_timing = false;
     bool force_generic_conv = false; // test hook: route BF16-mode convolutions through the CUDA-core kernel
-    bool tc_attr_set = false;
+    bool tc_attr_set = false, halo_attr_set = false, lstm_attr_set = false;
     std::mutex stat_mu;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
     double conv_flops = 0;
@@ -99,6 +99,9 @@ Act act_alloc(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C, bo
 // ---- conv_tc.cu : tcgen05 implicit GEMM ------------------------------------------------------------------------------
 bool conv_tc_supported(const ConvW&, const Act& in1, const Act& in2);
 void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled);
+// conv_halo.cu : 3x3 / pad 1 convolutions with the input patch loaded once per channel block (all nine taps from smem)
+bool conv_halo_supported(const ConvW&, const Act& in1, const Act& in2, const Act& out);
+void conv_halo_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled);
 
 // ---- weights.cu ------------------------------------------------------------------------------------------------------
 void load_craft(Handle*, const bbocr_tensor* t, int n);

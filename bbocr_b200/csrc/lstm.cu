@@ -172,7 +172,7 @@ void lstm_sequences(Handle* h, Lane& lane, const float* gates_in, const float* w
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (h->precision == BBOCR_PREC_BF16) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_lstm_cluster<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaFuncSetAttribute(k_lstm_cluster<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_lstm_cluster<__nv_bfloat16>, gates_in, w_hh, (__nv_bfloat16*)out, seqs_dev, groups_dev));
     } else {
         CUDA_CHECK(cudaFuncSetAttribute(k_lstm_cluster<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -159,7 +159,10 @@ void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, c
         CUDA_CHECK(cudaEventRecord(e0, st));
     }
     const bool tc = h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && conv_tc_supported(cw, in1, in2);
-    if (tc && (!pooled || (out.H >= 8 && out.H % 2 == 0 && ((flags & CONV_POOL21) || out.W % 2 == 0)))) {
+    const bool pool_ok = !pooled || (out.H >= 8 && out.H % 2 == 0 && ((flags & CONV_POOL21) || out.W % 2 == 0));
+    if (tc && pool_ok && conv_halo_supported(cw, in1, in2, out)) {
+        conv_halo_forward(h, st, cw, in1, in2, out, flags, pooled);     // patch-reuse kernel for the 3x3 layers
+    } else if (tc && pool_ok) {
         conv_tc_forward(h, st, cw, in1, in2, out, flags, pooled);       // max-pool fused into the epilogue
     } else {
         DevBuf tmp;

@@ -64,3 +64,15 @@ def test_tc_conv_matches_cuda_core_and_numpy(handle, shape):
     wb = torch.from_numpy(w).bfloat16().double()
     ref = F.relu(F.conv2d(xb, wb, torch.from_numpy(b).double(), padding=pad, dilation=dil)).permute(0, 2, 3, 1).numpy()
     assert np.abs(tc - ref).max() <= 2 ** -7 * max(1.0, np.abs(ref).max())
+
+
+def test_halo_patch_kernel_in_subprocess():
+    """conv_halo.cu (input patch loaded once, nine taps from shifted UMMA descriptors) is off by default; run the same
+    shape sweep with it enabled (the mode is latched per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, BBOCR_HALO="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "matches_cuda_core"], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
