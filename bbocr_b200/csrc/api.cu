@@ -331,27 +331,39 @@ int bbocr_dbg_conv(bbocr_handle* h, const float* in1, int C1, const float* in2, 
         DevBuf f1, f2, b1, b2, bo, fo;
         int64_t n1 = (int64_t)N * H * W * C1, n2 = (int64_t)N * H * W * C2;
         upload(lane, f1, in1, n1 * 4);
-        a1 = act_alloc(h, st, b1, N, H, W, C1);
-        act_from_f32(h, st, f1.as<float>(), a1.p, n1);
+        const bool split = force_generic == 2;          // 2: split-precision (hi/lo) input, FP32 output, tensor cores
+        if (split) {
+            Act src;
+            src.N = N; src.H = H; src.W = W; src.C = C1; src.p = f1.p;
+            a1 = act_alloc_split(h, st, b1, N, H, W, C1);
+            maxpool_f32_to_split(h, st, src, a1, 1, 1);
+        } else {
+            a1 = act_alloc(h, st, b1, N, H, W, C1);
+            act_from_f32(h, st, f1.as<float>(), a1.p, n1);
+        }
         if (C2 > 0) {
             upload(lane, f2, in2, n2 * 4);
             a2 = act_alloc(h, st, b2, N, H, W, C2);
             act_from_f32(h, st, f2.as<float>(), a2.p, n2);
         }
         int OH = H + 2 * pad - dil * (kh - 1), OW = W + 2 * pad - dil * (kw - 1);
-        o = act_alloc(h, st, bo, N, OH, OW, cout);
-        h->force_generic_conv = force_generic != 0;
+        o = act_alloc(h, st, bo, N, OH, OW, cout, split);
+        h->force_generic_conv = force_generic == 1;
         try {
-            conv_forward(h, st, cw, a1, a2, o, relu ? CONV_RELU : 0);
+            conv_forward(h, st, cw, a1, a2, o, (relu ? CONV_RELU : 0) | (split ? CONV_OUT_F32 : 0));
         } catch (...) {
             h->force_generic_conv = false;
             throw;
         }
         h->force_generic_conv = false;
         int64_t no = (int64_t)N * OH * OW * cout;
-        fo.alloc(no * 4, st);
-        act_to_f32(h, st, o.p, fo.as<float>(), no);
-        download(lane, out, fo.p, no * 4);
+        if (split) {
+            download(lane, out, o.p, no * 4);
+        } else {
+            fo.alloc(no * 4, st);
+            act_to_f32(h, st, o.p, fo.as<float>(), no);
+            download(lane, out, fo.p, no * 4);
+        }
     });
 }
 
@@ -540,17 +552,18 @@ void recognize_pass(Handle* h, Lane& lane, std::vector<CropJob>& jobs, const std
     crops_to_input_dev(h, st, aligned_buf.as<uint8_t>(), ddesc.as<CropDesc>(), n, max_w, inputs.as<float>());
     // feature extractor per width bucket -> one flat [rows][256] sequence tensor; sequence k = (bucket, slot)
     const int rows = (int)step_elems;
-    DevBuf seq((size_t)rows * 256 * act_elem_size(h) + 256, st);
+    DevBuf seqbuf;
+    Act seq = crnn_alloc_seq(h, st, seqbuf, rows);
     std::vector<SeqDesc> seqs;
     std::vector<int> seq_of_bucket_slot0(bucket_w.size());
     for (size_t q = 0; q < bucket_w.size(); ++q) {
         int T = bucket_w[q] / 4 - 1;
-        crnn_features_dev(h, st, inputs.as<float>() + bucket_off[q], bucket_n[q], bucket_w[q], seq.p, (int)step_off[q]);
+        crnn_features_dev(h, st, inputs.as<float>() + bucket_off[q], bucket_n[q], bucket_w[q], seq, (int)step_off[q]);
         seq_of_bucket_slot0[q] = (int)seqs.size();
         for (int sl = 0; sl < bucket_n[q]; ++sl) seqs.push_back(SeqDesc{(int)step_off[q] + sl * T, T});
     }
     // recurrent half + Prediction once over all crops, then greedy CTC over all rows
-    crnn_sequence_dev(h, lane, seq.p, rows, seqs, logits.as<float>());
+    crnn_sequence_dev(h, lane, seq, seqs, logits.as<float>());
     const int n_seq = (int)seqs.size();
     DevBuf dseq;
     upload(lane, dseq, seqs.data(), seqs.size() * sizeof(SeqDesc));

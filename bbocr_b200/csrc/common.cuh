@@ -91,6 +91,7 @@ struct PinnedBuf {
 // ---- activation tensors: NHWC, element type float (FP32 mode) or __nv_bfloat16 (BF16 mode) --------------------------
 struct Act {
     void* p = nullptr;
+    void* lo = nullptr;               // non-null: split-precision tensor x = bf16(p) + bf16(lo)  (3 x bf16 products ~ FP32)
     int N = 0, H = 0, W = 0, C = 0;
     int64_t elems() const { return (int64_t)N * H * W * C; }
 };
@@ -101,6 +102,7 @@ struct ConvW {
     int cout_pad = 0;                 // cout rounded up to 16 (BF16 weight rows)
     float* w_f32 = nullptr;           // [kh*kw][cin][cout]          (FP32 path; cout contiguous)
     __nv_bfloat16* w_bf16 = nullptr;  // [kh*kw][cout_pad][cin]      (tcgen05 path; K-major rows)
+    __nv_bfloat16* w_split = nullptr; // [kh*kw][cout_pad][3*cin] = [w_hi | w_hi | w_lo]  (split-precision recogniser)
     float* scale = nullptr;           // [cout_pad]
     float* bias = nullptr;            // [cout_pad]
 };

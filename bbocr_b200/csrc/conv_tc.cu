@@ -25,7 +25,7 @@ namespace {
 constexpr int BM = 128;
 
 struct TcParams {
-    int C1, C2;                 // channels of the two input segments (C2 may be 0)
+    int C1, C2, C3;             // channels of the input segments (C2, C3 may be 0); split precision: [x_hi | x_lo | x_hi]
     int taps_w, taps;           // kw, kh*kw
     int pad, dil;
     int TW, TH, tiles_x, tiles_y;
@@ -39,6 +39,9 @@ struct TcParams {
     int write_full;             // store the un-pooled tensor as well (skip connections)
     void* out;                  // un-pooled output [N][OH][OW][cout]
     void* out2;                 // pooled output    [N][OH/2][OW/(pool==1?2:1)][cout]
+    void* out_lo;               // split-precision output: out = bf16 hi part, out_lo = bf16(v - hi)
+    void* out2_lo;
+    int split_out;
     const float* scale;
     const float* bias;
     int stages;
@@ -175,9 +178,22 @@ __device__ __forceinline__ void store16<__nv_bfloat16>(__nv_bfloat16* o, const f
     }
 }
 
+// split-precision store: hi = bf16(v), lo = bf16(v - hi)
+__device__ __forceinline__ void store_split(void* hi_base, void* lo_base, int64_t off, const float* f, int nbase, int cout) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        hi[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
+        lo[j] = f[j] - hi[j];
+    }
+    store16(reinterpret_cast<__nv_bfloat16*>(hi_base) + off, hi, nbase, cout);
+    store16(reinterpret_cast<__nv_bfloat16*>(lo_base) + off, lo, nbase, cout);
+}
+
 template <int BK>
 __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtensorMap tmA1,
                                                  const __grid_constant__ CUtensorMap tmA2,
+                                                 const __grid_constant__ CUtensorMap tmA3,
                                                  const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
@@ -187,8 +203,8 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     const int B_BYTES = p.BN * BK * 2;
     const int STAGE_BYTES = A_BYTES + B_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kb1 = p.C1 / BK, kb2 = p.C2 / BK;
-    const int kiters = p.taps * (kb1 + kb2);
+    const int kb1 = p.C1 / BK, kb2 = p.C2 / BK, kb3 = p.C3 / BK;
+    const int kiters = p.taps * (kb1 + kb2 + kb3);
     uint32_t ncols = 32;
     while ((int)ncols < 2 * p.BN) ncols <<= 1;
 
@@ -219,16 +235,16 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             for (int tap = 0; tap < p.taps; ++tap) {
                 const int ky = tap / p.taps_w, kx = tap - ky * p.taps_w;
                 const int cx = tc.x0 - p.pad + kx * p.dil, cy = tc.y0 - p.pad + ky * p.dil;
-                for (int kb = 0; kb < kb1 + kb2; ++kb, ++it) {
+                for (int kb = 0; kb < kb1 + kb2 + kb3; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     mbar_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
-                    const bool second = kb >= kb1;
-                    const CUtensorMap* tma = second ? &tmA2 : &tmA1;
-                    const int c0 = (second ? kb - kb1 : kb) * BK;
+                    const int seg = kb < kb1 ? 0 : (kb < kb1 + kb2 ? 1 : 2);
+                    const CUtensorMap* tma = seg == 0 ? &tmA1 : (seg == 1 ? &tmA2 : &tmA3);
+                    const int c0 = (seg == 0 ? kb : (seg == 1 ? kb - kb1 : kb - kb1 - kb2)) * BK;
                     if (p.flat) tma_load_2d(sa, tma, &full_bar[s], c0, (int)tc.m0);
                     else tma_load_4d(sa, tma, &full_bar[s], c0, cx, cy, tc.img);
                     tma_load_3d(sb, &tmB, &full_bar[s], kb * BK, tc.n0, tap);
@@ -299,7 +315,8 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                 }
                 const int nbase = tc.n0 + c;
                 if (pix >= 0 && (!p.pool || p.write_full)) {
-                    if (p.out_f32) store16(reinterpret_cast<float*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
+                    if (p.split_out) store_split(p.out, p.out_lo, pix * p.cout + nbase, f, nbase, p.cout);
+                    else if (p.out_f32) store16(reinterpret_cast<float*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
                     else store16(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
                 }
                 if (p.pool) {
@@ -311,7 +328,8 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                         f[j] = m;
                     }
                     if (pix2 >= 0) {
-                        if (p.out_f32) store16(reinterpret_cast<float*>(p.out2) + pix2 * p.cout + nbase, f, nbase, p.cout);
+                        if (p.split_out) store_split(p.out2, p.out2_lo, pix2 * p.cout + nbase, f, nbase, p.cout);
+                        else if (p.out_f32) store16(reinterpret_cast<float*>(p.out2) + pix2 * p.cout + nbase, f, nbase, p.cout);
                         else store16(reinterpret_cast<__nv_bfloat16*>(p.out2) + pix2 * p.cout + nbase, f, nbase, p.cout);
                     }
                 }
@@ -388,8 +406,15 @@ bool conv_tc_supported(const ConvW& cw, const Act& in1, const Act& in2) {
 void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags,
                      Act* pooled) {
     const int bk = pick_bk(cw, in1, in2);
+    const bool split_in = in1.lo != nullptr;
+    if (split_in) {
+        ARG_CHECK(in2.C == 0 && cw.w_split, "split-precision convolution needs split weights and a single input");
+    }
     TcParams p;
-    p.C1 = in1.C; p.C2 = in2.C;
+    p.C1 = in1.C; p.C2 = split_in ? in1.C : in2.C; p.C3 = split_in ? in1.C : 0;
+    p.split_out = out.lo != nullptr ? 1 : 0;
+    p.out_lo = out.lo;
+    p.out2_lo = nullptr;
     p.taps_w = cw.kw; p.taps = cw.kh * cw.kw;
     p.pad = cw.pad; p.dil = cw.dil;
     p.OH = out.H; p.OW = out.W; p.NIMG = out.N;
@@ -416,6 +441,8 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
         ARG_CHECK(out.H % 2 == 0 && (p.pool == 2 || out.W % 2 == 0), "fused pooling needs even output dimensions");
         ARG_CHECK(pooled->H == out.H / 2 && pooled->W == (p.pool == 1 ? out.W / 2 : out.W) && pooled->C == out.C, "pooled geometry");
         p.out2 = pooled->p;
+        p.out2_lo = pooled->lo;
+        if (pooled->lo) p.split_out = 1;
         p.write_full = out.p != nullptr;
     }
     if (p.flat) p.m_tiles = (int)cdiv64(p.M, BM);
@@ -445,10 +472,17 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     };
     CUtensorMap mA1 = act_map(in1);
     CUtensorMap mA2 = in2.C > 0 ? act_map(in2) : mA1;
-    uint64_t wd[3] = {(uint64_t)cw.cin, (uint64_t)cw.cout_pad, (uint64_t)p.taps};
-    uint64_t ws[2] = {(uint64_t)cw.cin * 2, (uint64_t)cw.cout_pad * cw.cin * 2};
+    CUtensorMap mA3 = mA1;
+    if (split_in) {
+        Act lo = in1;
+        lo.p = in1.lo;
+        mA2 = act_map(lo);
+    }
+    const uint64_t wcin = split_in ? (uint64_t)cw.cin * 3 : (uint64_t)cw.cin;
+    uint64_t wd[3] = {wcin, (uint64_t)cw.cout_pad, (uint64_t)p.taps};
+    uint64_t ws[2] = {wcin * 2, (uint64_t)cw.cout_pad * wcin * 2};
     uint32_t wb[3] = {(uint32_t)bk, (uint32_t)p.BN, 1};
-    CUtensorMap mB = make_map(cw.w_bf16, 3, wd, ws, wb, bk);
+    CUtensorMap mB = make_map(split_in ? cw.w_split : cw.w_bf16, 3, wd, ws, wb, bk);
 
     // persistent grid: a multiple of the SM count (148 on B200), never more CTAs than tiles
     const unsigned grid = (unsigned)std::min<int64_t>(p.total_tiles, (int64_t)h->sm_count * (p.BN > 128 ? 1 : ctas_per_sm));
@@ -457,8 +491,8 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
         CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         h->tc_attr_set = true;
     }
-    if (bk == 64) k_conv_tc<64><<<grid, 256, smem, st>>>(mA1, mA2, mB, p);
-    else k_conv_tc<32><<<grid, 256, smem, st>>>(mA1, mA2, mB, p);
+    if (bk == 64) k_conv_tc<64><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mB, p);
+    else k_conv_tc<32><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mB, p);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 }

@@ -91,6 +91,9 @@ void upsample2x(Handle*, cudaStream_t, const Act& in, Act& out);          // bil
 void mean_rows(Handle*, cudaStream_t, const Act& in, Act& out);           // AdaptiveAvgPool2d((None,1)) after permute
 void cls_tail(Handle*, cudaStream_t, const ConvW& c3, const ConvW& c4, const Act& in, float* text, float* link);
 
+Act act_alloc_split(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C);
+void maxpool_f32_to_split(Handle*, cudaStream_t, const Act& in, Act& out, int kh, int kw);
+void mean_rows_split(Handle*, cudaStream_t, const Act& in, Act& out);
 void act_from_f32(Handle*, cudaStream_t, const float* in, void* out, int64_t n);
 void act_to_f32(Handle*, cudaStream_t, const void* in, float* out, int64_t n);
 size_t act_elem_size(const Handle*);
@@ -162,12 +165,13 @@ struct SeqDesc {                   // one crop's feature sequence inside the fla
     int row0, T;
 };
 // conv stack + row mean of one width bucket: x [N][64][Wm] FP32 -> seq rows [row0, row0 + N*(Wm/4-1)) of `seq` ([rows][256])
-void crnn_features_dev(Handle*, cudaStream_t, const float* x, int N, int Wm, void* seq, int row0);
+Act crnn_alloc_seq(Handle*, cudaStream_t, DevBuf& buf, int rows);
+void crnn_features_dev(Handle*, cudaStream_t, const float* x, int N, int Wm, const Act& seq, int row0);
 // both BiLSTM blocks + Prediction over all sequences at once: seq [rows][256] -> logits [rows][num_class] FP32
-void crnn_sequence_dev(Handle*, Lane&, void* seq, int rows, const std::vector<SeqDesc>& seqs, float* logits);
+void crnn_sequence_dev(Handle*, Lane&, const Act& seq, const std::vector<SeqDesc>& seqs, float* logits);
 void crnn_forward_dev(Handle*, Lane&, const float* x, int N, int Wm, float* logits);
 void lstm_sequences(Handle*, Lane&, const float* gates_in, const float* w_hh, const SeqDesc* seqs_host, int n_seq,
-                    const SeqDesc* seqs_dev, const int* groups_dev, int n_groups, void* out);
+                    const SeqDesc* seqs_dev, const int* groups_dev, int n_groups, void* out, void* out_lo = nullptr);
 int lstm_group_size(const Handle*);
 void lstm_sequences_tc(Handle*, Lane&, const float* gates_in, const float* w_hh, int n_seq, const SeqDesc* seqs_dev,
                        const int* groups_dev, int n_groups, void* out);

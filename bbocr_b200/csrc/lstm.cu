@@ -33,6 +33,7 @@ __device__ __forceinline__ void st_out(__nv_bfloat16* p, float v) { *p = __float
 template <typename TO>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
     k_lstm_cluster(const float* __restrict__ gates_in, const float* __restrict__ w_hh, TO* __restrict__ out,
+                   __nv_bfloat16* __restrict__ out_lo /* split-precision output when non-null (TO = bf16) */,
                    const SeqDesc* __restrict__ seqs, const int* __restrict__ groups /*[n_groups][NB], -1 = empty*/) {
     extern __shared__ __align__(16) float lsm[];
     float* Ws = lsm;                               // [256][COLS]
@@ -130,7 +131,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
                 float og = 1.f / (1.f + expf(-pre[3]));
                 cstate = fg * cstate + ig * gg;
                 hv = og * tanhf(cstate);
-                st_out(out + (size_t)(row0 + t) * 512 + dir * 256 + UNITS * r + pu, hv);
+                const size_t oidx = (size_t)(row0 + t) * 512 + dir * 256 + UNITS * r + pu;
+                st_out(out + oidx, hv);
+                if (out_lo) out_lo[oidx] = __float2bfloat16_rn(hv - __bfloat162float(__float2bfloat16_rn(hv)));
             }
             hstage[pb * UNITS + pu] = hv;
         }
@@ -151,10 +154,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
 
 // seqs: device array of n_seq descriptors; the host copy is used to form groups of NB sequences of similar length
 void lstm_sequences(Handle* h, Lane& lane, const float* gates_in, const float* w_hh, const SeqDesc* seqs_host, int n_seq,
-                    const SeqDesc* seqs_dev, const int* groups_dev, int n_groups, void* out) {
+                    const SeqDesc* seqs_dev, const int* groups_dev, int n_groups, void* out, void* out_lo) {
     cudaStream_t st = lane.stream;
     if (n_seq == 0) return;
-    if (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv) {      // throughput mode: mat-vec on the tensor cores
+    if (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && !out_lo && getenv("BBOCR_LSTM_TF32")) {   // optional TF32 tensor-core mat-vec
         lstm_sequences_tc(h, lane, gates_in, w_hh, n_seq, seqs_dev, groups_dev, n_groups, out);
         return;
     }
@@ -173,16 +176,16 @@ void lstm_sequences(Handle* h, Lane& lane, const float* gates_in, const float* w
     cfg.numAttrs = 1;
     if (h->precision == BBOCR_PREC_BF16) {
         cudaFuncSetAttribute(k_lstm_cluster<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_lstm_cluster<__nv_bfloat16>, gates_in, w_hh, (__nv_bfloat16*)out, seqs_dev, groups_dev));
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_lstm_cluster<__nv_bfloat16>, gates_in, w_hh, (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo, seqs_dev, groups_dev));
     } else {
         CUDA_CHECK(cudaFuncSetAttribute(k_lstm_cluster<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_lstm_cluster<float>, gates_in, w_hh, (float*)out, seqs_dev, groups_dev));
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_lstm_cluster<float>, gates_in, w_hh, (float*)out, (__nv_bfloat16*)nullptr, seqs_dev, groups_dev));
     }
     count_launch(h);
 }
 
 int lstm_group_size(const Handle* h) {
-    return (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv) ? lstm_tc_group_size() : NB;
+    return (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && getenv("BBOCR_LSTM_TF32")) ? lstm_tc_group_size() : NB;
 }
 
 }  // namespace bbocr

@@ -160,7 +160,7 @@ void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, c
     }
     const bool tc = h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && conv_tc_supported(cw, in1, in2);
     const bool pool_ok = !pooled || (out.H >= 8 && out.H % 2 == 0 && ((flags & CONV_POOL21) || out.W % 2 == 0));
-    if (tc && pool_ok && conv_halo_supported(cw, in1, in2, out)) {
+    if (tc && pool_ok && !in1.lo && !out.lo && conv_halo_supported(cw, in1, in2, out)) {
         conv_halo_forward(h, st, cw, in1, in2, out, flags, pooled);     // patch-reuse kernel for the 3x3 layers
     } else if (tc && pool_ok) {
         conv_tc_forward(h, st, cw, in1, in2, out, flags, pooled);       // max-pool fused into the epilogue
@@ -242,12 +242,13 @@ __global__ void __launch_bounds__(128) k_conv_first(const float* __restrict__ in
 
 void conv_first(Handle* h, cudaStream_t st, const ConvW& cw, const float* in, int N, int H, int W, int cstride, Act& out,
                 int flags) {
+    const bool force_f32 = (flags & CONV_OUT_F32) != 0;
     ARG_CHECK(cw.kh == 3 && cw.kw == 3 && cw.pad == 1 && cw.dil == 1 && cw.cin <= 3, "conv_first: unsupported shape");
     ARG_CHECK(cw.cout == 32 || cw.cout == 64, "conv_first: cout must be 32 or 64");
     int64_t M = (int64_t)N * H * W;
     unsigned grd = (unsigned)cdiv64(M, 128);
     int relu = (flags & CONV_RELU) ? 1 : 0;
-    const bool bf = h->precision == BBOCR_PREC_BF16;
+    const bool bf = h->precision == BBOCR_PREC_BF16 && !force_f32;
 #define LAUNCH(CO, TO) \
     k_conv_first<CO, TO><<<grd, 128, 0, st>>>(in, N, H, W, cstride, cw.cin, cw.w_f32, cw.cout_pad, cw.scale, cw.bias, (TO*)out.p, relu)
     if (cw.cout == 64) { if (bf) LAUNCH(64, __nv_bfloat16); else LAUNCH(64, float); }
@@ -426,6 +427,91 @@ void cls_tail(Handle* h, cudaStream_t st, const ConvW& c3, const ConvW& c4, cons
     CUDA_CHECK(cudaGetLastError());
 }
 
+
+// ---- split-precision (x = bf16 hi + bf16 lo) helpers for the recogniser in throughput mode ------------------------
+Act act_alloc_split(Handle* h, cudaStream_t st, DevBuf& buf, int N, int H, int W, int C) {
+    Act a;
+    a.N = N; a.H = H; a.W = W; a.C = C;
+    size_t half = ((size_t)a.elems() * 2 + 255) & ~(size_t)255;
+    buf.alloc(half * 2 + 256, st);
+    a.p = buf.p;
+    a.lo = (uint8_t*)buf.p + half;
+    return a;
+}
+
+__device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* lo, const float v[4]) {
+    float h4[4], l4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h4[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+        l4[j] = v[j] - h4[j];
+    }
+    store4(hi, h4);
+    store4(lo, l4);
+}
+
+// MaxPool2d on an FP32 tensor, output split
+__global__ void k_maxpool_f32_split(const float* __restrict__ in, __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo,
+                                    int N, int H, int W, int C, int OH, int OW, int kh, int kw) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int C4 = C >> 2;
+    int64_t total = (int64_t)N * OH * OW * C4;
+    if (idx >= total) return;
+    int c = (int)(idx % C4) * 4;
+    int64_t p = idx / C4;
+    int ox = (int)(p % OW);
+    p /= OW;
+    int oy = (int)(p % OH);
+    int n = (int)(p / OH);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int ky = 0; ky < kh; ++ky)
+        for (int kx = 0; kx < kw; ++kx) {
+            float v[4];
+            load4(in + (((int64_t)n * H + oy * kh + ky) * W + ox * kw + kx) * C + c, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], v[j]);
+        }
+    int64_t o = (((int64_t)n * OH + oy) * OW + ox) * C + c;
+    split_store4(ohi + o, olo + o, best);
+}
+
+void maxpool_f32_to_split(Handle* h, cudaStream_t st, const Act& in, Act& out, int kh, int kw) {
+    int64_t total = (int64_t)out.N * out.H * out.W * (in.C / 4);
+    k_maxpool_f32_split<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>((const float*)in.p, (__nv_bfloat16*)out.p, (__nv_bfloat16*)out.lo,
+                                                                      in.N, in.H, in.W, in.C, out.H, out.W, kh, kw);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// AdaptiveAvgPool over the H rows of a split tensor -> split [N][1][W][C]
+__global__ void k_mean_rows_split(const __nv_bfloat16* __restrict__ ihi, const __nv_bfloat16* __restrict__ ilo,
+                                  __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo, int N, int H, int W, int C) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)N * W * C;
+    if (idx >= total) return;
+    int c = (int)(idx % C);
+    int64_t p = idx / C;
+    int x = (int)(p % W);
+    int n = (int)(p / W);
+    float s = 0.f;
+    for (int y = 0; y < H; ++y) {
+        int64_t i = (((int64_t)n * H + y) * W + x) * C + c;
+        s += __bfloat162float(ihi[i]) + __bfloat162float(ilo[i]);
+    }
+    float v = s / (float)H;
+    __nv_bfloat16 hb = __float2bfloat16_rn(v);
+    ohi[idx] = hb;
+    olo[idx] = __float2bfloat16_rn(v - __bfloat162float(hb));
+}
+
+void mean_rows_split(Handle* h, cudaStream_t st, const Act& in, Act& out) {
+    int64_t total = (int64_t)in.N * in.W * in.C;
+    k_mean_rows_split<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>((const __nv_bfloat16*)in.p, (const __nv_bfloat16*)in.lo,
+                                                                    (__nv_bfloat16*)out.p, (__nv_bfloat16*)out.lo, in.N, in.H,
+                                                                    in.W, in.C);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
 
 // ---- dtype conversion between host-facing FP32 buffers and the activation dtype of the current precision mode -------
 template <typename T>

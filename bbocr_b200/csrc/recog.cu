@@ -246,34 +246,56 @@ void crops_to_input_dev(Handle* h, cudaStream_t st, const uint8_t* aligned, cons
 //   crnn_features_dev : VGG feature extractor + AdaptiveAvgPool of one bucket (N crops of identical model width Wm)
 //   crnn_sequence_dev : 2 x (input-projection GEMM -> clustered BiLSTM recurrence -> Linear) + Prediction, all crops
 // ------------------------------------------------------------------------------------------------------------------
-void crnn_features_dev(Handle* h, cudaStream_t st, const float* x, int N, int Wm, void* seq, int row0) {
+// Throughput mode keeps the recogniser at FP32-class accuracy on the tensor cores: activations are carried as a pair of
+// bf16 tensors (hi + lo) and every convolution / Linear is three bf16 GEMM segments x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
+// accumulated in FP32 (conv_tc.cu).  The recogniser is <5 % of the page's FLOPs, so the 3x costs little, and greedy CTC
+// strings then match the FP32 oracle (tests/test_gpu_recognizer.py).  BBOCR_CRNN_BF16=1 selects plain bf16 instead.
+bool crnn_split(const Handle* h) {
+    static const bool plain = getenv("BBOCR_CRNN_BF16") != nullptr;
+    return h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && !plain;
+}
+
+Act crnn_alloc_seq(Handle* h, cudaStream_t st, DevBuf& buf, int rows) {
+    if (crnn_split(h)) return act_alloc_split(h, st, buf, 1, 1, rows, 256);
+    return act_alloc(h, st, buf, 1, 1, rows, 256);
+}
+
+void crnn_features_dev(Handle* h, cudaStream_t st, const float* x, int N, int Wm, const Act& seq, int row0) {
     if (!h->crnn_loaded) fail(BBOCR_E_STATE, "CRNN weights not loaded (bbocr_load_crnn)");
     ARG_CHECK(N > 0 && Wm >= 64 && Wm % 4 == 0, "crnn: bad batch geometry (N=%d, W=%d)", N, Wm);
     const CrnnW& w = h->crnn;
     const Act none;
     const int R = CONV_RELU;
+    const bool split = crnn_split(h);
     DevBuf b0, b1;
-    auto conv = [&](const ConvW& cw, const Act& a, DevBuf& buf, int flags) {
-        Act o = act_alloc(h, st, buf, a.N, a.H + 2 * cw.pad - cw.dil * (cw.kh - 1), a.W + 2 * cw.pad - cw.dil * (cw.kw - 1), cw.cout);
-        conv_forward(h, st, cw, a, none, o, flags);
-        return o;
+    auto alloc = [&](DevBuf& buf, int n, int hh, int ww, int c) {
+        return split ? act_alloc_split(h, st, buf, n, hh, ww, c) : act_alloc(h, st, buf, n, hh, ww, c);
     };
-    auto pool = [&](const Act& a, DevBuf& buf, int kh, int kw) {
-        Act o = act_alloc(h, st, buf, a.N, a.H / kh, a.W / kw, a.C);
-        maxpool(h, st, a, o, kh, kw, kh, kw, 0, 0);
+    auto conv = [&](const ConvW& cw, const Act& a, DevBuf& buf, int flags) {
+        Act o = alloc(buf, a.N, a.H + 2 * cw.pad - cw.dil * (cw.kh - 1), a.W + 2 * cw.pad - cw.dil * (cw.kw - 1), cw.cout);
+        conv_forward(h, st, cw, a, none, o, flags);
         return o;
     };
     // conv + ReLU + max-pool in one launch (the pool runs in the tcgen05 kernel's epilogue)
     auto conv_pool = [&](const ConvW& cw, const Act& a, DevBuf& buf, int kh, int kw) {
         Act full;
         full.N = a.N; full.H = a.H; full.W = a.W; full.C = cw.cout; full.p = nullptr;
-        Act pooled = act_alloc(h, st, buf, a.N, a.H / kh, a.W / kw, cw.cout);
+        Act pooled = alloc(buf, a.N, a.H / kh, a.W / kw, cw.cout);
         conv_forward(h, st, cw, a, none, full, R | (kw == 2 ? CONV_POOL22 : CONV_POOL21), &pooled);
         return pooled;
     };
-    Act a = act_alloc(h, st, b0, N, 64, Wm, 32);
-    conv_first(h, st, w.c0, x, N, 64, Wm, 1, a, R);
-    a = pool(a, b1, 2, 2);               // 32 x Wm/2
+    Act a;
+    if (split) {
+        Act c0 = act_alloc(h, st, b0, N, 64, Wm, 32, true);                 // FP32 output of the direct first conv
+        conv_first(h, st, w.c0, x, N, 64, Wm, 1, c0, R | CONV_OUT_F32);
+        a = act_alloc_split(h, st, b1, N, 32, Wm / 2, 32);
+        maxpool_f32_to_split(h, st, c0, a, 2, 2);
+    } else {
+        Act c0 = act_alloc(h, st, b0, N, 64, Wm, 32);
+        conv_first(h, st, w.c0, x, N, 64, Wm, 1, c0, R);
+        a = act_alloc(h, st, b1, N, 32, Wm / 2, 32);
+        maxpool(h, st, c0, a, 2, 2, 2, 2, 0, 0);
+    }
     a = conv_pool(w.c1, a, b0, 2, 2);    // 16 x Wm/4
     a = conv(w.c2, a, b1, R);
     a = conv_pool(w.c3, a, b0, 2, 1);    // 8 x Wm/4
@@ -282,16 +304,24 @@ void crnn_features_dev(Handle* h, cudaStream_t st, const float* x, int N, int Wm
     a = conv(w.c6, a, b1, R);            // 3 x (Wm/4 - 1)
     Act s;
     s.N = N; s.H = 1; s.W = a.W; s.C = 256;
-    s.p = (uint8_t*)seq + (size_t)row0 * 256 * act_elem_size(h);
-    mean_rows(h, st, a, s);
+    if (split) {
+        s.p = (uint8_t*)seq.p + (size_t)row0 * 256 * 2;
+        s.lo = (uint8_t*)seq.lo + (size_t)row0 * 256 * 2;
+        mean_rows_split(h, st, a, s);
+    } else {
+        s.p = (uint8_t*)seq.p + (size_t)row0 * 256 * act_elem_size(h);
+        mean_rows(h, st, a, s);
+    }
 }
 
-void crnn_sequence_dev(Handle* h, Lane& lane, void* seq, int rows, const std::vector<SeqDesc>& seqs, float* logits) {
+void crnn_sequence_dev(Handle* h, Lane& lane, const Act& seq, const std::vector<SeqDesc>& seqs, float* logits) {
     cudaStream_t st = lane.stream;
     const CrnnW& w = h->crnn;
     const Act none;
+    const int rows = seq.W;
     const int n_seq = (int)seqs.size();
     if (rows == 0 || n_seq == 0) return;
+    const bool split = crnn_split(h);
     // groups of NB sequences of similar length (longest first) -> one cluster each per direction
     const int NBg = lstm_group_size(h);
     std::vector<int> order(n_seq);
@@ -313,15 +343,14 @@ void crnn_sequence_dev(Handle* h, Lane& lane, void* seq, int rows, const std::ve
     const int* groups_dev = dmeta.as<int>() + (size_t)n_seq * 2;
 
     DevBuf bg, bh, bs[2];
-    Act cur;
-    cur.N = 1; cur.H = 1; cur.W = rows; cur.C = 256; cur.p = seq;
+    Act cur = seq;
     for (int layer = 0; layer < 2; ++layer) {
         const LstmW& l = layer == 0 ? w.l0 : w.l1;
         Act gates = act_alloc(h, st, bg, 1, 1, rows, 2048, true);               // FP32 input projections, all time steps
         conv_forward(h, st, l.in_proj, cur, none, gates, CONV_OUT_F32);
-        Act hcat = act_alloc(h, st, bh, 1, 1, rows, 512);
-        lstm_sequences(h, lane, (const float*)gates.p, l.w_hh, seqs.data(), n_seq, seqs_dev, groups_dev, n_groups, hcat.p);
-        Act nxt = act_alloc(h, st, bs[layer], 1, 1, rows, 256);
+        Act hcat = split ? act_alloc_split(h, st, bh, 1, 1, rows, 512) : act_alloc(h, st, bh, 1, 1, rows, 512);
+        lstm_sequences(h, lane, (const float*)gates.p, l.w_hh, seqs.data(), n_seq, seqs_dev, groups_dev, n_groups, hcat.p, hcat.lo);
+        Act nxt = split ? act_alloc_split(h, st, bs[layer], 1, 1, rows, 256) : act_alloc(h, st, bs[layer], 1, 1, rows, 256);
         conv_forward(h, st, l.linear, hcat, none, nxt, 0);
         cur = nxt;
     }
@@ -332,11 +361,12 @@ void crnn_sequence_dev(Handle* h, Lane& lane, void* seq, int rows, const std::ve
 
 void crnn_forward_dev(Handle* h, Lane& lane, const float* x, int N, int Wm, float* logits) {
     const int T = Wm / 4 - 1, rows = N * T;
-    DevBuf seq((size_t)rows * 256 * act_elem_size(h) + 256, lane.stream);
-    crnn_features_dev(h, lane.stream, x, N, Wm, seq.p, 0);
+    DevBuf sb;
+    Act seq = crnn_alloc_seq(h, lane.stream, sb, rows);
+    crnn_features_dev(h, lane.stream, x, N, Wm, seq, 0);
     std::vector<SeqDesc> seqs(N);
     for (int i = 0; i < N; ++i) { seqs[i].row0 = i * T; seqs[i].T = T; }
-    crnn_sequence_dev(h, lane, seq.p, rows, seqs, logits);
+    crnn_sequence_dev(h, lane, seq, seqs, logits);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

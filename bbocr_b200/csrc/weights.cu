@@ -42,7 +42,7 @@ T* to_device(Handle* h, const std::vector<T>& v) {
 }
 
 // conv (+ optional BatchNorm, eval mode, eps 1e-5) -> ConvW.  y = scale * conv(x) + bias.
-ConvW make_conv(Handle* h, const Dict& d, const std::string& conv, const std::string& bn, int pad, int dil) {
+ConvW make_conv(Handle* h, const Dict& d, const std::string& conv, const std::string& bn, int pad, int dil, bool split = false) {
     const bbocr_tensor* w = d.get(conv + ".weight");
     ARG_CHECK(w->ndim == 4, "%s.weight must be 4-D", conv.c_str());
     const bbocr_tensor* b = d.get(conv + ".bias", false);
@@ -80,11 +80,26 @@ ConvW make_conv(Handle* h, const Dict& d, const std::string& conv, const std::st
     c.w_bf16 = to_device(h, wb);
     c.scale = to_device(h, scale);
     c.bias = to_device(h, bias);
+    if (split) {      // [tap][cout_pad][hi(cin) | hi(cin) | lo(cin)] : pairs with activations [x_hi | x_lo | x_hi]
+        std::vector<__nv_bfloat16> ws((size_t)taps * c.cout_pad * 3 * c.cin, __float2bfloat16(0.f));
+        for (int o = 0; o < c.cout; ++o)
+            for (int i = 0; i < c.cin; ++i)
+                for (int t = 0; t < taps; ++t) {
+                    float v = w->data[((int64_t)o * c.cin + i) * taps + t];
+                    __nv_bfloat16 hi = __float2bfloat16(v), lo = __float2bfloat16(v - __bfloat162float(hi));
+                    size_t base = ((size_t)t * c.cout_pad + o) * 3 * c.cin;
+                    ws[base + i] = hi;
+                    ws[base + c.cin + i] = hi;
+                    ws[base + 2 * c.cin + i] = lo;
+                }
+        c.w_split = to_device(h, ws);
+    }
     return c;
 }
 
 // nn.Linear / LSTM input projection as a 1x1 convolution: rows of `mats` are stacked along cout.
-ConvW make_linear(Handle* h, const std::vector<const bbocr_tensor*>& mats, const std::vector<std::vector<const bbocr_tensor*>>& biases) {
+ConvW make_linear(Handle* h, const std::vector<const bbocr_tensor*>& mats, const std::vector<std::vector<const bbocr_tensor*>>& biases,
+                  bool split = true) {
     ConvW c;
     c.cin = (int)mats[0]->shape[1];
     c.cout = 0;
@@ -97,6 +112,7 @@ ConvW make_linear(Handle* h, const std::vector<const bbocr_tensor*>& mats, const
     std::vector<float> scale(c.cout_pad, 0.f), bias(c.cout_pad, 0.f);
     std::vector<float> wf((size_t)c.cin * c.cout_pad, 0.f);
     std::vector<__nv_bfloat16> wb((size_t)c.cout_pad * c.cin, __float2bfloat16(0.f));
+    std::vector<__nv_bfloat16> ws(split ? (size_t)c.cout_pad * 3 * c.cin : 0, __float2bfloat16(0.f));
     int o0 = 0;
     for (size_t mi = 0; mi < mats.size(); ++mi) {
         const bbocr_tensor* m = mats[mi];
@@ -110,12 +126,20 @@ ConvW make_linear(Handle* h, const std::vector<const bbocr_tensor*>& mats, const
                 float v = m->data[(int64_t)o * c.cin + i];
                 wf[(size_t)i * c.cout_pad + o0 + o] = v;
                 wb[(size_t)(o0 + o) * c.cin + i] = __float2bfloat16(v);
+                if (split) {
+                    __nv_bfloat16 hi = __float2bfloat16(v), lo = __float2bfloat16(v - __bfloat162float(hi));
+                    size_t base = (size_t)(o0 + o) * 3 * c.cin;
+                    ws[base + i] = hi;
+                    ws[base + c.cin + i] = hi;
+                    ws[base + 2 * c.cin + i] = lo;
+                }
             }
         }
         o0 += rows;
     }
     c.w_f32 = to_device(h, wf);
     c.w_bf16 = to_device(h, wb);
+    if (split) c.w_split = to_device(h, ws);
     c.scale = to_device(h, scale);
     c.bias = to_device(h, bias);
     return c;
@@ -150,7 +174,7 @@ ConvW make_conv_raw(Handle* h, const float* w, const float* bias, int cout, int 
     t[0].shape[0] = cout; t[0].shape[1] = cin; t[0].shape[2] = kh; t[0].shape[3] = kw;
     t[1].name = "c.bias"; t[1].data = bias; t[1].ndim = 1; t[1].shape[0] = cout;
     Dict d(t, bias ? 2 : 1);
-    return make_conv(h, d, "c", "", pad, dil);
+    return make_conv(h, d, "c", "", pad, dil, true);
 }
 
 void load_craft(Handle* h, const bbocr_tensor* t, int n) {
@@ -205,12 +229,12 @@ void load_crnn(Handle* h, const bbocr_tensor* t, int n) {
     CrnnW& c = h->crnn;
     const std::string p = "FeatureExtraction.ConvNet.";
     c.c0 = make_conv(h, d, p + "0", "", 1, 1);
-    c.c1 = make_conv(h, d, p + "3", "", 1, 1);
-    c.c2 = make_conv(h, d, p + "6", "", 1, 1);
-    c.c3 = make_conv(h, d, p + "8", "", 1, 1);
-    c.c4 = make_conv(h, d, p + "11", p + "12", 1, 1);
-    c.c5 = make_conv(h, d, p + "14", p + "15", 1, 1);
-    c.c6 = make_conv(h, d, p + "18", "", 0, 1);
+    c.c1 = make_conv(h, d, p + "3", "", 1, 1, true);
+    c.c2 = make_conv(h, d, p + "6", "", 1, 1, true);
+    c.c3 = make_conv(h, d, p + "8", "", 1, 1, true);
+    c.c4 = make_conv(h, d, p + "11", p + "12", 1, 1, true);
+    c.c5 = make_conv(h, d, p + "14", p + "15", 1, 1, true);
+    c.c6 = make_conv(h, d, p + "18", "", 0, 1, true);
     c.l0 = make_lstm(h, d, "SequenceModeling.0.");
     c.l1 = make_lstm(h, d, "SequenceModeling.1.");
     c.pred = make_linear(h, {d.get("Prediction.weight")}, {{d.get("Prediction.bias")}});

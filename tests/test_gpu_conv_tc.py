@@ -66,6 +66,26 @@ def test_tc_conv_matches_cuda_core_and_numpy(handle, shape):
     assert np.abs(tc - ref).max() <= 2 ** -7 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("shape", [s for s in SHAPES if s[4] == 0])
+def test_split_precision_conv_is_fp32_class(handle, shape):
+    """3 x bf16 (hi/lo) convolution on the tensor cores: x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, FP32 accumulate -> matches an
+    exact convolution of the FP32 operands to ~1e-4 relative (vs ~1e-2 for plain bf16)."""
+    N, H, W, C1, C2, cout, k, pad, dil = shape
+    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 32))
+    x1 = np.ascontiguousarray(rng.standard_normal((N, H, W, C1)), np.float32)
+    w = np.ascontiguousarray(rng.standard_normal((cout, C1, k, k)) / np.sqrt(C1 * k * k), np.float32)
+    b = np.ascontiguousarray(rng.standard_normal(cout) * 0.1, np.float32)
+    handle.set_precision(_lib.PREC_BF16)
+    try:
+        got = dbg_conv(handle, x1, None, w, b, pad, dil, True, 2)
+    finally:
+        handle.set_precision(_lib.PREC_FP32)
+    ref = F.relu(F.conv2d(torch.from_numpy(x1).double().permute(0, 3, 1, 2), torch.from_numpy(w).double(),
+                          torch.from_numpy(b).double(), padding=pad, dilation=dil)).permute(0, 2, 3, 1).numpy()
+    err = np.abs(got - ref).max() / max(1.0, np.abs(ref).max())
+    assert err < 2e-4, err
+
+
 def test_halo_patch_kernel_in_subprocess():
     """conv_halo.cu (input patch loaded once, nine taps from shifted UMMA descriptors) is off by default; run the same
     shape sweep with it enabled (the mode is latched per process, hence the subprocess)."""

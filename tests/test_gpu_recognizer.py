@@ -64,7 +64,7 @@ def test_crnn_logits_fp32(gpu_reader, oracle_reader, case):
 
 
 def test_crnn_bf16_string_rate(gpu_reader, oracle_reader):
-    x = np.concatenate([_inputs(24, 256, 7)])
+    x = np.concatenate([_inputs(48, 256, 7)])
     want = oracle_reader.logits(x)
     gpu_reader.set_precision("bf16")
     try:
@@ -76,8 +76,9 @@ def test_crnn_bf16_string_rate(gpu_reader, oracle_reader):
     rate = np.mean([a == b for a, b in zip(s_want, s_got)])
     print("bf16 logits max-abs", np.abs(got - want.numpy()).max(), "identical-string rate", rate)
     # stated BF16 tolerance on logits: 5 % of the logit range (bf16 operands through 7 convs, 2 BiLSTMs, 3 linears)
-    assert np.abs(got - want.numpy()).max() < 0.08 * np.abs(want.numpy()).max()
-    assert rate >= 0.5
+    # throughput mode runs the recogniser in split precision (3 x bf16 ~ FP32): logits within 1e-3 of the logit range
+    assert np.abs(got - want.numpy()).max() < 1e-3 * np.abs(want.numpy()).max()
+    assert rate >= 0.995
 
 
 def test_ctc_decode_exact_given_logits(gpu_reader, oracle_reader):
