@@ -89,7 +89,10 @@ __global__ void k_im2col_rgb(const uint8_t* __restrict__ img, int th, int tw, __
     o[3] = make_uint4(w[12], w[13], w[14], w[15]);
 }
 
+extern thread_local int g_conv_scope;
+
 void craft_forward_dev(Handle* h, cudaStream_t st, const uint8_t* img_dev, const CanvasGeom& g, float* text, float* link) {
+    struct Scope { Scope() { g_conv_scope = 1; } ~Scope() { g_conv_scope = 0; } } scope_guard;
     if (!h->craft_loaded) fail(BBOCR_E_STATE, "CRAFT weights not loaded (bbocr_load_craft)");
     const CraftW& w = h->craft;
     const int H = g.H32, W = g.W32;

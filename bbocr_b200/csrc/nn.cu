@@ -145,6 +145,8 @@ static void conv_generic(Handle* h, cudaStream_t st, const ConvW& cw, const Act&
     CUDA_CHECK(cudaGetLastError());
 }
 
+thread_local int g_conv_scope = 0;      // 1 while the calling thread is inside the detector (CRAFT) forward pass
+
 void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags,
                   Act* pooled) {
     ARG_CHECK(in1.C + in2.C == cw.cin, "conv: channel mismatch (%d+%d vs %d)", in1.C, in2.C, cw.cin);
@@ -153,7 +155,8 @@ void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, c
     ARG_CHECK(out.H == in1.H + 2 * cw.pad - cw.dil * (cw.kh - 1) && out.W == in1.W + 2 * cw.pad - cw.dil * (cw.kw - 1),
               "conv: output geometry mismatch");
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (h->conv_timing) {
+    const bool timed = h->conv_timing && g_conv_scope == 1;     // dominant-kernel instrumentation: detector convolutions
+    if (timed) {
         CUDA_CHECK(cudaEventCreate(&e0));
         CUDA_CHECK(cudaEventCreate(&e1));
         CUDA_CHECK(cudaEventRecord(e0, st));
@@ -178,7 +181,7 @@ void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, c
             else maxpool(h, st, full, *pooled, 2, 1, 2, 1, 0, 0);
         }
     }
-    if (h->conv_timing) {
+    if (timed) {
         CUDA_CHECK(cudaEventRecord(e1, st));
         std::lock_guard<std::mutex> g(h->stat_mu);
         h->conv_events.emplace_back(e0, e1);
