@@ -1,5 +1,6 @@
 // api.cu -- the C ABI declared in include/bbocr.h and the readtext orchestration
 //   (easyocr/easyocr.py::Reader.readtext -> detect -> recognize, batch_size == 1 semantics).
+#include <condition_variable>
 #include <thread>
 
 #include "engine.h"
@@ -7,6 +8,10 @@
 struct bbocr_handle : bbocr::Handle {};
 
 using namespace bbocr;
+
+namespace bbocr {
+extern thread_local int g_conv_scope;
+}
 
 #include <chrono>
 
@@ -108,9 +113,14 @@ int bbocr_create(int device, bbocr_handle** out) {
         h->device = device;
         h->sm_count = prop.multiProcessorCount;
         {
-            const char* e = getenv("BBOCR_LANES");        // pages in flight per handle (streams + host threads)
+            const char* e = getenv("BBOCR_LANES");        // detector pages in flight per handle (streams + host threads)
             int nl = e ? atoi(e) : 8;
-            h->lanes.resize(std::min(std::max(nl, 1), 32));
+            h->n_det_lanes = std::min(std::max(nl, 1), 32);
+            const char* r = getenv("BBOCR_REC_LANES");    // recogniser groups in flight
+            int nr = r ? atoi(r) : 2;
+            const char* g = getenv("BBOCR_REC_GROUP");    // pages per recogniser group
+            h->rec_group = std::max(1, g ? atoi(g) : 16);
+            h->lanes.resize(h->n_det_lanes + std::min(std::max(nr, 1), 8));
         }
         for (auto& l : h->lanes) CUDA_CHECK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         // keep freed blocks in the stream-ordered pool instead of returning them to the driver after every sync
@@ -349,13 +359,16 @@ int bbocr_dbg_conv(bbocr_handle* h, const float* in1, int C1, const float* in2, 
         int OH = H + 2 * pad - dil * (kh - 1), OW = W + 2 * pad - dil * (kw - 1);
         o = act_alloc(h, st, bo, N, OH, OW, cout, split);
         h->force_generic_conv = force_generic == 1;
+        g_conv_scope = 1;                                // timed like a detector convolution (tools/layer_times.py)
         try {
             conv_forward(h, st, cw, a1, a2, o, (relu ? CONV_RELU : 0) | (split ? CONV_OUT_F32 : 0));
         } catch (...) {
             h->force_generic_conv = false;
+            g_conv_scope = 0;
             throw;
         }
         h->force_generic_conv = false;
+        g_conv_scope = 0;
         int64_t no = (int64_t)N * OH * OW * cout;
         if (split) {
             download(lane, out, o.p, no * 4);
@@ -591,13 +604,30 @@ void recognize_pass(Handle* h, Lane& lane, std::vector<CropJob>& jobs, const std
     }
 }
 
-// Reader.readtext for one page on one lane
-bbocr_results* readtext_page(Handle* h, Lane& lane, const bbocr_image& img, const bbocr_params& p) {
+// ---- readtext = detect (per page) -> recognize (per GROUP of pages) -> assemble (per page) ---------------------------------
+// Pages are independent, and with batch_size == 1 semantics every crop has its own model width, so the recogniser's result
+// for a crop does not depend on which other crops share its launch.  The detector half therefore runs page by page on the
+// detector lanes, while the recogniser half runs once over the crops of a whole group of pages: a few large launches
+// (and full 128-crop LSTM clusters) instead of ~120 tiny ones per page.
+struct PageWork {
+    int index = 0;
+    int H = 0, W = 0;
+    int n_labels = 0;
+    std::vector<CropJob> jobs;
+    DevBuf dcrops;                 // packed u8 crops of this page (device)
+    size_t crops_bytes = 0;
+    std::vector<Recognized> rec;   // final per-job result
+    int n_crops_run = 0;
+};
+
+// Reader.detect + utils.get_image_list for one page on one lane; leaves the page's crops on the device
+void detect_page(Handle* h, Lane& lane, const bbocr_image& img, const bbocr_params& p, PageWork& pw) {
     cudaStream_t st = lane.stream;
     ARG_CHECK(img.color && img.H > 0 && img.W > 0, "bad image");
     if (!h->craft_loaded || !h->crnn_loaded) fail(BBOCR_E_STATE, "weights not loaded");
     const int H = img.H, W = img.W;
-    DevBuf dcolor, dgray, dignore;
+    pw.H = H; pw.W = W;
+    DevBuf dcolor, dgray;
     const uint8_t* color = img.color;
     const uint8_t* gray = img.gray;
     if (!img.on_device) {
@@ -616,11 +646,6 @@ bbocr_results* readtext_page(Handle* h, Lane& lane, const bbocr_image& img, cons
         pp_gray(h, st, color, H, W, W * 3, dgray.as<uint8_t>());
         gray = dgray.as<uint8_t>();
     }
-    const uint8_t* ignore_dev = nullptr;
-    if (p.ignore) {
-        upload(lane, dignore, p.ignore, h->crnn.num_class);
-        ignore_dev = dignore.as<uint8_t>();
-    }
     // ---- detect -------------------------------------------------------------------------------------------------
     std::unique_ptr<StageTimer> tm(new StageTimer(h, 0));
     CanvasGeom g = canvas_geom(H, W, p.canvas_size, p.mag_ratio);
@@ -633,6 +658,7 @@ bbocr_results* readtext_page(Handle* h, Lane& lane, const bbocr_image& img, cons
     DetComponents dc;
     det_components_dev(h, lane, text, link, mh, mw, (float)p.text_threshold, (float)p.link_threshold, (float)p.low_text, dc);
     maps.release();
+    pw.n_labels = dc.n_labels;
     tm.reset(new StageTimer(h, 2));
     std::vector<float> boxes;
     boxes_from_components(dc, mh, mw, boxes);
@@ -640,8 +666,8 @@ bbocr_results* readtext_page(Handle* h, Lane& lane, const bbocr_image& img, cons
     std::vector<int32_t> hlist;
     std::vector<double> flist;
     group_boxes(boxes.data(), (int)boxes.size() / 8, g.ratio, gp, hlist, flist);
-    // ---- recognize (batch_size == 1 semantics: every box has its own max_width) -------------------------------------
-    std::vector<CropJob> jobs;
+    // ---- crops (batch_size == 1 semantics: every box has its own max_width) -----------------------------------------
+    std::vector<CropJob>& jobs = pw.jobs;
     std::vector<double> mats;
     size_t scratch_bytes = 0;
     for (size_t i = 0; i + 4 <= hlist.size(); i += 4) {
@@ -664,97 +690,150 @@ bbocr_results* readtext_page(Handle* h, Lane& lane, const bbocr_image& img, cons
         if (finish_geometry(j)) jobs.push_back(j);
     }
     const int n = (int)jobs.size();
-    bbocr_results* r = new bbocr_results();
-    memset(r, 0, sizeof *r);
-    r->n_components = dc.n_labels;
-    std::vector<Recognized> final_rec(n);
+    pw.rec.assign(n, Recognized());
     if (n > 0) {
         size_t crops_bytes = 0;
         for (auto& j : jobs) { j.d.off = (int)crops_bytes; crops_bytes += (size_t)j.d.ow * j.d.oh; }
+        pw.crops_bytes = crops_bytes;
         std::vector<CropDesc> descs(n);
         for (int i = 0; i < n; ++i) descs[i] = jobs[i].d;
-        DevBuf ddesc, dmats, dscratch(scratch_bytes + 16, st), dcrops(crops_bytes + 16, st);
+        DevBuf ddesc, dmats, dscratch(scratch_bytes + 16, st);
+        pw.dcrops.alloc(crops_bytes + 16, st);
         upload(lane, ddesc, descs.data(), descs.size() * sizeof(CropDesc));
         if (!mats.empty()) {
             CUDA_CHECK(cudaStreamSynchronize(st));
             upload(lane, dmats, mats.data(), mats.size() * 8);
         }
         crops_dev(h, st, gray, H, W, ddesc.as<CropDesc>(), n, descs.data(), dmats.as<double>(), dscratch.as<uint8_t>(),
-                  dcrops.as<uint8_t>());
-        CUDA_CHECK(cudaStreamSynchronize(st));             // pin_in (descs) is reused below
-        std::vector<int> all(n);
-        for (int i = 0; i < n; ++i) all[i] = i;
-        tm.reset(new StageTimer(h, 3));
-        std::vector<Recognized> rec1;
-        recognize_pass(h, lane, jobs, all, dcrops.as<uint8_t>(), crops_bytes, ignore_dev, rec1);
-        r->n_crops = n;
-        std::vector<int> low;
-        for (int i = 0; i < n; ++i)
-            if (rec1[i].conf < p.contrast_ths) low.push_back(i);
-        final_rec = rec1;
-        tm.reset(new StageTimer(h, 4));
-        if (!low.empty()) {
-            // second round: adjust_contrast_grey(target = adjust_contrast) on the low-confidence crops
-            const int nl = (int)low.size();
-            std::vector<CropDesc> ldesc(nl);
-            for (int k = 0; k < nl; ++k) ldesc[k] = jobs[low[k]].d;
-            DevBuf dl, dhist((size_t)nl * 256 * 4, st), dadj(crops_bytes + 16, st);
-            CUDA_CHECK(cudaStreamSynchronize(st));
-            upload(lane, dl, ldesc.data(), ldesc.size() * sizeof(CropDesc));
-            crop_hist_dev(h, st, dcrops.as<uint8_t>(), dl.as<CropDesc>(), nl, dhist.as<unsigned int>());
-            std::vector<unsigned int> hist((size_t)nl * 256);
-            download(lane, hist.data(), dhist.p, hist.size() * 4);
-            std::vector<double> lowv(nl), ratio(nl);
-            std::vector<int> apply(nl);
-            for (int k = 0; k < nl; ++k) {
-                int64_t np = (int64_t)ldesc[k].ow * ldesc[k].oh;
-                double high = percentile_from_hist(&hist[(size_t)k * 256], np, 90.0);
-                double lo = percentile_from_hist(&hist[(size_t)k * 256], np, 10.0);
-                double contrast = (high - lo) / std::max(10.0, high + lo);
-                apply[k] = contrast < p.adjust_contrast;
-                lowv[k] = lo;
-                ratio[k] = 200.0 / std::max(10.0, high - lo);
-            }
-            std::vector<uint8_t> packed((size_t)nl * 20);
-            DevBuf dpar;
-            std::vector<double> par((size_t)nl * 2);
-            memcpy(par.data(), lowv.data(), nl * 8);
-            memcpy(par.data() + nl, ratio.data(), nl * 8);
-            upload(lane, dpar, par.data(), par.size() * 8);
-            CUDA_CHECK(cudaStreamSynchronize(st));
-            DevBuf dapply;
-            upload(lane, dapply, apply.data(), (size_t)nl * 4);
-            crop_contrast_dev(h, st, dcrops.as<uint8_t>(), dl.as<CropDesc>(), nl, dpar.as<double>(), dpar.as<double>() + nl,
-                              dapply.as<int>(), dadj.as<uint8_t>());
-            CUDA_CHECK(cudaStreamSynchronize(st));
-            std::vector<Recognized> rec2;
-            recognize_pass(h, lane, jobs, low, dadj.as<uint8_t>(), crops_bytes, ignore_dev, rec2);
-            r->n_crops += nl;
-            for (int k = 0; k < nl; ++k)
-                if (!(rec1[low[k]].conf > rec2[k].conf)) final_rec[low[k]] = rec2[k];
+                  pw.dcrops.as<uint8_t>());
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));                 // the page's crops are complete; pinned staging is free again
+    lane.in_busy = false;
+}
+
+// Reader.recognize over the crops of a group of pages (pass 1, then the contrast-retry pass for low-confidence crops)
+void recognize_group(Handle* h, Lane& lane, const std::vector<PageWork*>& pages, const bbocr_params& p) {
+    cudaStream_t st = lane.stream;
+    // union of the pages' jobs; crop offsets rebased into one packed buffer
+    std::vector<CropJob> jobs;
+    std::vector<std::pair<int, int>> origin;       // (page slot, job index)
+    size_t crops_bytes = 0;
+    std::vector<size_t> page_base(pages.size());
+    for (size_t q = 0; q < pages.size(); ++q) {
+        page_base[q] = crops_bytes;
+        for (size_t i = 0; i < pages[q]->jobs.size(); ++i) {
+            CropJob j = pages[q]->jobs[i];
+            j.d.off += (int)crops_bytes;
+            jobs.push_back(j);
+            origin.emplace_back((int)q, (int)i);
+        }
+        crops_bytes += pages[q]->crops_bytes;
+    }
+    const int n = (int)jobs.size();
+    if (n == 0) return;
+    ARG_CHECK(crops_bytes < (size_t)INT32_MAX, "crop batch too large");
+    DevBuf dignore;
+    const uint8_t* ignore_dev = nullptr;
+    if (p.ignore) {
+        upload(lane, dignore, p.ignore, h->crnn.num_class);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        lane.in_busy = false;
+        ignore_dev = dignore.as<uint8_t>();
+    }
+    DevBuf dcrops(crops_bytes + 16, st);
+    for (size_t q = 0; q < pages.size(); ++q)
+        if (pages[q]->crops_bytes)
+            CUDA_CHECK(cudaMemcpyAsync(dcrops.as<uint8_t>() + page_base[q], pages[q]->dcrops.p, pages[q]->crops_bytes,
+                                       cudaMemcpyDeviceToDevice, st));
+    std::vector<int> all(n);
+    for (int i = 0; i < n; ++i) all[i] = i;
+    std::unique_ptr<StageTimer> tm(new StageTimer(h, 3));
+    std::vector<Recognized> rec1;
+    recognize_pass(h, lane, jobs, all, dcrops.as<uint8_t>(), crops_bytes, ignore_dev, rec1);
+    std::vector<int> low;
+    for (int i = 0; i < n; ++i)
+        if (rec1[i].conf < p.contrast_ths) low.push_back(i);
+    std::vector<Recognized> final_rec = rec1;
+    tm.reset(new StageTimer(h, 4));
+    if (!low.empty()) {
+        // second round: adjust_contrast_grey(target = adjust_contrast) on the low-confidence crops
+        const int nl = (int)low.size();
+        std::vector<CropDesc> ldesc(nl);
+        for (int k = 0; k < nl; ++k) ldesc[k] = jobs[low[k]].d;
+        DevBuf dl, dhist((size_t)nl * 256 * 4, st), dadj(crops_bytes + 16, st);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        upload(lane, dl, ldesc.data(), ldesc.size() * sizeof(CropDesc));
+        crop_hist_dev(h, st, dcrops.as<uint8_t>(), dl.as<CropDesc>(), nl, dhist.as<unsigned int>());
+        std::vector<unsigned int> hist((size_t)nl * 256);
+        download(lane, hist.data(), dhist.p, hist.size() * 4);
+        std::vector<double> par((size_t)nl * 2);
+        std::vector<int> apply(nl);
+        for (int k = 0; k < nl; ++k) {
+            int64_t np = (int64_t)ldesc[k].ow * ldesc[k].oh;
+            double high = percentile_from_hist(&hist[(size_t)k * 256], np, 90.0);
+            double lo = percentile_from_hist(&hist[(size_t)k * 256], np, 10.0);
+            double contrast = (high - lo) / std::max(10.0, high + lo);
+            apply[k] = contrast < p.adjust_contrast;
+            par[k] = lo;
+            par[(size_t)nl + k] = 200.0 / std::max(10.0, high - lo);
+        }
+        DevBuf dpar, dapply;
+        upload(lane, dpar, par.data(), par.size() * 8);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        upload(lane, dapply, apply.data(), (size_t)nl * 4);
+        crop_contrast_dev(h, st, dcrops.as<uint8_t>(), dl.as<CropDesc>(), nl, dpar.as<double>(), dpar.as<double>() + nl,
+                          dapply.as<int>(), dadj.as<uint8_t>());
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        std::vector<Recognized> rec2;
+        recognize_pass(h, lane, jobs, low, dadj.as<uint8_t>(), crops_bytes, ignore_dev, rec2);
+        for (int k = 0; k < nl; ++k) {
+            pages[origin[low[k]].first]->n_crops_run += 1;
+            if (!(rec1[low[k]].conf > rec2[k].conf)) final_rec[low[k]] = rec2[k];
         }
     }
     tm.reset();
-    // ---- assemble (horizontal boxes in group order, then free boxes) ----------------------------------------------
+    for (int i = 0; i < n; ++i) {
+        PageWork* pw = pages[origin[i].first];
+        pw->rec[origin[i].second] = std::move(final_rec[i]);
+        pw->n_crops_run += 1;
+    }
+}
+
+// result assembly (horizontal boxes in group order, then free boxes)
+bbocr_results* assemble_page(const PageWork& pw) {
+    const int n = (int)pw.jobs.size();
+    bbocr_results* r = new bbocr_results();
+    memset(r, 0, sizeof *r);
+    r->n_components = pw.n_labels;
+    r->n_crops = pw.n_crops_run;
     r->n = n;
     r->box = new double[(size_t)std::max(n, 1) * 8];
     r->is_free = new uint8_t[std::max(n, 1)];
     r->text_off = new int32_t[n + 1];
     r->conf = new double[std::max(n, 1)];
     size_t total = 0;
-    for (auto& f : final_rec) total += f.text.size();
+    for (auto& f : pw.rec) total += f.text.size();
     r->text_idx = new int32_t[std::max<size_t>(total, 1)];
     size_t off = 0;
     for (int i = 0; i < n; ++i) {
-        memcpy(r->box + (size_t)i * 8, jobs[i].box, 64);
-        r->is_free[i] = jobs[i].is_free;
+        memcpy(r->box + (size_t)i * 8, pw.jobs[i].box, 64);
+        r->is_free[i] = pw.jobs[i].is_free;
         r->text_off[i] = (int32_t)off;
-        memcpy(r->text_idx + off, final_rec[i].text.data(), final_rec[i].text.size() * 4);
-        off += final_rec[i].text.size();
-        r->conf[i] = final_rec[i].conf;
+        memcpy(r->text_idx + off, pw.rec[i].text.data(), pw.rec[i].text.size() * 4);
+        off += pw.rec[i].text.size();
+        r->conf[i] = pw.rec[i].conf;
     }
     r->text_off[n] = (int32_t)off;
     return r;
+}
+
+// Reader.readtext for one page on one lane
+bbocr_results* readtext_page(Handle* h, Lane& lane, const bbocr_image& img, const bbocr_params& p) {
+    PageWork pw;
+    detect_page(h, lane, img, p, pw);
+    std::vector<PageWork*> one{&pw};
+    recognize_group(h, lane, one, p);
+    return assemble_page(pw);
 }
 
 }  // namespace
@@ -786,29 +865,79 @@ int bbocr_readtext_batch(bbocr_handle* h, int n, const bbocr_image* imgs, const 
         bbocr_params dp;
         if (!p) { bbocr_default_params(&dp); p = &dp; }
         for (int i = 0; i < n; ++i) out[i] = nullptr;
-        // pages are independent: each lane (stream + pinned staging + host thread) takes pages off a shared counter
-        const int nl = std::min<int>((int)h->lanes.size(), std::max(n, 1));
+        if (n == 0) return;
+        // Detector lanes (stream + pinned staging + host thread each) take pages off a shared counter; recogniser lanes
+        // take GROUPS of finished pages off a ready queue (detection of later pages overlaps recognition of earlier ones).
+        const int nd = std::min<int>(h->n_det_lanes, n);
+        const int nr = std::min<int>((int)h->lanes.size() - h->n_det_lanes, std::max(1, cdiv(n, h->rec_group)));
+        std::vector<PageWork> work(n);
         std::atomic<int> next{0};
-        std::vector<std::string> errs(nl);
-        std::vector<int> codes(nl, 0);
+        std::mutex qmu;
+        std::condition_variable qcv;
+        std::vector<int> ready;
+        int det_done = 0;              // pages that left the detector (finished or abandoned)
+        bool failed = false;
+        std::vector<std::string> errs(nd + nr);
+        std::vector<int> codes(nd + nr, 0);
+        auto record = [&](int slot, int code, const std::string& msg) {
+            std::lock_guard<std::mutex> g(qmu);
+            codes[slot] = code;
+            errs[slot] = msg;
+            failed = true;
+            next.store(n);
+            qcv.notify_all();
+        };
         std::vector<std::thread> threads;
-        for (int l = 0; l < nl; ++l)
+        for (int l = 0; l < nd; ++l)
             threads.emplace_back([&, l] {
                 try {
                     CUDA_CHECK(cudaSetDevice(h->device));
-                    for (int i; (i = next.fetch_add(1)) < n;) out[i] = readtext_page(h, h->lanes[l], imgs[i], *p);
+                    for (int i; (i = next.fetch_add(1)) < n;) {
+                        work[i].index = i;
+                        detect_page(h, h->lanes[l], imgs[i], *p, work[i]);
+                        std::lock_guard<std::mutex> g(qmu);
+                        ready.push_back(i);
+                        ++det_done;
+                        qcv.notify_all();
+                    }
                 } catch (const Error& e) {
-                    errs[l] = e.what();
-                    codes[l] = e.code;
-                    next.store(n);
+                    record(l, e.code, e.what());
                 } catch (const std::exception& e) {
-                    errs[l] = e.what();
-                    codes[l] = BBOCR_E_ARG;
-                    next.store(n);
+                    record(l, BBOCR_E_ARG, e.what());
+                }
+                std::lock_guard<std::mutex> g(qmu);
+                qcv.notify_all();
+            });
+        for (int l = 0; l < nr; ++l)
+            threads.emplace_back([&, l] {
+                try {
+                    CUDA_CHECK(cudaSetDevice(h->device));
+                    Lane& lane = h->lanes[h->n_det_lanes + l];
+                    for (;;) {
+                        std::vector<PageWork*> group;
+                        {
+                            std::unique_lock<std::mutex> g(qmu);
+                            qcv.wait(g, [&] { return failed || (int)ready.size() >= h->rec_group || det_done >= n; });
+                            if (failed) return;
+                            if (ready.empty()) return;              // det_done == n and nothing left
+                            const int take = std::min<int>((int)ready.size(), h->rec_group);
+                            for (int k = 0; k < take; ++k) group.push_back(&work[ready[k]]);
+                            ready.erase(ready.begin(), ready.begin() + take);
+                        }
+                        recognize_group(h, lane, group, *p);
+                        for (PageWork* pw : group) {
+                            out[pw->index] = assemble_page(*pw);
+                            pw->dcrops.release();
+                        }
+                    }
+                } catch (const Error& e) {
+                    record(nd + l, e.code, e.what());
+                } catch (const std::exception& e) {
+                    record(nd + l, BBOCR_E_ARG, e.what());
                 }
             });
         for (auto& t : threads) t.join();
-        for (int l = 0; l < nl; ++l)
+        for (size_t l = 0; l < codes.size(); ++l)
             if (codes[l]) {
                 for (int i = 0; i < n; ++i) { bbocr_results_free(out[i]); out[i] = nullptr; }
                 throw Error(codes[l], errs[l]);

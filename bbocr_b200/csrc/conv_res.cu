@@ -1,0 +1,532 @@
+// conv_res.cu -- 3x3 / pad 1 implicit-GEMM convolution for the LOW-CHANNEL layers, with every operand reused from shared
+// memory (sm_100a).
+//
+// conv_tc.cu fetches one shifted 128-pixel tile AND one weight tile per filter tap.  For Cin, Cout <= 128 that is 24-32 KB
+// of L2->SM traffic per 128..256 tensor-core cycles: the layers at full and half resolution (conv1_2, conv2_x, the last
+// decoder stages) end up bound by the ~60 B/clk an SM can ingest, not by the tensor pipe
+// (profiles/r1_conv_tc_ncu_full.summary.txt: 9x the input volume crosses the L2->SM fabric).  Here
+//   * the CTA's weight slice  [9 taps][Cin][BN]  is loaded ONCE per persistent CTA and stays resident (<= 147 KB);
+//   * the input patch of an output tile -- 8 px wide, 16*MT px high, plus the 1-px halo; TMA out-of-bounds zero fill is the
+//     convolution padding -- is loaded ONCE per 64-channel block (10 x (16 MT + 2) px x 128 B);
+//   * tap (ky,kx) of M-tile mt is nothing but a shifted UMMA descriptor into that patch:
+//         start = patch + ((16 mt + ky) * 10 + kx) * 128 B,   8-row group stride (SBO) = one patch row = 1280 B.
+//     SWIZZLE_128B is a function of absolute shared-memory address bits for both the TMA write and the tensor-core read,
+//     so a start address that is not atom-aligned needs no base offset (verified on B200: tests/test_gpu_conv_tc.py).
+// L2->SM traffic drops from 9 x (16 + BN/8) KB to 23 KB per 128 output pixels; the kernel is then bound by the tensor
+// core's own operand reads from shared memory (N = 64: 48 clk per K = 16 step).
+//
+// Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer (warp-uniform loop, elect.sync for the issue),
+// warp 2 TMEM allocation, warps 4-7 epilogue (folded BN scale/bias, ReLU, optional fused 2x2 / 2x1 max-pool, bf16 NHWC
+// stores) on double-buffered TMEM accumulators.  Each CTA owns one BN-wide slice of the output channels for its whole
+// life (that is what keeps the weights resident) and walks the output tiles with a static stride.
+#include <cuda.h>
+
+#include "engine.h"
+
+namespace bbocr {
+
+CUtensorMap tc_make_map(void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int bk);
+
+namespace {
+
+constexpr int PWX = 10;                 // patch width in pixels: 8 output columns + halo
+constexpr int PPITCH = PWX * 128;       // bytes per patch row (64 bf16 channels per pixel)
+
+struct ResParams {
+    int tiles_x, tiles_y, OH, OW, NIMG;
+    int cout, BN, n_tiles, m_tiles;
+    int relu, out_f32, pool, write_full;
+    void* out;
+    void* out2;
+    const float* scale;
+    const float* bias;
+    int p_stages, patch_stride;
+    long long* trace;                   // optional: per-role cycle sums of CTA 0 (diagnostics)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "RWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra RDONE;\n\t"
+        "bra RWAIT_LOOP;\n\t"
+        "RDONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// K-major SWIZZLE_128B descriptor with an explicit stride between 8-row groups
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void store16(float* o, const float* f, int nbase, int cout) {
+    if ((cout & 3) == 0 && nbase + 16 <= cout) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+        for (int j = 0; j < 16; ++j)
+            if (nbase + j < cout) o[j] = f[j];
+    }
+}
+__device__ __forceinline__ void store16(__nv_bfloat16* o, const float* f, int nbase, int cout) {
+    if ((cout & 7) == 0 && nbase + 16 <= cout) {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+        for (int j = 0; j < 16; ++j)
+            if (nbase + j < cout) o[j] = __float2bfloat16_rn(f[j]);
+    }
+}
+
+struct RTile {
+    int img, x0, y0;
+};
+template <int MT>
+__device__ __forceinline__ RTile rtile(const ResParams& p, int m) {
+    RTile t;
+    int tx = m % p.tiles_x;
+    m /= p.tiles_x;
+    int ty = m % p.tiles_y;
+    t.img = m / p.tiles_y;
+    t.x0 = tx * 8;
+    t.y0 = ty * 16 * MT;
+    return t;
+}
+
+template <int NKB, int MT>
+__global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP,
+                                                     const ResParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t wfull, pfull[8], pempty[8], tfull[2], tempty[2];
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int PATCH_BYTES = (16 * MT + 2) * PPITCH;
+    const int W_TILE = p.BN * 128;                         // one (tap, k-block) weight tile
+    uint8_t* w_base = smem;
+    uint8_t* patch_base = smem + 9 * NKB * W_TILE;         // 9*NKB*BN*128 is a multiple of 1024 (BN % 8 == 0)
+    // epilogue staging (TMA-store sources): 2 x [128 px][BN] bf16 full-resolution tiles, 2 x [32 px][BN] pooled tiles
+    const int ST_BYTES = 128 * p.BN * 2, PST_BYTES = 32 * p.BN * 2;
+    uint8_t* st_base = patch_base + p.p_stages * p.patch_stride;
+    uint8_t* pst_base = st_base + (NKB == 1 ? 2 : 1) * ST_BYTES;      // one tile per epilogue team
+    __shared__ __align__(16) float s_scale[64];
+    __shared__ __align__(16) float s_bias[64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t ncols = 32;
+    while ((int)ncols < 2 * MT * p.BN) ncols <<= 1;
+    // this CTA's slice of the output channels and its share of the M tiles
+    const int nt = blockIdx.x % p.n_tiles, n0 = nt * p.BN;
+    const int m_first = blockIdx.x / p.n_tiles, m_step = gridDim.x / p.n_tiles;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0;
+
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + p.BN) {       // the CTA's channel slice never changes: keep scale/bias in smem
+        s_scale[threadIdx.x - 128] = p.scale[n0 + threadIdx.x - 128];
+        s_bias[threadIdx.x - 128] = p.bias[n0 + threadIdx.x - 128];
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&wfull, 1);
+        for (int s = 0; s < p.p_stages; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (NKB == 1 && MT == 2) ? 8 : 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer: the resident weight slice once, then one patch per (tile, k-block) ----------
+            mbar_expect_tx(&wfull, (uint32_t)(9 * NKB * W_TILE));
+            for (int tap = 0; tap < 9; ++tap)
+                for (int kb = 0; kb < NKB; ++kb) tma_load_3d(w_base + (tap * NKB + kb) * W_TILE, &tmB, &wfull, kb * 64, n0, tap);
+            int pit = 0;
+            for (int m = m_first; m < p.m_tiles; m += m_step) {
+                const RTile tc = rtile<MT>(p, m);
+                for (int kb = 0; kb < NKB; ++kb, ++pit) {
+                    const int ps = pit % p.p_stages;
+                    mbar_wait(&pempty[ps], ((pit / p.p_stages) & 1) ^ 1);
+                    mbar_expect_tx(&pfull[ps], (uint32_t)PATCH_BYTES);
+                    tma_load_4d(patch_base + ps * p.patch_stride, &tmA, &pfull[ps], kb * 64, tc.x0 - 1, tc.y0 - 1, tc.img);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (whole warp walks the loop; one elected lane issues) ----------------
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t w_addr = smem_u32(w_base), p_addr = smem_u32(patch_base);
+        long long c_tempty = 0, c_pfull = 0, c_issue = 0, t0 = 0;
+        int pit = 0, ti = 0;
+        mbar_wait(&wfull, 0);
+        for (int m = m_first; m < p.m_tiles; m += m_step, ++ti) {
+            const int as = ti & 1;
+            if (tr) t0 = clock64();
+            mbar_wait(&tempty[as], ((ti >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tr) { long long t1 = clock64(); c_tempty += t1 - t0; t0 = t1; }
+            const uint32_t tacc = tmem_base + (uint32_t)(as * MT * p.BN);
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb, ++pit) {
+                const int ps = pit % p.p_stages;
+                mbar_wait(&pfull[ps], (pit / p.p_stages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tr) { long long t1 = clock64(); c_pfull += t1 - t0; t0 = t1; }
+                if (elect_one()) {
+                    const uint64_t a0 = desc_sw128(p_addr + ps * p.patch_stride, PPITCH);
+                    const uint64_t b0 = desc_sw128(w_addr + kb * W_TILE, 1024);
+                    const uint32_t wstep = (uint32_t)(NKB * W_TILE) >> 4;            // descriptor units (16 B) per tap
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int ky = tap / 3, kx = tap % 3;
+                            const uint64_t ad = a0 + (uint64_t)((((mt * 16 + ky) * PWX + kx) * 128) >> 4);
+                            const uint64_t bd = b0 + (uint64_t)(tap * wstep);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_bf16(tacc + (uint32_t)(mt * p.BN), ad + 2 * kk, bd + 2 * kk, idesc, (kb | tap | kk) ? 1u : 0u);
+                        }
+                    umma_commit(&pempty[ps]);
+                    if (kb == NKB - 1) umma_commit(&tfull[as]);
+                }
+                __syncwarp();
+                if (tr) { long long t1 = clock64(); c_issue += t1 - t0; t0 = t1; }
+            }
+        }
+        if (tr && lane == 0) { p.trace[0] = c_tempty; p.trace[1] = c_pfull; p.trace[2] = c_issue; p.trace[3] = ti; }
+    } else if (warp >= 4) {
+        // ---------------- epilogue: M-tile mt = 8 px wide x 16 px high; TMEM lane r = hl * 8 + wl ----------------
+        // TMEM -> registers -> folded BN (+ReLU) -> bf16 -> swizzled smem tile -> ONE TMA store per tile (the TMA unit does
+        // the address generation and clips partial tiles); the 2x2 max-pool is taken from the staged bf16 tile (max commutes
+        // with the rounding) and stored the same way.
+        // Two independent teams of four warps take alternate M-tiles (own staging buffer, own named barrier), so an M-tile's
+        // epilogue may take twice the tensor-core time of an M-tile before it stalls the MMA issuer.  Two-k-block layers
+        // spend twice as long per M-tile on the tensor core and get by with one team (their weights need the smem).
+        constexpr int N_TEAMS = NKB == 1 ? 2 : 1;
+        const int team = (warp - 4) >> 2;
+        const int bar_id = 1 + team;
+        const int wq = warp & 3;
+        const int r = wq * 32 + lane;                      // TMEM lane = row of the staged tile
+        const int et = (threadIdx.x - 128) & 127;          // 0..127 within the team
+        const bool leader = et == 0;
+        const int chunks = p.BN >> 3;                      // 16-byte chunks per pixel (8 for BN = 64, 4 for BN = 32)
+        const int row_bytes = p.BN * 2;
+        // 16-byte chunk c of row q sits at (c ^ f(q)) : SWIZZLE_128B f = q & 7 (128-byte rows), SWIZZLE_64B f = (q >> 1) & 3
+        auto swz = [&](int q, int c) { return p.BN == 64 ? (c ^ (q & 7)) : (c ^ ((q >> 1) & 3)); };
+        long long c_wait = 0, c_work = 0, t0 = 0;
+        int ti = 0;
+        uint8_t* st = st_base + team * ST_BYTES;
+        uint8_t* pst = pst_base + team * PST_BYTES;
+        if (team < N_TEAMS)
+        for (int m = m_first; m < p.m_tiles; m += m_step, ++ti) {
+            if (MT == 1 && (ti % N_TEAMS) != team) continue;
+            const RTile tc = rtile<MT>(p, m);
+            const int as = ti & 1;
+            if (tr) t0 = clock64();
+            mbar_wait(&tfull[as], (ti >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tr) { long long t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                if (MT == 2 && (mt % N_TEAMS) != team) continue;
+                const uint32_t trow = tmem_base + (uint32_t)((as * MT + mt) * p.BN) + ((uint32_t)(wq * 32) << 16);
+                uint32_t w[32];                                // the thread's pixel: up to 64 bf16 channels
+#pragma unroll
+                for (int c = 0; c < 64; c += 32) {
+                    if (c < p.BN) {
+                        uint32_t v[32];
+                        tmem_ld32(trow + c, v);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + j);
+                            const float4 bi = *reinterpret_cast<const float4*>(s_bias + c + j);
+                            float a0 = fmaf(__uint_as_float(v[j]), sc.x, bi.x), a1 = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
+                            float a2 = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z), a3 = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
+                            if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+                            __nv_bfloat162 lo2 = __floats2bfloat162_rn(a0, a1), hi2 = __floats2bfloat162_rn(a2, a3);
+                            w[(c + j) >> 1] = *reinterpret_cast<uint32_t*>(&lo2);
+                            w[((c + j) >> 1) + 1] = *reinterpret_cast<uint32_t*>(&hi2);
+                        }
+                    }
+                }
+                if (mt == MT - 1 || N_TEAMS == 2) {            // this team is done with the tile's accumulators
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                }
+                // the TMA store that read this team's staging tile last time has finished reading it (it had the whole
+                // accumulator drain above to do so)
+                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (q < chunks)
+                        *reinterpret_cast<uint4*>(st + r * row_bytes + (swz(r, q) << 4)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (p.pool) {
+                    // pooled tile: 4 px wide x 8 px high; thread -> pooled pixel pp, 16-byte chunk(s) of its channels
+                    const int per = chunks >> 2;               // chunks per thread (2 for BN = 64, 1 for BN = 32)
+                    const int pp = et >> 2, py = pp >> 2, px = pp & 3;
+                    const int r00 = (2 * py) * 8 + 2 * px;
+                    for (int k = 0; k < per; ++k) {
+                        const int c = (et & 3) * per + k;
+                        const uint4 q00 = *reinterpret_cast<const uint4*>(st + r00 * row_bytes + (swz(r00, c) << 4));
+                        const uint4 q01 = *reinterpret_cast<const uint4*>(st + (r00 + 1) * row_bytes + (swz(r00 + 1, c) << 4));
+                        const uint4 q10 = *reinterpret_cast<const uint4*>(st + (r00 + 8) * row_bytes + (swz(r00 + 8, c) << 4));
+                        const uint4 q11 = *reinterpret_cast<const uint4*>(st + (r00 + 9) * row_bytes + (swz(r00 + 9, c) << 4));
+                        auto mx = [](uint32_t a, uint32_t b) {
+                            __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a), y = *reinterpret_cast<__nv_bfloat162*>(&b);
+                            __nv_bfloat162 z = __hmax2(x, y);
+                            return *reinterpret_cast<uint32_t*>(&z);
+                        };
+                        uint4 o;
+                        o.x = mx(mx(q00.x, q01.x), mx(q10.x, q11.x));
+                        o.y = mx(mx(q00.y, q01.y), mx(q10.y, q11.y));
+                        o.z = mx(mx(q00.z, q01.z), mx(q10.z, q11.z));
+                        o.w = mx(mx(q00.w, q01.w), mx(q10.w, q11.w));
+                        *reinterpret_cast<uint4*>(pst + pp * row_bytes + (swz(pp, c) << 4)) = o;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                }
+                if (leader) {
+                    const int y0 = tc.y0 + mt * 16;
+                    if (!p.pool || p.write_full)
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmO),
+                                     "r"(smem_u32(st)), "r"(n0), "r"(tc.x0), "r"(y0), "r"(tc.img)
+                                     : "memory");
+                    if (p.pool)
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmP),
+                                     "r"(smem_u32(pst)), "r"(n0), "r"(tc.x0 >> 1), "r"(y0 >> 1), "r"(tc.img)
+                                     : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            if (tr) { long long t1 = clock64(); c_work += t1 - t0; t0 = t1; }
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all stores have landed before the CTA exits
+        if (tr && warp == 4 && lane == 0) { p.trace[4] = c_wait; p.trace[5] = c_work; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+int res_mode() {          // BBOCR_RES=0 turns the kernel off (A/B against conv_tc.cu)
+    static const int m = getenv("BBOCR_RES") ? atoi(getenv("BBOCR_RES")) : 1;
+    return m;
+}
+
+struct ResPlan {
+    int nkb, BN, MT, p_stages, patch_stride;
+    size_t smem;
+};
+bool res_plan(const ConvW& cw, const Act& in1, const Act& out, ResPlan& pl) {
+    pl.nkb = in1.C / 64;
+    if (pl.nkb < 1 || pl.nkb > 2) return false;
+    // two-k-block layers are tensor-bound at N = 64 (48 clk per step) and lose to conv_tc.cu's N = 128/256 tiles: forced mode only
+    if (pl.nkb == 2 && res_mode() != 2) return false;
+    pl.BN = std::min(cw.cout_pad, 64);
+    if ((pl.BN != 32 && pl.BN != 64) || cw.cout % pl.BN != 0) return false;      // staged tile rows of 64 / 128 bytes
+    const size_t wbytes = (size_t)9 * pl.nkb * pl.BN * 128;
+    const size_t staging = (size_t)(pl.nkb == 1 ? 2 : 1) * (128 + 32) * pl.BN * 2;       // one tile + pooled tile per epilogue team
+    const size_t budget = 226 * 1024 - 1024 - wbytes - staging;
+    for (int mt = 2; mt >= 1; --mt) {
+        if (mt == 2 && (out.H < 32 || pl.nkb > 1)) continue;
+        if (2 * mt * pl.BN > 512) continue;
+        const int stride = (((16 * mt + 2) * PPITCH) + 1023) & ~1023;
+        const int stages = (int)std::min<size_t>(4, budget / stride);
+        if (stages >= 2) {
+            pl.MT = mt;
+            pl.p_stages = stages;
+            pl.patch_stride = stride;
+            pl.smem = wbytes + (size_t)stages * stride + staging + 1024;
+            return true;
+        }
+    }
+    return false;
+}
+
+}  // namespace
+
+bool conv_res_supported(const ConvW& cw, const Act& in1, const Act& in2, const Act& out) {
+    if (!res_mode()) return false;
+    if (cw.kh != 3 || cw.kw != 3 || cw.pad != 1 || cw.dil != 1) return false;
+    if (in2.C != 0 || in1.C % 64 != 0 || !cw.w_bf16) return false;
+    if (out.H < 16 || out.W < 8 || out.H % 2 || out.W % 2) return false;
+    // worth it only where many tiles amortise the resident-weight load
+    if (res_mode() != 2 && (int64_t)out.N * out.H * out.W < (int64_t)128 * 148 * 4) return false;      // 2: tests force it
+    ResPlan pl;
+    return res_plan(cw, in1, out, pl);
+}
+
+void conv_res_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags,
+                      Act* pooled) {
+    ResPlan pl;
+    ARG_CHECK(res_plan(cw, in1, out, pl), "conv_res: unsupported geometry");
+    ResParams p;
+    p.OH = out.H; p.OW = out.W; p.NIMG = out.N;
+    p.cout = cw.cout;
+    p.BN = pl.BN;
+    p.n_tiles = cw.cout_pad / pl.BN;
+    p.tiles_x = cdiv(out.W, 8);
+    p.tiles_y = cdiv(out.H, 16 * pl.MT);
+    p.m_tiles = p.tiles_x * p.tiles_y * out.N;
+    p.relu = (flags & CONV_RELU) ? 1 : 0;
+    ARG_CHECK(!(flags & CONV_OUT_F32) && !(flags & CONV_POOL21), "conv_res: bf16 outputs and 2x2 pooling only");
+    p.out_f32 = 0;
+    p.out = out.p;
+    p.out2 = nullptr;
+    p.pool = 0;
+    p.write_full = 1;
+    p.scale = cw.scale;
+    p.bias = cw.bias;
+    p.p_stages = pl.p_stages;
+    p.patch_stride = pl.patch_stride;
+    p.trace = nullptr;
+    if (pooled) {
+        p.pool = (flags & CONV_POOL22) ? 1 : 2;
+        ARG_CHECK(out.H % 2 == 0 && (p.pool == 2 || out.W % 2 == 0), "fused pooling needs even output dimensions");
+        p.out2 = pooled->p;
+        p.write_full = out.p != nullptr;
+    }
+    uint64_t dims[4] = {(uint64_t)in1.C, (uint64_t)in1.W, (uint64_t)in1.H, (uint64_t)in1.N};
+    uint64_t str[3] = {(uint64_t)in1.C * 2, (uint64_t)in1.W * in1.C * 2, (uint64_t)in1.H * in1.W * in1.C * 2};
+    uint32_t box[4] = {64, (uint32_t)PWX, (uint32_t)(16 * pl.MT + 2), 1};
+    CUtensorMap mA = tc_make_map(in1.p, 4, dims, str, box, 64);
+    uint64_t wd[3] = {(uint64_t)cw.cin, (uint64_t)cw.cout_pad, 9};
+    uint64_t ws[2] = {(uint64_t)cw.cin * 2, (uint64_t)cw.cout_pad * cw.cin * 2};
+    uint32_t wb[3] = {64, (uint32_t)pl.BN, 1};
+    CUtensorMap mB = tc_make_map(cw.w_bf16, 3, wd, ws, wb, 64);
+    // TMA-store maps: full-resolution tile [BN ch x 8 px x 16 rows], pooled tile [BN ch x 4 px x 8 rows]
+    auto out_map = [&](void* base, int OH, int OW, uint32_t bw, uint32_t bh) {
+        uint64_t od[4] = {(uint64_t)cw.cout, (uint64_t)OW, (uint64_t)OH, (uint64_t)out.N};
+        uint64_t os[3] = {(uint64_t)cw.cout * 2, (uint64_t)OW * cw.cout * 2, (uint64_t)OH * OW * cw.cout * 2};
+        uint32_t ob[4] = {(uint32_t)pl.BN, bw, bh, 1};
+        return tc_make_map(base, 4, od, os, ob, pl.BN);
+    };
+    CUtensorMap mO = p.write_full && out.p ? out_map(out.p, out.H, out.W, 8, 16) : mA;
+    CUtensorMap mP = p.pool ? out_map(p.out2, out.H / 2, out.W / 2, 4, 8) : mO;
+    // persistent grid: one CTA per SM, a multiple of the number of channel slices
+    int grid = std::min(h->sm_count, p.m_tiles * p.n_tiles);
+    grid -= grid % p.n_tiles;
+    ARG_CHECK(grid >= p.n_tiles, "conv_res: grid too small");
+    static const bool want_trace = getenv("BBOCR_RES_TRACE") != nullptr;
+    DevBuf dtrace;
+    if (want_trace) {
+        dtrace.alloc(8 * 8, st);
+        CUDA_CHECK(cudaMemsetAsync(dtrace.p, 0, 64, st));
+        p.trace = dtrace.as<long long>();
+    }
+    if (!h->res_attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        h->res_attr_set = true;
+    }
+    if (pl.nkb == 1 && pl.MT == 2) k_conv_res<1, 2><<<grid, 384, pl.smem, st>>>(mA, mB, mO, mP, p);
+    else if (pl.nkb == 1) k_conv_res<1, 1><<<grid, 384, pl.smem, st>>>(mA, mB, mO, mP, p);
+    else k_conv_res<2, 1><<<grid, 384, pl.smem, st>>>(mA, mB, mO, mP, p);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+    if (want_trace) {
+        long long t[8];
+        CUDA_CHECK(cudaMemcpyAsync(t, p.trace, 64, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        const double n = t[3] > 0 ? (double)t[3] : 1.0;
+        fprintf(stderr, "[conv_res trace] %dx%d cin %d cout %d BN %d MT %d stages %d grid %d | CTA0: %lld tiles; per tile: mma wait-tmem %.0f "
+                        "wait-patch %.0f issue %.0f | epilogue wait %.0f work %.0f cycles\n",
+                out.H, out.W, cw.cin, cw.cout, pl.BN, pl.MT, pl.p_stages, grid, t[3], t[0] / n, t[1] / n, t[2] / n, t[4] / n, t[5] / n);
+    }
+}
+
+}  // namespace bbocr

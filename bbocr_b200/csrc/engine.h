@@ -40,11 +40,13 @@ struct Handle {
     CraftW craft;
     CrnnW crnn;
     std::vector<void*> owned;       // weight allocations
-    std::vector<Lane> lanes;
+    std::vector<Lane> lanes;         // [0, n_det_lanes) detector lanes, then the recogniser lanes
+    int n_det_lanes = 8;
+    int rec_group = 16;              // pages per recogniser launch group (bbocr_readtext_batch)
     // dominant-kernel instrumentation (bench.py roofline): CUDA events around every implicit-GEMM conv launch
     bool conv_timing = false;
     bool force_generic_conv = false; // test hook: route BF16-mode convolutions through the CUDA-core kernel
-    bool tc_attr_set = false, halo_attr_set = false, lstm_attr_set = false;
+    bool tc_attr_set = false, halo_attr_set = false, lstm_attr_set = false, lstm_mma_attr_set = false, res_attr_set = false;
     std::mutex stat_mu;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
     double conv_flops = 0;
@@ -105,6 +107,10 @@ void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const 
 // conv_halo.cu : 3x3 / pad 1 convolutions with the input patch loaded once per channel block (all nine taps from smem)
 bool conv_halo_supported(const ConvW&, const Act& in1, const Act& in2, const Act& out);
 void conv_halo_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled);
+
+// conv_res.cu : 3x3 / pad 1 convolutions of the low-channel layers with resident weights and a halo patch per tile
+bool conv_res_supported(const ConvW&, const Act& in1, const Act& in2, const Act& out);
+void conv_res_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled);
 
 // ---- weights.cu ------------------------------------------------------------------------------------------------------
 void load_craft(Handle*, const bbocr_tensor* t, int n);
@@ -176,6 +182,10 @@ int lstm_group_size(const Handle*);
 void lstm_sequences_tc(Handle*, Lane&, const float* gates_in, const float* w_hh, int n_seq, const SeqDesc* seqs_dev,
                        const int* groups_dev, int n_groups, void* out);
 int lstm_tc_group_size();
+// lstm_mma.cu: 128 crops per 16-CTA cluster, split-precision tcgen05 recurrence (throughput mode default)
+void lstm_sequences_mma(Handle*, Lane&, const float* gates_in, const float* w_hh, int n_seq, const SeqDesc* seqs_dev,
+                        const int* groups_dev, int n_groups, void* out, void* out_lo, int out_mode);
+int lstm_mma_group_size();
 // greedy CTC over all rows: per-row argmax / renormalised max probability, then per-sequence collapse
 void ctc_decode_dev(Handle*, cudaStream_t, const float* logits, int rows, int C, const uint8_t* ignore_dev,
                     const SeqDesc* seqs_dev, int n_seq, int32_t* text_idx /*[rows]*/, int32_t* text_len /*[n_seq]*/,

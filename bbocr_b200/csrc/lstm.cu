@@ -152,12 +152,31 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
 
 }  // namespace
 
+// recurrence kernel: FP32 mode = the CUDA-core cluster kernel above (parity mode).  BF16 (throughput) mode = lstm_mma.cu
+// (BBOCR_LSTM=cluster | tf32 select the older kernels for comparison).
+static int lstm_variant(const Handle* h) {
+    if (h->precision != BBOCR_PREC_BF16 || h->force_generic_conv) return 0;
+    static const int v = [] {
+        const char* e = getenv("BBOCR_LSTM");
+        if (!e) return 2;
+        if (!strcmp(e, "cluster")) return 0;
+        if (!strcmp(e, "tf32")) return 1;
+        return 2;
+    }();
+    return v;
+}
+
 // seqs: device array of n_seq descriptors; the host copy is used to form groups of NB sequences of similar length
 void lstm_sequences(Handle* h, Lane& lane, const float* gates_in, const float* w_hh, const SeqDesc* seqs_host, int n_seq,
                     const SeqDesc* seqs_dev, const int* groups_dev, int n_groups, void* out, void* out_lo) {
     cudaStream_t st = lane.stream;
     if (n_seq == 0) return;
-    if (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && !out_lo && getenv("BBOCR_LSTM_TF32")) {   // optional TF32 tensor-core mat-vec
+    const int variant = lstm_variant(h);
+    if (variant == 2) {            // crops on the UMMA M dimension, split precision (lstm_mma.cu)
+        lstm_sequences_mma(h, lane, gates_in, w_hh, n_seq, seqs_dev, groups_dev, n_groups, out, out_lo, out_lo ? 1 : 0);
+        return;
+    }
+    if (variant == 1 && !out_lo) { // optional TF32 tensor-core mat-vec (lstm_tc.cu)
         lstm_sequences_tc(h, lane, gates_in, w_hh, n_seq, seqs_dev, groups_dev, n_groups, out);
         return;
     }
@@ -185,7 +204,8 @@ void lstm_sequences(Handle* h, Lane& lane, const float* gates_in, const float* w
 }
 
 int lstm_group_size(const Handle* h) {
-    return (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && getenv("BBOCR_LSTM_TF32")) ? lstm_tc_group_size() : NB;
+    const int v = lstm_variant(h);
+    return v == 2 ? lstm_mma_group_size() : (v == 1 ? lstm_tc_group_size() : NB);
 }
 
 }  // namespace bbocr

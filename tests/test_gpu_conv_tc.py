@@ -25,6 +25,10 @@ SHAPES = [
     (3, 32, 36, 64, 0, 128, 3, 1, 1),       # CRNN conv3, batch of crops
     (1, 30, 40, 256, 512, 256, 1, 0, 1),    # upconv2 1x1 concat
     (1, 8, 8, 512, 0, 512, 3, 1, 1),
+    (1, 70, 44, 64, 0, 64, 3, 1, 1),        # conv_res.cu: two stacked M tiles per patch, partial tiles on both edges
+    (2, 40, 24, 128, 0, 64, 3, 1, 1),       # conv_res.cu: two 64-channel k-blocks per tile
+    (1, 34, 20, 64, 0, 32, 3, 1, 1),        # conv_res.cu: N = 32
+    (1, 48, 32, 128, 0, 128, 3, 1, 1),      # conv_res.cu: two resident channel slices of 64
 ]
 
 
@@ -93,6 +97,18 @@ def test_halo_patch_kernel_in_subprocess():
     import subprocess
     import sys
     env = dict(os.environ, BBOCR_HALO="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "matches_cuda_core"], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_resident_weight_kernel_in_subprocess():
+    """conv_res.cu (resident weights + halo patch) only takes layers with >= 75 k output pixels by default; BBOCR_RES=2
+    forces it for every supported geometry, so the same shape sweep runs through it (mode latched per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, BBOCR_RES="2")
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "matches_cuda_core"], env=env,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -81,6 +81,21 @@ def test_crnn_bf16_string_rate(gpu_reader, oracle_reader):
     assert rate >= 0.995
 
 
+def test_crnn_bf16_two_lstm_groups(gpu_reader, oracle_reader):
+    """> 128 crops: the throughput-mode recurrence (lstm_mma.cu) runs two 16-CTA clusters per direction, the second one
+    partly empty; logits must stay FP32-class for every crop."""
+    x = _inputs(150, 128, 11)
+    want = oracle_reader.logits(x).numpy()
+    gpu_reader.set_precision("bf16")
+    try:
+        got = gpu_reader.handle.crnn_forward(x)
+    finally:
+        gpu_reader.set_precision("fp32")
+    err = np.abs(got - want).reshape(150, -1).max(1)
+    print("worst crop", int(err.argmax()), "max-abs", float(err.max()), "logit range", float(np.abs(want).max()))
+    assert err.max() < 1e-3 * np.abs(want).max()
+
+
 def test_ctc_decode_exact_given_logits(gpu_reader, oracle_reader):
     x = _inputs(16, 320, 9)
     logits = oracle_reader.logits(x)
