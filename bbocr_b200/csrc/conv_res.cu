@@ -29,8 +29,19 @@ CUtensorMap tc_make_map(void* base, int rank, const uint64_t* dims, const uint64
 
 namespace {
 
-constexpr int PWX = 10;                 // patch width in pixels: 8 output columns + halo
-constexpr int PPITCH = PWX * 128;       // bytes per patch row (64 bf16 channels per pixel)
+// Geometry of one variant: KB channels per k-block (64 -> 128-byte pixel rows, SWIZZLE_128B; 32 -> 64-byte rows, SWIZZLE_64B),
+// TAPS = 9 (3x3, pad 1: 1-px halo) or 1 (1x1: the patch is the tile itself), MT M-tiles of 8 x 16 px stacked vertically.
+template <int KB, int TAPS, int MT>
+struct Geo {
+    static constexpr int PIX = KB * 2;                       // bytes per pixel row of the operand tiles
+    static constexpr int HALO = TAPS == 9 ? 1 : 0;
+    static constexpr int PW = 8 + 2 * HALO;                  // patch width in pixels
+    static constexpr int PH = 16 * MT + 2 * HALO;            // patch height
+    static constexpr int PPITCH = PW * PIX;                  // bytes per patch row = stride between 8-pixel groups
+    static constexpr int PATCH_BYTES = PH * PPITCH;
+    static constexpr int KSTEPS = KB / 16;                   // UMMA_K = 16 steps per k-block
+    static constexpr uint64_t LAYOUT = KB == 64 ? 2 : 4;     // UMMA layout code: SWIZZLE_128B / SWIZZLE_64B
+};
 
 struct ResParams {
     int tiles_x, tiles_y, OH, OW, NIMG;
@@ -92,9 +103,9 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
         "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-// K-major SWIZZLE_128B descriptor with an explicit stride between 8-row groups
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// K-major swizzled descriptor with an explicit stride between 8-row groups
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t sbo_bytes, uint64_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -170,7 +181,7 @@ __device__ __forceinline__ RTile rtile(const ResParams& p, int m) {
     return t;
 }
 
-template <int NKB, int MT>
+template <int KB, int TAPS, int NKB, int MT>
 __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP,
                                                      const ResParams p) {
@@ -178,10 +189,11 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
     __shared__ uint64_t wfull, pfull[8], pempty[8], tfull[2], tempty[2];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int PATCH_BYTES = (16 * MT + 2) * PPITCH;
-    const int W_TILE = p.BN * 128;                         // one (tap, k-block) weight tile
+    using G = Geo<KB, TAPS, MT>;
+    constexpr int PATCH_BYTES = G::PATCH_BYTES;
+    const int W_TILE = p.BN * G::PIX;                      // one (tap, k-block) weight tile
     uint8_t* w_base = smem;
-    uint8_t* patch_base = smem + 9 * NKB * W_TILE;         // 9*NKB*BN*128 is a multiple of 1024 (BN % 8 == 0)
+    uint8_t* patch_base = smem + ((TAPS * NKB * W_TILE + 1023) & ~1023);
     // epilogue staging (TMA-store sources): 2 x [128 px][BN] bf16 full-resolution tiles, 2 x [32 px][BN] pooled tiles
     const int ST_BYTES = 128 * p.BN * 2, PST_BYTES = 32 * p.BN * 2;
     uint8_t* st_base = patch_base + p.p_stages * p.patch_stride;
@@ -223,9 +235,9 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer: the resident weight slice once, then one patch per (tile, k-block) ----------
-            mbar_expect_tx(&wfull, (uint32_t)(9 * NKB * W_TILE));
-            for (int tap = 0; tap < 9; ++tap)
-                for (int kb = 0; kb < NKB; ++kb) tma_load_3d(w_base + (tap * NKB + kb) * W_TILE, &tmB, &wfull, kb * 64, n0, tap);
+            mbar_expect_tx(&wfull, (uint32_t)(TAPS * NKB * W_TILE));
+            for (int tap = 0; tap < TAPS; ++tap)
+                for (int kb = 0; kb < NKB; ++kb) tma_load_3d(w_base + (tap * NKB + kb) * W_TILE, &tmB, &wfull, kb * KB, n0, tap);
             int pit = 0;
             for (int m = m_first; m < p.m_tiles; m += m_step) {
                 const RTile tc = rtile<MT>(p, m);
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
                     const int ps = pit % p.p_stages;
                     mbar_wait(&pempty[ps], ((pit / p.p_stages) & 1) ^ 1);
                     mbar_expect_tx(&pfull[ps], (uint32_t)PATCH_BYTES);
-                    tma_load_4d(patch_base + ps * p.patch_stride, &tmA, &pfull[ps], kb * 64, tc.x0 - 1, tc.y0 - 1, tc.img);
+                    tma_load_4d(patch_base + ps * p.patch_stride, &tmA, &pfull[ps], kb * KB, tc.x0 - G::HALO, tc.y0 - G::HALO, tc.img);
                 }
             }
         }
@@ -258,18 +270,18 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tr) { long long t1 = clock64(); c_pfull += t1 - t0; t0 = t1; }
                 if (elect_one()) {
-                    const uint64_t a0 = desc_sw128(p_addr + ps * p.patch_stride, PPITCH);
-                    const uint64_t b0 = desc_sw128(w_addr + kb * W_TILE, 1024);
+                    const uint64_t a0 = desc_kmajor(p_addr + ps * p.patch_stride, G::PPITCH, G::LAYOUT);
+                    const uint64_t b0 = desc_kmajor(w_addr + kb * W_TILE, 8 * G::PIX, G::LAYOUT);
                     const uint32_t wstep = (uint32_t)(NKB * W_TILE) >> 4;            // descriptor units (16 B) per tap
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
+                        for (int tap = 0; tap < TAPS; ++tap) {
                             const int ky = tap / 3, kx = tap % 3;
-                            const uint64_t ad = a0 + (uint64_t)((((mt * 16 + ky) * PWX + kx) * 128) >> 4);
+                            const uint64_t ad = a0 + (uint64_t)((((mt * 16 + ky) * G::PW + kx) * G::PIX) >> 4);
                             const uint64_t bd = b0 + (uint64_t)(tap * wstep);
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
+                            for (int kk = 0; kk < G::KSTEPS; ++kk)
                                 umma_bf16(tacc + (uint32_t)(mt * p.BN), ad + 2 * kk, bd + 2 * kk, idesc, (kb | tap | kk) ? 1u : 0u);
                         }
                     umma_commit(&pempty[ps]);
@@ -407,23 +419,28 @@ int res_mode() {          // BBOCR_RES=0 turns the kernel off (A/B against conv_
 }
 
 struct ResPlan {
-    int nkb, BN, MT, p_stages, patch_stride;
+    int kb, taps, nkb, BN, MT, p_stages, patch_stride;
     size_t smem;
 };
 bool res_plan(const ConvW& cw, const Act& in1, const Act& out, ResPlan& pl) {
-    pl.nkb = in1.C / 64;
+    pl.taps = cw.kh * cw.kw;
+    if (in1.C % 64 == 0) { pl.kb = 64; pl.nkb = in1.C / 64; }
+    else if (in1.C == 32) { pl.kb = 32; pl.nkb = 1; }
+    else return false;
     if (pl.nkb < 1 || pl.nkb > 2) return false;
+    if (pl.taps == 1 && pl.kb != 32) return false;              // the 1x1 variant exists for the K = 32 stem (conv1_1)
     // two-k-block layers are tensor-bound at N = 64 (48 clk per step) and lose to conv_tc.cu's N = 128/256 tiles: forced mode only
     if (pl.nkb == 2 && res_mode() != 2) return false;
     pl.BN = std::min(cw.cout_pad, 64);
     if ((pl.BN != 32 && pl.BN != 64) || cw.cout % pl.BN != 0) return false;      // staged tile rows of 64 / 128 bytes
-    const size_t wbytes = (size_t)9 * pl.nkb * pl.BN * 128;
+    const int pix = pl.kb * 2, halo = pl.taps == 9 ? 1 : 0;
+    const size_t wbytes = ((size_t)pl.taps * pl.nkb * pl.BN * pix + 1023) & ~(size_t)1023;
     const size_t staging = (size_t)(pl.nkb == 1 ? 2 : 1) * (128 + 32) * pl.BN * 2;       // one tile + pooled tile per epilogue team
     const size_t budget = 226 * 1024 - 1024 - wbytes - staging;
     for (int mt = 2; mt >= 1; --mt) {
         if (mt == 2 && (out.H < 32 || pl.nkb > 1)) continue;
         if (2 * mt * pl.BN > 512) continue;
-        const int stride = (((16 * mt + 2) * PPITCH) + 1023) & ~1023;
+        const int stride = (((16 * mt + 2 * halo) * (8 + 2 * halo) * pix) + 1023) & ~1023;
         const int stages = (int)std::min<size_t>(4, budget / stride);
         if (stages >= 2) {
             pl.MT = mt;
@@ -436,12 +453,23 @@ bool res_plan(const ConvW& cw, const Act& in1, const Act& out, ResPlan& pl) {
     return false;
 }
 
+template <int KB, int TAPS, int NKB, int MT>
+void res_launch(int grid, size_t smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO,
+                const CUtensorMap& mP, const ResParams& p) {
+    static std::once_flag once;        // one device per process in this library (one rank per GPU)
+    std::call_once(once, [] {
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<KB, TAPS, NKB, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    });
+    k_conv_res<KB, TAPS, NKB, MT><<<grid, 384, smem, st>>>(mA, mB, mO, mP, p);
+}
+
 }  // namespace
 
 bool conv_res_supported(const ConvW& cw, const Act& in1, const Act& in2, const Act& out) {
     if (!res_mode()) return false;
-    if (cw.kh != 3 || cw.kw != 3 || cw.pad != 1 || cw.dil != 1) return false;
-    if (in2.C != 0 || in1.C % 64 != 0 || !cw.w_bf16) return false;
+    const bool k3 = cw.kh == 3 && cw.kw == 3 && cw.pad == 1 && cw.dil == 1, k1 = cw.kh == 1 && cw.kw == 1 && cw.pad == 0;
+    if (!k3 && !k1) return false;
+    if (in2.C != 0 || !cw.w_bf16) return false;
     if (out.H < 16 || out.W < 8 || out.H % 2 || out.W % 2) return false;
     // worth it only where many tiles amortise the resident-weight load
     if (res_mode() != 2 && (int64_t)out.N * out.H * out.W < (int64_t)128 * 148 * 4) return false;      // 2: tests force it
@@ -481,12 +509,13 @@ void conv_res_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in
     }
     uint64_t dims[4] = {(uint64_t)in1.C, (uint64_t)in1.W, (uint64_t)in1.H, (uint64_t)in1.N};
     uint64_t str[3] = {(uint64_t)in1.C * 2, (uint64_t)in1.W * in1.C * 2, (uint64_t)in1.H * in1.W * in1.C * 2};
-    uint32_t box[4] = {64, (uint32_t)PWX, (uint32_t)(16 * pl.MT + 2), 1};
-    CUtensorMap mA = tc_make_map(in1.p, 4, dims, str, box, 64);
-    uint64_t wd[3] = {(uint64_t)cw.cin, (uint64_t)cw.cout_pad, 9};
+    const int halo = pl.taps == 9 ? 1 : 0;
+    uint32_t box[4] = {(uint32_t)pl.kb, (uint32_t)(8 + 2 * halo), (uint32_t)(16 * pl.MT + 2 * halo), 1};
+    CUtensorMap mA = tc_make_map(in1.p, 4, dims, str, box, pl.kb);
+    uint64_t wd[3] = {(uint64_t)cw.cin, (uint64_t)cw.cout_pad, (uint64_t)pl.taps};
     uint64_t ws[2] = {(uint64_t)cw.cin * 2, (uint64_t)cw.cout_pad * cw.cin * 2};
-    uint32_t wb[3] = {64, (uint32_t)pl.BN, 1};
-    CUtensorMap mB = tc_make_map(cw.w_bf16, 3, wd, ws, wb, 64);
+    uint32_t wb[3] = {(uint32_t)pl.kb, (uint32_t)pl.BN, 1};
+    CUtensorMap mB = tc_make_map(cw.w_bf16, 3, wd, ws, wb, pl.kb);
     // TMA-store maps: full-resolution tile [BN ch x 8 px x 16 rows], pooled tile [BN ch x 4 px x 8 rows]
     auto out_map = [&](void* base, int OH, int OW, uint32_t bw, uint32_t bh) {
         uint64_t od[4] = {(uint64_t)cw.cout, (uint64_t)OW, (uint64_t)OH, (uint64_t)out.N};
@@ -507,15 +536,17 @@ void conv_res_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in
         CUDA_CHECK(cudaMemsetAsync(dtrace.p, 0, 64, st));
         p.trace = dtrace.as<long long>();
     }
-    if (!h->res_attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        h->res_attr_set = true;
+    const int key = pl.kb * 1000 + pl.taps * 100 + pl.nkb * 10 + pl.MT;
+    switch (key) {
+        case 64000 + 900 + 10 + 2: res_launch<64, 9, 1, 2>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 64000 + 900 + 10 + 1: res_launch<64, 9, 1, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 64000 + 900 + 20 + 1: res_launch<64, 9, 2, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 32000 + 900 + 10 + 2: res_launch<32, 9, 1, 2>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 32000 + 900 + 10 + 1: res_launch<32, 9, 1, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 32000 + 100 + 10 + 2: res_launch<32, 1, 1, 2>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 32000 + 100 + 10 + 1: res_launch<32, 1, 1, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        default: fail(BBOCR_E_ARG, "conv_res: no kernel variant for kb %d taps %d nkb %d MT %d", pl.kb, pl.taps, pl.nkb, pl.MT);
     }
-    if (pl.nkb == 1 && pl.MT == 2) k_conv_res<1, 2><<<grid, 384, pl.smem, st>>>(mA, mB, mO, mP, p);
-    else if (pl.nkb == 1) k_conv_res<1, 1><<<grid, 384, pl.smem, st>>>(mA, mB, mO, mP, p);
-    else k_conv_res<2, 1><<<grid, 384, pl.smem, st>>>(mA, mB, mO, mP, p);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
     if (want_trace) {
@@ -523,9 +554,9 @@ void conv_res_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in
         CUDA_CHECK(cudaMemcpyAsync(t, p.trace, 64, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         const double n = t[3] > 0 ? (double)t[3] : 1.0;
-        fprintf(stderr, "[conv_res trace] %dx%d cin %d cout %d BN %d MT %d stages %d grid %d | CTA0: %lld tiles; per tile: mma wait-tmem %.0f "
+        fprintf(stderr, "[conv_res trace] %dx%d k%d cin %d cout %d BN %d MT %d stages %d grid %d | CTA0: %lld tiles; per tile: mma wait-tmem %.0f "
                         "wait-patch %.0f issue %.0f | epilogue wait %.0f work %.0f cycles\n",
-                out.H, out.W, cw.cin, cw.cout, pl.BN, pl.MT, pl.p_stages, grid, t[3], t[0] / n, t[1] / n, t[2] / n, t[4] / n, t[5] / n);
+                out.H, out.W, cw.kh, cw.cin, cw.cout, pl.BN, pl.MT, pl.p_stages, grid, t[3], t[0] / n, t[1] / n, t[2] / n, t[4] / n, t[5] / n);
     }
 }
 

@@ -29,6 +29,8 @@ SHAPES = [
     (2, 40, 24, 128, 0, 64, 3, 1, 1),       # conv_res.cu: two 64-channel k-blocks per tile
     (1, 34, 20, 64, 0, 32, 3, 1, 1),        # conv_res.cu: N = 32
     (1, 48, 32, 128, 0, 128, 3, 1, 1),      # conv_res.cu: two resident channel slices of 64
+    (1, 36, 28, 32, 0, 32, 3, 1, 1),        # conv_res.cu: 32-channel k-block (SWIZZLE_64B patch), conv_cls geometry
+    (1, 34, 26, 32, 0, 64, 1, 0, 1),        # conv_res.cu: 1x1 over the 32-channel gathered stem (conv1_1)
 ]
 
 
