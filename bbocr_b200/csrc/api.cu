@@ -119,7 +119,7 @@ int bbocr_create(int device, bbocr_handle** out) {
             const char* r = getenv("BBOCR_REC_LANES");    // recogniser groups in flight
             int nr = r ? atoi(r) : 2;
             const char* g = getenv("BBOCR_REC_GROUP");    // pages per recogniser group
-            h->rec_group = std::max(1, g ? atoi(g) : 16);
+            h->rec_group = std::max(1, g ? atoi(g) : 32);
             h->lanes.resize(h->n_det_lanes + std::min(std::max(nr, 1), 8));
         }
         for (auto& l : h->lanes) CUDA_CHECK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
@@ -501,9 +501,134 @@ double confidence_of(const float* prob, const int32_t* idx, int T) {
     return std::pow((double)prod, 2.0 / std::sqrt((double)cnt));
 }
 
+// Throughput-mode variant of recognize_pass: the crops of the pass are laid side by side in strip images (at most
+// `max_cols` columns each) and the feature extractor runs once per strip; the sequence half and the decoder run once.
+void recognize_pass_ragged(Handle* h, Lane& lane, std::vector<CropJob>& jobs, const std::vector<int>& which, const uint8_t* crops,
+                           size_t crops_bytes, const uint8_t* ignore_dev, std::vector<Recognized>& out) {
+    cudaStream_t st = lane.stream;
+    const int n = (int)which.size();
+    out.assign(n, Recognized());
+    if (n == 0) return;
+    constexpr int GAP = 16;
+    static const int max_cols = getenv("BBOCR_REC_COLS") ? std::max(4096, atoi(getenv("BBOCR_REC_COLS"))) : 65536;
+    size_t aligned_extra = 0, scratch_max = 0;
+    for (int i : which)
+        if (jobs[i].tall) {
+            aligned_extra += (size_t)64 * jobs[i].d.resized_w;
+            scratch_max = std::max(scratch_max, (size_t)jobs[i].d.oh * std::max(jobs[i].d.resized_w, jobs[i].d.ow));
+        }
+    DevBuf aligned_buf(crops_bytes + aligned_extra + 16, st), pil_scratch(scratch_max + 16, st);
+    CUDA_CHECK(cudaMemcpyAsync(aligned_buf.p, crops, crops_bytes, cudaMemcpyDeviceToDevice, st));
+    size_t acur = crops_bytes;
+    std::vector<CropDesc> descs(n);
+    std::vector<SeqDesc> seqs(n);
+    int rows = 0, max_w = 0;
+    for (int k = 0; k < n; ++k) {
+        CropJob& j = jobs[which[k]];
+        if (j.tall) {
+            pil_resize_bicubic_dev(h, st, aligned_buf.as<uint8_t>() + j.d.off, j.d.oh, j.d.ow,
+                                   aligned_buf.as<uint8_t>() + acur, 64, j.d.resized_w, pil_scratch.as<uint8_t>());
+            j.d.aoff = (int)acur;
+            acur += (size_t)64 * j.d.resized_w;
+        } else {
+            j.d.aoff = j.d.off;
+        }
+        descs[k] = j.d;
+        const int T = j.d.model_w / 4 - 1;
+        seqs[k] = SeqDesc{rows, T};
+        rows += T;
+        max_w = std::max(max_w, j.d.model_w);
+    }
+    // strips: consecutive crops until the column budget is reached
+    struct Strip { int first, count, Wtot, t_max; };
+    std::vector<Strip> strips;
+    std::vector<int> xoff(n);
+    for (int k = 0; k < n;) {
+        Strip s{k, 0, 0, 0};
+        while (k < n && (s.count == 0 || s.Wtot + descs[k].model_w + GAP <= max_cols)) {
+            xoff[k] = s.Wtot;
+            s.Wtot += descs[k].model_w + GAP;
+            s.t_max = std::max(s.t_max, descs[k].model_w / 4 - 1);
+            ++s.count;
+            ++k;
+        }
+        strips.push_back(s);
+    }
+    // one upload: descs | xoff | meta (col0, T, row0 per crop) | masks of every strip
+    size_t mask_bytes = 0;
+    for (auto& s : strips) mask_bytes += (size_t)s.Wtot / 2 + s.Wtot / 4;
+    const size_t o_desc = 0, o_xoff = o_desc + (size_t)n * sizeof(CropDesc), o_meta = o_xoff + (size_t)n * 4,
+                 o_seq = o_meta + (size_t)n * 12, o_mask = o_seq + (size_t)n * sizeof(SeqDesc),
+                 total = ((o_mask + mask_bytes + 15) & ~(size_t)15);
+    std::vector<uint8_t> blob(total, 0);
+    memcpy(blob.data() + o_desc, descs.data(), (size_t)n * sizeof(CropDesc));
+    memcpy(blob.data() + o_seq, seqs.data(), (size_t)n * sizeof(SeqDesc));
+    memcpy(blob.data() + o_xoff, xoff.data(), (size_t)n * 4);
+    int* meta = reinterpret_cast<int*>(blob.data() + o_meta);
+    std::vector<size_t> strip_mask_off(strips.size());
+    {
+        size_t mo = o_mask;
+        for (size_t q = 0; q < strips.size(); ++q) {
+            const Strip& s = strips[q];
+            strip_mask_off[q] = mo;
+            uint8_t* m1 = blob.data() + mo;
+            uint8_t* m2 = m1 + s.Wtot / 2;
+            for (int k = s.first; k < s.first + s.count; ++k) {
+                memset(m1 + xoff[k] / 2, 1, descs[k].model_w / 2);
+                memset(m2 + xoff[k] / 4, 1, descs[k].model_w / 4);
+                meta[3 * k] = xoff[k] / 4;
+                meta[3 * k + 1] = seqs[k].T;
+                meta[3 * k + 2] = seqs[k].row0;
+            }
+            mo += (size_t)s.Wtot / 2 + s.Wtot / 4;
+        }
+    }
+    DevBuf dblob;
+    upload(lane, dblob, blob.data(), blob.size());
+    const uint8_t* db = dblob.as<uint8_t>();
+    const CropDesc* ddesc = reinterpret_cast<const CropDesc*>(db + o_desc);
+    const int* dxoff = reinterpret_cast<const int*>(db + o_xoff);
+    const int* dmeta = reinterpret_cast<const int*>(db + o_meta);
+    DevBuf seqbuf;
+    Act seq = crnn_alloc_seq(h, st, seqbuf, rows);
+    for (size_t q = 0; q < strips.size(); ++q) {
+        const Strip& s = strips[q];
+        DevBuf strip((size_t)64 * s.Wtot * 4, st);
+        crops_to_strip_dev(h, st, aligned_buf.as<uint8_t>(), ddesc + s.first, dxoff + s.first, s.count, max_w, s.Wtot, strip.as<float>());
+        crnn_features_strip_dev(h, st, strip.as<float>(), s.Wtot, db + strip_mask_off[q], db + strip_mask_off[q] + s.Wtot / 2,
+                                dmeta + 3 * s.first, s.count, s.t_max, seq);
+    }
+    const int C = h->crnn.num_class;
+    DevBuf logits((size_t)rows * C * 4, st);
+    crnn_sequence_dev(h, lane, seq, seqs, logits.as<float>());
+    const SeqDesc* dseq = reinterpret_cast<const SeqDesc*>(db + o_seq);
+    const size_t step_elems = (size_t)rows;
+    DevBuf dec((step_elems * 3 + (size_t)n) * 4, st);
+    int32_t* text_idx = dec.as<int32_t>();
+    int32_t* step_idx = text_idx + step_elems;
+    float* step_prob = reinterpret_cast<float*>(step_idx + step_elems);
+    int32_t* text_len = reinterpret_cast<int32_t*>(step_prob + step_elems);
+    ctc_decode_dev(h, st, logits.as<float>(), rows, C, ignore_dev, dseq, n, text_idx, text_len, step_prob, step_idx);
+    std::vector<int32_t> hdec(step_elems * 3 + n);
+    download(lane, hdec.data(), dec.p, hdec.size() * 4);
+    const int32_t* h_text = hdec.data();
+    const int32_t* h_sidx = h_text + step_elems;
+    const float* h_prob = reinterpret_cast<const float*>(h_sidx + step_elems);
+    const int32_t* h_len = reinterpret_cast<const int32_t*>(h_prob + step_elems);
+    for (int k = 0; k < n; ++k) {
+        const size_t so = (size_t)seqs[k].row0;
+        out[k].text.assign(h_text + so, h_text + so + h_len[k]);
+        out[k].conf = confidence_of(h_prob + so, h_sidx + so, seqs[k].T);
+    }
+}
+
 // One pass of AlignCollate -> CRNN -> decode over `jobs` whose (possibly contrast-adjusted) crops live in `crops`.
 void recognize_pass(Handle* h, Lane& lane, std::vector<CropJob>& jobs, const std::vector<int>& which, const uint8_t* crops,
                     size_t crops_bytes, const uint8_t* ignore_dev, std::vector<Recognized>& out) {
+    if (crnn_ragged(h)) {
+        recognize_pass_ragged(h, lane, jobs, which, crops, crops_bytes, ignore_dev, out);
+        return;
+    }
     cudaStream_t st = lane.stream;
     const int n = (int)which.size();
     out.assign(n, Recognized());
@@ -924,7 +1049,8 @@ int bbocr_readtext_batch(bbocr_handle* h, int n, const bbocr_image* imgs, const 
                             for (int k = 0; k < take; ++k) group.push_back(&work[ready[k]]);
                             ready.erase(ready.begin(), ready.begin() + take);
                         }
-                        recognize_group(h, lane, group, *p);
+                        static const bool skip_rec = getenv("BBOCR_DIAG_SKIP_REC") != nullptr;     // diagnostics: detector-only throughput
+                        if (!skip_rec) recognize_group(h, lane, group, *p);
                         for (PageWork* pw : group) {
                             out[pw->index] = assemble_page(*pw);
                             pw->dcrops.release();

@@ -53,6 +53,10 @@ struct ResParams {
     const float* bias;
     int p_stages, patch_stride;
     long long* trace;                   // optional: per-role cycle sums of CTA 0 (diagnostics)
+    // fused classifier tail (EPI == 1): relu(conv) [16 ch] -> 1x1 16->16 + ReLU -> 1x1 16->2 -> text / link planes (FP32)
+    const float* w3; const float* b3; const float* w4; const float* b4;
+    int cp3, cp4;
+    float* text; float* link;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -181,7 +185,7 @@ __device__ __forceinline__ RTile rtile(const ResParams& p, int m) {
     return t;
 }
 
-template <int KB, int TAPS, int NKB, int MT>
+template <int KB, int TAPS, int NKB, int MT, int EPI>
 __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP,
                                                      const ResParams p) {
@@ -200,6 +204,7 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
     uint8_t* pst_base = st_base + (NKB == 1 ? 2 : 1) * ST_BYTES;      // one tile per epilogue team
     __shared__ __align__(16) float s_scale[64];
     __shared__ __align__(16) float s_bias[64];
+    __shared__ __align__(16) float s_w3[EPI == 1 ? 256 : 4], s_b3[EPI == 1 ? 16 : 4], s_w4[EPI == 1 ? 32 : 4], s_b4[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t ncols = 32;
     while ((int)ncols < 2 * MT * p.BN) ncols <<= 1;
@@ -211,6 +216,12 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
     if (threadIdx.x >= 128 && threadIdx.x < 128 + p.BN) {       // the CTA's channel slice never changes: keep scale/bias in smem
         s_scale[threadIdx.x - 128] = p.scale[n0 + threadIdx.x - 128];
         s_bias[threadIdx.x - 128] = p.bias[n0 + threadIdx.x - 128];
+    }
+    if (EPI == 1) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_w3[i] = p.w3[(i / 16) * p.cp3 + (i % 16)];     // [cin][cout]
+        if (threadIdx.x < 32) s_w4[threadIdx.x] = p.w4[(threadIdx.x / 2) * p.cp4 + (threadIdx.x % 2)];
+        if (threadIdx.x < 16) s_b3[threadIdx.x] = p.b3[threadIdx.x];
+        if (threadIdx.x < 2) s_b4[threadIdx.x] = p.b4[threadIdx.x];
     }
     if (threadIdx.x == 0) {
         mbar_init(&wfull, 1);
@@ -328,6 +339,37 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
             for (int mt = 0; mt < MT; ++mt) {
                 if (MT == 2 && (mt % N_TEAMS) != team) continue;
                 const uint32_t trow = tmem_base + (uint32_t)((as * MT + mt) * p.BN) + ((uint32_t)(wq * 32) << 16);
+                if (EPI == 1) {
+                    // classifier tail in registers: this thread's pixel never leaves the SM between conv_cls[4] and the maps
+                    uint32_t v[16];
+                    tmem_ld16(trow, v);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                    float x[16], y3[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) x[j] = fmaxf(fmaf(__uint_as_float(v[j]), s_scale[j], s_bias[j]), 0.f);
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) a = fmaf(x[c], s_w3[c * 16 + o], a);
+                        y3[o] = fmaxf(a + s_b3[o], 0.f);
+                    }
+                    float t = 0.f, l = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        t = fmaf(y3[c], s_w4[c * 2], t);
+                        l = fmaf(y3[c], s_w4[c * 2 + 1], l);
+                    }
+                    const int y = tc.y0 + mt * 16 + (r >> 3), xx = tc.x0 + (r & 7);
+                    if (y < p.OH && xx < p.OW) {
+                        const int64_t pix = ((int64_t)tc.img * p.OH + y) * p.OW + xx;
+                        p.text[pix] = t + s_b4[0];
+                        p.link[pix] = l + s_b4[1];
+                    }
+                    continue;
+                }
                 uint32_t w[32];                                // the thread's pixel: up to 64 bf16 channels
 #pragma unroll
                 for (int c = 0; c < 64; c += 32) {
@@ -422,7 +464,7 @@ struct ResPlan {
     int kb, taps, nkb, BN, MT, p_stages, patch_stride;
     size_t smem;
 };
-bool res_plan(const ConvW& cw, const Act& in1, const Act& out, ResPlan& pl) {
+bool res_plan(const ConvW& cw, const Act& in1, const Act& out, ResPlan& pl, bool tail = false) {
     pl.taps = cw.kh * cw.kw;
     if (in1.C % 64 == 0) { pl.kb = 64; pl.nkb = in1.C / 64; }
     else if (in1.C == 32) { pl.kb = 32; pl.nkb = 1; }
@@ -432,11 +474,12 @@ bool res_plan(const ConvW& cw, const Act& in1, const Act& out, ResPlan& pl) {
     // two-k-block layers are tensor-bound at N = 64 (48 clk per step) and lose to conv_tc.cu's N = 128/256 tiles: forced mode only
     if (pl.nkb == 2 && res_mode() != 2) return false;
     pl.BN = std::min(cw.cout_pad, 64);
-    if ((pl.BN != 32 && pl.BN != 64) || cw.cout % pl.BN != 0) return false;      // staged tile rows of 64 / 128 bytes
+    if (tail) { if (cw.cout != 16 || cw.cout_pad != 16) return false; }
+    else if ((pl.BN != 32 && pl.BN != 64) || cw.cout % pl.BN != 0) return false;      // staged tile rows of 64 / 128 bytes
     const int pix = pl.kb * 2, halo = pl.taps == 9 ? 1 : 0;
     const size_t wbytes = ((size_t)pl.taps * pl.nkb * pl.BN * pix + 1023) & ~(size_t)1023;
     const size_t staging = (size_t)(pl.nkb == 1 ? 2 : 1) * (128 + 32) * pl.BN * 2;       // one tile + pooled tile per epilogue team
-    const size_t budget = 226 * 1024 - 1024 - wbytes - staging;
+    const size_t budget = 222 * 1024 - 1024 - wbytes - staging;
     for (int mt = 2; mt >= 1; --mt) {
         if (mt == 2 && (out.H < 32 || pl.nkb > 1)) continue;
         if (2 * mt * pl.BN > 512) continue;
@@ -453,14 +496,14 @@ bool res_plan(const ConvW& cw, const Act& in1, const Act& out, ResPlan& pl) {
     return false;
 }
 
-template <int KB, int TAPS, int NKB, int MT>
+template <int KB, int TAPS, int NKB, int MT, int EPI = 0>
 void res_launch(int grid, size_t smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO,
                 const CUtensorMap& mP, const ResParams& p) {
     static std::once_flag once;        // one device per process in this library (one rank per GPU)
     std::call_once(once, [] {
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<KB, TAPS, NKB, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<KB, TAPS, NKB, MT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
     });
-    k_conv_res<KB, TAPS, NKB, MT><<<grid, 384, smem, st>>>(mA, mB, mO, mP, p);
+    k_conv_res<KB, TAPS, NKB, MT, EPI><<<grid, 384, smem, st>>>(mA, mB, mO, mP, p);
 }
 
 }  // namespace
@@ -558,6 +601,48 @@ void conv_res_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in
                         "wait-patch %.0f issue %.0f | epilogue wait %.0f work %.0f cycles\n",
                 out.H, out.W, cw.kh, cw.cin, cw.cout, pl.BN, pl.MT, pl.p_stages, grid, t[3], t[0] / n, t[1] / n, t[2] / n, t[4] / n, t[5] / n);
     }
+}
+
+// conv_cls[4] (3x3, 32 -> 16, ReLU) with the rest of the classifier (1x1 16 -> 16 + ReLU, 1x1 16 -> 2) in its epilogue:
+// writes the text and link score maps directly.  craft.py::CRAFT.conv_cls tail; SURVEY.md §8a B4.
+bool conv_res_cls_tail_supported(const ConvW& c2, const ConvW& c3, const ConvW& c4, const Act& in) {
+    if (!res_mode() || !c2.w_bf16) return false;
+    if (c2.kh != 3 || c2.kw != 3 || c2.pad != 1 || c2.dil != 1 || in.C != 32) return false;
+    if (c3.cin != 16 || c3.cout != 16 || c4.cin != 16 || c4.cout != 2 || c3.kh != 1 || c4.kh != 1) return false;
+    if (in.H < 32 || in.W < 8) return false;
+    ResPlan pl;
+    return res_plan(c2, in, in, pl, true) && pl.MT == 2;
+}
+
+void conv_res_cls_tail(Handle* h, cudaStream_t st, const ConvW& c2, const ConvW& c3, const ConvW& c4, const Act& in, float* text,
+                       float* link) {
+    ResPlan pl;
+    ARG_CHECK(res_plan(c2, in, in, pl, true) && pl.MT == 2, "conv_res_cls_tail: unsupported geometry");
+    ResParams p;
+    memset(&p, 0, sizeof p);
+    p.OH = in.H; p.OW = in.W; p.NIMG = in.N;
+    p.cout = 16; p.BN = 16; p.n_tiles = 1;
+    p.tiles_x = cdiv(in.W, 8);
+    p.tiles_y = cdiv(in.H, 32);
+    p.m_tiles = p.tiles_x * p.tiles_y * in.N;
+    p.relu = 1;
+    p.scale = c2.scale; p.bias = c2.bias;
+    p.p_stages = pl.p_stages; p.patch_stride = pl.patch_stride;
+    p.w3 = c3.w_f32; p.b3 = c3.bias; p.cp3 = c3.cout_pad;
+    p.w4 = c4.w_f32; p.b4 = c4.bias; p.cp4 = c4.cout_pad;
+    p.text = text; p.link = link;
+    uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)in.N};
+    uint64_t str[3] = {(uint64_t)in.C * 2, (uint64_t)in.W * in.C * 2, (uint64_t)in.H * in.W * in.C * 2};
+    uint32_t box[4] = {32, 10, 34, 1};
+    CUtensorMap mA = tc_make_map(in.p, 4, dims, str, box, 32);
+    uint64_t wd[3] = {(uint64_t)c2.cin, (uint64_t)c2.cout_pad, 9};
+    uint64_t ws[2] = {(uint64_t)c2.cin * 2, (uint64_t)c2.cout_pad * c2.cin * 2};
+    uint32_t wb[3] = {32, 16, 1};
+    CUtensorMap mB = tc_make_map(c2.w_bf16, 3, wd, ws, wb, 32);
+    const int grid = std::min(h->sm_count, p.m_tiles);
+    res_launch<32, 9, 1, 2, 1>(grid, pl.smem, st, mA, mB, mA, mA, p);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace bbocr

@@ -44,6 +44,7 @@ struct TcParams {
     int split_out;
     const float* scale;
     const float* bias;
+    const uint8_t* colmask;     // optional [OW]: output columns with 0 are written as zeros (gaps between concatenated crops)
     int stages;
 };
 
@@ -288,12 +289,14 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             mbar_wait(&tfull_bar[as], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int64_t pix = -1, pix2 = -1;
+            bool colvalid = true;
             if (p.flat) {
                 if (tc.m0 + r < p.M) pix = tc.m0 + r;
             } else {
                 const int hl = r / p.TW, wl = r - hl * p.TW;
                 const int y = tc.y0 + hl, x = tc.x0 + wl;
                 if (y < p.OH && x < p.OW) pix = ((int64_t)tc.img * p.OH + y) * p.OW + x;
+                if (p.colmask && x < p.OW) colvalid = __ldg(p.colmask + x) != 0;
                 if (p.pool) {
                     // TW == 16: lane = (hl & 1) * 16 + wl ; the 2x2 (2x1) window lives in lanes {l, l^1, l^16, l^17} ({l, l^16})
                     const int POH = p.OH >> 1, POW = p.pool == 1 ? p.OW >> 1 : p.OW;
@@ -312,6 +315,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                     const int n = tc.n0 + c + j;
                     float a = fmaf(__uint_as_float(v[j]), __ldg(p.scale + n), __ldg(p.bias + n));   // padded to cout_pad
                     f[j] = p.relu ? fmaxf(a, 0.f) : a;
+                    if (!colvalid) f[j] = 0.f;
                 }
                 const int nbase = tc.n0 + c;
                 if (pix >= 0 && (!p.pool || p.write_full)) {
@@ -404,7 +408,7 @@ bool conv_tc_supported(const ConvW& cw, const Act& in1, const Act& in2) {
 // pooled: optional second output (fused MaxPool2d(2,2) when flags & CONV_POOL22, MaxPool2d((2,1)) when CONV_POOL21);
 // out.p may be null together with a pooled output when only the pooled tensor is needed.
 void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags,
-                     Act* pooled) {
+                     Act* pooled, const uint8_t* colmask) {
     const int bk = pick_bk(cw, in1, in2);
     const bool split_in = in1.lo != nullptr;
     if (split_in) {
@@ -423,6 +427,15 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     p.cout = cw.cout;
     static const int bn_max = getenv("BBOCR_TC_BN") ? atoi(getenv("BBOCR_TC_BN")) : 256;
     p.BN = cw.cout_pad <= 128 ? cw.cout_pad : ((bn_max >= 256 && cw.cout_pad % 256 == 0) ? 256 : 128);
+    if (p.BN == 256) {
+        // One CTA per SM works through ceil(tiles / SMs) tiles of cost ~BN each.  For the small layers (1/16 resolution,
+        // recogniser strips) the wave quantisation of 256-wide tiles costs more than their better operand reuse saves:
+        // take 128-wide tiles when they shorten the longest SM's queue by more than 10 % (1x1) / 30 % (3x3: 128-wide tiles
+        // pull 1.5x the operand bytes per FLOP through the L2->SM fabric, measured on fc6).
+        const int64_t mt = cdiv64((int64_t)out.N * out.H * out.W, BM);
+        const int64_t w256 = cdiv64(mt * (cw.cout_pad / 256), h->sm_count) * 256, w128 = cdiv64(mt * (cw.cout_pad / 128), h->sm_count) * 128;
+        if (w256 * 10 > w128 * (p.flat ? 11 : 13)) p.BN = 128;
+    }
     p.n_tiles = cw.cout_pad / p.BN;
     p.relu = (flags & CONV_RELU) ? 1 : 0;
     p.out_f32 = (flags & CONV_OUT_F32) ? 1 : 0;
@@ -432,6 +445,7 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     p.write_full = 1;
     p.scale = cw.scale;
     p.bias = cw.bias;
+    p.colmask = colmask;
     if (p.flat) { p.TW = 128; p.TH = 1; p.tiles_x = p.tiles_y = 1; }
     else if (out.H >= 8) { p.TW = 16; p.TH = 8; }
     else { p.TW = 32; p.TH = 4; }

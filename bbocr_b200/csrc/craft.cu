@@ -194,6 +194,19 @@ void craft_forward_dev(Handle* h, cudaStream_t st, const uint8_t* img_dev, const
     b_r22.release();
     a = conv(w.cls0, a, none, b0, R);
     a = conv(w.cls1, a, none, b1, R);
+    if (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && conv_res_cls_tail_supported(w.cls2, w.cls3, w.cls4, a)) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;            // counted with the detector convolutions (bench.py roofline)
+        if (h->conv_timing) { CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventRecord(e0, st)); }
+        conv_res_cls_tail(h, st, w.cls2, w.cls3, w.cls4, a, text, link);      // conv_cls[4] + the 1x1 tail in one launch
+        if (h->conv_timing) {
+            CUDA_CHECK(cudaEventRecord(e1, st));
+            std::lock_guard<std::mutex> g(h->stat_mu);
+            h->conv_events.emplace_back(e0, e1);
+            h->conv_flops += 2.0 * (double)a.N * a.H * a.W * (16.0 * 32 * 9 + 16 * 16 + 16 * 2);
+            h->conv_launches += 1;
+        }
+        return;
+    }
     a = conv(w.cls2, a, none, b0, R);
     cls_tail(h, st, w.cls3, w.cls4, a, text, link);
 }

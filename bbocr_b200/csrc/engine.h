@@ -42,7 +42,7 @@ struct Handle {
     std::vector<void*> owned;       // weight allocations
     std::vector<Lane> lanes;         // [0, n_det_lanes) detector lanes, then the recogniser lanes
     int n_det_lanes = 8;
-    int rec_group = 16;              // pages per recogniser launch group (bbocr_readtext_batch)
+    int rec_group = 32;              // pages per recogniser launch group (bbocr_readtext_batch)
     // dominant-kernel instrumentation (bench.py roofline): CUDA events around every implicit-GEMM conv launch
     bool conv_timing = false;
     bool force_generic_conv = false; // test hook: route BF16-mode convolutions through the CUDA-core kernel
@@ -84,7 +84,7 @@ enum ConvFlags { CONV_RELU = 1, CONV_OUT_F32 = 2, CONV_POOL22 = 4, CONV_POOL21 =
 // `pooled` (optional): also produce MaxPool2d(2,2) [CONV_POOL22] / MaxPool2d((2,1)) [CONV_POOL21] of the output; out.p may
 // then be null when only the pooled tensor is needed.
 void conv_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags,
-                  Act* pooled = nullptr);
+                  Act* pooled = nullptr, const uint8_t* colmask = nullptr);     // colmask [out.W]: 0 = write zeros (tcgen05 path only)
 // cin in {1,3(stored 4)} direct convolution from an FP32 NHWC tensor (canvas / crop batch)
 void conv_first(Handle*, cudaStream_t, const ConvW&, const float* in, int N, int H, int W, int cstride, Act& out,
                 int flags);
@@ -94,7 +94,9 @@ void mean_rows(Handle*, cudaStream_t, const Act& in, Act& out);           // Ada
 void cls_tail(Handle*, cudaStream_t, const ConvW& c3, const ConvW& c4, const Act& in, float* text, float* link);
 
 Act act_alloc_split(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C);
-void maxpool_f32_to_split(Handle*, cudaStream_t, const Act& in, Act& out, int kh, int kw);
+void maxpool_f32_to_split(Handle*, cudaStream_t, const Act& in, Act& out, int kh, int kw, const uint8_t* colmask = nullptr);
+// ragged AdaptiveAvgPool: crop i = columns [meta[3i], meta[3i] + meta[3i+1]) of `in` ([1][H][W][C] split) -> rows meta[3i+2].. of out
+void mean_rows_split_ragged(Handle*, cudaStream_t, const Act& in, const Act& out, const int* meta_dev, int n_crops, int t_max);
 void mean_rows_split(Handle*, cudaStream_t, const Act& in, Act& out);
 void act_from_f32(Handle*, cudaStream_t, const float* in, void* out, int64_t n);
 void act_to_f32(Handle*, cudaStream_t, const void* in, float* out, int64_t n);
@@ -103,7 +105,8 @@ Act act_alloc(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C, bo
 
 // ---- conv_tc.cu : tcgen05 implicit GEMM ------------------------------------------------------------------------------
 bool conv_tc_supported(const ConvW&, const Act& in1, const Act& in2);
-void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled);
+void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled,
+                     const uint8_t* colmask = nullptr);
 // conv_halo.cu : 3x3 / pad 1 convolutions with the input patch loaded once per channel block (all nine taps from smem)
 bool conv_halo_supported(const ConvW&, const Act& in1, const Act& in2, const Act& out);
 void conv_halo_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled);
@@ -111,6 +114,9 @@ void conv_halo_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, cons
 // conv_res.cu : 3x3 / pad 1 convolutions of the low-channel layers with resident weights and a halo patch per tile
 bool conv_res_supported(const ConvW&, const Act& in1, const Act& in2, const Act& out);
 void conv_res_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled);
+
+bool conv_res_cls_tail_supported(const ConvW& c2, const ConvW& c3, const ConvW& c4, const Act& in);
+void conv_res_cls_tail(Handle*, cudaStream_t, const ConvW& c2, const ConvW& c3, const ConvW& c4, const Act& in, float* text, float* link);
 
 // ---- weights.cu ------------------------------------------------------------------------------------------------------
 void load_craft(Handle*, const bbocr_tensor* t, int n);
@@ -173,6 +179,13 @@ struct SeqDesc {                   // one crop's feature sequence inside the fla
 // conv stack + row mean of one width bucket: x [N][64][Wm] FP32 -> seq rows [row0, row0 + N*(Wm/4-1)) of `seq` ([rows][256])
 Act crnn_alloc_seq(Handle*, cudaStream_t, DevBuf& buf, int rows);
 void crnn_features_dev(Handle*, cudaStream_t, const float* x, int N, int Wm, const Act& seq, int row0);
+// ragged variant (throughput mode): all crops side by side in ONE strip image [64][Wtot] with >= 16 zero columns between
+// neighbours; mask1 [Wtot/2] / mask2 [Wtot/4] mark the crop columns at the two pooled resolutions; meta as above
+bool crnn_ragged(const Handle*);
+void crnn_features_strip_dev(Handle*, cudaStream_t, const float* strip, int Wtot, const uint8_t* mask1, const uint8_t* mask2,
+                             const int* meta_dev, int n_crops, int t_max, const Act& seq);
+void crops_to_strip_dev(Handle*, cudaStream_t, const uint8_t* aligned, const CropDesc* descs_dev, const int* xoff_dev, int n,
+                        int max_model_w, int Wtot, float* strip);
 // both BiLSTM blocks + Prediction over all sequences at once: seq [rows][256] -> logits [rows][num_class] FP32
 void crnn_sequence_dev(Handle*, Lane&, const Act& seq, const std::vector<SeqDesc>& seqs, float* logits);
 void crnn_forward_dev(Handle*, Lane&, const float* x, int N, int Wm, float* logits);

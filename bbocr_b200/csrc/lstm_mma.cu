@@ -94,7 +94,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 __global__ void __launch_bounds__(256, 1)
     k_lstm_mma(const __grid_constant__ CUtensorMap tmS, const float* __restrict__ gates_in, const float* __restrict__ w_hh,
                void* __restrict__ out, void* __restrict__ out_lo, int out_mode, __nv_bfloat16* __restrict__ stage,
-               const SeqDesc* __restrict__ seqs, const int* __restrict__ groups /*[n_groups][MB], -1 = empty*/,
+               const SeqDesc* __restrict__ seqs, const int* __restrict__ groups /*[n_groups][MB], -1 = empty*/, int fence_gpu,
                long long* __restrict__ trace /* optional: clock64 stamps of CTA 0, 8 per step */) {
     extern __shared__ uint8_t lm_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lm_raw) + 1023) & ~(uintptr_t)1023);
@@ -275,8 +275,10 @@ __global__ void __launch_bounds__(256, 1)
             __nv_bfloat16* sp = stage + ((size_t)(stage_row0 + ((s + 1) & 1) * 2 * MB + crop) * 256 + UN * r + 8 * half);
             *reinterpret_cast<uint4*>(sp) = pack8(hi);
             *reinterpret_cast<uint4*>(sp + (size_t)MB * 256) = pack8(lo);
-            __threadfence();
-            asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy global writes -> visible to the peers' TMA reads
+            // generic-proxy global writes -> visible to the peers' TMA reads (async proxy); the release/acquire pair of the
+            // cluster barrier at the top of the next step orders them across the CTAs
+            if (fence_gpu) __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         LM_STAMP(7);
@@ -320,6 +322,7 @@ void lstm_sequences_mma(Handle* h, Lane& lane, const float* gates_in, const floa
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     static const bool want_trace = getenv("BBOCR_LSTM_TRACE") != nullptr;
+    static const int fence_gpu = getenv("BBOCR_LSTM_FENCE") ? atoi(getenv("BBOCR_LSTM_FENCE")) : 0;
     DevBuf dtrace;
     long long* trace = nullptr;
     if (want_trace) {
@@ -328,7 +331,7 @@ void lstm_sequences_mma(Handle* h, Lane& lane, const float* gates_in, const floa
         trace = dtrace.as<long long>();
     }
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_lstm_mma, tmS, gates_in, w_hh, out, out_lo, out_mode, stage.as<__nv_bfloat16>(), seqs_dev,
-                                  groups_dev, trace));
+                                  groups_dev, fence_gpu, trace));
     count_launch(h);
     if (want_trace) {           // diagnostic: per-phase cycles of CTA 0, averaged over steps 8..39
         std::vector<long long> t(64 * 8);

@@ -148,7 +148,7 @@ static void conv_generic(Handle* h, cudaStream_t st, const ConvW& cw, const Act&
 thread_local int g_conv_scope = 0;      // 1 while the calling thread is inside the detector (CRAFT) forward pass
 
 void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags,
-                  Act* pooled) {
+                  Act* pooled, const uint8_t* colmask) {
     ARG_CHECK(in1.C + in2.C == cw.cin, "conv: channel mismatch (%d+%d vs %d)", in1.C, in2.C, cw.cin);
     ARG_CHECK(in1.C % 16 == 0 && in2.C % 16 == 0, "conv: channel segments must be multiples of 16");
     ARG_CHECK(out.C == cw.cout, "conv: output channel mismatch");
@@ -162,13 +162,14 @@ void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, c
         CUDA_CHECK(cudaEventRecord(e0, st));
     }
     const bool tc = h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && conv_tc_supported(cw, in1, in2);
+    ARG_CHECK(!colmask || tc, "conv: a column mask needs the tcgen05 path");
     const bool pool_ok = !pooled || (out.H >= 8 && out.H % 2 == 0 && ((flags & CONV_POOL21) || out.W % 2 == 0));
-    if (tc && pool_ok && !in1.lo && !out.lo && !(flags & (CONV_OUT_F32 | CONV_POOL21)) && conv_res_supported(cw, in1, in2, out)) {
+    if (tc && pool_ok && !colmask && !in1.lo && !out.lo && !(flags & (CONV_OUT_F32 | CONV_POOL21)) && conv_res_supported(cw, in1, in2, out)) {
         conv_res_forward(h, st, cw, in1, in2, out, flags, pooled);      // resident weights + halo patch (low-channel 3x3 layers)
     } else if (tc && pool_ok && !in1.lo && !out.lo && conv_halo_supported(cw, in1, in2, out)) {
         conv_halo_forward(h, st, cw, in1, in2, out, flags, pooled);     // patch-reuse kernel for the 3x3 layers
     } else if (tc && pool_ok) {
-        conv_tc_forward(h, st, cw, in1, in2, out, flags, pooled);       // max-pool fused into the epilogue
+        conv_tc_forward(h, st, cw, in1, in2, out, flags, pooled, colmask);       // max-pool fused into the epilogue
     } else {
         DevBuf tmp;
         Act full = out;
@@ -176,6 +177,7 @@ void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, c
             bool f32 = (flags & CONV_OUT_F32) != 0;
             full = act_alloc(h, st, tmp, out.N, out.H, out.W, out.C, f32);
         }
+        ARG_CHECK(!colmask, "conv: column mask with an unfused pool is not supported");
         if (tc) conv_tc_forward(h, st, cw, in1, in2, full, flags, nullptr);
         else conv_generic(h, st, cw, in1, in2, full, flags);
         if (pooled) {
@@ -340,7 +342,77 @@ __global__ void k_upsample(const T* __restrict__ in, T* __restrict__ out, int N,
     store4(out + (((int64_t)n * OH + oy) * OW + ox) * C + c, o);
 }
 
+// bf16, exact x2: one thread per INPUT pixel and 8 channels produces the 2x2 output quad from the clamped 3x3 input
+// neighbourhood (9 x 16-byte loads for 4 x 16-byte stores instead of 16 x 8-byte loads).  Every output is evaluated with the
+// same expression and the same operands as k_upsample, so the two kernels are bit-identical.
+__global__ void __launch_bounds__(256) k_upsample2x_bf16(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N,
+                                                         int H, int W, int C) {
+    const int C8 = C >> 3;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total_x = W * C8;
+    if (idx >= total_x) return;
+    const int j = idx / C8, c = (idx - j * C8) * 8;
+    const int i = blockIdx.y, n = blockIdx.z;
+    const int OH = 2 * H, OW = 2 * W;
+    const int rows[3] = {max(i - 1, 0), i, min(i + 1, H - 1)}, cols[3] = {max(j - 1, 0), j, min(j + 1, W - 1)};
+    float v[3][3][8];
+    const __nv_bfloat16* base = in + (size_t)n * H * W * C + c;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)rows[a] * W + cols[b]) * C));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+                v[a][b][2 * k] = __low2float(t);
+                v[a][b][2 * k + 1] = __high2float(t);
+            }
+        }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const int oy = 2 * i + dy;
+        const float fy = fmaxf(0.5f * ((float)oy + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)fy;
+        const float ly = fy - (float)y0, hy = 1.f - ly;
+        // (y0, y1) = (i-1, i) for the upper output row of an interior pixel, else (i, min(i+1, H-1)); row slot = y - i + 1
+        const bool up = dy == 0 && i >= 1;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int ox = 2 * j + dx;
+            const float fx = fmaxf(0.5f * ((float)ox + 0.5f) - 0.5f, 0.f);
+            const int x0 = (int)fx;
+            const float lx = fx - (float)x0, hx = 1.f - lx;
+            const bool left = dx == 0 && j >= 1;
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                float o[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float a = up ? (left ? v[0][0][k + e] : v[0][1][k + e]) : (left ? v[1][0][k + e] : v[1][1][k + e]);
+                    const float b = up ? (left ? v[0][1][k + e] : v[0][2][k + e]) : (left ? v[1][1][k + e] : v[1][2][k + e]);
+                    const float cc = up ? (left ? v[1][0][k + e] : v[1][1][k + e]) : (left ? v[2][0][k + e] : v[2][1][k + e]);
+                    const float d = up ? (left ? v[1][1][k + e] : v[1][2][k + e]) : (left ? v[2][1][k + e] : v[2][2][k + e]);
+                    o[e] = hy * (hx * a + lx * b) + ly * (hx * cc + lx * d);
+                }
+                const __nv_bfloat162 t = __floats2bfloat162_rn(o[0], o[1]);
+                w[k >> 1] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(out + (((size_t)n * OH + oy) * OW + ox) * C + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
 void upsample2x(Handle* h, cudaStream_t st, const Act& in, Act& out) {
+    if (h->precision == BBOCR_PREC_BF16 && in.C % 8 == 0 && out.H == 2 * in.H && out.W == 2 * in.W && out.C == in.C) {
+        k_upsample2x_bf16<<<dim3(cdiv(in.W * (in.C / 8), 256), in.H, in.N), 256, 0, st>>>(
+            (const __nv_bfloat16*)in.p, (__nv_bfloat16*)out.p, in.N, in.H, in.W, in.C);
+        count_launch(h);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     ARG_CHECK(in.C % 4 == 0 && out.C == in.C, "upsample: channels");
     int64_t total = (int64_t)out.N * out.H * out.W * (in.C / 4);
     unsigned grd = (unsigned)cdiv64(total, 256);
@@ -457,7 +529,7 @@ __device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* l
 
 // MaxPool2d on an FP32 tensor, output split
 __global__ void k_maxpool_f32_split(const float* __restrict__ in, __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo,
-                                    int N, int H, int W, int C, int OH, int OW, int kh, int kw) {
+                                    int N, int H, int W, int C, int OH, int OW, int kh, int kw, const uint8_t* __restrict__ colmask) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int C4 = C >> 2;
     int64_t total = (int64_t)N * OH * OW * C4;
@@ -476,14 +548,15 @@ __global__ void k_maxpool_f32_split(const float* __restrict__ in, __nv_bfloat16*
 #pragma unroll
             for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], v[j]);
         }
+    if (colmask && !colmask[ox]) best[0] = best[1] = best[2] = best[3] = 0.f;      // gap between concatenated crops
     int64_t o = (((int64_t)n * OH + oy) * OW + ox) * C + c;
     split_store4(ohi + o, olo + o, best);
 }
 
-void maxpool_f32_to_split(Handle* h, cudaStream_t st, const Act& in, Act& out, int kh, int kw) {
+void maxpool_f32_to_split(Handle* h, cudaStream_t st, const Act& in, Act& out, int kh, int kw, const uint8_t* colmask) {
     int64_t total = (int64_t)out.N * out.H * out.W * (in.C / 4);
     k_maxpool_f32_split<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>((const float*)in.p, (__nv_bfloat16*)out.p, (__nv_bfloat16*)out.lo,
-                                                                      in.N, in.H, in.W, in.C, out.H, out.W, kh, kw);
+                                                                      in.N, in.H, in.W, in.C, out.H, out.W, kh, kw, colmask);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -514,6 +587,35 @@ void mean_rows_split(Handle* h, cudaStream_t st, const Act& in, Act& out) {
     k_mean_rows_split<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>((const __nv_bfloat16*)in.p, (const __nv_bfloat16*)in.lo,
                                                                     (__nv_bfloat16*)out.p, (__nv_bfloat16*)out.lo, in.N, in.H,
                                                                     in.W, in.C);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ragged AdaptiveAvgPool over the H rows: crop i owns columns [col0, col0 + T) of the strip, its sequence starts at row0
+__global__ void k_mean_rows_split_ragged(const __nv_bfloat16* __restrict__ ihi, const __nv_bfloat16* __restrict__ ilo,
+                                         __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo, int H, int W, int C,
+                                         const int* __restrict__ meta) {
+    const int crop = blockIdx.y;
+    const int col0 = meta[3 * crop], T = meta[3 * crop + 1], row0 = meta[3 * crop + 2];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = idx / C, c = idx - t * C;
+    if (t >= T) return;
+    float s = 0.f;
+    for (int y = 0; y < H; ++y) {
+        const int64_t i = ((int64_t)y * W + col0 + t) * C + c;
+        s += __bfloat162float(ihi[i]) + __bfloat162float(ilo[i]);
+    }
+    const float v = s / (float)H;
+    const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+    const int64_t o = (int64_t)(row0 + t) * C + c;
+    ohi[o] = hb;
+    olo[o] = __float2bfloat16_rn(v - __bfloat162float(hb));
+}
+
+void mean_rows_split_ragged(Handle* h, cudaStream_t st, const Act& in, const Act& out, const int* meta_dev, int n_crops, int t_max) {
+    if (n_crops == 0) return;
+    k_mean_rows_split_ragged<<<dim3(cdiv(t_max * in.C, 256), n_crops), 256, 0, st>>>(
+        (const __nv_bfloat16*)in.p, (const __nv_bfloat16*)in.lo, (__nv_bfloat16*)out.p, (__nv_bfloat16*)out.lo, in.H, in.W, in.C, meta_dev);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 }

@@ -240,6 +240,30 @@ void crops_to_input_dev(Handle* h, cudaStream_t st, const uint8_t* aligned, cons
     CUDA_CHECK(cudaGetLastError());
 }
 
+// Ragged batch: every crop is written side by side into ONE strip image [64][Wtot] at column xoff[crop]; the columns
+// between crops stay zero (the strip is cleared first), which is exactly the zero padding each crop's convolutions see
+// when it is processed alone.
+__global__ void k_crops_to_strip(const uint8_t* __restrict__ aligned, const CropDesc* __restrict__ descs, const int* __restrict__ xoff,
+                                 int Wtot, float* __restrict__ strip) {
+    const CropDesc d = descs[blockIdx.z];
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= d.model_w) return;
+    int sx = min(x, d.resized_w - 1);
+    float v = (float)aligned[(int64_t)d.aoff + (int64_t)y * d.resized_w + sx];
+    v = __fdiv_rn(v, 255.f);
+    v = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+    strip[(int64_t)y * Wtot + xoff[blockIdx.z] + x] = v;
+}
+
+void crops_to_strip_dev(Handle* h, cudaStream_t st, const uint8_t* aligned, const CropDesc* descs_dev, const int* xoff_dev, int n,
+                        int max_model_w, int Wtot, float* strip) {
+    if (n == 0) return;
+    CUDA_CHECK(cudaMemsetAsync(strip, 0, (size_t)64 * Wtot * 4, st));
+    k_crops_to_strip<<<dim3(cdiv(max_model_w, 128), 64, n), 128, 0, st>>>(aligned, descs_dev, xoff_dev, Wtot, strip);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // vgg_model.Model.forward, split at the sequence boundary so that the recurrent half runs ONCE per page over the crops
 // of every width bucket:
@@ -312,6 +336,48 @@ void crnn_features_dev(Handle* h, cudaStream_t st, const float* x, int N, int Wm
         s.p = (uint8_t*)seq.p + (size_t)row0 * 256 * act_elem_size(h);
         mean_rows(h, st, a, s);
     }
+}
+
+// Ragged feature extractor (throughput mode): ONE launch per layer over the strip of all crops instead of one launch
+// chain per width bucket.  Output columns that lie between crops are re-zeroed by every layer (column masks in the
+// max-pool / tcgen05 epilogues), so each crop keeps seeing zero padding at its own borders and its features are the same
+// as when it is run alone.  Widths and offsets are multiples of 16 at the input, hence even at every pooled resolution.
+bool crnn_ragged(const Handle* h) {
+    static const bool off = getenv("BBOCR_CRNN_BUCKETS") != nullptr;
+    return crnn_split(h) && !off;
+}
+
+void crnn_features_strip_dev(Handle* h, cudaStream_t st, const float* strip, int Wtot, const uint8_t* mask1, const uint8_t* mask2,
+                             const int* meta_dev, int n_crops, int t_max, const Act& seq) {
+    if (!h->crnn_loaded) fail(BBOCR_E_STATE, "CRNN weights not loaded (bbocr_load_crnn)");
+    ARG_CHECK(crnn_split(h) && Wtot % 16 == 0, "crnn: the ragged path needs split precision and 16-aligned strips");
+    const CrnnW& w = h->crnn;
+    const Act none;
+    const int R = CONV_RELU;
+    DevBuf b0, b1;
+    auto conv = [&](const ConvW& cw, const Act& a, DevBuf& buf, int flags, const uint8_t* mask) {
+        Act o = act_alloc_split(h, st, buf, a.N, a.H + 2 * cw.pad - cw.dil * (cw.kh - 1), a.W + 2 * cw.pad - cw.dil * (cw.kw - 1), cw.cout);
+        conv_forward(h, st, cw, a, none, o, flags, nullptr, mask);
+        return o;
+    };
+    auto conv_pool = [&](const ConvW& cw, const Act& a, DevBuf& buf, int kh, int kw, const uint8_t* mask) {
+        Act full;
+        full.N = a.N; full.H = a.H; full.W = a.W; full.C = cw.cout; full.p = nullptr;
+        Act pooled = act_alloc_split(h, st, buf, a.N, a.H / kh, a.W / kw, cw.cout);
+        conv_forward(h, st, cw, a, none, full, R | (kw == 2 ? CONV_POOL22 : CONV_POOL21), &pooled, mask);
+        return pooled;
+    };
+    Act c0 = act_alloc(h, st, b0, 1, 64, Wtot, 32, true);                   // FP32 output of the direct first conv
+    conv_first(h, st, w.c0, strip, 1, 64, Wtot, 1, c0, R | CONV_OUT_F32);
+    Act a = act_alloc_split(h, st, b1, 1, 32, Wtot / 2, 32);
+    maxpool_f32_to_split(h, st, c0, a, 2, 2, mask1);
+    a = conv_pool(w.c1, a, b0, 2, 2, mask1);        // 16 x Wtot/4   (mask at the conv's own resolution, before the pool)
+    a = conv(w.c2, a, b1, R, mask2);
+    a = conv_pool(w.c3, a, b0, 2, 1, mask2);        // 8 x Wtot/4
+    a = conv(w.c4, a, b1, R, mask2);
+    a = conv_pool(w.c5, a, b0, 2, 1, mask2);        // 4 x Wtot/4
+    a = conv(w.c6, a, b1, R, nullptr);              // 3 x (Wtot/4 - 1); the columns that straddle two crops are never read
+    mean_rows_split_ragged(h, st, a, seq, meta_dev, n_crops, t_max);
 }
 
 void crnn_sequence_dev(Handle* h, Lane& lane, const Act& seq, const std::vector<SeqDesc>& seqs, float* logits) {

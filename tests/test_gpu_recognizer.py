@@ -157,3 +157,33 @@ def test_batched_equals_single(gpu_reader):
     finally:
         gpu_reader.set_precision("fp32")
     assert batched == single
+
+
+def test_ragged_strip_equals_width_buckets(gpu_reader, tmp_path):
+    """Throughput mode runs the feature extractor once over a strip of all crops (column masks re-zero the gaps); the
+    per-width-bucket path (BBOCR_CRNN_BUCKETS=1, latched per process) must give the same boxes, strings and confidences."""
+    import json
+    import os
+    import subprocess
+    import sys
+    pages = [synth.title_page(80 + i, 800, 608) for i in range(3)] + [synth.book_cover(90, 800, 608)]
+    gpu_reader.set_precision("bf16")
+    try:
+        got = gpu_reader.readtext_batched(pages)
+    finally:
+        gpu_reader.set_precision("fp32")
+    script = (
+        "import json, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import bbocr_b200\n"
+        "from bbocr_b200 import synth\n"
+        "pages = [synth.title_page(80 + i, 800, 608) for i in range(3)] + [synth.book_cover(90, 800, 608)]\n"
+        "r = bbocr_b200.Reader(['en'], gpu=True, verbose=False, precision='bf16')\n"
+        "json.dump(r.readtext_batched(pages), open(%r, 'w'))\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "buckets.json"))
+    r = subprocess.run([sys.executable, "-c", script], env=dict(os.environ, BBOCR_CRNN_BUCKETS="1"), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    want = json.load(open(tmp_path / "buckets.json"))
+    assert sum(len(p) for p in want) > 20
+    assert json.loads(json.dumps(got)) == want
