@@ -52,6 +52,7 @@ struct ResParams {
     const float* scale;
     const float* bias;
     int p_stages, patch_stride;
+    int b_stages;                       // STREAM variant: depth of the weight-tile ring
     long long* trace;                   // optional: per-role cycle sums of CTA 0 (diagnostics)
     // fused classifier tail (EPI == 1): relu(conv) [16 ch] -> 1x1 16->16 + ReLU -> 1x1 16->2 -> text / link planes (FP32)
     const float* w3; const float* b3; const float* w4; const float* b4;
@@ -185,25 +186,27 @@ __device__ __forceinline__ RTile rtile(const ResParams& p, int m) {
     return t;
 }
 
-template <int KB, int TAPS, int NKB, int MT, int EPI>
+// STREAM = 0: the CTA's weight slice is resident.  STREAM = 1 (Cin = 128, 128-wide channel slices): weight tiles stream
+// through a ring, one per (k-block, tap), each feeding the MT stacked M-tiles of the resident patch.
+template <int KB, int TAPS, int NKB, int MT, int EPI, int STREAM>
 __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP,
                                                      const ResParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t wfull, pfull[8], pempty[8], tfull[2], tempty[2];
+    __shared__ uint64_t wfull, pfull[8], pempty[8], tfull[2], tempty[2], bfull[8], bempty[8];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     using G = Geo<KB, TAPS, MT>;
     constexpr int PATCH_BYTES = G::PATCH_BYTES;
     const int W_TILE = p.BN * G::PIX;                      // one (tap, k-block) weight tile
     uint8_t* w_base = smem;
-    uint8_t* patch_base = smem + ((TAPS * NKB * W_TILE + 1023) & ~1023);
+    uint8_t* patch_base = smem + (((STREAM ? p.b_stages : TAPS * NKB) * W_TILE + 1023) & ~1023);
     // epilogue staging (TMA-store sources): 2 x [128 px][BN] bf16 full-resolution tiles, 2 x [32 px][BN] pooled tiles
     const int ST_BYTES = 128 * p.BN * 2, PST_BYTES = 32 * p.BN * 2;
     uint8_t* st_base = patch_base + p.p_stages * p.patch_stride;
     uint8_t* pst_base = st_base + (NKB == 1 ? 2 : 1) * ST_BYTES;      // one tile per epilogue team
-    __shared__ __align__(16) float s_scale[64];
-    __shared__ __align__(16) float s_bias[64];
+    __shared__ __align__(16) float s_scale[128];
+    __shared__ __align__(16) float s_bias[128];
     __shared__ __align__(16) float s_w3[EPI == 1 ? 256 : 4], s_b3[EPI == 1 ? 16 : 4], s_w4[EPI == 1 ? 32 : 4], s_b4[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t ncols = 32;
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
     const int m_first = blockIdx.x / p.n_tiles, m_step = gridDim.x / p.n_tiles;
     const bool tr = p.trace != nullptr && blockIdx.x == 0;
 
-    if (threadIdx.x >= 128 && threadIdx.x < 128 + p.BN) {       // the CTA's channel slice never changes: keep scale/bias in smem
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + p.BN) {       // the CTA's channel slice never changes: keep scale/bias in smem (BN <= 128)
         s_scale[threadIdx.x - 128] = p.scale[n0 + threadIdx.x - 128];
         s_bias[threadIdx.x - 128] = p.bias[n0 + threadIdx.x - 128];
     }
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
     if (threadIdx.x == 0) {
         mbar_init(&wfull, 1);
         for (int s = 0; s < p.p_stages; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
+        if (STREAM) for (int s = 0; s < p.b_stages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (NKB == 1 && MT == 2) ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -246,10 +250,12 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer: the resident weight slice once, then one patch per (tile, k-block) ----------
-            mbar_expect_tx(&wfull, (uint32_t)(TAPS * NKB * W_TILE));
-            for (int tap = 0; tap < TAPS; ++tap)
-                for (int kb = 0; kb < NKB; ++kb) tma_load_3d(w_base + (tap * NKB + kb) * W_TILE, &tmB, &wfull, kb * KB, n0, tap);
-            int pit = 0;
+            if (!STREAM) {
+                mbar_expect_tx(&wfull, (uint32_t)(TAPS * NKB * W_TILE));
+                for (int tap = 0; tap < TAPS; ++tap)
+                    for (int kb = 0; kb < NKB; ++kb) tma_load_3d(w_base + (tap * NKB + kb) * W_TILE, &tmB, &wfull, kb * KB, n0, tap);
+            }
+            int pit = 0, bit = 0;
             for (int m = m_first; m < p.m_tiles; m += m_step) {
                 const RTile tc = rtile<MT>(p, m);
                 for (int kb = 0; kb < NKB; ++kb, ++pit) {
@@ -257,6 +263,14 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
                     mbar_wait(&pempty[ps], ((pit / p.p_stages) & 1) ^ 1);
                     mbar_expect_tx(&pfull[ps], (uint32_t)PATCH_BYTES);
                     tma_load_4d(patch_base + ps * p.patch_stride, &tmA, &pfull[ps], kb * KB, tc.x0 - G::HALO, tc.y0 - G::HALO, tc.img);
+                    if (STREAM) {
+                        for (int tap = 0; tap < TAPS; ++tap, ++bit) {
+                            const int bs = bit % p.b_stages;
+                            mbar_wait(&bempty[bs], ((bit / p.b_stages) & 1) ^ 1);
+                            mbar_expect_tx(&bfull[bs], (uint32_t)W_TILE);
+                            tma_load_3d(w_base + bs * W_TILE, &tmB, &bfull[bs], kb * KB, n0, tap);
+                        }
+                    }
                 }
             }
         }
@@ -265,8 +279,8 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t w_addr = smem_u32(w_base), p_addr = smem_u32(patch_base);
         long long c_tempty = 0, c_pfull = 0, c_issue = 0, t0 = 0;
-        int pit = 0, ti = 0;
-        mbar_wait(&wfull, 0);
+        int pit = 0, ti = 0, bit = 0;
+        if (!STREAM) mbar_wait(&wfull, 0);
         for (int m = m_first; m < p.m_tiles; m += m_step, ++ti) {
             const int as = ti & 1;
             if (tr) t0 = clock64();
@@ -280,23 +294,50 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
                 mbar_wait(&pfull[ps], (pit / p.p_stages) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tr) { long long t1 = clock64(); c_pfull += t1 - t0; t0 = t1; }
-                if (elect_one()) {
+                if (!STREAM) {
+                    if (elect_one()) {
+                        const uint64_t a0 = desc_kmajor(p_addr + ps * p.patch_stride, G::PPITCH, G::LAYOUT);
+                        const uint64_t b0 = desc_kmajor(w_addr + kb * W_TILE, 8 * G::PIX, G::LAYOUT);
+                        const uint32_t wstep = (uint32_t)(NKB * W_TILE) >> 4;            // descriptor units (16 B) per tap
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                            for (int tap = 0; tap < TAPS; ++tap) {
+                                const int ky = tap / 3, kx = tap % 3;
+                                const uint64_t ad = a0 + (uint64_t)((((mt * 16 + ky) * G::PW + kx) * G::PIX) >> 4);
+                                const uint64_t bd = b0 + (uint64_t)(tap * wstep);
+#pragma unroll
+                                for (int kk = 0; kk < G::KSTEPS; ++kk)
+                                    umma_bf16(tacc + (uint32_t)(mt * p.BN), ad + 2 * kk, bd + 2 * kk, idesc, (kb | tap | kk) ? 1u : 0u);
+                            }
+                        umma_commit(&pempty[ps]);
+                        if (kb == NKB - 1) umma_commit(&tfull[as]);
+                    }
+                } else {
                     const uint64_t a0 = desc_kmajor(p_addr + ps * p.patch_stride, G::PPITCH, G::LAYOUT);
-                    const uint64_t b0 = desc_kmajor(w_addr + kb * W_TILE, 8 * G::PIX, G::LAYOUT);
-                    const uint32_t wstep = (uint32_t)(NKB * W_TILE) >> 4;            // descriptor units (16 B) per tap
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                        for (int tap = 0; tap < TAPS; ++tap) {
+                    for (int tap = 0; tap < TAPS; ++tap, ++bit) {
+                        const int bs = bit % p.b_stages;
+                        mbar_wait(&bfull[bs], (bit / p.b_stages) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (elect_one()) {
                             const int ky = tap / 3, kx = tap % 3;
-                            const uint64_t ad = a0 + (uint64_t)((((mt * 16 + ky) * G::PW + kx) * G::PIX) >> 4);
-                            const uint64_t bd = b0 + (uint64_t)(tap * wstep);
+                            const uint64_t bd = desc_kmajor(w_addr + bs * W_TILE, 8 * G::PIX, G::LAYOUT);
 #pragma unroll
-                            for (int kk = 0; kk < G::KSTEPS; ++kk)
-                                umma_bf16(tacc + (uint32_t)(mt * p.BN), ad + 2 * kk, bd + 2 * kk, idesc, (kb | tap | kk) ? 1u : 0u);
+                            for (int mt = 0; mt < MT; ++mt) {
+                                const uint64_t ad = a0 + (uint64_t)((((mt * 16 + ky) * G::PW + kx) * G::PIX) >> 4);
+#pragma unroll
+                                for (int kk = 0; kk < G::KSTEPS; ++kk)
+                                    umma_bf16(tacc + (uint32_t)(mt * p.BN), ad + 2 * kk, bd + 2 * kk, idesc, (kb | tap | kk) ? 1u : 0u);
+                            }
+                            umma_commit(&bempty[bs]);
+                            if (tap == TAPS - 1) {
+                                umma_commit(&pempty[ps]);
+                                if (kb == NKB - 1) umma_commit(&tfull[as]);
+                            }
                         }
-                    umma_commit(&pempty[ps]);
-                    if (kb == NKB - 1) umma_commit(&tfull[as]);
+                        __syncwarp();
+                    }
                 }
                 __syncwarp();
                 if (tr) { long long t1 = clock64(); c_issue += t1 - t0; t0 = t1; }
@@ -318,14 +359,17 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
         const int r = wq * 32 + lane;                      // TMEM lane = row of the staged tile
         const int et = (threadIdx.x - 128) & 127;          // 0..127 within the team
         const bool leader = et == 0;
-        const int chunks = p.BN >> 3;                      // 16-byte chunks per pixel (8 for BN = 64, 4 for BN = 32)
-        const int row_bytes = p.BN * 2;
+        // the tile is staged in sub-tiles of SUB = min(BN, 64) channels (one TMA store each: 128-byte rows are the widest a
+        // swizzled box takes)
+        const int SUB = p.BN < 64 ? p.BN : 64, n_sub = p.BN / SUB;
+        const int chunks = SUB >> 3;                       // 16-byte chunks per pixel (8 for SUB = 64, 4 for SUB = 32)
+        const int row_bytes = SUB * 2;
         // 16-byte chunk c of row q sits at (c ^ f(q)) : SWIZZLE_128B f = q & 7 (128-byte rows), SWIZZLE_64B f = (q >> 1) & 3
-        auto swz = [&](int q, int c) { return p.BN == 64 ? (c ^ (q & 7)) : (c ^ ((q >> 1) & 3)); };
+        auto swz = [&](int q, int c) { return SUB == 64 ? (c ^ (q & 7)) : (c ^ ((q >> 1) & 3)); };
         long long c_wait = 0, c_work = 0, t0 = 0;
         int ti = 0;
-        uint8_t* st = st_base + team * ST_BYTES;
-        uint8_t* pst = pst_base + team * PST_BYTES;
+        uint8_t* st_team = st_base + team * ST_BYTES;
+        uint8_t* pst_team = pst_base + team * PST_BYTES;
         if (team < N_TEAMS)
         for (int m = m_first; m < p.m_tiles; m += m_step, ++ti) {
             if (MT == 1 && (ti % N_TEAMS) != team) continue;
@@ -370,16 +414,19 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
                     }
                     continue;
                 }
+                for (int sub = 0; sub < n_sub; ++sub) {
+                uint8_t* st = st_team + sub * (128 * 128);
+                uint8_t* pst = pst_team + sub * (32 * 128);
                 uint32_t w[32];                                // the thread's pixel: up to 64 bf16 channels
 #pragma unroll
                 for (int c = 0; c < 64; c += 32) {
-                    if (c < p.BN) {
+                    if (c < SUB) {
                         uint32_t v[32];
-                        tmem_ld32(trow + c, v);
+                        tmem_ld32(trow + sub * 64 + c, v);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + j);
-                            const float4 bi = *reinterpret_cast<const float4*>(s_bias + c + j);
+                            const float4 sc = *reinterpret_cast<const float4*>(s_scale + sub * 64 + c + j);
+                            const float4 bi = *reinterpret_cast<const float4*>(s_bias + sub * 64 + c + j);
                             float a0 = fmaf(__uint_as_float(v[j]), sc.x, bi.x), a1 = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
                             float a2 = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z), a3 = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
                             if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
@@ -389,14 +436,17 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
                         }
                     }
                 }
-                if (mt == MT - 1 || N_TEAMS == 2) {            // this team is done with the tile's accumulators
+                if ((mt == MT - 1 || N_TEAMS == 2) && sub == n_sub - 1) {            // this team is done with the tile's accumulators
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[as]);
                 }
                 // the TMA store that read this team's staging tile last time has finished reading it (it had the whole
                 // accumulator drain above to do so)
-                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (leader) {
+                    if (n_sub == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                }
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
@@ -434,14 +484,15 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
                     const int y0 = tc.y0 + mt * 16;
                     if (!p.pool || p.write_full)
                         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmO),
-                                     "r"(smem_u32(st)), "r"(n0), "r"(tc.x0), "r"(y0), "r"(tc.img)
+                                     "r"(smem_u32(st)), "r"(n0 + sub * 64), "r"(tc.x0), "r"(y0), "r"(tc.img)
                                      : "memory");
                     if (p.pool)
                         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmP),
-                                     "r"(smem_u32(pst)), "r"(n0), "r"(tc.x0 >> 1), "r"(y0 >> 1), "r"(tc.img)
+                                     "r"(smem_u32(pst)), "r"(n0 + sub * 64), "r"(tc.x0 >> 1), "r"(y0 >> 1), "r"(tc.img)
                                      : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+                            }
             }
             if (tr) { long long t1 = clock64(); c_work += t1 - t0; t0 = t1; }
         }
@@ -455,13 +506,14 @@ __global__ void __launch_bounds__(384, 1) k_conv_res(const __grid_constant__ CUt
     }
 }
 
-int res_mode() {          // BBOCR_RES=0 turns the kernel off (A/B against conv_tc.cu)
+int res_mode() {          // BBOCR_RES=0 off (A/B against conv_tc.cu), 2 = force wherever supported (tests), 3 = force, no streamed variant
     static const int m = getenv("BBOCR_RES") ? atoi(getenv("BBOCR_RES")) : 1;
     return m;
 }
 
 struct ResPlan {
     int kb, taps, nkb, BN, MT, p_stages, patch_stride;
+    int stream, b_stages;
     size_t smem;
 };
 bool res_plan(const ConvW& cw, const Act& in1, const Act& out, ResPlan& pl, bool tail = false) {
@@ -471,8 +523,25 @@ bool res_plan(const ConvW& cw, const Act& in1, const Act& out, ResPlan& pl, bool
     else return false;
     if (pl.nkb < 1 || pl.nkb > 2) return false;
     if (pl.taps == 1 && pl.kb != 32) return false;              // the 1x1 variant exists for the K = 32 stem (conv1_1)
-    // two-k-block layers are tensor-bound at N = 64 (48 clk per step) and lose to conv_tc.cu's N = 128/256 tiles: forced mode only
-    if (pl.nkb == 2 && res_mode() != 2) return false;
+    pl.stream = 0;
+    pl.b_stages = 0;
+    if (pl.nkb == 2 && !tail && pl.taps == 9 && cw.cout % 128 == 0 && out.H >= 32 && res_mode() != 3) {
+        // Cin = 128, Cout a multiple of 128: 128-wide channel slices (tensor-bound at the full N = 128 rate), two stacked
+        // M-tiles per patch, weight tiles streamed through a ring (each 16 KB tile feeds 8 MMAs = 512 tensor cycles)
+        pl.stream = 1;
+        pl.BN = 128;
+        pl.MT = 2;
+        pl.patch_stride = (((16 * 2 + 2) * 10 * 128) + 1023) & ~1023;
+        pl.p_stages = 2;
+        const size_t staging = (size_t)(128 + 32) * 128 * 2;                      // one epilogue team
+        const size_t budget = 222 * 1024 - 1024 - 2 * (size_t)pl.patch_stride - staging;
+        pl.b_stages = (int)std::min<size_t>(8, budget / (128 * 128));
+        if (pl.b_stages < 3) return false;
+        pl.smem = (size_t)pl.b_stages * 128 * 128 + 2 * (size_t)pl.patch_stride + staging + 1024;
+        return true;
+    }
+    // other two-k-block layers would be tensor-bound at N = 64 (48 clk per step) and lose to conv_tc.cu: forced mode only
+    if (pl.nkb == 2 && res_mode() < 2) return false;
     pl.BN = std::min(cw.cout_pad, 64);
     if (tail) { if (cw.cout != 16 || cw.cout_pad != 16) return false; }
     else if ((pl.BN != 32 && pl.BN != 64) || cw.cout % pl.BN != 0) return false;      // staged tile rows of 64 / 128 bytes
@@ -496,14 +565,14 @@ bool res_plan(const ConvW& cw, const Act& in1, const Act& out, ResPlan& pl, bool
     return false;
 }
 
-template <int KB, int TAPS, int NKB, int MT, int EPI = 0>
+template <int KB, int TAPS, int NKB, int MT, int EPI = 0, int STREAM = 0>
 void res_launch(int grid, size_t smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO,
                 const CUtensorMap& mP, const ResParams& p) {
     static std::once_flag once;        // one device per process in this library (one rank per GPU)
     std::call_once(once, [] {
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<KB, TAPS, NKB, MT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<KB, TAPS, NKB, MT, EPI, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
     });
-    k_conv_res<KB, TAPS, NKB, MT, EPI><<<grid, 384, smem, st>>>(mA, mB, mO, mP, p);
+    k_conv_res<KB, TAPS, NKB, MT, EPI, STREAM><<<grid, 384, smem, st>>>(mA, mB, mO, mP, p);
 }
 
 }  // namespace
@@ -543,6 +612,7 @@ void conv_res_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in
     p.bias = cw.bias;
     p.p_stages = pl.p_stages;
     p.patch_stride = pl.patch_stride;
+    p.b_stages = pl.b_stages;
     p.trace = nullptr;
     if (pooled) {
         p.pool = (flags & CONV_POOL22) ? 1 : 2;
@@ -563,8 +633,9 @@ void conv_res_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in
     auto out_map = [&](void* base, int OH, int OW, uint32_t bw, uint32_t bh) {
         uint64_t od[4] = {(uint64_t)cw.cout, (uint64_t)OW, (uint64_t)OH, (uint64_t)out.N};
         uint64_t os[3] = {(uint64_t)cw.cout * 2, (uint64_t)OW * cw.cout * 2, (uint64_t)OH * OW * cw.cout * 2};
-        uint32_t ob[4] = {(uint32_t)pl.BN, bw, bh, 1};
-        return tc_make_map(base, 4, od, os, ob, pl.BN);
+        const int sub = std::min(pl.BN, 64);                 // staged sub-tiles of at most 64 channels (128-byte rows)
+        uint32_t ob[4] = {(uint32_t)sub, bw, bh, 1};
+        return tc_make_map(base, 4, od, os, ob, sub);
     };
     CUtensorMap mO = p.write_full && out.p ? out_map(out.p, out.H, out.W, 8, 16) : mA;
     CUtensorMap mP = p.pool ? out_map(p.out2, out.H / 2, out.W / 2, 4, 8) : mO;
@@ -579,8 +650,9 @@ void conv_res_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in
         CUDA_CHECK(cudaMemsetAsync(dtrace.p, 0, 64, st));
         p.trace = dtrace.as<long long>();
     }
-    const int key = pl.kb * 1000 + pl.taps * 100 + pl.nkb * 10 + pl.MT;
+    const int key = pl.kb * 1000 + pl.taps * 100 + pl.nkb * 10 + pl.MT + (pl.stream ? 100000 : 0);
     switch (key) {
+        case 100000 + 64000 + 900 + 20 + 2: res_launch<64, 9, 2, 2, 0, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
         case 64000 + 900 + 10 + 2: res_launch<64, 9, 1, 2>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
         case 64000 + 900 + 10 + 1: res_launch<64, 9, 1, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
         case 64000 + 900 + 20 + 1: res_launch<64, 9, 2, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
@@ -597,9 +669,9 @@ void conv_res_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in
         CUDA_CHECK(cudaMemcpyAsync(t, p.trace, 64, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         const double n = t[3] > 0 ? (double)t[3] : 1.0;
-        fprintf(stderr, "[conv_res trace] %dx%d k%d cin %d cout %d BN %d MT %d stages %d grid %d | CTA0: %lld tiles; per tile: mma wait-tmem %.0f "
+        fprintf(stderr, "[conv_res trace] %dx%d k%d cin %d cout %d BN %d MT %d stages %d b-stages %d grid %d | CTA0: %lld tiles; per tile: mma wait-tmem %.0f "
                         "wait-patch %.0f issue %.0f | epilogue wait %.0f work %.0f cycles\n",
-                out.H, out.W, cw.kh, cw.cin, cw.cout, pl.BN, pl.MT, pl.p_stages, grid, t[3], t[0] / n, t[1] / n, t[2] / n, t[4] / n, t[5] / n);
+                out.H, out.W, cw.kh, cw.cin, cw.cout, pl.BN, pl.MT, pl.p_stages, pl.b_stages, grid, t[3], t[0] / n, t[1] / n, t[2] / n, t[4] / n, t[5] / n);
     }
 }
 

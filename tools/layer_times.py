@@ -6,7 +6,7 @@ import numpy as np, torch
 from bbocr_b200 import _lib
 h = _lib.Handle(0); h.set_precision(_lib.PREC_BF16)
 L = h.L
-shapes = [("conv1_1", 1440, 1920, 32, 64, 1), ("cls0", 720, 960, 32, 32), ("conv1_2", 1440, 1920, 64, 64), ("conv2_1", 720, 960, 64, 128), ("conv2_2", 720, 960, 128, 128), ("up3b", 360, 480, 128, 64),
+shapes = [("conv1_1", 1440, 1920, 32, 64, 1), ("cls0", 720, 960, 32, 32), ("conv1_2", 1440, 1920, 64, 64), ("conv2_1", 720, 960, 64, 128), ("conv2_2", 720, 960, 128, 128), ("conv3_1", 360, 480, 128, 256), ("up3b", 360, 480, 128, 64),
           ("up4b", 720, 960, 64, 32), ("conv3_2", 360, 480, 256, 256), ("conv4_2", 180, 240, 512, 512)]
 for name, H, W, ci, co, *kk in shapes:
     k = kk[0] if kk else 3
