@@ -65,7 +65,7 @@ SYMBOLS = [
     "bbocr_pp_clahe", "bbocr_pp_unsharp", "bbocr_pp_adaptive_threshold", "bbocr_pp_deskew", "bbocr_craft_forward",
     "bbocr_det_boxes", "bbocr_min_area_box", "bbocr_group_boxes", "bbocr_crop_horizontal", "bbocr_crop_free",
     "bbocr_crnn_forward", "bbocr_ctc_decode", "bbocr_default_params", "bbocr_readtext", "bbocr_readtext_batch",
-    "bbocr_results_free", "bbocr_launch_count", "bbocr_reset_launch_count", "bbocr_conv_stats",
+    "bbocr_recognize", "bbocr_results_free", "bbocr_launch_count", "bbocr_reset_launch_count", "bbocr_conv_stats",
     "bbocr_enable_conv_timing",
 ]
 
@@ -342,6 +342,18 @@ class Handle:
         p = C.byref(params) if params is not None else None
         self._check(self.L.bbocr_readtext_batch(self._h, C.c_int(n), arr, p, outs))
         return [self._unpack(outs[i]) for i in range(n)]
+
+    def recognize_raw(self, gray, horizontal_list, free_list, params: Params | None = None):
+        """Reader.recognize on a host gray page: boxes -> [(box, is_free, class indices, confidence)] (bbocr_recognize)."""
+        g, gp = _u8(gray)
+        hl = np.ascontiguousarray(np.asarray(horizontal_list, np.int32).reshape(-1, 4))
+        fl = np.ascontiguousarray(np.asarray(free_list, np.float64).reshape(-1, 8))
+        out = C.c_void_p()
+        p = C.byref(params) if params is not None else None
+        self._check(self.L.bbocr_recognize(self._h, gp, C.c_int(g.shape[0]), C.c_int(g.shape[1]), C.c_int(0),
+                                           hl.ctypes.data_as(C.c_void_p), C.c_int(len(hl)), fl.ctypes.data_as(C.c_void_p),
+                                           C.c_int(len(fl)), p, C.byref(out)))
+        return self._unpack(out)
 
     # ---- instrumentation -------------------------------------------------------------------------------------------
     def launch_count(self) -> int:

@@ -745,6 +745,53 @@ struct PageWork {
     int n_crops_run = 0;
 };
 
+// utils.get_image_list for the boxes of one page (batch_size == 1 semantics: every box has its own max_width): crop jobs in
+// upstream order (horizontal list, then free list) and the packed u8 crops on the device
+void build_crops(Handle* h, Lane& lane, const uint8_t* gray, int H, int W, const std::vector<int32_t>& hlist,
+                 const std::vector<double>& flist, PageWork& pw) {
+    cudaStream_t st = lane.stream;
+    std::vector<CropJob>& jobs = pw.jobs;
+    std::vector<double> mats;
+    size_t scratch_bytes = 0;
+    for (size_t i = 0; i + 4 <= hlist.size(); i += 4) {
+        CropJob j;
+        horizontal_job(&hlist[i], H, W, j);
+        if (finish_geometry(j)) jobs.push_back(j);
+    }
+    for (size_t i = 0; i + 8 <= flist.size(); i += 8) {
+        CropJob j;
+        int mwid, mhei;
+        double M[9];
+        free_box_transform(&flist[i], &mwid, &mhei, M);
+        if (mwid <= 0 || mhei <= 0) fail(BBOCR_E_ARG, "degenerate free-form box");
+        j.is_free = true;
+        memcpy(j.box, &flist[i], 64);
+        j.d.free_idx = (int)mats.size() / 9;
+        mats.insert(mats.end(), M, M + 9);
+        j.d.x0 = (int)scratch_bytes; j.d.y0 = 0; j.d.w = mwid; j.d.h = mhei;
+        scratch_bytes += (size_t)mwid * mhei;
+        if (finish_geometry(j)) jobs.push_back(j);
+    }
+    const int n = (int)jobs.size();
+    pw.rec.assign(n, Recognized());
+    if (n > 0) {
+        size_t crops_bytes = 0;
+        for (auto& j : jobs) { j.d.off = (int)crops_bytes; crops_bytes += (size_t)j.d.ow * j.d.oh; }
+        pw.crops_bytes = crops_bytes;
+        std::vector<CropDesc> descs(n);
+        for (int i = 0; i < n; ++i) descs[i] = jobs[i].d;
+        DevBuf ddesc, dmats, dscratch(scratch_bytes + 16, st);
+        pw.dcrops.alloc(crops_bytes + 16, st);
+        upload(lane, ddesc, descs.data(), descs.size() * sizeof(CropDesc));
+        if (!mats.empty()) {
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            upload(lane, dmats, mats.data(), mats.size() * 8);
+        }
+        crops_dev(h, st, gray, H, W, ddesc.as<CropDesc>(), n, descs.data(), dmats.as<double>(), dscratch.as<uint8_t>(),
+                  pw.dcrops.as<uint8_t>());
+    }
+}
+
 // Reader.detect + utils.get_image_list for one page on one lane; leaves the page's crops on the device
 void detect_page(Handle* h, Lane& lane, const bbocr_image& img, const bbocr_params& p, PageWork& pw) {
     cudaStream_t st = lane.stream;
@@ -791,47 +838,7 @@ void detect_page(Handle* h, Lane& lane, const bbocr_image& img, const bbocr_para
     std::vector<int32_t> hlist;
     std::vector<double> flist;
     group_boxes(boxes.data(), (int)boxes.size() / 8, g.ratio, gp, hlist, flist);
-    // ---- crops (batch_size == 1 semantics: every box has its own max_width) -----------------------------------------
-    std::vector<CropJob>& jobs = pw.jobs;
-    std::vector<double> mats;
-    size_t scratch_bytes = 0;
-    for (size_t i = 0; i + 4 <= hlist.size(); i += 4) {
-        CropJob j;
-        horizontal_job(&hlist[i], H, W, j);
-        if (finish_geometry(j)) jobs.push_back(j);
-    }
-    for (size_t i = 0; i + 8 <= flist.size(); i += 8) {
-        CropJob j;
-        int mwid, mhei;
-        double M[9];
-        free_box_transform(&flist[i], &mwid, &mhei, M);
-        if (mwid <= 0 || mhei <= 0) fail(BBOCR_E_ARG, "degenerate free-form box");
-        j.is_free = true;
-        memcpy(j.box, &flist[i], 64);
-        j.d.free_idx = (int)mats.size() / 9;
-        mats.insert(mats.end(), M, M + 9);
-        j.d.x0 = (int)scratch_bytes; j.d.y0 = 0; j.d.w = mwid; j.d.h = mhei;
-        scratch_bytes += (size_t)mwid * mhei;
-        if (finish_geometry(j)) jobs.push_back(j);
-    }
-    const int n = (int)jobs.size();
-    pw.rec.assign(n, Recognized());
-    if (n > 0) {
-        size_t crops_bytes = 0;
-        for (auto& j : jobs) { j.d.off = (int)crops_bytes; crops_bytes += (size_t)j.d.ow * j.d.oh; }
-        pw.crops_bytes = crops_bytes;
-        std::vector<CropDesc> descs(n);
-        for (int i = 0; i < n; ++i) descs[i] = jobs[i].d;
-        DevBuf ddesc, dmats, dscratch(scratch_bytes + 16, st);
-        pw.dcrops.alloc(crops_bytes + 16, st);
-        upload(lane, ddesc, descs.data(), descs.size() * sizeof(CropDesc));
-        if (!mats.empty()) {
-            CUDA_CHECK(cudaStreamSynchronize(st));
-            upload(lane, dmats, mats.data(), mats.size() * 8);
-        }
-        crops_dev(h, st, gray, H, W, ddesc.as<CropDesc>(), n, descs.data(), dmats.as<double>(), dscratch.as<uint8_t>(),
-                  pw.dcrops.as<uint8_t>());
-    }
+    build_crops(h, lane, gray, H, W, hlist, flist, pw);
     CUDA_CHECK(cudaStreamSynchronize(st));                 // the page's crops are complete; pinned staging is free again
     lane.in_busy = false;
 }
@@ -981,6 +988,30 @@ int bbocr_readtext(bbocr_handle* h, const bbocr_image* img, const bbocr_params* 
         bbocr_params dp;
         if (!p) { bbocr_default_params(&dp); p = &dp; }
         *out = readtext_page(h, h->lanes[0], *img, *p);
+    });
+}
+
+int bbocr_recognize(bbocr_handle* h, const uint8_t* gray, int H, int W, int on_device, const int32_t* hlist, int nh,
+                    const double* flist, int nf, const bbocr_params* p, bbocr_results** out) {
+    return guarded(h, [&] {
+        ARG_CHECK(gray && out && H > 0 && W > 0 && nh >= 0 && nf >= 0 && (nh == 0 || hlist) && (nf == 0 || flist), "bad arguments");
+        if (!h->crnn_loaded) fail(BBOCR_E_STATE, "weights not loaded");
+        bbocr_params dp;
+        if (!p) { bbocr_default_params(&dp); p = &dp; }
+        Lane& lane = h->lanes[0];
+        DevBuf dgray;
+        const uint8_t* g = gray;
+        if (!on_device) { upload(lane, dgray, gray, (size_t)H * W); g = dgray.as<uint8_t>(); }
+        PageWork pw;
+        pw.H = H; pw.W = W;
+        std::vector<int32_t> hl(hlist, hlist + (size_t)nh * 4);
+        std::vector<double> fl(flist, flist + (size_t)nf * 8);
+        build_crops(h, lane, g, H, W, hl, fl, pw);
+        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        lane.in_busy = false;
+        std::vector<PageWork*> one{&pw};
+        recognize_group(h, lane, one, *p);
+        *out = assemble_page(pw);
     });
 }
 

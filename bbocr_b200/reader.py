@@ -199,6 +199,26 @@ class Reader:
         hl, fl = _lib.group_boxes(boxes, ratio, slope_ths, ycenter_ths, height_ths, width_ths, add_margin, min_size)
         return [[list(map(int, b)) for b in hl]], [[[[float(x), float(y)] for x, y in q] for q in fl]]
 
+    def recognize(self, img_cv_grey, horizontal_list=None, free_list=None, decoder="greedy", beamWidth=5, batch_size=1,
+                  workers=0, allowlist=None, blocklist=None, detail=1, rotation_info=None, paragraph=False, contrast_ths=0.1,
+                  adjust_contrast=0.5, filter_ths=0.003, y_ths=0.5, x_ths=1.0, reformat=True, output_format="standard",
+                  **_ignored):
+        """Reader.recognize -> [(box, text, confidence)] for the given boxes (upstream order: horizontal, then free).
+        With both lists None the whole image is one horizontal box, like upstream."""
+        self._check_unsupported(decoder, rotation_info, paragraph)
+        if reformat:
+            _, img_cv_grey = reformat_input(img_cv_grey) if not (isinstance(img_cv_grey, np.ndarray) and img_cv_grey.ndim == 2) \
+                else (None, img_cv_grey)
+            if img_cv_grey is None:
+                raise ValueError("recognize needs a gray image (2-D array, path or bytes)")
+        if horizontal_list is None and free_list is None:
+            y_max, x_max = img_cv_grey.shape
+            horizontal_list, free_list = [[0, x_max, 0, y_max]], []
+        p, keep = self._params({"contrast_ths": contrast_ths, "adjust_contrast": adjust_contrast}, allowlist, blocklist)
+        with self._lock:
+            raw, _ = self._h.recognize_raw(np.ascontiguousarray(img_cv_grey), horizontal_list or [], free_list or [], p)
+        return self._format(raw, detail, output_format)
+
     def score_maps(self, img, canvas_size=2560, mag_ratio=1.0):
         with self._lock:
             return self._h.craft_forward(img, canvas_size, mag_ratio)

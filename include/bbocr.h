@@ -176,6 +176,11 @@ typedef struct {
 int bbocr_readtext(bbocr_handle* h, const bbocr_image* img, const bbocr_params* p, bbocr_results** out);
 /* readtext over n independent pages, pipelined over the handle's streams; out[i] filled per page. */
 int bbocr_readtext_batch(bbocr_handle* h, int n, const bbocr_image* imgs, const bbocr_params* p, bbocr_results** out);
+/* Reader.recognize (easyocr/easyocr.py): crops (utils.get_image_list), AlignCollate, CRNN, greedy CTC and the
+ * contrast-retry pass for given boxes of one gray page.  hlist: nh x [x_min, x_max, y_min, y_max]; flist: nf x 4 (x,y)
+ * corners.  Results in upstream order: horizontal boxes, then free boxes. */
+int bbocr_recognize(bbocr_handle* h, const uint8_t* gray, int H, int W, int on_device, const int32_t* hlist, int nh,
+                    const double* flist, int nf, const bbocr_params* p, bbocr_results** out);
 void bbocr_results_free(bbocr_results* r);
 
 /* ---- instrumentation -------------------------------------------------------------------------------------------- */

@@ -187,3 +187,27 @@ def test_ragged_strip_equals_width_buckets(gpu_reader, tmp_path):
     want = json.load(open(tmp_path / "buckets.json"))
     assert sum(len(p) for p in want) > 20
     assert json.loads(json.dumps(got)) == want
+
+
+def test_detect_then_recognize_equals_readtext(gpu_reader):
+    """Reader.detect + Reader.recognize (the upstream stage boundary) give exactly readtext's result; recognition-only on
+    a strip of synthetic text lines (BASELINE config 4 in miniature) returns one result per box in box order."""
+    img = synth.title_page(95, 800, 608)
+    want = gpu_reader.readtext(img)
+    hl, fl = gpu_reader.detect(img)
+    grey = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+    got = gpu_reader.recognize(grey, hl[0], fl[0])
+    assert got == want and len(want) > 3
+    rng = np.random.default_rng(4)
+    lines = [synth.text_line_crop(rng, width_px=int(w)) for w in (90, 200, 333, 512, 700, 801)]
+    H = sum(c.shape[0] for c in lines) + 10 * len(lines)
+    page = np.full((H, 832), 235, np.uint8)
+    boxes, y = [], 5
+    for c in lines:
+        page[y:y + c.shape[0], 8:8 + c.shape[1]] = c
+        boxes.append([8, 8 + c.shape[1], y, y + c.shape[0]])
+        y += c.shape[0] + 10
+    res = gpu_reader.recognize(page, boxes, [])
+    assert [r[0] for r in res] == [[[b[0], b[2]], [b[1], b[2]], [b[1], b[3]], [b[0], b[3]]] for b in boxes]
+    single = [gpu_reader.recognize(page, [b], [])[0] for b in boxes]
+    assert res == single                                    # batching crops never changes a crop's result
