@@ -311,11 +311,14 @@ class Handle:
         r = C.cast(rp, C.POINTER(Results)).contents
         n = r.n
         out = []
-        offs = [r.text_off[i] for i in range(n + 1)]
-        for i in range(n):
-            box = np.array([r.box[i * 8 + j] for j in range(8)], np.float64).reshape(4, 2)
-            txt = [r.text_idx[k] for k in range(offs[i], offs[i + 1])]
-            out.append((box, bool(r.is_free[i]), txt, float(r.conf[i])))
+        if n > 0:                                   # bulk views over the result arrays (no per-element ctypes access)
+            boxes = np.ctypeslib.as_array(r.box, (n, 4, 2)).copy()
+            free = np.ctypeslib.as_array(r.is_free, (n,)).astype(bool).tolist()
+            offs = np.ctypeslib.as_array(r.text_off, (n + 1,)).tolist()
+            conf = np.ctypeslib.as_array(r.conf, (n,)).tolist()
+            idx = np.ctypeslib.as_array(r.text_idx, (max(offs[n], 1),)).tolist()
+            for i in range(n):
+                out.append((boxes[i], free[i], idx[offs[i]:offs[i + 1]], conf[i]))
         stats = {"n_crops": r.n_crops, "n_components": r.n_components}
         self.L.bbocr_results_free(rp)
         return out, stats

@@ -125,12 +125,10 @@ class Reader:
 
     def _format(self, raw, detail=1, output_format="standard"):
         out = []
+        chars = self.character
         for box, is_free, idx, conf in raw:
-            text = "".join(self.character[i - 1] for i in idx)
-            if is_free:
-                b = [[float(x), float(y)] for x, y in box]
-            else:
-                b = [[int(x), int(y)] for x, y in box]
+            text = "".join([chars[i - 1] for i in idx])
+            b = box.tolist() if is_free else box.astype(np.int64).tolist()      # upstream: floats for free boxes, ints otherwise
             out.append((b, text, conf))
         if detail == 0:
             return [item[1] for item in out]
