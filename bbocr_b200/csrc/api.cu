@@ -118,6 +118,8 @@ int bbocr_create(int device, bbocr_handle** out) {
             h->n_det_lanes = std::min(std::max(nl, 1), 32);
             const char* r = getenv("BBOCR_REC_LANES");    // recogniser groups in flight
             int nr = r ? atoi(r) : 2;
+            const char* b = getenv("BBOCR_DET_BATCH");    // same-size pages per detector-network launch chain
+            h->det_batch = std::min(std::max(b ? atoi(b) : 2, 1), 16);
             const char* g = getenv("BBOCR_REC_GROUP");    // pages per recogniser group
             h->rec_group = std::max(1, g ? atoi(g) : 32);
             h->lanes.resize(h->n_det_lanes + std::min(std::max(nr, 1), 8));
@@ -132,7 +134,7 @@ int bbocr_create(int device, bbocr_handle** out) {
             // Reserve the working set up front: growing the pool later means cudaMalloc-class calls that serialise
             // every lane.  180 GB of HBM3e per GPU; the default reservation covers 8 pages of 1920x1440 in flight.
             const char* e = getenv("BBOCR_POOL_GB");
-            double gb = e ? atof(e) : 16.0;
+            double gb = e ? atof(e) : 32.0;
             size_t free_b = 0, total_b = 0;
             CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
             size_t want = std::min((size_t)(gb * (1ull << 30)), free_b / 2);
@@ -793,54 +795,71 @@ void build_crops(Handle* h, Lane& lane, const uint8_t* gray, int H, int W, const
 }
 
 // Reader.detect + utils.get_image_list for one page on one lane; leaves the page's crops on the device
-void detect_page(Handle* h, Lane& lane, const bbocr_image& img, const bbocr_params& p, PageWork& pw) {
+// k pages of identical size on one lane: the detector network runs them as ONE batch (every layer one launch), the
+// per-page part (components, boxes, crops) follows page by page.
+void detect_pages(Handle* h, Lane& lane, const bbocr_image* const* imgs, int k, const bbocr_params& p, PageWork* const* pws) {
     cudaStream_t st = lane.stream;
-    ARG_CHECK(img.color && img.H > 0 && img.W > 0, "bad image");
     if (!h->craft_loaded || !h->crnn_loaded) fail(BBOCR_E_STATE, "weights not loaded");
-    const int H = img.H, W = img.W;
-    pw.H = H; pw.W = W;
-    DevBuf dcolor, dgray;
-    const uint8_t* color = img.color;
-    const uint8_t* gray = img.gray;
-    if (!img.on_device) {
-        size_t cb = (size_t)H * W * 3, gb = img.gray ? (size_t)H * W : 0;
-        uint8_t* pin = (uint8_t*)staging(lane, cb + gb);
-        memcpy(pin, img.color, cb);
-        if (gb) memcpy(pin + cb, img.gray, gb);
-        dcolor.alloc(cb + gb, st);
-        CUDA_CHECK(cudaMemcpyAsync(dcolor.p, pin, cb + gb, cudaMemcpyHostToDevice, st));
-        lane.in_busy = true;
-        color = dcolor.as<uint8_t>();
-        gray = gb ? dcolor.as<uint8_t>() + cb : nullptr;
-    }
-    if (!gray) {                                      // reformat_input: cv2.cvtColor(image, COLOR_BGR2GRAY)
-        dgray.alloc((size_t)H * W, st);
-        pp_gray(h, st, color, H, W, W * 3, dgray.as<uint8_t>());
-        gray = dgray.as<uint8_t>();
+    ARG_CHECK(k >= 1 && k <= 16, "bad detector batch");
+    const int H = imgs[0]->H, W = imgs[0]->W;
+    std::vector<DevBuf> dcolor(k), dgray(k);
+    std::vector<const uint8_t*> color(k), gray(k);
+    for (int i = 0; i < k; ++i) {
+        const bbocr_image& img = *imgs[i];
+        ARG_CHECK(img.color && img.H == H && img.W == W && H > 0 && W > 0, "bad image");
+        pws[i]->H = H; pws[i]->W = W;
+        color[i] = img.color;
+        gray[i] = img.gray;
+        if (!img.on_device) {
+            size_t cb = (size_t)H * W * 3, gb = img.gray ? (size_t)H * W : 0;
+            uint8_t* pin = (uint8_t*)staging(lane, cb + gb);
+            memcpy(pin, img.color, cb);
+            if (gb) memcpy(pin + cb, img.gray, gb);
+            dcolor[i].alloc(cb + gb, st);
+            CUDA_CHECK(cudaMemcpyAsync(dcolor[i].p, pin, cb + gb, cudaMemcpyHostToDevice, st));
+            lane.in_busy = true;
+            color[i] = dcolor[i].as<uint8_t>();
+            gray[i] = gb ? dcolor[i].as<uint8_t>() + cb : nullptr;
+        }
+        if (!gray[i]) {                                   // reformat_input: cv2.cvtColor(image, COLOR_BGR2GRAY)
+            dgray[i].alloc((size_t)H * W, st);
+            pp_gray(h, st, color[i], H, W, W * 3, dgray[i].as<uint8_t>());
+            gray[i] = dgray[i].as<uint8_t>();
+        }
     }
     // ---- detect -------------------------------------------------------------------------------------------------
     std::unique_ptr<StageTimer> tm(new StageTimer(h, 0));
     CanvasGeom g = canvas_geom(H, W, p.canvas_size, p.mag_ratio);
     const int mh = g.H32 / 2, mw = g.W32 / 2;
-    DevBuf maps((size_t)mh * mw * 8, st);
+    const size_t plane = (size_t)mh * mw;
+    DevBuf maps((size_t)k * plane * 8, st);
     float* text = maps.as<float>();
-    float* link = text + (size_t)mh * mw;
-    craft_forward_dev(h, st, color, g, text, link);
-    tm.reset(new StageTimer(h, 1));
-    DetComponents dc;
-    det_components_dev(h, lane, text, link, mh, mw, (float)p.text_threshold, (float)p.link_threshold, (float)p.low_text, dc);
-    maps.release();
-    pw.n_labels = dc.n_labels;
-    tm.reset(new StageTimer(h, 2));
-    std::vector<float> boxes;
-    boxes_from_components(dc, mh, mw, boxes);
-    bbocr_group_params gp{p.slope_ths, p.ycenter_ths, p.height_ths, p.width_ths, p.add_margin, p.min_size};
-    std::vector<int32_t> hlist;
-    std::vector<double> flist;
-    group_boxes(boxes.data(), (int)boxes.size() / 8, g.ratio, gp, hlist, flist);
-    build_crops(h, lane, gray, H, W, hlist, flist, pw);
-    CUDA_CHECK(cudaStreamSynchronize(st));                 // the page's crops are complete; pinned staging is free again
+    float* link = text + (size_t)k * plane;
+    craft_forward_batch_dev(h, st, color.data(), k, g, text, link);
+    for (int i = 0; i < k; ++i) {
+        tm.reset(new StageTimer(h, 1));
+        DetComponents dc;
+        det_components_dev(h, lane, text + i * plane, link + i * plane, mh, mw, (float)p.text_threshold, (float)p.link_threshold,
+                           (float)p.low_text, dc);
+        pws[i]->n_labels = dc.n_labels;
+        tm.reset(new StageTimer(h, 2));
+        std::vector<float> boxes;
+        boxes_from_components(dc, mh, mw, boxes);
+        bbocr_group_params gp{p.slope_ths, p.ycenter_ths, p.height_ths, p.width_ths, p.add_margin, p.min_size};
+        std::vector<int32_t> hlist;
+        std::vector<double> flist;
+        group_boxes(boxes.data(), (int)boxes.size() / 8, g.ratio, gp, hlist, flist);
+        build_crops(h, lane, gray[i], H, W, hlist, flist, *pws[i]);
+    }
+    tm.reset();
+    CUDA_CHECK(cudaStreamSynchronize(st));                 // the pages' crops are complete; pinned staging is free again
     lane.in_busy = false;
+}
+
+void detect_page(Handle* h, Lane& lane, const bbocr_image& img, const bbocr_params& p, PageWork& pw) {
+    const bbocr_image* ip = &img;
+    PageWork* pp = &pw;
+    detect_pages(h, lane, &ip, 1, p, &pp);
 }
 
 // Reader.recognize over the crops of a group of pages (pass 1, then the contrast-retry pass for low-confidence crops)
@@ -1024,7 +1043,7 @@ int bbocr_readtext_batch(bbocr_handle* h, int n, const bbocr_image* imgs, const 
         if (n == 0) return;
         // Detector lanes (stream + pinned staging + host thread each) take pages off a shared counter; recogniser lanes
         // take GROUPS of finished pages off a ready queue (detection of later pages overlaps recognition of earlier ones).
-        const int nd = std::min<int>(h->n_det_lanes, n);
+        const int nd = std::min<int>(h->n_det_lanes, cdiv(n, h->det_batch));
         const int nr = std::min<int>((int)h->lanes.size() - h->n_det_lanes, std::max(1, cdiv(n, h->rec_group)));
         std::vector<PageWork> work(n);
         std::atomic<int> next{0};
@@ -1048,13 +1067,27 @@ int bbocr_readtext_batch(bbocr_handle* h, int n, const bbocr_image* imgs, const 
             threads.emplace_back([&, l] {
                 try {
                     CUDA_CHECK(cudaSetDevice(h->device));
-                    for (int i; (i = next.fetch_add(1)) < n;) {
-                        work[i].index = i;
-                        detect_page(h, h->lanes[l], imgs[i], *p, work[i]);
-                        std::lock_guard<std::mutex> g(qmu);
-                        ready.push_back(i);
-                        ++det_done;
-                        qcv.notify_all();
+                    const int db = h->det_batch;
+                    for (int i0; (i0 = next.fetch_add(db)) < n;) {
+                        const int kmax = std::min(db, n - i0);
+                        for (int j = 0; j < kmax;) {
+                            // consecutive pages of identical size go through the detector network as one batch
+                            int k = 1;
+                            while (j + k < kmax && imgs[i0 + j + k].H == imgs[i0 + j].H && imgs[i0 + j + k].W == imgs[i0 + j].W) ++k;
+                            const bbocr_image* ip[16];
+                            PageWork* pp[16];
+                            for (int q = 0; q < k; ++q) {
+                                work[i0 + j + q].index = i0 + j + q;
+                                ip[q] = &imgs[i0 + j + q];
+                                pp[q] = &work[i0 + j + q];
+                            }
+                            detect_pages(h, h->lanes[l], ip, k, *p, pp);
+                            std::lock_guard<std::mutex> g(qmu);
+                            for (int q = 0; q < k; ++q) ready.push_back(i0 + j + q);
+                            det_done += k;
+                            qcv.notify_all();
+                            j += k;
+                        }
                     }
                 } catch (const Error& e) {
                     record(l, e.code, e.what());

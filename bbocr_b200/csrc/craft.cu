@@ -92,29 +92,39 @@ __global__ void k_im2col_rgb(const uint8_t* __restrict__ img, int th, int tw, __
 extern thread_local int g_conv_scope;
 
 void craft_forward_dev(Handle* h, cudaStream_t st, const uint8_t* img_dev, const CanvasGeom& g, float* text, float* link) {
+    craft_forward_batch_dev(h, st, &img_dev, 1, g, text, link);
+}
+
+// nimg images of identical geometry through the network as ONE batch (NHWC with N = nimg): every layer is one launch, so
+// the per-launch fixed costs (prologue, resident-weight load, tail wave) are shared and the small 1/16-resolution layers
+// get nimg x the tiles.  text / link: [nimg][H32/2][W32/2] planes.
+void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* imgs_dev, int nimg, const CanvasGeom& g, float* text,
+                             float* link) {
     struct Scope { Scope() { g_conv_scope = 1; } ~Scope() { g_conv_scope = 0; } } scope_guard;
     if (!h->craft_loaded) fail(BBOCR_E_STATE, "CRAFT weights not loaded (bbocr_load_craft)");
     const CraftW& w = h->craft;
     const int H = g.H32, W = g.W32;
-    DevBuf resized;
-    const uint8_t* src = img_dev;
-    if (g.th != g.H || g.tw != g.W) {
-        resized.alloc((size_t)g.th * g.tw * 3, st);
-        resize_bilinear_u8(h, st, img_dev, g.H, g.W, g.W * 3, 3, resized.as<uint8_t>(), g.th, g.tw);
-        src = resized.as<uint8_t>();
-    }
+    ARG_CHECK(nimg >= 1 && nimg <= 16, "craft: batch of %d images", nimg);
     const float m0 = (float)(0.485 * 255.0), m1 = (float)(0.456 * 255.0), m2 = (float)(0.406 * 255.0);
     const float s0 = (float)(0.229 * 255.0), s1 = (float)(0.224 * 255.0), s2 = (float)(0.225 * 255.0);
     const bool tc_first = h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv;
-    DevBuf canvas;
-    if (tc_first) {
-        canvas.alloc((size_t)H * W * 64, st);
-        k_im2col_rgb<<<dim3(cdiv(W, 128), H), 128, 0, st>>>(src, g.th, g.tw, canvas.as<__nv_bfloat16>(), H, W, m0, m1, m2, s0, s1, s2);
-    } else {
-        canvas.alloc((size_t)H * W * 16, st);
-        k_canvas<<<dim3(cdiv(W, 256), H), 256, 0, st>>>(src, g.th, g.tw, canvas.as<float>(), H, W, m0, m1, m2, s0, s1, s2);
+    const size_t canvas_px_bytes = tc_first ? 64 : 16;
+    DevBuf canvas((size_t)nimg * H * W * canvas_px_bytes, st), resized;
+    const bool need_resize = g.th != g.H || g.tw != g.W;
+    if (need_resize) resized.alloc((size_t)g.th * g.tw * 3, st);
+    for (int i = 0; i < nimg; ++i) {
+        const uint8_t* src = imgs_dev[i];
+        if (need_resize) {
+            resize_bilinear_u8(h, st, imgs_dev[i], g.H, g.W, g.W * 3, 3, resized.as<uint8_t>(), g.th, g.tw);
+            src = resized.as<uint8_t>();
+        }
+        uint8_t* dst = canvas.as<uint8_t>() + (size_t)i * H * W * canvas_px_bytes;
+        if (tc_first)
+            k_im2col_rgb<<<dim3(cdiv(W, 128), H), 128, 0, st>>>(src, g.th, g.tw, reinterpret_cast<__nv_bfloat16*>(dst), H, W, m0, m1, m2, s0, s1, s2);
+        else
+            k_canvas<<<dim3(cdiv(W, 256), H), 256, 0, st>>>(src, g.th, g.tw, reinterpret_cast<float*>(dst), H, W, m0, m1, m2, s0, s1, s2);
+        count_launch(h);
     }
-    count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 
     const Act none;
@@ -146,13 +156,13 @@ void craft_forward_dev(Handle* h, cudaStream_t st, const uint8_t* img_dev, const
     const int R = CONV_RELU;
     DevBuf b0, b1, b_r22, b_r32, b_r43, b_r53;
     // slice1
-    Act a = act_alloc(h, st, b0, 1, H, W, 64);
+    Act a = act_alloc(h, st, b0, nimg, H, W, 64);
     if (tc_first) {
         Act x32;
-        x32.N = 1; x32.H = H; x32.W = W; x32.C = 32; x32.p = canvas.p;
+        x32.N = nimg; x32.H = H; x32.W = W; x32.C = 32; x32.p = canvas.p;
         conv_forward(h, st, w.c1_1_tc, x32, none, a, R);
     } else {
-        conv_first(h, st, w.c1_1, canvas.as<float>(), 1, H, W, 4, a, R);
+        conv_first(h, st, w.c1_1, canvas.as<float>(), nimg, H, W, 4, a, R);
     }
     canvas.release();
     a = conv_pool(w.c1_2, a, nullptr, b1, nullptr);
@@ -172,7 +182,7 @@ void craft_forward_dev(Handle* h, cudaStream_t st, const uint8_t* img_dev, const
     a = conv(w.c5_1, a, none, b0, R);
     Act r53 = conv(w.c5_2, a, none, b_r53, 0);        // followed by MaxPool, not ReLU: stays the raw BN output
     // slice5
-    a = act_alloc(h, st, b0, 1, r53.H, r53.W, 512);
+    a = act_alloc(h, st, b0, nimg, r53.H, r53.W, 512);
     maxpool(h, st, r53, a, 3, 3, 1, 1, 1, 1);
     a = conv(w.fc6, a, none, b1, 0);
     Act fc7 = conv(w.fc7, a, none, b0, 0);

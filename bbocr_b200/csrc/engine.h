@@ -42,6 +42,7 @@ struct Handle {
     std::vector<void*> owned;       // weight allocations
     std::vector<Lane> lanes;         // [0, n_det_lanes) detector lanes, then the recogniser lanes
     int n_det_lanes = 8;
+    int det_batch = 2;               // same-size pages that share one detector-network launch chain
     int rec_group = 32;              // pages per recogniser launch group (bbocr_readtext_batch)
     // dominant-kernel instrumentation (bench.py roofline): CUDA events around every implicit-GEMM conv launch
     bool conv_timing = false;
@@ -133,6 +134,8 @@ struct CanvasGeom {
 CanvasGeom canvas_geom(int H, int W, int canvas_size, double mag_ratio);
 // img_dev: HxWx3 u8 device.  text/link: device float maps (H32/2 x W32/2)
 void craft_forward_dev(Handle*, cudaStream_t, const uint8_t* img_dev, const CanvasGeom&, float* text, float* link);
+void craft_forward_batch_dev(Handle*, cudaStream_t, const uint8_t* const* imgs_dev, int nimg, const CanvasGeom&, float* text,
+                             float* link);     // nimg same-size images as one NHWC batch; maps [nimg][H32/2][W32/2]
 void resize_bilinear_u8(Handle*, cudaStream_t, const uint8_t* src, int sH, int sW, int sstride, int C, uint8_t* dst,
                         int dH, int dW);
 

@@ -148,6 +148,22 @@ def test_readtext_input_kinds_and_errors(gpu_reader, oracle_reader, tmp_path):
     assert [(g[0], g[1]) for g in got] == [([[int(v) for v in pt] for pt in w[0]], w[1]) for w in want]
 
 
+def test_mixed_size_batch_equals_single(gpu_reader):
+    """BASELINE config 5 in miniature: covers and info pages of different sizes in one batch.  Same-size neighbours share a
+    detector launch chain (pairs), odd ones run alone, the recogniser runs once over everybody's crops; every page must
+    still get exactly its single-page result, in input order."""
+    pages = [synth.book_cover(100, 640, 480), synth.title_page(101, 800, 608), synth.title_page(102, 800, 608),
+             synth.book_cover(103, 640, 480), synth.title_page(104, 800, 608), synth.book_cover(105, 640, 480),
+             synth.book_cover(106, 640, 480)]
+    gpu_reader.set_precision("bf16")
+    try:
+        single = [gpu_reader.readtext(p) for p in pages]
+        batched = gpu_reader.readtext_batched(pages)
+    finally:
+        gpu_reader.set_precision("fp32")
+    assert batched == single and sum(len(r) for r in single) > 20
+
+
 def test_batched_equals_single(gpu_reader):
     pages = [synth.title_page(70 + i, 640, 480) for i in range(6)]
     gpu_reader.set_precision("bf16")
