@@ -65,7 +65,7 @@ SYMBOLS = [
     "bbocr_pp_clahe", "bbocr_pp_unsharp", "bbocr_pp_adaptive_threshold", "bbocr_pp_deskew", "bbocr_craft_forward",
     "bbocr_det_boxes", "bbocr_min_area_box", "bbocr_group_boxes", "bbocr_crop_horizontal", "bbocr_crop_free",
     "bbocr_crnn_forward", "bbocr_ctc_decode", "bbocr_default_params", "bbocr_readtext", "bbocr_readtext_batch",
-    "bbocr_recognize", "bbocr_results_free", "bbocr_launch_count", "bbocr_reset_launch_count", "bbocr_conv_stats",
+    "bbocr_recognize", "bbocr_thumbnail_u8", "bbocr_results_free", "bbocr_launch_count", "bbocr_reset_launch_count", "bbocr_conv_stats",
     "bbocr_enable_conv_timing",
 ]
 
@@ -300,6 +300,18 @@ class Handle:
                                             idx.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p),
                                             conf.ctypes.data_as(C.c_void_p)))
         return [idx[i, :ln[i]].copy() for i in range(N)], conf
+
+    def thumbnail(self, gray, max_dim: int) -> np.ndarray:
+        """PIL Image.thumbnail((max_dim, max_dim)) (BICUBIC) of a gray u8 image (bbocr_thumbnail_u8)."""
+        g, gp = _u8(gray)
+        H, W = g.shape
+        oh, ow = C.c_int(), C.c_int()
+        self._check(self.L.bbocr_thumbnail_u8(self._h, gp, C.c_int(H), C.c_int(W), C.c_int(0), C.c_int(int(max_dim)), None,
+                                              C.c_int(0), C.byref(oh), C.byref(ow)))
+        out = np.empty((oh.value, ow.value), np.uint8)
+        self._check(self.L.bbocr_thumbnail_u8(self._h, gp, C.c_int(H), C.c_int(W), C.c_int(0), C.c_int(int(max_dim)),
+                                              out.ctypes.data_as(C.c_void_p), C.c_int(0), C.byref(oh), C.byref(ow)))
+        return out
 
     # ---- whole stage -----------------------------------------------------------------------------------------------
     def default_params(self) -> Params:

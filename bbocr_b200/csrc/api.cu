@@ -266,6 +266,49 @@ int bbocr_pp_deskew(bbocr_handle* h, const uint8_t* src, int H, int W, float max
     });
 }
 
+// ---- extractor glue ------------------------------------------------------------------------------------
+// PIL.Image.thumbnail((m, m)) size rule (Image.py::thumbnail, default BICUBIC, reducing_gap = 2.0):
+// aspect-preserving, never enlarges; round_aspect picks floor/ceil by the smaller aspect error (floor on ties), at least 1.
+static void pil_thumbnail_size(int W, int H, int m, int* ow, int* oh) {
+    int x = m, y = m;
+    if (x >= W && y >= H) { *ow = W; *oh = H; return; }
+    const double aspect = (double)W / (double)H;
+    auto round_aspect = [](double number, auto key) {
+        const double f = std::floor(number), c = std::ceil(number);
+        const double best = key(f) <= key(c) ? f : c;
+        return std::max((int)best, 1);
+    };
+    if ((double)x / (double)y >= aspect) x = round_aspect(y * aspect, [&](double n) { return std::fabs(aspect - n / y); });
+    else y = round_aspect(x / aspect, [&](double n) { return n == 0 ? 0.0 : std::fabs(aspect - x / n); });
+    *ow = x; *oh = y;
+}
+
+extern "C" int bbocr_thumbnail_u8(bbocr_handle* h, const uint8_t* src, int H, int W, int in_on_device, int max_dim, uint8_t* out,
+                                  int out_on_device, int* outH, int* outW) {
+    return guarded(h, [&] {
+        ARG_CHECK(H > 0 && W > 0 && max_dim > 0 && outH && outW, "bad arguments");
+        int ow, oh;
+        pil_thumbnail_size(W, H, max_dim, &ow, &oh);
+        *outW = ow; *outH = oh;
+        if (!out) return;                                   // size query
+        ARG_CHECK(src, "null image");
+        // Image.resize(reducing_gap = 2.0) inserts an integer box-reduce pass once an axis shrinks by >= 4x
+        if ((int)((double)W / ow / 2.0) > 1 || (int)((double)H / oh / 2.0) > 1)
+            fail(BBOCR_E_UNSUPPORTED, "thumbnail: %dx%d -> %dx%d shrinks by >= 4x (Pillow's reduce() pre-pass is not implemented)", W, H, ow, oh);
+        Lane& lane = h->lanes[0];
+        cudaStream_t st = lane.stream;
+        DevBuf din, dout, scratch((size_t)H * std::max(ow, W) + 16, st);
+        const uint8_t* s = src;
+        if (!in_on_device) { upload(lane, din, src, (size_t)H * W); s = din.as<uint8_t>(); }
+        uint8_t* d = out;
+        if (!out_on_device) { dout.alloc((size_t)oh * ow, st); d = dout.as<uint8_t>(); }
+        if (ow == W && oh == H) CUDA_CHECK(cudaMemcpyAsync(d, s, (size_t)H * W, cudaMemcpyDeviceToDevice, st));
+        else pil_resize_bicubic_dev(h, st, s, H, W, d, oh, ow, scratch.as<uint8_t>());
+        if (!out_on_device) download(lane, out, d, (size_t)oh * ow);
+        else CUDA_CHECK(cudaStreamSynchronize(st));
+    });
+}
+
 // ---- detector ---------------------------------------------------------------------------------------------------------
 int bbocr_craft_forward(bbocr_handle* h, const uint8_t* img, int H, int W, int on_device, int canvas_size,
                         double mag_ratio, float* score_text, float* score_link, int* mapH, int* mapW, double* ratio) {

@@ -1,0 +1,58 @@
+"""In-memory version of the OCR-stage glue of BB-OCR's extractor.
+
+Reference: pipeline_demo/extractor/enhanced_extractor.py::extract_text_with_ocr (:413-561).  There the stage is
+    preprocess_for_book_cover(path) -> PNG on disk (:431) -> PIL reopen -> thumbnail cap 1600 / 2400 px -> JPEG q90/95 on disk
+    (:486-512) -> easyocr Reader.readtext(jpeg_path, paragraph=False, batch_size=1, workers=0) -> " ".join(texts) (:520-521)
+i.e. about a second of PNG/JPEG encode/decode per page around the OCR itself.  Here the same steps run on the device and
+the image never leaves memory.  The one deliberate deviation: the lossy JPEG round trip between the cap and readtext is
+dropped (the reference only uses it as a transport format); everything else is bit-exact against Pillow / the
+preprocessing oracle (tests/test_gpu_extractor.py).
+"""
+from __future__ import annotations
+
+import cv2
+import numpy as np
+
+from .preprocess import CURRENT, pp_params
+
+
+def ocr_max_dim(image_index=None) -> int:
+    """enhanced_extractor.py:494 -- covers (index None / 0) are capped harder than the other pages."""
+    return 1600 if (image_index is None or image_index == 0) else 2400
+
+
+def ocr_input_image(reader, gray: np.ndarray, image_index=None) -> np.ndarray:
+    """enhanced_extractor.py:486-512 without the JPEG: PIL thumbnail((m, m)) (BICUBIC) when max(size) > m, on the device."""
+    if gray.ndim != 2 or gray.dtype != np.uint8:
+        raise ValueError("ocr_input_image expects a gray uint8 image (the preprocessing output)")
+    m = ocr_max_dim(image_index)
+    if max(gray.shape) <= m:
+        return gray
+    return reader.handle.thumbnail(gray, m)
+
+
+def extract_text_with_ocr(reader, image, *, use_preprocessing=True, image_index=None, return_results=False):
+    """extract_text_with_ocr (:413-561) in memory: [preprocess_for_book_cover] -> OCR-input cap -> readtext -> joined text.
+    `image`: path or BGR / gray uint8 array.  Errors are swallowed into "" exactly like :529-531."""
+    try:
+        if isinstance(image, str):
+            bgr = cv2.imread(image)
+            if bgr is None:
+                raise ValueError(f"Could not load image from {image}")
+        else:
+            bgr = image
+        if use_preprocessing:
+            if bgr.ndim != 3:
+                raise ValueError("preprocessing expects a BGR image")
+            if bgr.dtype != np.uint8 or bgr.shape[2] != 3:
+                raise ValueError("expected an HxWx3 uint8 BGR image")
+            gray = reader.handle.preprocess(bgr, pp_params(CURRENT, 0))        # same handle (and device) as the reader
+        else:
+            gray = bgr if bgr.ndim == 2 else cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+        ocr_in = ocr_input_image(reader, gray, image_index)
+        results = reader.readtext(ocr_in, paragraph=False, batch_size=1, workers=0)
+        text = " ".join([r[1] for r in results])
+    except Exception as e:                                   # noqa: BLE001 -- mirrors the reference's blanket handler
+        print(f"    OCR failed: {e}")
+        results, text = [], ""
+    return (text, results) if return_results else text

@@ -183,6 +183,14 @@ int bbocr_recognize(bbocr_handle* h, const uint8_t* gray, int H, int W, int on_d
                     const double* flist, int nf, const bbocr_params* p, bbocr_results** out);
 void bbocr_results_free(bbocr_results* r);
 
+/* ---- extractor glue ---------------------------------------------------------------------------- */
+/* The OCR-input cap of extract_text_with_ocr (pipeline_demo/extractor/enhanced_extractor.py:486-512): PIL
+ * Image.thumbnail((max_dim, max_dim)) = aspect-preserving BICUBIC down-scale (Pillow's fixed-point two-pass convolution),
+ * for one gray u8 plane, without the lossy JPEG round trip the reference adds.  out == NULL: size query only.  Shrinks
+ * by 4x or more (where Pillow inserts reduce()) return BBOCR_E_UNSUPPORTED. */
+int bbocr_thumbnail_u8(bbocr_handle* h, const uint8_t* src, int H, int W, int in_on_device, int max_dim, uint8_t* out,
+                       int out_on_device, int* outH, int* outW);
+
 /* ---- instrumentation -------------------------------------------------------------------------------------------- */
 /* Kernels launched by this handle since the last reset (the bench's gpu_launches claim). */
 int64_t bbocr_launch_count(const bbocr_handle* h);
