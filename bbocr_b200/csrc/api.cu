@@ -847,15 +847,26 @@ void detect_pages(Handle* h, Lane& lane, const bbocr_image* const* imgs, int k, 
     const int H = imgs[0]->H, W = imgs[0]->W;
     std::vector<DevBuf> dcolor(k), dgray(k);
     std::vector<const uint8_t*> color(k), gray(k);
+    // host pages: one pinned staging area for the whole batch (no stream sync between the pages' uploads)
+    size_t pin_total = 0;
+    std::vector<size_t> pin_off(k, 0);
     for (int i = 0; i < k; ++i) {
         const bbocr_image& img = *imgs[i];
         ARG_CHECK(img.color && img.H == H && img.W == W && H > 0 && W > 0, "bad image");
+        if (!img.on_device) {
+            pin_off[i] = pin_total;
+            pin_total += (((size_t)H * W * (img.gray ? 4 : 3)) + 255) & ~(size_t)255;
+        }
+    }
+    uint8_t* pin_base = pin_total ? (uint8_t*)staging(lane, pin_total) : nullptr;
+    for (int i = 0; i < k; ++i) {
+        const bbocr_image& img = *imgs[i];
         pws[i]->H = H; pws[i]->W = W;
         color[i] = img.color;
         gray[i] = img.gray;
         if (!img.on_device) {
             size_t cb = (size_t)H * W * 3, gb = img.gray ? (size_t)H * W : 0;
-            uint8_t* pin = (uint8_t*)staging(lane, cb + gb);
+            uint8_t* pin = pin_base + pin_off[i];
             memcpy(pin, img.color, cb);
             if (gb) memcpy(pin + cb, img.gray, gb);
             dcolor[i].alloc(cb + gb, st);

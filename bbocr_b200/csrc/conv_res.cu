@@ -566,12 +566,17 @@ bool res_plan(const ConvW& cw, const Act& in1, const Act& out, ResPlan& pl, bool
 }
 
 template <int KB, int TAPS, int NKB, int MT, int EPI = 0, int STREAM = 0>
-void res_launch(int grid, size_t smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO,
+void res_launch(Handle* h, int grid, size_t smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mO,
                 const CUtensorMap& mP, const ResParams& p) {
-    static std::once_flag once;        // one device per process in this library (one rank per GPU)
-    std::call_once(once, [] {
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<KB, TAPS, NKB, MT, EPI, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-    });
+    // the opt-in shared-memory size is a per-device function attribute: remember it per handle (one handle = one device)
+    const int key = ((((KB * 10 + TAPS) * 10 + NKB) * 10 + MT) * 10 + EPI) * 10 + STREAM;
+    {
+        std::lock_guard<std::mutex> g(h->stat_mu);
+        if (!h->res_attr_done.count(key)) {
+            CUDA_CHECK(cudaFuncSetAttribute(k_conv_res<KB, TAPS, NKB, MT, EPI, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+            h->res_attr_done.insert(key);
+        }
+    }
     k_conv_res<KB, TAPS, NKB, MT, EPI, STREAM><<<grid, 384, smem, st>>>(mA, mB, mO, mP, p);
 }
 
@@ -652,14 +657,14 @@ void conv_res_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in
     }
     const int key = pl.kb * 1000 + pl.taps * 100 + pl.nkb * 10 + pl.MT + (pl.stream ? 100000 : 0);
     switch (key) {
-        case 100000 + 64000 + 900 + 20 + 2: res_launch<64, 9, 2, 2, 0, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
-        case 64000 + 900 + 10 + 2: res_launch<64, 9, 1, 2>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
-        case 64000 + 900 + 10 + 1: res_launch<64, 9, 1, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
-        case 64000 + 900 + 20 + 1: res_launch<64, 9, 2, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
-        case 32000 + 900 + 10 + 2: res_launch<32, 9, 1, 2>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
-        case 32000 + 900 + 10 + 1: res_launch<32, 9, 1, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
-        case 32000 + 100 + 10 + 2: res_launch<32, 1, 1, 2>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
-        case 32000 + 100 + 10 + 1: res_launch<32, 1, 1, 1>(grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 100000 + 64000 + 900 + 20 + 2: res_launch<64, 9, 2, 2, 0, 1>(h, grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 64000 + 900 + 10 + 2: res_launch<64, 9, 1, 2>(h, grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 64000 + 900 + 10 + 1: res_launch<64, 9, 1, 1>(h, grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 64000 + 900 + 20 + 1: res_launch<64, 9, 2, 1>(h, grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 32000 + 900 + 10 + 2: res_launch<32, 9, 1, 2>(h, grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 32000 + 900 + 10 + 1: res_launch<32, 9, 1, 1>(h, grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 32000 + 100 + 10 + 2: res_launch<32, 1, 1, 2>(h, grid, pl.smem, st, mA, mB, mO, mP, p); break;
+        case 32000 + 100 + 10 + 1: res_launch<32, 1, 1, 1>(h, grid, pl.smem, st, mA, mB, mO, mP, p); break;
         default: fail(BBOCR_E_ARG, "conv_res: no kernel variant for kb %d taps %d nkb %d MT %d", pl.kb, pl.taps, pl.nkb, pl.MT);
     }
     count_launch(h);
@@ -712,7 +717,7 @@ void conv_res_cls_tail(Handle* h, cudaStream_t st, const ConvW& c2, const ConvW&
     uint32_t wb[3] = {32, 16, 1};
     CUtensorMap mB = tc_make_map(c2.w_bf16, 3, wd, ws, wb, 32);
     const int grid = std::min(h->sm_count, p.m_tiles);
-    res_launch<32, 9, 1, 2, 1>(grid, pl.smem, st, mA, mB, mA, mA, p);
+    res_launch<32, 9, 1, 2, 1>(h, grid, pl.smem, st, mA, mB, mA, mA, p);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 }
