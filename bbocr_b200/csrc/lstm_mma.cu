@@ -184,8 +184,7 @@ __global__ void __launch_bounds__(256, 1)
         }
         if (s > 0) {
             // every CTA of the cluster has stored its slice of h(s-1): release/acquire at cluster scope
-            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // arrived at the end of step s-1
             LM_STAMP(1);
             const uint32_t ph = (uint32_t)((s - 1) & 1);
             if (tid == 0) {
@@ -258,17 +257,6 @@ __global__ void __launch_bounds__(256, 1)
             hi[j] = __bfloat162float(__float2bfloat16_rn(hv[j]));
             lo[j] = hv[j] - hi[j];
         }
-        if (active) {
-            const size_t o = (size_t)(row0 + t) * 512 + dir * 256 + UN * r + 8 * half;
-            if (out_mode == 2) {
-                float* op = reinterpret_cast<float*>(out) + o;
-                *reinterpret_cast<float4*>(op) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                *reinterpret_cast<float4*>(op + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-            } else {
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = pack8(hi);
-                if (out_mode == 1) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_lo) + o) = pack8(lo);
-            }
-        }
         LM_STAMP(6);
         if (s + 1 < Tmax) {
             // h(s) for the next step's operand: staging[parity (s+1)&1][hi|lo][crop][16r + 8*half ..]
@@ -279,6 +267,21 @@ __global__ void __launch_bounds__(256, 1)
             // cluster barrier at the top of the next step orders them across the CTAs
             if (fence_gpu) __threadfence();
             asm volatile("fence.proxy.async;" ::: "memory");
+            // arrive now, wait at the top of the next step: the layer-output stores below and the next step's input
+            // projections are in flight while the cluster synchronises
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        }
+        if (active) {
+            const size_t o = (size_t)(row0 + t) * 512 + dir * 256 + UN * r + 8 * half;
+            if (out_mode == 2) {
+                float* op = reinterpret_cast<float*>(out) + o;
+                *reinterpret_cast<float4*>(op) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                *reinterpret_cast<float4*>(op + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+            } else {
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = pack8(hi);
+                if (out_mode == 1) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_lo) + o) = pack8(lo);
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         LM_STAMP(7);

@@ -154,7 +154,8 @@ def test_mixed_size_batch_equals_single(gpu_reader):
     still get exactly its single-page result, in input order."""
     pages = [synth.book_cover(100, 640, 480), synth.title_page(101, 800, 608), synth.title_page(102, 800, 608),
              synth.book_cover(103, 640, 480), synth.title_page(104, 800, 608), synth.book_cover(105, 640, 480),
-             synth.book_cover(106, 640, 480)]
+             synth.book_cover(106, 640, 480), synth.title_page(107, 700, 500), synth.title_page(108, 700, 500),     # padded canvas
+             synth.title_page(109, 333, 250)]
     gpu_reader.set_precision("bf16")
     try:
         single = [gpu_reader.readtext(p) for p in pages]
