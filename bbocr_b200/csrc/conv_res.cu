@@ -4,7 +4,7 @@
 // conv_tc.cu fetches one shifted 128-pixel tile AND one weight tile per filter tap.  For Cin, Cout <= 128 that is 24-32 KB
 // of L2->SM traffic per 128..256 tensor-core cycles: the layers at full and half resolution (conv1_2, conv2_x, the last
 // decoder stages) end up bound by the ~60 B/clk an SM can ingest, not by the tensor pipe
-// (profiles/r1_conv_tc_ncu_full.summary.txt: 9x the input volume crosses the L2->SM fabric).  Here
+// (measured with ncu at the start of round 1: 9x the input volume crossed the L2->SM fabric).  Here
 //   * the CTA's weight slice  [9 taps][Cin][BN]  is loaded ONCE per persistent CTA and stays resident (<= 147 KB);
 //   * the input patch of an output tile -- 8 px wide, 16*MT px high, plus the 1-px halo; TMA out-of-bounds zero fill is the
 //     convolution padding -- is loaded ONCE per 64-channel block (10 x (16 MT + 2) px x 128 B);

@@ -48,7 +48,7 @@ struct Handle {
     // dominant-kernel instrumentation (bench.py roofline): CUDA events around every implicit-GEMM conv launch
     bool conv_timing = false;
     bool force_generic_conv = false; // test hook: route BF16-mode convolutions through the CUDA-core kernel
-    bool tc_attr_set = false, halo_attr_set = false, lstm_attr_set = false, lstm_mma_attr_set = false, res_attr_set = false;
+    bool tc_attr_set = false, lstm_attr_set = false, lstm_mma_attr_set = false;
     std::mutex stat_mu;
     std::set<int> res_attr_done;     // conv_res.cu kernel variants whose smem attribute is set on this device
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
@@ -110,9 +110,6 @@ Act act_alloc(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C, bo
 bool conv_tc_supported(const ConvW&, const Act& in1, const Act& in2);
 void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled,
                      const uint8_t* colmask = nullptr);
-// conv_halo.cu : 3x3 / pad 1 convolutions with the input patch loaded once per channel block (all nine taps from smem)
-bool conv_halo_supported(const ConvW&, const Act& in1, const Act& in2, const Act& out);
-void conv_halo_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled);
 
 // conv_res.cu : 3x3 / pad 1 convolutions of the low-channel layers with resident weights and a halo patch per tile
 bool conv_res_supported(const ConvW&, const Act& in1, const Act& in2, const Act& out);
@@ -197,9 +194,6 @@ void crnn_forward_dev(Handle*, Lane&, const float* x, int N, int Wm, float* logi
 void lstm_sequences(Handle*, Lane&, const float* gates_in, const float* w_hh, const SeqDesc* seqs_host, int n_seq,
                     const SeqDesc* seqs_dev, const int* groups_dev, int n_groups, void* out, void* out_lo = nullptr);
 int lstm_group_size(const Handle*);
-void lstm_sequences_tc(Handle*, Lane&, const float* gates_in, const float* w_hh, int n_seq, const SeqDesc* seqs_dev,
-                       const int* groups_dev, int n_groups, void* out);
-int lstm_tc_group_size();
 // lstm_mma.cu: 128 crops per 16-CTA cluster, split-precision tcgen05 recurrence (throughput mode default)
 void lstm_sequences_mma(Handle*, Lane&, const float* gates_in, const float* w_hh, int n_seq, const SeqDesc* seqs_dev,
                         const int* groups_dev, int n_groups, void* out, void* out_lo, int out_mode);

@@ -153,14 +153,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
 }  // namespace
 
 // recurrence kernel: FP32 mode = the CUDA-core cluster kernel above (parity mode).  BF16 (throughput) mode = lstm_mma.cu
-// (BBOCR_LSTM=cluster | tf32 select the older kernels for comparison).
+// (BBOCR_LSTM=cluster selects the CUDA-core kernel in throughput mode as well, for comparison).
 static int lstm_variant(const Handle* h) {
     if (h->precision != BBOCR_PREC_BF16 || h->force_generic_conv) return 0;
     static const int v = [] {
         const char* e = getenv("BBOCR_LSTM");
         if (!e) return 2;
         if (!strcmp(e, "cluster")) return 0;
-        if (!strcmp(e, "tf32")) return 1;
         return 2;
     }();
     return v;
@@ -174,10 +173,6 @@ void lstm_sequences(Handle* h, Lane& lane, const float* gates_in, const float* w
     const int variant = lstm_variant(h);
     if (variant == 2) {            // crops on the UMMA M dimension, split precision (lstm_mma.cu)
         lstm_sequences_mma(h, lane, gates_in, w_hh, n_seq, seqs_dev, groups_dev, n_groups, out, out_lo, out_lo ? 1 : 0);
-        return;
-    }
-    if (variant == 1 && !out_lo) { // optional TF32 tensor-core mat-vec (lstm_tc.cu)
-        lstm_sequences_tc(h, lane, gates_in, w_hh, n_seq, seqs_dev, groups_dev, n_groups, out);
         return;
     }
     const size_t smem = (size_t)(256 * COLS + 2 * NB * 256 + KPARTS * COLS * NB + NB * UNITS) * sizeof(float);
@@ -205,7 +200,7 @@ void lstm_sequences(Handle* h, Lane& lane, const float* gates_in, const float* w
 
 int lstm_group_size(const Handle* h) {
     const int v = lstm_variant(h);
-    return v == 2 ? lstm_mma_group_size() : (v == 1 ? lstm_tc_group_size() : NB);
+    return v == 2 ? lstm_mma_group_size() : NB;
 }
 
 }  // namespace bbocr

@@ -166,8 +166,6 @@ void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, c
     const bool pool_ok = !pooled || (out.H >= 8 && out.H % 2 == 0 && ((flags & CONV_POOL21) || out.W % 2 == 0));
     if (tc && pool_ok && !colmask && !in1.lo && !out.lo && !(flags & (CONV_OUT_F32 | CONV_POOL21)) && conv_res_supported(cw, in1, in2, out)) {
         conv_res_forward(h, st, cw, in1, in2, out, flags, pooled);      // resident weights + halo patch (low-channel 3x3 layers)
-    } else if (tc && pool_ok && !in1.lo && !out.lo && conv_halo_supported(cw, in1, in2, out)) {
-        conv_halo_forward(h, st, cw, in1, in2, out, flags, pooled);     // patch-reuse kernel for the 3x3 layers
     } else if (tc && pool_ok) {
         conv_tc_forward(h, st, cw, in1, in2, out, flags, pooled, colmask);       // max-pool fused into the epilogue
     } else {

@@ -92,18 +92,6 @@ def test_split_precision_conv_is_fp32_class(handle, shape):
     assert err < 2e-4, err
 
 
-def test_halo_patch_kernel_in_subprocess():
-    """conv_halo.cu (input patch loaded once, nine taps from shifted UMMA descriptors) is off by default; run the same
-    shape sweep with it enabled (the mode is latched per process, hence the subprocess)."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, BBOCR_HALO="2")
-    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "matches_cuda_core"], env=env,
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-
-
 def test_resident_weight_kernel_in_subprocess():
     """conv_res.cu (resident weights + halo patch) only takes layers with >= 75 k output pixels by default; BBOCR_RES=2
     forces it for every supported geometry, so the same shape sweep runs through it (mode latched per process)."""
