@@ -98,6 +98,8 @@ void cls_tail(Handle*, cudaStream_t, const ConvW& c3, const ConvW& c4, const Act
 
 Act act_alloc_split(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C);
 void maxpool_f32_to_split(Handle*, cudaStream_t, const Act& in, Act& out, int kh, int kw, const uint8_t* colmask = nullptr);
+// CRNN stem fused: Conv(1->32) + ReLU + MaxPool2d(2,2) -> split tensor (bit-identical to conv_first + maxpool_f32_to_split)
+void conv0_pool_split(Handle*, cudaStream_t, const ConvW&, const float* in, int N, int H, int W, Act& out, const uint8_t* colmask = nullptr);
 // ragged AdaptiveAvgPool: crop i = columns [meta[3i], meta[3i] + meta[3i+1]) of `in` ([1][H][W][C] split) -> rows meta[3i+2].. of out
 void mean_rows_split_ragged(Handle*, cudaStream_t, const Act& in, const Act& out, const int* meta_dev, int n_crops, int t_max);
 void mean_rows_split(Handle*, cudaStream_t, const Act& in, Act& out);

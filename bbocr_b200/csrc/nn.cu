@@ -589,6 +589,78 @@ void mean_rows_split(Handle* h, cudaStream_t st, const Act& in, Act& out) {
     CUDA_CHECK(cudaGetLastError());
 }
 
+// CRNN stem in one pass: Conv(1 -> 32, 3x3, pad 1) + ReLU + MaxPool2d(2,2) -> split (hi/lo bf16) tensor, optional column
+// mask (strips).  One thread per pooled pixel: the four convolution outputs of its window are evaluated with exactly the
+// FMA order of k_conv_first (ky, kx ascending; a zero-padded tap adds +0), so the result is bit-identical to
+// conv_first + maxpool_f32_to_split while the 32-channel FP32 full-resolution tensor never goes to HBM.
+__global__ void __launch_bounds__(128) k_conv0_pool_split(const float* __restrict__ in, int N, int H, int W,
+                                                          const float* __restrict__ w /*[9][1][cout_pad]*/, int cout_pad,
+                                                          const float* __restrict__ scale, const float* __restrict__ bias,
+                                                          __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo,
+                                                          const uint8_t* __restrict__ colmask) {
+    __shared__ float sw[9 * 32];
+    __shared__ float ss[32], sb[32];
+    for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) sw[i] = w[(int64_t)(i >> 5) * cout_pad + (i & 31)];
+    if (threadIdx.x < 32) { ss[threadIdx.x] = scale[threadIdx.x]; sb[threadIdx.x] = bias[threadIdx.x]; }
+    __syncthreads();
+    const int OH = H >> 1, OW = W >> 1;
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= (int64_t)N * OH * OW) return;
+    const int n_img = (int)(m / ((int64_t)OH * OW));
+    const int r = (int)(m - (int64_t)n_img * OH * OW);
+    const int py = r / OW, px = r - py * OW;
+    float v[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int iy = 2 * py - 1 + a, ix = 2 * px - 1 + b;
+            v[a][b] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(in + ((int64_t)n_img * H + iy) * W + ix) : 0.f;
+        }
+    float best[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) best[c] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            float acc[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int iy = 2 * py + dy - 1 + ky, ix = 2 * px + dx - 1 + kx;
+                    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;      // k_conv_first skips the padded taps
+                    const float x = v[dy + ky][dx + kx];
+                    const float* wr = sw + (ky * 3 + kx) * 32;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) acc[c] = fmaf(x, wr[c], acc[c]);
+                }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) best[c] = fmaxf(best[c], fmaxf(fmaf(acc[c], ss[c], sb[c]), 0.f));
+        }
+    if (colmask && !colmask[px]) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) best[c] = 0.f;
+    }
+    const int64_t o = m * 32;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) split_store4(ohi + o + c, olo + o + c, best + c);
+}
+
+void conv0_pool_split(Handle* h, cudaStream_t st, const ConvW& cw, const float* in, int N, int H, int W, Act& out,
+                      const uint8_t* colmask) {
+    ARG_CHECK(cw.kh == 3 && cw.kw == 3 && cw.pad == 1 && cw.dil == 1 && cw.cin == 1 && cw.cout == 32 && out.lo, "conv0_pool_split: shape");
+    ARG_CHECK(H % 2 == 0 && W % 2 == 0 && out.H == H / 2 && out.W == W / 2 && out.C == 32 && out.N == N, "conv0_pool_split: geometry");
+    const int64_t M = (int64_t)N * (H / 2) * (W / 2);
+    k_conv0_pool_split<<<(unsigned)cdiv64(M, 128), 128, 0, st>>>(in, N, H, W, cw.w_f32, cw.cout_pad, cw.scale, cw.bias,
+                                                                  (__nv_bfloat16*)out.p, (__nv_bfloat16*)out.lo, colmask);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 // ragged AdaptiveAvgPool over the H rows: crop i owns columns [col0, col0 + T) of the strip, its sequence starts at row0
 __global__ void k_mean_rows_split_ragged(const __nv_bfloat16* __restrict__ ihi, const __nv_bfloat16* __restrict__ ilo,
                                          __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo, int H, int W, int C,

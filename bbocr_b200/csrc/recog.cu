@@ -310,10 +310,8 @@ void crnn_features_dev(Handle* h, cudaStream_t st, const float* x, int N, int Wm
     };
     Act a;
     if (split) {
-        Act c0 = act_alloc(h, st, b0, N, 64, Wm, 32, true);                 // FP32 output of the direct first conv
-        conv_first(h, st, w.c0, x, N, 64, Wm, 1, c0, R | CONV_OUT_F32);
         a = act_alloc_split(h, st, b1, N, 32, Wm / 2, 32);
-        maxpool_f32_to_split(h, st, c0, a, 2, 2);
+        conv0_pool_split(h, st, w.c0, x, N, 64, Wm, a);                      // conv0 + ReLU + 2x2 pool + hi/lo split in one pass
     } else {
         Act c0 = act_alloc(h, st, b0, N, 64, Wm, 32);
         conv_first(h, st, w.c0, x, N, 64, Wm, 1, c0, R);
@@ -367,10 +365,8 @@ void crnn_features_strip_dev(Handle* h, cudaStream_t st, const float* strip, int
         conv_forward(h, st, cw, a, none, full, R | (kw == 2 ? CONV_POOL22 : CONV_POOL21), &pooled, mask);
         return pooled;
     };
-    Act c0 = act_alloc(h, st, b0, 1, 64, Wtot, 32, true);                   // FP32 output of the direct first conv
-    conv_first(h, st, w.c0, strip, 1, 64, Wtot, 1, c0, R | CONV_OUT_F32);
     Act a = act_alloc_split(h, st, b1, 1, 32, Wtot / 2, 32);
-    maxpool_f32_to_split(h, st, c0, a, 2, 2, mask1);
+    conv0_pool_split(h, st, w.c0, strip, 1, 64, Wtot, a, mask1);            // conv0 + ReLU + 2x2 pool + hi/lo split + gap mask
     a = conv_pool(w.c1, a, b0, 2, 2, mask1);        // 16 x Wtot/4   (mask at the conv's own resolution, before the pool)
     a = conv(w.c2, a, b1, R, mask2);
     a = conv_pool(w.c3, a, b0, 2, 1, mask2);        // 8 x Wtot/4
