@@ -65,7 +65,7 @@ SYMBOLS = [
     "bbocr_pp_clahe", "bbocr_pp_unsharp", "bbocr_pp_adaptive_threshold", "bbocr_pp_deskew", "bbocr_craft_forward",
     "bbocr_det_boxes", "bbocr_min_area_box", "bbocr_group_boxes", "bbocr_crop_horizontal", "bbocr_crop_free",
     "bbocr_crnn_forward", "bbocr_ctc_decode", "bbocr_default_params", "bbocr_readtext", "bbocr_readtext_batch",
-    "bbocr_recognize", "bbocr_thumbnail_u8", "bbocr_results_free", "bbocr_launch_count", "bbocr_reset_launch_count", "bbocr_conv_stats",
+    "bbocr_recognize", "bbocr_thumbnail_u8", "bbocr_autocrop_rect", "bbocr_external_boxes", "bbocr_rect_morph", "bbocr_results_free", "bbocr_launch_count", "bbocr_reset_launch_count", "bbocr_conv_stats",
     "bbocr_enable_conv_timing",
 ]
 
@@ -311,6 +311,53 @@ class Handle:
         out = np.empty((oh.value, ow.value), np.uint8)
         self._check(self.L.bbocr_thumbnail_u8(self._h, gp, C.c_int(H), C.c_int(W), C.c_int(0), C.c_int(int(max_dim)),
                                               out.ctypes.data_as(C.c_void_p), C.c_int(0), C.byref(oh), C.byref(ow)))
+        return out
+
+    def autocrop_rect(self, bgr, margin: int = 0, debug: bool = False):
+        """_auto_crop_text_region up to the slice (bbocr_autocrop_rect): (x0, y0, x1, y1) or None.  With debug=True also a
+        dict with the reference's `mask`, `merged`, the external-contour boxes and the two Otsu thresholds."""
+        a = np.ascontiguousarray(bgr, dtype=np.uint8)
+        if not (a.ndim == 2 or (a.ndim == 3 and a.shape[2] == 3)):
+            raise ValueError("autocrop_rect expects an HxWx3 BGR or HxW gray uint8 image")
+        H, W = a.shape[:2]
+        ch = 3 if a.ndim == 3 else 1
+        rect = (C.c_int32 * 4)()
+        found, nb = C.c_int(), C.c_int()
+        mask = merged = boxes = None
+        otsu = (C.c_int32 * 2)()
+        cap = 0
+        if debug:
+            mask, merged = np.empty((H, W), np.uint8), np.empty((H, W), np.uint8)
+            cap = 1 << 16
+            boxes = np.zeros((cap, 4), np.int32)
+        vp = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None      # noqa: E731
+        self._check(self.L.bbocr_autocrop_rect(self._h, vp(a), C.c_int(H), C.c_int(W), C.c_int(ch), C.c_int(W * ch), C.c_int(0),
+                                               C.c_int(int(margin)), rect, C.byref(found), vp(mask), vp(merged), vp(boxes),
+                                               C.c_int(cap), C.byref(nb) if debug else None, otsu if debug else None))
+        r = tuple(int(v) for v in rect) if found.value else None
+        if not debug:
+            return r
+        return r, {"mask": mask, "merged": merged, "boxes": boxes[:min(nb.value, cap)].astype(np.int64), "nboxes": nb.value,
+                   "otsu": (int(otsu[0]), int(otsu[1]))}
+
+    def external_boxes(self, binary) -> np.ndarray:
+        """cv2.findContours(RETR_EXTERNAL) + boundingRect on the device: rows (x, y, w, h) sorted by (y, x, w, h)."""
+        b, bp = _u8(binary)
+        H, W = b.shape
+        nb = C.c_int()
+        self._check(self.L.bbocr_external_boxes(self._h, bp, C.c_int(H), C.c_int(W), None, C.c_int(0), C.byref(nb)))
+        out = np.zeros((max(nb.value, 1), 4), np.int32)
+        self._check(self.L.bbocr_external_boxes(self._h, bp, C.c_int(H), C.c_int(W), out.ctypes.data_as(C.c_void_p),
+                                                C.c_int(out.shape[0]), C.byref(nb)))
+        return out[:nb.value].astype(np.int64)
+
+    def rect_morph(self, binary, kw: int, kh: int, erode: bool) -> np.ndarray:
+        """cv2.dilate / cv2.erode of a binary u8 image with a kw x kh rectangle (default border)."""
+        b, bp = _u8(binary)
+        H, W = b.shape
+        out = np.empty((H, W), np.uint8)
+        self._check(self.L.bbocr_rect_morph(self._h, bp, C.c_int(H), C.c_int(W), C.c_int(kw), C.c_int(kh), C.c_int(int(erode)),
+                                            out.ctypes.data_as(C.c_void_p)))
         return out
 
     # ---- whole stage -----------------------------------------------------------------------------------------------

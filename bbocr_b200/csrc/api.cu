@@ -309,6 +309,53 @@ extern "C" int bbocr_thumbnail_u8(bbocr_handle* h, const uint8_t* src, int H, in
     });
 }
 
+// ---- page crops ---------------------------------------------------------------------------------------
+extern "C" int bbocr_autocrop_rect(bbocr_handle* h, const uint8_t* bgr, int H, int W, int channels, int stride, int in_on_device, int margin,
+                                   int32_t rect[4], int* found, uint8_t* mask_out, uint8_t* merged_out, int32_t* boxes_out,
+                                   int boxes_cap, int* nboxes, int32_t* otsu_out) {
+    return guarded(h, [&] {
+        ARG_CHECK(bgr && rect && found && H > 0 && W > 0 && margin >= 0, "bad arguments");
+        ARG_CHECK((channels == 3 && stride >= W * 3) || (channels == 1 && stride == W), "channels must be 3 (BGR) or 1 (packed gray)");
+        Lane& lane = h->lanes[0];
+        DevBuf din;
+        const uint8_t* src = bgr;
+        if (!in_on_device) { upload(lane, din, bgr, (size_t)H * stride); src = din.as<uint8_t>(); }
+        const bool want_dbg = mask_out || merged_out || boxes_out || nboxes || otsu_out;
+        AutoCropDebug dbg;
+        dbg.mask = mask_out;
+        dbg.merged = merged_out;
+        rect[0] = rect[1] = rect[2] = rect[3] = -1;
+        *found = autocrop_dev(h, lane.stream, src, H, W, channels, stride, margin, rect, want_dbg ? &dbg : nullptr) ? 1 : 0;
+        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        lane.in_busy = false;
+        if (nboxes) *nboxes = (int)(dbg.boxes.size() / 4);
+        if (boxes_out) memcpy(boxes_out, dbg.boxes.data(), std::min((size_t)std::max(boxes_cap, 0) * 16, dbg.boxes.size() * 4));
+        if (otsu_out) { otsu_out[0] = dbg.otsu[0]; otsu_out[1] = dbg.otsu[1]; }
+    });
+}
+
+extern "C" int bbocr_external_boxes(bbocr_handle* h, const uint8_t* binary, int H, int W, int32_t* boxes_out, int boxes_cap,
+                                    int* nboxes) {
+    return guarded(h, [&] {
+        ARG_CHECK(binary && nboxes && H > 0 && W > 0, "bad arguments");
+        Lane& lane = h->lanes[0];
+        DevBuf din;
+        upload(lane, din, binary, (size_t)H * W);
+        std::vector<int32_t> boxes;
+        external_boxes_dev(h, lane.stream, din.as<uint8_t>(), H, W, boxes);
+        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        lane.in_busy = false;
+        *nboxes = (int)(boxes.size() / 4);
+        if (boxes_out) memcpy(boxes_out, boxes.data(), std::min((size_t)std::max(boxes_cap, 0) * 16, boxes.size() * 4));
+    });
+}
+
+extern "C" int bbocr_rect_morph(bbocr_handle* h, const uint8_t* binary, int H, int W, int kw, int kh, int erode, uint8_t* out) {
+    return pp_step(h, binary, (size_t)H * W, out, (size_t)H * W, [&](cudaStream_t st, const uint8_t* s, uint8_t* d) {
+        rect_morph_dev(h, st, s, H, W, kw, kh, erode != 0, d);
+    });
+}
+
 // ---- detector ---------------------------------------------------------------------------------------------------------
 int bbocr_craft_forward(bbocr_handle* h, const uint8_t* img, int H, int W, int on_device, int canvas_size,
                         double mag_ratio, float* score_text, float* score_link, int* mapH, int* mapW, double* ratio) {

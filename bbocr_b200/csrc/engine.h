@@ -81,6 +81,19 @@ void preprocess_chain_dev(Handle*, cudaStream_t, const uint8_t* bgr, int H, int 
 int preprocess_launches_per_image();
 float pp_deskew(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int H, int W, float max_deg);
 
+// ---- autocrop.cu (enhanced_extractor.py:239-372) ---------------------------------------------------------
+struct AutoCropDebug {             // optional parity outputs (host memory)
+    uint8_t* mask = nullptr;       // HxW composite text mask (0/255)
+    uint8_t* merged = nullptr;     // HxW mask after the two morphology variants
+    int otsu[2] = {0, 0};          // Otsu thresholds of the equalised image and of the Sobel magnitude
+    std::vector<int32_t> boxes;    // (x, y, w, h) of every external contour of `merged`, sorted by (y, x, w, h)
+};
+// img: device HxWx3 BGR (row stride in bytes) or a packed HxW gray plane (channels = 1).  Returns false for the reference's "no crop" (None); rect = (x0, y0, x1, y1).
+bool autocrop_dev(Handle*, cudaStream_t, const uint8_t* img, int H, int W, int channels, int stride, int margin, int32_t rect[4],
+                  AutoCropDebug* dbg);
+void external_boxes_dev(Handle*, cudaStream_t, const uint8_t* binary_dev, int H, int W, std::vector<int32_t>& boxes);
+void rect_morph_dev(Handle*, cudaStream_t, const uint8_t* binary_dev, int H, int W, int kw, int kh, bool erode, uint8_t* out_dev);
+
 // ---- nn.cu : layer kernels (NHWC; T = float | __nv_bfloat16 chosen by Handle::precision) ------------------------------
 enum ConvFlags { CONV_RELU = 1, CONV_OUT_F32 = 2, CONV_POOL22 = 4, CONV_POOL21 = 8 };
 // out = epilogue(conv(concat_channels(in1, in2)))   in2 may be empty (C == 0).  'same' geometry unless pad says otherwise.

@@ -242,7 +242,9 @@ __global__ void k_gaussian3(const uint8_t* __restrict__ src, uint8_t* __restrict
 }
 
 void gaussian3_kernel_q8(float sigma, int* k0, int* k1) {
-    // OpenCV getGaussianKernelBitExact -> 8-bit fixed point; centre tap absorbs the rounding residue
+    // OpenCV getGaussianKernelBitExact -> 8-bit fixed point; centre tap absorbs the rounding residue.
+    // sigma <= 0 with ksize 3 selects cv2's fixed table [0.25, 0.5, 0.25] (enhanced_extractor.py:254 uses it).
+    if (!(sigma > 0.f)) { *k0 = 64; *k1 = 128; return; }
     double e = exp(-1.0 / (2.0 * (double)sigma * sigma));
     double norm = 1.0 + 2.0 * e;
     int q0 = (int)lrint(e / norm * 256.0), q1 = (int)lrint(1.0 / norm * 256.0);

@@ -31,9 +31,37 @@ def ocr_input_image(reader, gray: np.ndarray, image_index=None) -> np.ndarray:
     return reader.handle.thumbnail(gray, m)
 
 
-def extract_text_with_ocr(reader, image, *, use_preprocessing=True, image_index=None, return_results=False):
-    """extract_text_with_ocr (:413-561) in memory: [preprocess_for_book_cover] -> OCR-input cap -> readtext -> joined text.
-    `image`: path or BGR / gray uint8 array.  Errors are swallowed into "" exactly like :529-531."""
+def central_edge_crop(img: np.ndarray, percent: float):
+    """_central_edge_crop (:374-397) in memory: the centred view with `percent` removed from each edge, or None when the
+    reference returns None (percent <= 0, or the rest would be under max(16 px, 20 %) of a side)."""
+    if percent <= 0.0:
+        return None
+    h, w = img.shape[:2]
+    mx = int(round(w * (percent / 100.0)))
+    my = int(round(h * (percent / 100.0)))
+    x0, y0, x1, y1 = max(0, mx), max(0, my), min(w, w - mx), min(h, h - my)
+    if x1 - x0 < max(16, w * 0.2) or y1 - y0 < max(16, h * 0.2):
+        return None
+    return img[y0:y1, x0:x1]
+
+
+def auto_crop_text_region(reader, img: np.ndarray, margin: int):
+    """_auto_crop_text_region (:239-372) in memory: the view img[y0:y1, x0:x1] of the dominant text region, or None for
+    "no crop".  The rectangle comes from the device (bbocr_autocrop_rect: text-cue mask, rectangle morphology, external
+    components), identical to the cv2 result; `img` is an HxWx3 BGR page or the gray preprocessing output."""
+    rect = reader.handle.autocrop_rect(img, int(margin))
+    if rect is None:
+        return None
+    x0, y0, x1, y1 = rect
+    return img[y0:y1, x0:x1]
+
+
+def extract_text_with_ocr(reader, image, *, use_preprocessing=True, image_index=None, return_results=False,
+                          edge_crop_percent=0.0, crop_for_ocr=False, crop_margin=16):
+    """extract_text_with_ocr (:413-561) in memory: [preprocess_for_book_cover] -> [edge crop] -> [auto crop] -> OCR-input
+    cap -> readtext -> joined text.  `image`: path or BGR / gray uint8 array.  edge_crop_percent / crop_for_ocr /
+    crop_margin are the extractor's attributes of the same names (:452-484; a failing crop keeps the current image, like
+    there).  Errors are swallowed into "" exactly like :529-531."""
     try:
         if isinstance(image, str):
             bgr = cv2.imread(image)
@@ -49,6 +77,17 @@ def extract_text_with_ocr(reader, image, *, use_preprocessing=True, image_index=
             gray = reader.handle.preprocess(bgr, pp_params(CURRENT, 0))        # same handle (and device) as the reader
         else:
             gray = bgr if bgr.ndim == 2 else cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+        if edge_crop_percent > 0.0:
+            central = central_edge_crop(gray, edge_crop_percent)
+            if central is not None:
+                gray = np.ascontiguousarray(central)
+        if crop_for_ocr:
+            try:
+                cropped = auto_crop_text_region(reader, gray, crop_margin)
+                if cropped is not None:
+                    gray = np.ascontiguousarray(cropped)
+            except Exception as e:                           # noqa: BLE001 -- :483-484
+                print(f"    Auto-cropping failed: {e}")
         ocr_in = ocr_input_image(reader, gray, image_index)
         results = reader.readtext(ocr_in, paragraph=False, batch_size=1, workers=0)
         text = " ".join([r[1] for r in results])

@@ -161,3 +161,23 @@ def score_maps_for(mask: np.ndarray, rng=None):
     text = text + rng.normal(0, 0.01, text.shape).astype(np.float32)
     link = link + rng.normal(0, 0.01, link.shape).astype(np.float32)
     return np.ascontiguousarray(text.astype(np.float32)), np.ascontiguousarray(link.astype(np.float32))
+
+
+def sparse_page(seed: int, width: int = 1100, height: int = 800, frame: bool = False) -> np.ndarray:
+    """A clean scan for the auto-crop heuristic: flat paper without sensor noise, a few separated text
+    blocks, and optionally a ruled frame around one block, which makes the components inside it non-external.  BGR u8."""
+    rng = np.random.default_rng(seed)
+    img = Image.new("L", (width, height), int(rng.integers(225, 250)))
+    d = ImageDraw.Draw(img)
+    blocks = [(0.18, 0.15, 3), (0.30, 0.52, 2), (0.12, 0.80, 2)]
+    for bx, by, nl in blocks:
+        y = int(height * by)
+        for _ in range(nl):
+            px = int(rng.integers(18, 34))
+            d.text((int(width * bx), y), _phrase(rng, int(rng.integers(2, 5))), fill=int(rng.integers(10, 70)), font=_font(px))
+            y += int(px * 1.5)
+    if frame:
+        x0, y0, x1, y1 = int(width * 0.22), int(height * 0.46), int(width * 0.9), int(height * 0.66)
+        d.rectangle((x0, y0, x1, y1), outline=30, width=3)
+    g = np.asarray(img)
+    return np.ascontiguousarray(np.stack([g, g, g], axis=-1))

@@ -191,6 +191,24 @@ void bbocr_results_free(bbocr_results* r);
 int bbocr_thumbnail_u8(bbocr_handle* h, const uint8_t* src, int H, int W, int in_on_device, int max_dim, uint8_t* out,
                        int out_on_device, int* outH, int* outW);
 
+/* ---- page crops in front of the OCR stage ---------------------------------------------------------- */
+/* _auto_crop_text_region (pipeline_demo/extractor/enhanced_extractor.py:239-372) up to the slice it writes: the crop
+ * rectangle rect = (x0, y0, x1, y1) of a page for the given margin; *found = 0 is the reference's `return None`
+ * ("no crop").  channels = 3: BGR u8 (what cv2.imread gives the reference); channels = 1: a gray plane, e.g. the
+ * preprocessing output (cv2.imread of a gray PNG yields three equal channels, whose BGR2GRAY is the plane itself).  The composite text mask, the rectangle morphology, the external-contour bounding boxes all run on the
+ * device, bit-exact against cv2; the caller slices img[y0:y1, x0:x1] itself (no PNG round trip).
+ * Optional parity outputs (host pointers, each may be NULL): mask_out / merged_out HxW u8 (0/255) = the reference's `mask`
+ * and `merged`; boxes_out = up to boxes_cap rows (x, y, w, h) = boundingRect of every RETR_EXTERNAL contour of `merged`
+ * sorted by (y, x, w, h), *nboxes = their total number; otsu_out[2] = the two Otsu thresholds. */
+int bbocr_autocrop_rect(bbocr_handle* h, const uint8_t* img, int H, int W, int channels, int stride_bytes, int in_on_device, int margin,
+                        int32_t rect[4], int* found, uint8_t* mask_out, uint8_t* merged_out, int32_t* boxes_out,
+                        int boxes_cap, int* nboxes, int32_t* otsu_out);
+/* Building blocks of the above on host buffers (parity-test surface): cv2.findContours(RETR_EXTERNAL) + boundingRect of a
+ * binary u8 image (non-zero = foreground; rows (x, y, w, h) sorted by (y, x, w, h)), and cv2.dilate / cv2.erode with a
+ * kw x kh rectangle (odd sizes, kw <= 63, centre anchor, default border). */
+int bbocr_external_boxes(bbocr_handle* h, const uint8_t* binary, int H, int W, int32_t* boxes_out, int boxes_cap, int* nboxes);
+int bbocr_rect_morph(bbocr_handle* h, const uint8_t* binary, int H, int W, int kw, int kh, int erode, uint8_t* out);
+
 /* ---- instrumentation -------------------------------------------------------------------------------------------- */
 /* Kernels launched by this handle since the last reset (the bench's gpu_launches claim). */
 int64_t bbocr_launch_count(const bbocr_handle* h);
