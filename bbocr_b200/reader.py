@@ -9,6 +9,7 @@ exceptions; the caller swallows them).  There is no CPU fallback: constructing a
 """
 from __future__ import annotations
 
+import json
 import os
 import threading
 
@@ -58,6 +59,65 @@ def reformat_input(image):
     if img.dtype != np.uint8:
         raise ValueError("Invalid input: image must be uint8")
     return img, img_cv_grey
+
+
+def get_paragraph(raw_result, x_ths=1, y_ths=0.5, mode="ltr"):
+    """easyocr/utils.py::get_paragraph -- the `paragraph=True` post-pass of Reader.recognize: greedy clustering of the
+    result boxes into paragraphs, then reading order inside each one.  Host logic on a handful of boxes per page.
+    -> [[box, text], ...] (no confidence), box = the paragraph's axis-aligned rectangle as four [x, y] int corners."""
+    n = len(raw_result)
+    text = [r[1] for r in raw_result]
+    xs = [[int(c[0]) for c in r[0]] for r in raw_result]
+    ys = [[int(c[1]) for c in r[0]] for r in raw_result]
+    x_lo, x_hi = [min(v) for v in xs], [max(v) for v in xs]
+    y_lo, y_hi = [min(v) for v in ys], [max(v) for v in ys]
+    height = [b - a for a, b in zip(y_lo, y_hi)]
+    y_mid = [0.5 * (a + b) for a, b in zip(y_lo, y_hi)]
+    group = [0] * n                                            # 0 = not assigned yet
+    current, members, pending = 1, [], list(range(n))
+    while pending:
+        if not members:                                        # the first unassigned box opens the group
+            k = pending.pop(0)
+            group[k] = current
+            members = [k]
+            continue
+        mean_h = float(np.mean([height[k] for k in members]))
+        gx0 = min(x_lo[k] for k in members) - x_ths * mean_h
+        gx1 = max(x_hi[k] for k in members) + x_ths * mean_h
+        gy0 = min(y_lo[k] for k in members) - y_ths * mean_h
+        gy1 = max(y_hi[k] for k in members) + y_ths * mean_h
+        for pos, k in enumerate(pending):                      # first box (input order) that touches the grown group
+            if ((gx0 <= x_lo[k] <= gx1) or (gx0 <= x_hi[k] <= gx1)) and ((gy0 <= y_lo[k] <= gy1) or (gy0 <= y_hi[k] <= gy1)):
+                group[k] = current
+                members.append(k)
+                del pending[pos]
+                break
+        else:                                                  # nothing joins any more: next group
+            current += 1
+            members = []
+    out = []
+    for g in sorted(set(group)):
+        left = [k for k in range(n) if group[k] == g]          # input order
+        mean_h = float(np.mean([height[k] for k in left]))
+        rect = (min(x_lo[k] for k in left), max(x_hi[k] for k in left), min(y_lo[k] for k in left), max(y_hi[k] for k in left))
+        words = []
+        while left:
+            top = min(y_mid[k] for k in left)
+            line = [k for k in left if y_mid[k] < top + 0.4 * mean_h]
+            if mode == "ltr":
+                edge = min(x_lo[k] for k in line)
+                pick = [k for k in line if x_lo[k] == edge][-1]
+            else:                                              # 'rtl'
+                edge = max(x_hi[k] for k in line)
+                pick = [k for k in line if x_hi[k] == edge][-1]
+            words.append(text[pick])
+            # upstream removes by list equality, i.e. the first box with the same fields as the pick
+            same = next(k for k in left if (text[k], x_lo[k], x_hi[k], y_lo[k], y_hi[k]) ==
+                        (text[pick], x_lo[pick], x_hi[pick], y_lo[pick], y_hi[pick]))
+            left.remove(same)
+        gx0, gx1, gy0, gy1 = rect
+        out.append([[[gx0, gy0], [gx1, gy0], [gx1, gy1], [gx0, gy1]], " ".join(words)])
+    return out
 
 
 class Reader:
@@ -123,27 +183,38 @@ class Reader:
             p.ignore = ignore.ctypes.data
         return p, ignore
 
-    def _format(self, raw, detail=1, output_format="standard"):
+    def _format(self, raw, detail=1, output_format="standard", paragraph=False, x_ths=1.0, y_ths=0.5):
+        """Tail of Reader.recognize / readtext (easyocr/easyocr.py): paragraph merge, then detail / output_format."""
         out = []
         chars = self.character
         for box, is_free, idx, conf in raw:
             text = "".join([chars[i - 1] for i in idx])
             b = box.tolist() if is_free else box.astype(np.int64).tolist()      # upstream: floats for free boxes, ints otherwise
             out.append((b, text, conf))
+        if paragraph:
+            out = get_paragraph(out, x_ths=x_ths, y_ths=y_ths, mode="ltr")      # 'rtl' only for the arabic model
         if detail == 0:
             return [item[1] for item in out]
         if output_format == "dict":
+            if paragraph:
+                return [{"boxes": item[0], "text": item[1]} for item in out]
             return [{"boxes": item[0], "text": item[1], "confident": item[2]} for item in out]
+        if output_format == "json":
+            rows = [{"boxes": [list(map(int, c)) for c in item[0]], "text": item[1]} for item in out]
+            if not paragraph:
+                for row, item in zip(rows, out):
+                    row["confident"] = item[2]
+            return [json.dumps(row, ensure_ascii=False) for row in rows]
+        if output_format != "standard":
+            raise NotImplementedError(f"output_format={output_format!r} is not implemented (SURVEY.md §8f-3)")
         return out
 
     @staticmethod
-    def _check_unsupported(decoder, rotation_info, paragraph):
+    def _check_unsupported(decoder, rotation_info):
         if decoder != "greedy":
             raise NotImplementedError("only decoder='greedy' is implemented (SURVEY.md §8f-3)")
         if rotation_info:
             raise NotImplementedError("rotation_info is not implemented (SURVEY.md §8f-3)")
-        if paragraph:
-            raise NotImplementedError("paragraph=True is not implemented (SURVEY.md §8f-3)")
 
     def readtext(self, image, decoder="greedy", beamWidth=5, batch_size=1, workers=0, allowlist=None, blocklist=None,
                  detail=1, rotation_info=None, paragraph=False, min_size=20, contrast_ths=0.1, adjust_contrast=0.5,
@@ -157,13 +228,13 @@ class Reader:
                                      text_threshold=text_threshold, low_text=low_text, link_threshold=link_threshold,
                                      canvas_size=canvas_size, mag_ratio=mag_ratio, slope_ths=slope_ths,
                                      ycenter_ths=ycenter_ths, height_ths=height_ths, width_ths=width_ths,
-                                     add_margin=add_margin, output_format=output_format)[0]
+                                     add_margin=add_margin, y_ths=y_ths, x_ths=x_ths, output_format=output_format)[0]
 
     def readtext_batched(self, images, decoder="greedy", allowlist=None, blocklist=None, detail=1, rotation_info=None,
-                         paragraph=False, output_format="standard", return_stats=False, **kw):
+                         paragraph=False, output_format="standard", return_stats=False, y_ths=0.5, x_ths=1.0, **kw):
         """Batched extension: independent pages pipelined over the handle's CUDA streams; per-page semantics are exactly
         those of readtext(batch_size=1)."""
-        self._check_unsupported(decoder, rotation_info, paragraph)
+        self._check_unsupported(decoder, rotation_info)
         p, keep = self._params(kw, allowlist, blocklist)
         pages = []
         for im in images:
@@ -172,7 +243,7 @@ class Reader:
                           img.shape[0], img.shape[1]))
         with self._lock:
             raw = self._h.readtext_raw(pages, p)
-        res = [self._format(r, detail, output_format) for r, _ in raw]
+        res = [self._format(r, detail, output_format, paragraph, x_ths, y_ths) for r, _ in raw]
         if return_stats:
             return res, [s for _, s in raw]
         return res
@@ -203,7 +274,7 @@ class Reader:
                   **_ignored):
         """Reader.recognize -> [(box, text, confidence)] for the given boxes (upstream order: horizontal, then free).
         With both lists None the whole image is one horizontal box, like upstream."""
-        self._check_unsupported(decoder, rotation_info, paragraph)
+        self._check_unsupported(decoder, rotation_info)
         if reformat:
             _, img_cv_grey = reformat_input(img_cv_grey) if not (isinstance(img_cv_grey, np.ndarray) and img_cv_grey.ndim == 2) \
                 else (None, img_cv_grey)
@@ -215,7 +286,7 @@ class Reader:
         p, keep = self._params({"contrast_ths": contrast_ths, "adjust_contrast": adjust_contrast}, allowlist, blocklist)
         with self._lock:
             raw, _ = self._h.recognize_raw(np.ascontiguousarray(img_cv_grey), horizontal_list or [], free_list or [], p)
-        return self._format(raw, detail, output_format)
+        return self._format(raw, detail, output_format, paragraph, x_ths, y_ths)
 
     def score_maps(self, img, canvas_size=2560, mag_ratio=1.0):
         with self._lock:

@@ -569,6 +569,63 @@ def decode_probs(preds_prob: np.ndarray, character=CHARACTERS):
 # Reader
 # ======================================================================================================================
 
+def get_paragraph(raw_result, x_ths=1, y_ths=0.5, mode="ltr"):
+    """easyocr/utils.py::get_paragraph, restated statement by statement (rows are
+    [text, min_x, max_x, min_y, max_y, height, y_centre, group])."""
+    box_group = []
+    for box in raw_result:
+        all_x = [int(coord[0]) for coord in box[0]]
+        all_y = [int(coord[1]) for coord in box[0]]
+        min_x, max_x, min_y, max_y = min(all_x), max(all_x), min(all_y), max(all_y)
+        box_group.append([box[1], min_x, max_x, min_y, max_y, max_y - min_y, 0.5 * (min_y + max_y), 0])
+    current_group = 1
+    while len([b for b in box_group if b[7] == 0]) > 0:
+        box_group0 = [b for b in box_group if b[7] == 0]
+        if len([b for b in box_group if b[7] == current_group]) == 0:
+            box_group0[0][7] = current_group
+        else:
+            cur = [b for b in box_group if b[7] == current_group]
+            mean_height = np.mean([b[5] for b in cur])
+            min_gx = min(b[1] for b in cur) - x_ths * mean_height
+            max_gx = max(b[2] for b in cur) + x_ths * mean_height
+            min_gy = min(b[3] for b in cur) - y_ths * mean_height
+            max_gy = max(b[4] for b in cur) + y_ths * mean_height
+            add_box = False
+            for b in box_group0:
+                same_horizontal_level = (min_gx <= b[1] <= max_gx) or (min_gx <= b[2] <= max_gx)
+                same_vertical_level = (min_gy <= b[3] <= max_gy) or (min_gy <= b[4] <= max_gy)
+                if same_horizontal_level and same_vertical_level:
+                    b[7] = current_group
+                    add_box = True
+                    break
+            if not add_box:
+                current_group += 1
+    result = []
+    for i in set(b[7] for b in box_group):
+        cur = [b for b in box_group if b[7] == i]
+        mean_height = np.mean([b[5] for b in cur])
+        min_gx, max_gx = min(b[1] for b in cur), max(b[2] for b in cur)
+        min_gy, max_gy = min(b[3] for b in cur), max(b[4] for b in cur)
+        text = ""
+        while len(cur) > 0:
+            highest = min(b[6] for b in cur)
+            candidates = [b for b in cur if b[6] < highest + 0.4 * mean_height]
+            if mode == "ltr":
+                most_left = min(b[1] for b in candidates)
+                for b in candidates:
+                    if b[1] == most_left:
+                        best_box = b
+            elif mode == "rtl":
+                most_right = max(b[2] for b in candidates)
+                for b in candidates:
+                    if b[2] == most_right:
+                        best_box = b
+            text += " " + best_box[0]
+            cur.remove(best_box)
+        result.append([[[min_gx, min_gy], [max_gx, min_gy], [max_gx, max_gy], [min_gx, max_gy]], text[1:]])
+    return result
+
+
 class Reader:
     """Restated easyocr.Reader(['en']) -- CPU, greedy decoder, the options BB-OCR exercises."""
 

@@ -127,3 +127,51 @@ def test_two_rank_gloo_sharding(tmp_path):
     outs = [p.communicate(timeout=120)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_get_paragraph_matches_the_restated_upstream():
+    """paragraph=True post-pass (easyocr/utils.py::get_paragraph; SURVEY.md §8f-3): product vs oracle on random layouts."""
+    from bbocr_b200.reader import get_paragraph
+    rng = np.random.default_rng(7)
+    words = ["the", "red", "men", "of", "iowa", "x", "x", "history"]
+    for it in range(300):
+        n = int(rng.integers(1, 25))
+        res = []
+        for _ in range(n):
+            x, y = int(rng.integers(0, 900)), int(rng.integers(0, 12)) * int(rng.integers(20, 70))
+            w, h = int(rng.integers(20, 300)), int(rng.integers(10, 60))
+            if rng.random() < 0.2:                               # a free-form (float) quad
+                q = [[x + rng.random(), y - 3.5], [x + w + 0.25, y + 2.0], [x + w - 0.5, y + h + 4.75], [x - 1.5, y + h]]
+            else:
+                q = [[x, y], [x + w, y], [x + w, y + h], [x, y + h]]
+            res.append((q, str(words[int(rng.integers(len(words)))]), float(rng.random())))
+        if it % 5 == 0 and n > 1:
+            res[-1] = res[0]                                    # exact duplicates exercise the remove-by-equality rule
+        for mode in ("ltr", "rtl"):
+            x_ths, y_ths = float(rng.choice([1.0, 0.3, 2.5])), float(rng.choice([0.5, 0.1, 1.5]))
+            assert get_paragraph(res, x_ths, y_ths, mode) == E.get_paragraph(res, x_ths, y_ths, mode), (it, mode)
+    assert get_paragraph([]) == [] == E.get_paragraph([])
+
+
+def test_format_tail_detail_and_output_formats():
+    """Reader._format without a device: detail=0, dict / json, paragraph variants (easyocr/easyocr.py::readtext tail)."""
+    import json
+    import bbocr_b200
+    r = bbocr_b200.Reader.__new__(bbocr_b200.Reader)
+    r.character = bbocr_b200.reader.CHARACTERS
+    idx = lambda t: np.array([r.character.index(c) + 1 for c in t], np.int32)          # noqa: E731
+    raw = [(np.array([[10, 10], [90, 10], [90, 40], [10, 40]], np.float32), False, idx("Red"), 0.9),
+           (np.array([[100, 12], [180, 12], [180, 41], [100, 41]], np.float32), False, idx("Men"), 0.5),
+           (np.array([[10.5, 300.25], [90, 310], [88, 340], [9, 330]], np.float32), True, idx("1854"), 0.25)]
+    std = r._format(raw)
+    assert std[0] == ([[10, 10], [90, 10], [90, 40], [10, 40]], "Red", 0.9) and isinstance(std[2][0][0][0], float)
+    assert r._format(raw, detail=0) == ["Red", "Men", "1854"]
+    assert r._format(raw, output_format="dict")[1] == {"boxes": std[1][0], "text": "Men", "confident": 0.5}
+    assert json.loads(r._format(raw, output_format="json")[2]) == {"boxes": [[10, 300], [90, 310], [88, 340], [9, 330]], "text": "1854", "confident": 0.25}
+    para = r._format(raw, paragraph=True)
+    assert para == [[[[10, 10], [180, 10], [180, 41], [10, 41]], "Red Men"], [[[9, 300], [90, 300], [90, 340], [9, 340]], "1854"]]
+    assert para == E.get_paragraph(std)
+    assert r._format(raw, detail=0, paragraph=True) == ["Red Men", "1854"]
+    assert r._format(raw, output_format="dict", paragraph=True)[0] == {"boxes": para[0][0], "text": "Red Men"}
+    with pytest.raises(NotImplementedError):
+        r._format(raw, output_format="free_merge")
