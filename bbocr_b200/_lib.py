@@ -60,7 +60,7 @@ _lock = threading.Lock()
 # every symbol include/bbocr.h declares (tests check the export table against this list)
 SYMBOLS = [
     "bbocr_create", "bbocr_destroy", "bbocr_last_error", "bbocr_version", "bbocr_load_craft", "bbocr_load_crnn",
-    "bbocr_set_precision", "bbocr_get_precision", "bbocr_preprocess_u8", "bbocr_preprocess_launches_per_image",
+    "bbocr_set_precision", "bbocr_get_precision", "bbocr_preprocess_u8", "bbocr_preprocess_batch_u8", "bbocr_preprocess_launches_per_image",
     "bbocr_pp_gray", "bbocr_pp_resize_cubic", "bbocr_pp_gaussian3", "bbocr_pp_contrast", "bbocr_pp_brightness",
     "bbocr_pp_clahe", "bbocr_pp_unsharp", "bbocr_pp_adaptive_threshold", "bbocr_pp_deskew", "bbocr_craft_forward",
     "bbocr_det_boxes", "bbocr_min_area_box", "bbocr_group_boxes", "bbocr_crop_horizontal", "bbocr_crop_free",
@@ -217,6 +217,34 @@ class Handle:
                                                C.byref(oh), C.byref(ow)))
         assert (oh.value, ow.value) == (dH, dW)
         return out
+
+    def preprocess_batch(self, images, params: PPParams):
+        """The chain over a list of same-size host BGR images (bbocr_preprocess_batch_u8) -> list of host gray images."""
+        if not images:
+            return []
+        arrs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        H, W = arrs[0].shape[:2]
+        if any(a.shape != (H, W, 3) for a in arrs):
+            raise ValueError("preprocess_batch expects same-size HxWx3 uint8 images")
+        dH, dW = int(H * params.scale), int(W * params.scale)
+        outs = [np.empty((dH, dW), np.uint8) for _ in arrs]
+        n = len(arrs)
+        ins = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        ous = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        oh, ow = C.c_int(), C.c_int()
+        self._check(self.L.bbocr_preprocess_batch_u8(self._h, C.c_int(n), ins, C.c_int(H), C.c_int(W), C.c_int(W * 3), C.c_int(0),
+                                                     C.byref(params), ous, C.c_int(0), C.byref(oh), C.byref(ow)))
+        return outs
+
+    def preprocess_batch_dev(self, bgr_ptrs, H: int, W: int, params: PPParams, out_ptrs):
+        """Device-resident batch (raw CUDA pointers): one call, photos pipelined over the handle's streams."""
+        n = len(bgr_ptrs)
+        ins = (C.c_void_p * n)(*bgr_ptrs)
+        ous = (C.c_void_p * n)(*out_ptrs)
+        oh, ow = C.c_int(), C.c_int()
+        self._check(self.L.bbocr_preprocess_batch_u8(self._h, C.c_int(n), ins, C.c_int(H), C.c_int(W), C.c_int(W * 3), C.c_int(1),
+                                                     C.byref(params), ous, C.c_int(1), C.byref(oh), C.byref(ow)))
+        return oh.value, ow.value
 
     def preprocess_dev(self, bgr_ptr: int, H: int, W: int, params: PPParams, out_ptr: int):
         """Device-resident variant (raw CUDA pointers, e.g. torch.Tensor.data_ptr())."""

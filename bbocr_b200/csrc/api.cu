@@ -164,6 +164,7 @@ void bbocr_destroy(bbocr_handle* h) {
     for (auto& l : h->lanes)
         if (l.stream) cudaStreamDestroy(l.stream);
     for (void* p : h->owned) cudaFree(p);
+    for (auto& kv : h->cubic_cache) cudaFree(kv.second.first);
     for (auto& ev : h->conv_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     delete h;
 }
@@ -208,6 +209,40 @@ int bbocr_preprocess_u8(bbocr_handle* h, const uint8_t* bgr, int H, int W, int s
         preprocess_chain_dev(h, lane.stream, src, H, W, stride, *p, dst, outH, outW);
         if (!out_on_device) download(lane, out, dst, (size_t)dH * dW);
         else CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+    });
+}
+
+// n same-size photos: photo i runs on lane i % n_lanes (its own stream and pinned staging), so the seven launches of
+// different photos overlap and there is one synchronisation per lane instead of one per photo.
+int bbocr_preprocess_batch_u8(bbocr_handle* h, int n, const uint8_t* const* bgr, int H, int W, int stride, int in_on_device,
+                              const bbocr_pp_params* p, uint8_t* const* out, int out_on_device, int* outH, int* outW) {
+    return guarded(h, [&] {
+        ARG_CHECK(n >= 0 && bgr && p && out && outH && outW && H > 0 && W > 0 && stride >= W * 3, "bad arguments");
+        const int dH = (int)(H * (double)p->scale), dW = (int)(W * (double)p->scale);
+        ARG_CHECK(dH > 0 && dW > 0, "empty output");
+        *outH = dH; *outW = dW;
+        const int nl = std::min<int>(h->n_det_lanes, std::max(n, 1));
+        const size_t in_bytes = (size_t)H * stride, out_bytes = (size_t)dH * dW;
+        for (int base = 0; base < n; base += nl) {
+            const int m = std::min(nl, n - base);
+            std::vector<DevBuf> din(m), dout(m);
+            for (int k = 0; k < m; ++k) {
+                ARG_CHECK(bgr[base + k] && out[base + k], "null image %d", base + k);
+                Lane& lane = h->lanes[k];
+                const uint8_t* src = bgr[base + k];
+                if (!in_on_device) { upload(lane, din[k], src, in_bytes); src = din[k].as<uint8_t>(); }
+                uint8_t* dst = out[base + k];
+                if (!out_on_device) { dout[k].alloc(out_bytes, lane.stream); dst = dout[k].as<uint8_t>(); }
+                int oh, ow;
+                preprocess_chain_dev(h, lane.stream, src, H, W, stride, *p, dst, &oh, &ow);
+            }
+            for (int k = 0; k < m; ++k) {
+                Lane& lane = h->lanes[k];
+                if (!out_on_device) download(lane, out[base + k], dout[k].p, out_bytes);
+                else CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+                lane.in_busy = false;
+            }
+        }
     });
 }
 

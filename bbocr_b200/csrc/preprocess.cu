@@ -160,36 +160,157 @@ __global__ void k_resize_cubic(const uint8_t* __restrict__ src, int sH, int sW, 
     dst[(int64_t)y * dW + x] = o;
 }
 
+// Tiled variant (the default whenever a 128 x 32 output tile needs at most RS_W x RS_H source pixels, i.e. any scale
+// factor >= ~1.4): the source patch is staged in shared memory, the horizontal pass runs ONCE per (source row, output
+// column) into an int32 / float plane in shared memory, and the vertical pass reads it as 16-byte vectors, four output
+// pixels per thread.  Arithmetic (and therefore every output bit) is the same as k_resize_cubic.
+constexpr int RT_W = 128, RT_H = 32, RS_W = 96, RS_H = 28;
+__global__ void __launch_bounds__(256) k_resize_cubic_tile(const uint8_t* __restrict__ src, int sH, int sW, uint8_t* __restrict__ dst,
+                                                           int dH, int dW, const int32_t* __restrict__ xidx,
+                                                           const int32_t* __restrict__ xci, const float* __restrict__ xcf,
+                                                           const int32_t* __restrict__ yidx, const int32_t* __restrict__ yci,
+                                                           const float* __restrict__ ycf, int mode) {
+    __shared__ uint8_t s_src[RS_H][RS_W];
+    __shared__ __align__(16) int s_h[RS_H][RT_W];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * RT_W, y0 = blockIdx.y * RT_H;
+    const int x1 = min(x0 + RT_W, dW) - 1, y1 = min(y0 + RT_H, dH) - 1;
+    const int sx_lo = __ldg(xidx + 4 * x0), sx_hi = __ldg(xidx + 4 * x1 + 3);
+    const int sy_lo = __ldg(yidx + 4 * y0), sy_hi = __ldg(yidx + 4 * y1 + 3);
+    const int sw = sx_hi - sx_lo + 1, sh = sy_hi - sy_lo + 1;
+    for (int i = tid; i < sh * sw; i += 256) {
+        int r = i / sw, c = i - r * sw;
+        s_src[r][c] = src[(int64_t)(sy_lo + r) * sW + sx_lo + c];
+    }
+    __syncthreads();
+    {
+        const int tx = tid & (RT_W - 1), x = x0 + tx;
+        if (x <= x1) {
+            int4 xi = __ldg(reinterpret_cast<const int4*>(xidx) + x);
+            xi.x -= sx_lo; xi.y -= sx_lo; xi.z -= sx_lo; xi.w -= sx_lo;
+            if (mode == 0) {
+                const int4 ax = __ldg(reinterpret_cast<const int4*>(xci) + x);
+                for (int r = tid >> 7; r < sh; r += 2) {
+                    const uint8_t* p = s_src[r];
+                    s_h[r][tx] = p[xi.x] * ax.x + p[xi.y] * ax.y + p[xi.z] * ax.z + p[xi.w] * ax.w;
+                }
+            } else {
+                const float4 cx = __ldg(reinterpret_cast<const float4*>(xcf) + x);
+                for (int r = tid >> 7; r < sh; r += 2) {
+                    const uint8_t* p = s_src[r];
+                    float a = __fmul_rn((float)p[xi.x], cx.x);
+                    a = __fadd_rn(a, __fmul_rn((float)p[xi.y], cx.y));
+                    a = __fadd_rn(a, __fmul_rn((float)p[xi.z], cx.z));
+                    a = __fadd_rn(a, __fmul_rn((float)p[xi.w], cx.w));
+                    s_h[r][tx] = __float_as_int(a);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int cg = (tid & 31) * 4;
+    const int xvec_end = (dW / 8) * 8;
+    for (int ry = tid >> 5; ry < RT_H; ry += 8) {
+        const int y = y0 + ry;
+        if (y > y1) break;
+        int4 yi = __ldg(reinterpret_cast<const int4*>(yidx) + y);
+        const int4 S0 = *reinterpret_cast<const int4*>(&s_h[yi.x - sy_lo][cg]);
+        const int4 S1 = *reinterpret_cast<const int4*>(&s_h[yi.y - sy_lo][cg]);
+        const int4 S2 = *reinterpret_cast<const int4*>(&s_h[yi.z - sy_lo][cg]);
+        const int4 S3 = *reinterpret_cast<const int4*>(&s_h[yi.w - sy_lo][cg]);
+        const int a0[4] = {S0.x, S0.y, S0.z, S0.w}, a1[4] = {S1.x, S1.y, S1.z, S1.w};
+        const int a2[4] = {S2.x, S2.y, S2.z, S2.w}, a3[4] = {S3.x, S3.y, S3.z, S3.w};
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ycf) + y);
+        const int4 by = __ldg(reinterpret_cast<const int4*>(yci) + y);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int x = x0 + cg + c;
+            int v;
+            if (mode == 0) {
+                if (x < xvec_end) {
+                    float acc = __fmul_rn((float)a3[c], b.w);
+                    acc = __fadd_rn(__fmul_rn((float)a2[c], b.z), acc);
+                    acc = __fadd_rn(__fmul_rn((float)a1[c], b.y), acc);
+                    acc = __fadd_rn(__fmul_rn((float)a0[c], b.x), acc);
+                    v = __float2int_rn(acc);
+                } else {
+                    v = (a0[c] * by.x + a1[c] * by.y + a2[c] * by.z + a3[c] * by.w + (1 << 21)) >> 22;
+                }
+            } else {
+                float a = __fmul_rn(__int_as_float(a0[c]), b.x);
+                a = __fadd_rn(a, __fmul_rn(__int_as_float(a1[c]), b.y));
+                a = __fadd_rn(a, __fmul_rn(__int_as_float(a2[c]), b.z));
+                a = __fadd_rn(a, __fmul_rn(__int_as_float(a3[c]), b.w));
+                v = __float2int_rn(a);
+            }
+            packed |= (uint32_t)min(max(v, 0), 255) << (8 * c);
+        }
+        uint8_t* out = dst + (int64_t)y * dW + x0 + cg;
+        if (x0 + cg + 3 <= x1 && (dW & 3) == 0) {
+            *reinterpret_cast<uint32_t*>(out) = packed;
+        } else {
+            for (int c = 0; c < 4 && x0 + cg + c <= x1; ++c) out[c] = (uint8_t)(packed >> (8 * c));
+        }
+    }
+}
+
 struct CubicTables {
-    DevBuf buf;
     int32_t *xidx, *xci, *yidx, *yci;
     float *xcf, *ycf;
+    bool tiled = false;            // every 128 x 32 output tile fits the shared-memory source patch
 };
 
-static void upload_cubic_tables(cudaStream_t st, int sH, int sW, int dH, int dW, int mode, CubicTables& t) {
-    CubicAxis ax = cubic_axis(sW, dW, false), ay = cubic_axis(sH, dH, mode == 0);
-    size_t nx = (size_t)dW * 4, ny = (size_t)dH * 4;
-    std::vector<int32_t> host((nx + ny) * 3);
-    memcpy(&host[0], ax.idx.data(), nx * 4);
-    memcpy(&host[nx], ax.ci.data(), nx * 4);
-    memcpy(&host[2 * nx], ax.cf.data(), nx * 4);
-    memcpy(&host[3 * nx], ay.idx.data(), ny * 4);
-    memcpy(&host[3 * nx + ny], ay.ci.data(), ny * 4);
-    memcpy(&host[3 * nx + 2 * ny], ay.cf.data(), ny * 4);
-    t.buf.alloc(host.size() * 4, st);
-    CUDA_CHECK(cudaMemcpyAsync(t.buf.p, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));     // host vector goes out of scope (pageable copy is staged, but be explicit)
-    int32_t* b = t.buf.as<int32_t>();
+// Coefficient tables live on the device for the lifetime of the handle, one set per (source size, target size, mode):
+// a batch of same-size photos builds and uploads them once.
+static CubicTables cubic_tables(Handle* h, int sH, int sW, int dH, int dW, int mode) {
+    std::lock_guard<std::mutex> lk(h->stat_mu);
+    const std::array<int, 5> key = {sH, sW, dH, dW, mode};
+    auto it = h->cubic_cache.find(key);
+    if (it == h->cubic_cache.end()) {
+        CubicAxis ax = cubic_axis(sW, dW, false), ay = cubic_axis(sH, dH, mode == 0);
+        size_t nx = (size_t)dW * 4, ny = (size_t)dH * 4;
+        bool tiled = true;
+        for (int x0 = 0; x0 < dW && tiled; x0 += RT_W)
+            tiled = ax.idx[4 * (size_t)(std::min(x0 + RT_W, dW) - 1) + 3] - ax.idx[4 * (size_t)x0] + 1 <= RS_W;
+        for (int y0 = 0; y0 < dH && tiled; y0 += RT_H)
+            tiled = ay.idx[4 * (size_t)(std::min(y0 + RT_H, dH) - 1) + 3] - ay.idx[4 * (size_t)y0] + 1 <= RS_H;
+        std::vector<int32_t> host((nx + ny) * 3);
+        memcpy(&host[0], ax.idx.data(), nx * 4);
+        memcpy(&host[nx], ax.ci.data(), nx * 4);
+        memcpy(&host[2 * nx], ax.cf.data(), nx * 4);
+        memcpy(&host[3 * nx], ay.idx.data(), ny * 4);
+        memcpy(&host[3 * nx + ny], ay.ci.data(), ny * 4);
+        memcpy(&host[3 * nx + 2 * ny], ay.cf.data(), ny * 4);
+        if (h->cubic_cache.size() >= 32) {                   // bound the cache: sizes seen long ago are rebuilt on demand
+            CUDA_CHECK(cudaDeviceSynchronize());
+            for (auto& kv : h->cubic_cache) cudaFree(kv.second.first);
+            h->cubic_cache.clear();
+        }
+        void* dev = nullptr;
+        CUDA_CHECK(cudaMalloc(&dev, host.size() * 4));
+        CUDA_CHECK(cudaMemcpy(dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+        it = h->cubic_cache.emplace(key, std::make_pair(dev, tiled)).first;
+    }
+    const size_t nx = (size_t)dW * 4, ny = (size_t)dH * 4;
+    int32_t* b = static_cast<int32_t*>(it->second.first);
+    CubicTables t;
     t.xidx = b; t.xci = b + nx; t.xcf = reinterpret_cast<float*>(b + 2 * nx);
     t.yidx = b + 3 * nx; t.yci = b + 3 * nx + ny; t.ycf = reinterpret_cast<float*>(b + 3 * nx + 2 * ny);
+    t.tiled = it->second.second;
+    return t;
 }
 
 void pp_resize_cubic(Handle* h, cudaStream_t st, const uint8_t* src, int sH, int sW, uint8_t* dst, int dH, int dW,
                      int mode) {
-    CubicTables t;
-    upload_cubic_tables(st, sH, sW, dH, dW, mode, t);
-    dim3 blk(64, 4), grd(cdiv(dW, 64), cdiv(dH, 4));
-    k_resize_cubic<<<grd, blk, 0, st>>>(src, sH, sW, dst, dH, dW, t.xidx, t.xci, t.xcf, t.yidx, t.yci, t.ycf, mode);
+    const CubicTables t = cubic_tables(h, sH, sW, dH, dW, mode);
+    if (t.tiled) {
+        k_resize_cubic_tile<<<dim3(cdiv(dW, RT_W), cdiv(dH, RT_H)), 256, 0, st>>>(src, sH, sW, dst, dH, dW, t.xidx, t.xci, t.xcf,
+                                                                                  t.yidx, t.yci, t.ycf, mode);
+    } else {
+        dim3 blk(64, 4), grd(cdiv(dW, 64), cdiv(dH, 4));
+        k_resize_cubic<<<grd, blk, 0, st>>>(src, sH, sW, dst, dH, dW, t.xidx, t.xci, t.xcf, t.yidx, t.yci, t.ycf, mode);
+    }
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -500,6 +621,170 @@ __global__ void k_unsharp(const uint8_t* __restrict__ src, uint8_t* __restrict__
     }
 }
 
+// Tiled variant used by pp_unsharp (k_unsharp above is kept as the plain restatement the tile kernel was checked against).
+// 128 x 32 output pixels per block, four pixels per thread in every phase:
+//   0. per-column / per-row CLAHE interpolation terms of the tile (they only depend on x or on y)
+//   1. tone LUT + CLAHE blend of the tile and its halo into shared memory: one aligned 32-bit load per four pixels and ONE
+//      32-bit table load per pixel -- k_clahe_quadlut packs, for each of the 9 x 9 possible (tile, neighbour tile) pairs
+//      per axis, the four tile-LUT entries a pixel value blends (already seen through the tone LUT) into one word
+//   2. the three horizontal box passes in registers: 10 input bytes (three 32-bit words) -> 8 -> 6 -> 4 values
+//   3. the three vertical passes the same way down 10 rows, then the unsharp combine and one 32-bit store per row
+// Per-pass edge replication at the image border = copying the border value outwards before each pass.
+// Shared tile column c <-> image x = 128 * blockIdx.x - 4 + c (4-byte aligned); columns 1..3 and 132..134 are the halo.
+constexpr int UT_W = 128, UT_H = 32, UA_P = UT_W + 8, UA_H = UT_H + 2 * US_H;
+
+__global__ void k_clahe_quadlut(const uint8_t* __restrict__ luts, const uint8_t* __restrict__ tone, uint32_t* __restrict__ quad) {
+    const int qy = blockIdx.x / 9, qx = blockIdx.x % 9, v = threadIdx.x;
+    const int ty1 = max(qy - 1, 0), ty2 = min(qy, 7), tx1 = max(qx - 1, 0), tx2 = min(qx, 7);
+    const int p = tone ? tone[v] : v;
+    quad[blockIdx.x * 256 + v] = (uint32_t)luts[((ty1 * 8 + tx1) << 8) + p] | ((uint32_t)luts[((ty1 * 8 + tx2) << 8) + p] << 8) |
+                                 ((uint32_t)luts[((ty2 * 8 + tx1) << 8) + p] << 16) | ((uint32_t)luts[((ty2 * 8 + tx2) << 8) + p] << 24);
+}
+
+__device__ __forceinline__ unsigned box_px(unsigned c, unsigned l, unsigned r, unsigned ww, unsigned fw) {
+    return (c * ww + (l + r) * fw + (1u << 23)) >> 24;
+}
+
+// v[0..9] (tile coordinate of v[i] = base + i) -> three box passes -> v[3..6]
+__device__ __forceinline__ void box3_passes(unsigned (&v)[10], int base, int c0, int c1, bool edge, unsigned ww, unsigned fw) {
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const int lo = pass, hi = 9 - pass;               // valid input range of this pass
+        if (edge) {
+#pragma unroll
+            for (int i = 8; i >= 0; --i)
+                if (i >= lo && i < hi && base + i < c0) v[i] = v[i + 1];
+#pragma unroll
+            for (int i = 1; i <= 9; ++i)
+                if (i > lo && i <= hi && base + i > c1) v[i] = v[i - 1];
+        }
+        unsigned prev = v[lo];
+#pragma unroll
+        for (int i = 1; i <= 8; ++i) {
+            if (i > lo && i < hi) {
+                unsigned cur = v[i];
+                v[i] = box_px(cur, prev, v[i + 1], ww, fw);
+                prev = cur;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t clahe_blend(uint32_t q4, float xa, float xa1, float ya, float ya1) {
+    const float fa = (float)(q4 & 255u), fb = (float)((q4 >> 8) & 255u), fc = (float)((q4 >> 16) & 255u), fd = (float)(q4 >> 24);
+    const float top = __fadd_rn(__fmul_rn(fa, xa1), __fmul_rn(fb, xa));
+    const float bot = __fadd_rn(__fmul_rn(fc, xa1), __fmul_rn(fd, xa));
+    const int q = __float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya)));
+    return (uint32_t)min(max(q, 0), 255);
+}
+
+__global__ void __launch_bounds__(256) k_unsharp_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
+                                                      unsigned ww, unsigned fw, int percent, int threshold, ClaheGeom g,
+                                                      const uint32_t* __restrict__ quad) {
+    __shared__ __align__(16) uint8_t a[UA_H][UA_P];
+    __shared__ __align__(16) uint8_t hb[UA_H][UT_W];
+    __shared__ __align__(16) float s_xa[UA_P];
+    __shared__ __align__(16) int s_xq[UA_P];             // quad-table offset of the column: 256 * qx
+    __shared__ float s_ya[UA_H];
+    __shared__ int s_yq[UA_H];                            // 256 * 9 * qy
+    const int tid = threadIdx.x;
+    const int bx = blockIdx.x * UT_W - 4, by = blockIdx.y * UT_H - US_H;
+    if (quad) {
+        if (tid < UA_P) {
+            float txf = __fsub_rn(__fmul_rn((float)(bx + tid), g.inv_tw), 0.5f);
+            int t1 = (int)floorf(txf);
+            s_xa[tid] = __fsub_rn(txf, (float)t1);
+            s_xq[tid] = min(max(t1 + 1, 0), 8) << 8;
+        } else if (tid < UA_P + UA_H) {
+            const int r = tid - UA_P;
+            float tyf = __fsub_rn(__fmul_rn((float)(by + r), g.inv_th), 0.5f);
+            int t1 = (int)floorf(tyf);
+            s_ya[r] = __fsub_rn(tyf, (float)t1);
+            s_yq[r] = min(max(t1 + 1, 0), 8) * (9 * 256);
+        }
+        __syncthreads();
+    }
+    const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0;
+    for (int it = tid; it < UA_H * (UA_P / 4); it += 256) {
+        const int ty = it / (UA_P / 4), gq = it - ty * (UA_P / 4);
+        const int gy = by + ty, gx = bx + 4 * gq;
+        uint32_t w = 0;
+        if (gy >= 0 && gy < H && gx + 3 >= 0 && gx < W) {
+            const uint8_t* row = src + (int64_t)gy * W;
+            if (vec_ok && gx >= 0 && gx + 3 < W) {
+                w = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (gx + c >= 0 && gx + c < W) w |= (uint32_t)row[gx + c] << (8 * c);
+            }
+            if (quad) {
+                const float4 xa = *reinterpret_cast<const float4*>(&s_xa[4 * gq]);
+                const int4 xq = *reinterpret_cast<const int4*>(&s_xq[4 * gq]);
+                const float ya = s_ya[ty], ya1 = __fsub_rn(1.0f, ya);
+                const uint32_t* qrow = quad + s_yq[ty];
+                const uint32_t o0 = clahe_blend(__ldg(qrow + xq.x + (w & 255u)), xa.x, __fsub_rn(1.0f, xa.x), ya, ya1);
+                const uint32_t o1 = clahe_blend(__ldg(qrow + xq.y + ((w >> 8) & 255u)), xa.y, __fsub_rn(1.0f, xa.y), ya, ya1);
+                const uint32_t o2 = clahe_blend(__ldg(qrow + xq.z + ((w >> 16) & 255u)), xa.z, __fsub_rn(1.0f, xa.z), ya, ya1);
+                const uint32_t o3 = clahe_blend(__ldg(qrow + xq.w + (w >> 24)), xa.w, __fsub_rn(1.0f, xa.w), ya, ya1);
+                w = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+            }
+        }
+        reinterpret_cast<uint32_t*>(a[ty])[gq] = w;
+    }
+    __syncthreads();
+    const int cx0 = max(0, -bx), cx1 = min(UA_P - 1, W - 1 - bx);
+    const int cy0 = max(0, -by), cy1 = min(UA_H - 1, H - 1 - by);
+    const bool edge_x = cx0 > 0 || cx1 < UA_P - 1, edge_y = cy0 > 0 || cy1 < UA_H - 1;
+    for (int it = tid; it < UA_H * 32; it += 256) {
+        const int ty = it >> 5, j = it & 31;
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(a[ty]) + j;
+        const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];       // tile columns 4j .. 4j+11; the window is 4j+1 .. 4j+10
+        unsigned v[10] = {(w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24, w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u,
+                          w1 >> 24, w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u};
+        box3_passes(v, 4 * j + 1, cx0, cx1, edge_x, ww, fw);
+        reinterpret_cast<uint32_t*>(hb[ty])[j] = v[3] | (v[4] << 8) | (v[5] << 16) | (v[6] << 24);
+    }
+    __syncthreads();
+    {
+        const int j = tid & 31, rg = tid >> 5;
+        uint32_t w[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) w[i] = reinterpret_cast<const uint32_t*>(hb[4 * rg + i])[j];
+        uint32_t orig[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) orig[k] = reinterpret_cast<const uint32_t*>(a[4 * rg + US_H + k])[1 + j];
+        uint32_t out[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            unsigned v[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) v[i] = (w[i] >> (8 * c)) & 255u;
+            box3_passes(v, 4 * rg, cy0, cy1, edge_y, ww, fw);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int s = (orig[k] >> (8 * c)) & 255u, d = s - (int)v[3 + k];
+                int o = s;
+                if (abs(d) > threshold) o = min(max(s + d * percent / 100, 0), 255);
+                out[k] |= (uint32_t)o << (8 * c);
+            }
+        }
+        const int gx = blockIdx.x * UT_W + 4 * j;
+        const bool st_vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int gy = blockIdx.y * UT_H + 4 * rg + k;
+            if (gy >= H || gx >= W) continue;
+            uint8_t* o = dst + (int64_t)gy * W + gx;
+            if (st_vec && gx + 3 < W) {
+                *reinterpret_cast<uint32_t*>(o) = out[k];
+            } else {
+                for (int c = 0; c < 4 && gx + c < W; ++c) o[c] = (uint8_t)(out[k] >> (8 * c));
+            }
+        }
+    }
+}
+
 static void pil_box_params(float radius_sigma, unsigned* ww, unsigned* fw) {
     // Pillow BoxBlur.c: _gaussian_blur_radius (all float) then ImagingLineBoxBlur8 weights
     float sigma2 = radius_sigma * radius_sigma / 3;
@@ -558,8 +843,14 @@ void pp_unsharp(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, in
     unsigned ww, fw;
     pil_box_params(1.0f, &ww, &fw);
     ClaheGeom g = clahe_geom(H, W);
-    k_unsharp<<<dim3(cdiv(W, US_T), cdiv(H, US_T)), 256, 0, st>>>(src, dst, H, W, ww, fw, percent, threshold, g, tone,
-                                                                  clahe_luts);
+    DevBuf quad;
+    if (clahe_luts) {
+        quad.alloc(81 * 256 * 4, st);
+        k_clahe_quadlut<<<81, 256, 0, st>>>(clahe_luts, tone, quad.as<uint32_t>());
+        count_launch(h);
+    }
+    k_unsharp_tile<<<dim3(cdiv(W, UT_W), cdiv(H, UT_H)), 256, 0, st>>>(src, dst, H, W, ww, fw, percent, threshold, g,
+                                                                        clahe_luts ? quad.as<uint32_t>() : nullptr);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -642,9 +933,9 @@ void pp_adaptive_threshold(Handle* h, cudaStream_t st, const uint8_t* src, uint8
 
 // ------------------------------------------------------------------------------------------------------------------
 // A11  preprocess_for_book_cover minus file I/O, all on one stream; device in, device out.
-//   launches: gray, resize, gaussian(+sum), tone LUT, CLAHE hist, CLAHE lut, fused CLAHE-apply+unsharp  (7)
+//   launches: gray, resize, gaussian(+sum), tone LUT, CLAHE hist, CLAHE lut, quad table, fused CLAHE-apply+unsharp  (8)
 // ------------------------------------------------------------------------------------------------------------------
-int preprocess_launches_per_image() { return 7; }
+int preprocess_launches_per_image() { return 8; }
 
 void preprocess_chain_dev(Handle* h, cudaStream_t st, const uint8_t* bgr, int H, int W, int stride,
                           const bbocr_pp_params& p, uint8_t* out, int* outH, int* outW) {

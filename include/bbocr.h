@@ -73,7 +73,12 @@ typedef struct {
  * CLAHE(8x8), unsharp.  out must hold int(H*scale)*int(W*scale) bytes.  *_on_device select device pointers. */
 int bbocr_preprocess_u8(bbocr_handle* h, const uint8_t* bgr, int H, int W, int stride_bytes, int in_on_device,
                         const bbocr_pp_params* p, uint8_t* out, int out_on_device, int* outH, int* outW);
-/* Size of one batch slot for bbocr_preprocess_batch_dev and number of kernels the chain launches per image. */
+/* The same chain over n same-size photos (BASELINE config 3): bgr[i] / out[i] are n pointers (all host or all device);
+ * photos are spread over the handle's streams so their launches overlap, one synchronisation per stream. */
+int bbocr_preprocess_batch_u8(bbocr_handle* h, int n, const uint8_t* const* bgr, int H, int W, int stride_bytes,
+                              int in_on_device, const bbocr_pp_params* p, uint8_t* const* out, int out_on_device, int* outH,
+                              int* outW);
+/* Number of kernels the chain launches per image. */
 int bbocr_preprocess_launches_per_image(void);
 
 /* single steps, host buffers (parity-test surface; each mirrors one ImagePreprocessor method) */
