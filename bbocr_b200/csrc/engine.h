@@ -50,7 +50,7 @@ struct Handle {
     bool force_generic_conv = false; // test hook: route BF16-mode convolutions through the CUDA-core kernel
     bool tc_attr_set = false, lstm_attr_set = false, lstm_mma_attr_set = false;
     std::mutex stat_mu;
-    std::map<std::array<int, 5>, std::pair<void*, bool>> cubic_cache;   // preprocess.cu: INTER_CUBIC tables per geometry
+    std::map<std::array<int, 5>, std::pair<void*, int>> cubic_cache;   // preprocess.cu: INTER_CUBIC tables per geometry
     std::set<int> res_attr_done;     // conv_res.cu kernel variants whose smem attribute is set on this device
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
     double conv_flops = 0;

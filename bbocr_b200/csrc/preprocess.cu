@@ -259,6 +259,7 @@ struct CubicTables {
     int32_t *xidx, *xci, *yidx, *yci;
     float *xcf, *ycf;
     bool tiled = false;            // every 128 x 32 output tile fits the shared-memory source patch
+    bool fused = false;            // ... and so does every 130 x 34 tile of k_gray_resize_gauss
 };
 
 // Coefficient tables live on the device for the lifetime of the handle, one set per (source size, target size, mode):
@@ -275,6 +276,11 @@ static CubicTables cubic_tables(Handle* h, int sH, int sW, int dH, int dW, int m
             tiled = ax.idx[4 * (size_t)(std::min(x0 + RT_W, dW) - 1) + 3] - ax.idx[4 * (size_t)x0] + 1 <= RS_W;
         for (int y0 = 0; y0 < dH && tiled; y0 += RT_H)
             tiled = ay.idx[4 * (size_t)(std::min(y0 + RT_H, dH) - 1) + 3] - ay.idx[4 * (size_t)y0] + 1 <= RS_H;
+        bool fused = true;
+        for (int x0 = 0; x0 < dW && fused; x0 += 128)
+            fused = ax.idx[4 * (size_t)std::min(x0 + 128, dW - 1) + 3] - ax.idx[4 * (size_t)std::max(x0 - 1, 0)] + 1 <= 100;
+        for (int y0 = 0; y0 < dH && fused; y0 += 32)
+            fused = ay.idx[4 * (size_t)std::min(y0 + 32, dH - 1) + 3] - ay.idx[4 * (size_t)std::max(y0 - 1, 0)] + 1 <= 30;
         std::vector<int32_t> host((nx + ny) * 3);
         memcpy(&host[0], ax.idx.data(), nx * 4);
         memcpy(&host[nx], ax.ci.data(), nx * 4);
@@ -290,14 +296,15 @@ static CubicTables cubic_tables(Handle* h, int sH, int sW, int dH, int dW, int m
         void* dev = nullptr;
         CUDA_CHECK(cudaMalloc(&dev, host.size() * 4));
         CUDA_CHECK(cudaMemcpy(dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
-        it = h->cubic_cache.emplace(key, std::make_pair(dev, tiled)).first;
+        it = h->cubic_cache.emplace(key, std::make_pair(dev, (tiled ? 1 : 0) | (fused ? 2 : 0))).first;
     }
     const size_t nx = (size_t)dW * 4, ny = (size_t)dH * 4;
     int32_t* b = static_cast<int32_t*>(it->second.first);
     CubicTables t;
     t.xidx = b; t.xci = b + nx; t.xcf = reinterpret_cast<float*>(b + 2 * nx);
     t.yidx = b + 3 * nx; t.yci = b + 3 * nx + ny; t.ycf = reinterpret_cast<float*>(b + 3 * nx + 2 * ny);
-    t.tiled = it->second.second;
+    t.tiled = it->second.second & 1;
+    t.fused = (it->second.second & 2) != 0;
     return t;
 }
 
@@ -362,6 +369,140 @@ __global__ void k_gaussian3(const uint8_t* __restrict__ src, uint8_t* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// A2 + A3 + A4 fused for the chain: BGR -> gray -> INTER_CUBIC -> 3x3 Gaussian (+ global sum of the output) in one
+// kernel.  A block owns 128 x 32 OUTPUT pixels; it resizes the 130 x 34 pixels the Gaussian needs (the halo columns /
+// rows are the BORDER_REFLECT_101 images of real columns / rows, so they are resized like any other) from a source
+// patch staged (and gray-converted) in shared memory.  Per-pixel arithmetic is that of the three single kernels, so the
+// bytes are identical; the gray plane and the resized plane never go to HBM.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int FT_W = 128, FT_H = 32, FR_W = FT_W + 2, FR_P = 136, FR_H = FT_H + 2, FS_W = 100, FS_H = 30;
+__global__ void __launch_bounds__(256) k_gray_resize_gauss(const uint8_t* __restrict__ src, int channels, int stride, int sH, int sW,
+                                                           uint8_t* __restrict__ dst, int dH, int dW,
+                                                           const int32_t* __restrict__ xidx, const int32_t* __restrict__ xci,
+                                                           const float* __restrict__ xcf, const int32_t* __restrict__ yidx,
+                                                           const int32_t* __restrict__ yci, const float* __restrict__ ycf, int mode,
+                                                           int k0, int k1, unsigned long long* __restrict__ sum_out) {
+    __shared__ uint8_t s_src[FS_H][FS_W];
+    __shared__ int4 s_xi[FR_W], s_xc[FR_W];
+    __shared__ __align__(16) int s_h[FS_H][FR_P];
+    __shared__ __align__(16) uint8_t s_r[FR_H][FR_P];
+    __shared__ unsigned int wsum[8];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
+    const int xa = max(x0 - 1, 0), xb = min(x0 + FT_W, dW - 1), ya = max(y0 - 1, 0), yb = min(y0 + FT_H, dH - 1);
+    const int sx_lo = __ldg(xidx + 4 * xa), sx_hi = __ldg(xidx + 4 * xb + 3);
+    const int sy_lo = __ldg(yidx + 4 * ya), sy_hi = __ldg(yidx + 4 * yb + 3);
+    const int sw = sx_hi - sx_lo + 1, sh = sy_hi - sy_lo + 1;
+    for (int i = tid; i < sh * sw; i += 256) {
+        const int r = i / sw, c = i - r * sw;
+        const uint8_t* p = src + (int64_t)(sy_lo + r) * stride + (int64_t)(sx_lo + c) * channels;
+        s_src[r][c] = channels == 3 ? (uint8_t)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15) : p[0];
+    }
+    if (tid < FR_W) {
+        const int X = reflect101(min(x0 - 1 + tid, dW), dW);          // columns past the halo are never used
+        int4 xi = __ldg(reinterpret_cast<const int4*>(xidx) + X);
+        xi.x -= sx_lo; xi.y -= sx_lo; xi.z -= sx_lo; xi.w -= sx_lo;
+        s_xi[tid] = xi;
+        s_xc[tid] = mode == 0 ? __ldg(reinterpret_cast<const int4*>(xci) + X) : __ldg(reinterpret_cast<const int4*>(xcf) + X);
+    }
+    __syncthreads();
+    for (int it = tid; it < sh * FR_W; it += 256) {
+        const int r = it / FR_W, c = it - r * FR_W;
+        const int4 xi = s_xi[c], xc = s_xc[c];
+        const uint8_t* p = s_src[r];
+        if (mode == 0) {
+            s_h[r][c] = p[xi.x] * xc.x + p[xi.y] * xc.y + p[xi.z] * xc.z + p[xi.w] * xc.w;
+        } else {
+            float a = __fmul_rn((float)p[xi.x], __int_as_float(xc.x));
+            a = __fadd_rn(a, __fmul_rn((float)p[xi.y], __int_as_float(xc.y)));
+            a = __fadd_rn(a, __fmul_rn((float)p[xi.z], __int_as_float(xc.z)));
+            a = __fadd_rn(a, __fmul_rn((float)p[xi.w], __int_as_float(xc.w)));
+            s_h[r][c] = __float_as_int(a);
+        }
+    }
+    __syncthreads();
+    const int xvec_end = (dW / 8) * 8;
+    for (int it = tid; it < FR_H * (FR_P / 4 - 1); it += 256) {          // 34 rows x 33 groups of four columns (0..131)
+        const int ry = it / (FR_P / 4 - 1), gq = it - ry * (FR_P / 4 - 1);
+        const int Y = reflect101(min(y0 - 1 + ry, dH), dH);
+        const int4 yi = __ldg(reinterpret_cast<const int4*>(yidx) + Y);
+        const int4 S0 = *reinterpret_cast<const int4*>(&s_h[yi.x - sy_lo][4 * gq]);
+        const int4 S1 = *reinterpret_cast<const int4*>(&s_h[yi.y - sy_lo][4 * gq]);
+        const int4 S2 = *reinterpret_cast<const int4*>(&s_h[yi.z - sy_lo][4 * gq]);
+        const int4 S3 = *reinterpret_cast<const int4*>(&s_h[yi.w - sy_lo][4 * gq]);
+        const int a0[4] = {S0.x, S0.y, S0.z, S0.w}, a1[4] = {S1.x, S1.y, S1.z, S1.w};
+        const int a2[4] = {S2.x, S2.y, S2.z, S2.w}, a3[4] = {S3.x, S3.y, S3.z, S3.w};
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ycf) + Y);
+        const int4 by = __ldg(reinterpret_cast<const int4*>(yci) + Y);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int v;
+            if (mode == 0) {
+                const int X = reflect101(min(x0 - 1 + 4 * gq + c, dW), dW);
+                if (X < xvec_end) {
+                    float acc = __fmul_rn((float)a3[c], b.w);
+                    acc = __fadd_rn(__fmul_rn((float)a2[c], b.z), acc);
+                    acc = __fadd_rn(__fmul_rn((float)a1[c], b.y), acc);
+                    acc = __fadd_rn(__fmul_rn((float)a0[c], b.x), acc);
+                    v = __float2int_rn(acc);
+                } else {
+                    v = (a0[c] * by.x + a1[c] * by.y + a2[c] * by.z + a3[c] * by.w + (1 << 21)) >> 22;
+                }
+            } else {
+                float a = __fmul_rn(__int_as_float(a0[c]), b.x);
+                a = __fadd_rn(a, __fmul_rn(__int_as_float(a1[c]), b.y));
+                a = __fadd_rn(a, __fmul_rn(__int_as_float(a2[c]), b.z));
+                a = __fadd_rn(a, __fmul_rn(__int_as_float(a3[c]), b.w));
+                v = __float2int_rn(a);
+            }
+            packed |= (uint32_t)min(max(v, 0), 255) << (8 * c);
+        }
+        reinterpret_cast<uint32_t*>(s_r[ry])[gq] = packed;
+    }
+    __syncthreads();
+    unsigned int local = 0;
+    const int j = tid & 31;
+    const bool st_vec = (dW & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
+    for (int oy = tid >> 5; oy < FT_H; oy += 8) {
+        const int y = y0 + oy, x = x0 + 4 * j;
+        if (y >= dH || x >= dW) continue;
+        int hsum[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const uint32_t w0 = reinterpret_cast<const uint32_t*>(s_r[oy + r])[j], w1 = reinterpret_cast<const uint32_t*>(s_r[oy + r])[j + 1];
+            const int p[6] = {(int)(w0 & 255u), (int)((w0 >> 8) & 255u), (int)((w0 >> 16) & 255u), (int)(w0 >> 24),
+                              (int)(w1 & 255u), (int)((w1 >> 8) & 255u)};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) hsum[r][c] = p[c] * k0 + p[c + 1] * k1 + p[c + 2] * k0;
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int v = (hsum[0][c] * k0 + hsum[1][c] * k1 + hsum[2][c] * k0 + (1 << 15)) >> 16;
+            packed |= (uint32_t)v << (8 * c);
+            if (x + c < dW) local += v;
+        }
+        uint8_t* o = dst + (int64_t)y * dW + x;
+        if (st_vec && x + 3 < dW) {
+            *reinterpret_cast<uint32_t*>(o) = packed;
+        } else {
+            for (int c = 0; c < 4 && x + c < dW; ++c) o[c] = (uint8_t)(packed >> (8 * c));
+        }
+    }
+    if (sum_out) {
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if ((tid & 31) == 0) wsum[tid >> 5] = local;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long s = 0;
+            for (int i = 0; i < 8; ++i) s += wsum[i];
+            atomicAdd(sum_out, s);
+        }
+    }
+}
+
 void gaussian3_kernel_q8(float sigma, int* k0, int* k1) {
     // OpenCV getGaussianKernelBitExact -> 8-bit fixed point; centre tap absorbs the rounding residue.
     // sigma <= 0 with ksize 3 selects cv2's fixed table [0.25, 0.5, 0.25] (enhanced_extractor.py:254 uses it).
@@ -381,6 +522,27 @@ void pp_gaussian3(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, 
     k_gaussian3<<<dim3(cdiv(W, 128), cdiv(H, 16)), 256, 0, st>>>(src, dst, H, W, k0, k1, sum_out);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
+}
+
+// gray (channels == 3) -> INTER_CUBIC -> GaussianBlur 3x3, with the global sum of the result; one launch when the
+// geometry fits the fused kernel's shared-memory patch (any up-scale), else the three single kernels.
+static int pp_gray_resize_gauss(Handle* h, cudaStream_t st, const uint8_t* bgr, int H, int W, int stride, uint8_t* dst, int dH,
+                                int dW, int mode, float sigma, unsigned long long* sum_out) {
+    const CubicTables t = cubic_tables(h, H, W, dH, dW, mode);
+    if (t.fused) {
+        int k0, k1;
+        gaussian3_kernel_q8(sigma, &k0, &k1);
+        k_gray_resize_gauss<<<dim3(cdiv(dW, FT_W), cdiv(dH, FT_H)), 256, 0, st>>>(bgr, 3, stride, H, W, dst, dH, dW, t.xidx, t.xci,
+                                                                                  t.xcf, t.yidx, t.yci, t.ycf, mode, k0, k1, sum_out);
+        count_launch(h);
+        CUDA_CHECK(cudaGetLastError());
+        return 1;
+    }
+    DevBuf gray((size_t)H * W, st), resized((size_t)dH * dW, st);
+    pp_gray(h, st, bgr, H, W, stride, gray.as<uint8_t>());
+    pp_resize_cubic(h, st, gray.as<uint8_t>(), H, W, resized.as<uint8_t>(), dH, dW, mode);
+    pp_gaussian3(h, st, resized.as<uint8_t>(), dst, dH, dW, sigma, sum_out);
+    return 3;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -933,9 +1095,10 @@ void pp_adaptive_threshold(Handle* h, cudaStream_t st, const uint8_t* src, uint8
 
 // ------------------------------------------------------------------------------------------------------------------
 // A11  preprocess_for_book_cover minus file I/O, all on one stream; device in, device out.
-//   launches: gray, resize, gaussian(+sum), tone LUT, CLAHE hist, CLAHE lut, quad table, fused CLAHE-apply+unsharp  (8)
+//   launches: fused gray+resize+gaussian(+sum), tone LUT, CLAHE hist, CLAHE lut, quad table, fused CLAHE-apply+unsharp  (6;
+//   8 when the resize is a strong down-scale and the fused kernel's shared-memory patch does not fit)
 // ------------------------------------------------------------------------------------------------------------------
-int preprocess_launches_per_image() { return 8; }
+int preprocess_launches_per_image() { return 6; }
 
 void preprocess_chain_dev(Handle* h, cudaStream_t st, const uint8_t* bgr, int H, int W, int stride,
                           const bbocr_pp_params& p, uint8_t* out, int* outH, int* outW) {
@@ -943,16 +1106,14 @@ void preprocess_chain_dev(Handle* h, cudaStream_t st, const uint8_t* bgr, int H,
     int dH = (int)(H * (double)p.scale), dW = (int)(W * (double)p.scale);     // int(h * scale_factor) in Python doubles
     ARG_CHECK(dH > 0 && dW > 0, "preprocess: empty output");
     int64_t n = (int64_t)dH * dW;
-    DevBuf gray((size_t)H * W, st), resized((size_t)n, st), blurred((size_t)n, st);
+    DevBuf blurred((size_t)n, st);
     DevBuf small(8 + 256 + 64 * 256 * 4 + 64 * 256, st);
     unsigned long long* sum = small.as<unsigned long long>();
     uint8_t* tone = small.as<uint8_t>() + 8;
     unsigned int* hist = reinterpret_cast<unsigned int*>(small.as<uint8_t>() + 8 + 256);
     uint8_t* luts = small.as<uint8_t>() + 8 + 256 + 64 * 256 * 4;
-    pp_gray(h, st, bgr, H, W, stride, gray.as<uint8_t>());
-    pp_resize_cubic(h, st, gray.as<uint8_t>(), H, W, resized.as<uint8_t>(), dH, dW, p.resize_mode);
     CUDA_CHECK(cudaMemsetAsync(sum, 0, 8, st));
-    pp_gaussian3(h, st, resized.as<uint8_t>(), blurred.as<uint8_t>(), dH, dW, p.sigma, sum);
+    pp_gray_resize_gauss(h, st, bgr, H, W, stride, blurred.as<uint8_t>(), dH, dW, p.resize_mode, p.sigma, sum);
     pp_tone_lut(h, st, sum, n, p.contrast, p.brightness, tone);
     pp_clahe_luts(h, st, blurred.as<uint8_t>(), dH, dW, p.clahe_clip, tone, hist, luts);
     pp_unsharp(h, st, blurred.as<uint8_t>(), out, dH, dW, p.sharpen_percent, 3, tone, luts);
