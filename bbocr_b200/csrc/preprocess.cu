@@ -626,23 +626,45 @@ void pp_apply_lut(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, 
 // ------------------------------------------------------------------------------------------------------------------
 // Histogram of every tile of the (reflect-101 padded) image, pixels optionally mapped through a tone LUT first.
 // grid = (8 tiles x, 8 tiles y, row chunks); block = 256 threads over a chunk of the tile's rows.
-__global__ void k_clahe_hist(const uint8_t* __restrict__ src, int H, int W, int tw, int th, int rows_per_chunk,
-                             const uint8_t* __restrict__ tone, unsigned int* __restrict__ hist) {
-    __shared__ unsigned int sh[256];
+__global__ void __launch_bounds__(256) k_clahe_hist(const uint8_t* __restrict__ src, int H, int W, int tw, int th,
+                                                    int rows_per_chunk, const uint8_t* __restrict__ tone,
+                                                    unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[8][256];                 // one private histogram per warp: fewer same-address collisions
     __shared__ uint8_t stone[256];
-    sh[threadIdx.x] = 0;
-    stone[threadIdx.x] = tone ? tone[threadIdx.x] : (uint8_t)threadIdx.x;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 8 * 256; i += 256) (&sh[0][0])[i] = 0;
+    stone[tid] = tone ? tone[tid] : (uint8_t)tid;
     __syncthreads();
+    unsigned int* my = sh[tid >> 5];
     const int tx = blockIdx.x, ty = blockIdx.y;
     const int y0 = blockIdx.z * rows_per_chunk, y1 = min(th, y0 + rows_per_chunk);
-    const int n = (y1 - y0) * tw;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int yy = y0 + i / tw, xx = i % tw;
-        int gy = reflect101(ty * th + yy, H), gx = reflect101(tx * tw + xx, W);
-        atomicAdd(&sh[stone[src[(int64_t)gy * W + gx]]], 1u);
+    const int xb = tx * tw, xe = xb + tw;              // tile columns in padded coordinates
+    const int xa = xb & ~3;                             // groups of four columns aligned to 4 in the image
+    const int ng = (xe - xa + 3) >> 2;
+    const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0;
+    for (int i = tid; i < (y1 - y0) * ng; i += 256) {
+        const int r = i / ng, gq = i - r * ng;
+        const int gy = reflect101(ty * th + y0 + r, H);
+        const int gx0 = xa + 4 * gq;
+        const uint8_t* row = src + (int64_t)gy * W;
+        if (vec && gx0 >= xb && gx0 + 3 < xe && gx0 + 3 < W) {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(row + gx0));
+            atomicAdd(&my[stone[w & 255u]], 1u);
+            atomicAdd(&my[stone[(w >> 8) & 255u]], 1u);
+            atomicAdd(&my[stone[(w >> 16) & 255u]], 1u);
+            atomicAdd(&my[stone[w >> 24]], 1u);
+        } else {
+            for (int c = 0; c < 4; ++c) {
+                const int x = gx0 + c;
+                if (x >= xb && x < xe) atomicAdd(&my[stone[row[reflect101(x, W)]]], 1u);
+            }
+        }
     }
     __syncthreads();
-    if (sh[threadIdx.x]) atomicAdd(&hist[(ty * 8 + tx) * 256 + threadIdx.x], sh[threadIdx.x]);
+    unsigned int tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += sh[w][tid];
+    if (tot) atomicAdd(&hist[(ty * 8 + tx) * 256 + tid], tot);
 }
 
 // One block per tile: clip, redistribute, cumulative sum, scale -> LUT.
@@ -1065,10 +1087,116 @@ __global__ void k_at_cols(const uint8_t* __restrict__ src, const float* __restri
     dst[(int64_t)y * W + x] = inv ? (d <= -idelta ? 255 : 0) : (d > -idelta ? 255 : 0);
 }
 
+// Tiled variant for the block sizes this repository uses (11, 31, 35; template parameter so that every tap is a
+// compile-time index and the weights are immediate constant-bank operands): a 64 x 64 output tile; the source patch with
+// its replicate border is staged in shared memory, the row pass produces the (64 + 2r) x 64 intermediate plane (float
+// for GAUSSIAN_C, exact int sums for MEAN_C) four pixels per thread from 32-bit words, and the column pass reads it
+// back as 16-byte vectors.  Same per-pixel operation order as k_at_rows / k_at_cols (a leading fma(p, k0, +0) is the
+// product p * k0), hence the same bytes.
+struct AtWeights { float k[36]; };
+constexpr int AT_T = 64;
+template <int BLOCK, bool GAUSSIAN>
+__global__ void __launch_bounds__(256) k_at_tile(const uint8_t* __restrict__ src, int H, int W, const AtWeights kw, int inv,
+                                                 int idelta, uint8_t* __restrict__ dst) {
+    constexpr int R = BLOCK / 2, ROWS = AT_T + 2 * R, NW = (BLOCK + 3 + 3) / 4, SP = (AT_T / 4 - 1 + NW) * 4;
+    __shared__ __align__(16) uint8_t s_src[ROWS][SP];
+    __shared__ __align__(16) int s_mid[ROWS][AT_T];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * AT_T, y0 = blockIdx.y * AT_T;
+    for (int i = tid; i < ROWS * SP; i += 256) {
+        const int ty = i / SP, tx = i - ty * SP;
+        const int gy = min(max(y0 - R + ty, 0), H - 1), gx = min(max(x0 - R + tx, 0), W - 1);
+        s_src[ty][tx] = src[(int64_t)gy * W + gx];
+    }
+    __syncthreads();
+    // row pass: thread -> (tile row, four output columns 4g .. 4g+3); output c uses inputs c .. c + BLOCK - 1
+    for (int it = tid; it < ROWS * (AT_T / 4); it += 256) {
+        const int ty = it / (AT_T / 4), g = it - ty * (AT_T / 4);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_src[ty]) + g;
+        float facc[4] = {0.f, 0.f, 0.f, 0.f};
+        int iacc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int wi = 0; wi < NW; ++wi) {
+            const uint32_t w = wp[wi];
+#pragma unroll
+            for (int bsel = 0; bsel < 4; ++bsel) {
+                const int i = 4 * wi + bsel;
+                const unsigned pv = (w >> (8 * bsel)) & 255u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int t = i - c;
+                    if (t >= 0 && t < BLOCK) {
+                        if (GAUSSIAN) facc[c] = __fmaf_rn((float)pv, kw.k[t], facc[c]);
+                        else iacc[c] += (int)pv;
+                    }
+                }
+            }
+        }
+        *reinterpret_cast<int4*>(&s_mid[ty][4 * g]) =
+            GAUSSIAN ? make_int4(__float_as_int(facc[0]), __float_as_int(facc[1]), __float_as_int(facc[2]), __float_as_int(facc[3]))
+                     : make_int4(iacc[0], iacc[1], iacc[2], iacc[3]);
+    }
+    __syncthreads();
+    const bool st_vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
+    for (int it = tid; it < AT_T * (AT_T / 4); it += 256) {
+        const int oy = it / (AT_T / 4), g = it - oy * (AT_T / 4);
+        const int y = y0 + oy, x = x0 + 4 * g;
+        if (y >= H || x >= W) continue;
+        int mean[4];
+        if (GAUSSIAN) {
+            const int4 c4 = *reinterpret_cast<const int4*>(&s_mid[oy + R][4 * g]);
+            float acc[4] = {__fmul_rn(__int_as_float(c4.x), kw.k[R]), __fmul_rn(__int_as_float(c4.y), kw.k[R]),
+                            __fmul_rn(__int_as_float(c4.z), kw.k[R]), __fmul_rn(__int_as_float(c4.w), kw.k[R])};
+#pragma unroll
+            for (int j = 1; j <= R; ++j) {
+                const int4 a4 = *reinterpret_cast<const int4*>(&s_mid[oy + R + j][4 * g]);
+                const int4 b4 = *reinterpret_cast<const int4*>(&s_mid[oy + R - j][4 * g]);
+                acc[0] = __fmaf_rn(__fadd_rn(__int_as_float(a4.x), __int_as_float(b4.x)), kw.k[R + j], acc[0]);
+                acc[1] = __fmaf_rn(__fadd_rn(__int_as_float(a4.y), __int_as_float(b4.y)), kw.k[R + j], acc[1]);
+                acc[2] = __fmaf_rn(__fadd_rn(__int_as_float(a4.z), __int_as_float(b4.z)), kw.k[R + j], acc[2]);
+                acc[3] = __fmaf_rn(__fadd_rn(__int_as_float(a4.w), __int_as_float(b4.w)), kw.k[R + j], acc[3]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) mean[c] = min(max(__float2int_rn(acc[c]), 0), 255);
+        } else {
+            int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < BLOCK; ++i) {
+                const int4 a4 = *reinterpret_cast<const int4*>(&s_mid[oy + i][4 * g]);
+                acc[0] += a4.x; acc[1] += a4.y; acc[2] += a4.z; acc[3] += a4.w;
+            }
+            const double inv_area = 1.0 / ((double)BLOCK * BLOCK);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) mean[c] = min(max(__double2int_rn((double)acc[c] * inv_area), 0), 255);
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int d = (int)s_src[oy + R][4 * g + c + R] - mean[c];
+            const uint32_t o = inv ? (d <= -idelta ? 255u : 0u) : (d > -idelta ? 255u : 0u);
+            packed |= o << (8 * c);
+        }
+        uint8_t* o = dst + (int64_t)y * W + x;
+        if (st_vec && x + 3 < W) {
+            *reinterpret_cast<uint32_t*>(o) = packed;
+        } else {
+            for (int c = 0; c < 4 && x + c < W; ++c) o[c] = (uint8_t)(packed >> (8 * c));
+        }
+    }
+}
+
+template <int BLOCK>
+static void at_tile_launch(cudaStream_t st, const uint8_t* src, int H, int W, const AtWeights& kw, bool gaussian, int inv, int idelta,
+                           uint8_t* dst) {
+    dim3 grd(cdiv(W, AT_T), cdiv(H, AT_T));
+    if (gaussian) k_at_tile<BLOCK, true><<<grd, 256, 0, st>>>(src, H, W, kw, inv, idelta, dst);
+    else k_at_tile<BLOCK, false><<<grd, 256, 0, st>>>(src, H, W, kw, inv, idelta, dst);
+}
+
 void pp_adaptive_threshold(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, int H, int W, int method,
                            int inv, int block, float delta) {
     ARG_CHECK(block % 2 == 1 && block > 1 && block <= 255, "adaptiveThreshold: block must be odd, 3..255");
-    DevBuf tmp((size_t)H * W * 4, st), kbuf(256 * 4, st);
+    std::vector<float> kf(block, 0.f);
     if (method == 1) {
         double sigma = ((block - 1) * 0.5 - 1) * 0.3 + 0.8;
         std::vector<double> kd(block);
@@ -1078,12 +1206,25 @@ void pp_adaptive_threshold(Handle* h, cudaStream_t st, const uint8_t* src, uint8
             kd[i] = exp(-(x * x) / (2.0 * sigma * sigma));
             s += kd[i];
         }
-        std::vector<float> kf(block);
         for (int i = 0; i < block; ++i) kf[i] = (float)(kd[i] / s);
+    }
+    int idelta = inv ? (int)floor((double)delta) : (int)ceil((double)delta);
+    if (block == 11 || block == 31 || block == 35) {
+        AtWeights kw;
+        memset(&kw, 0, sizeof kw);
+        memcpy(kw.k, kf.data(), block * sizeof(float));
+        if (block == 11) at_tile_launch<11>(st, src, H, W, kw, method == 1, inv, idelta, dst);
+        else if (block == 31) at_tile_launch<31>(st, src, H, W, kw, method == 1, inv, idelta, dst);
+        else at_tile_launch<35>(st, src, H, W, kw, method == 1, inv, idelta, dst);
+        count_launch(h);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
+    DevBuf tmp((size_t)H * W * 4, st), kbuf(256 * 4, st);
+    if (method == 1) {
         CUDA_CHECK(cudaMemcpyAsync(kbuf.p, kf.data(), block * 4, cudaMemcpyHostToDevice, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
     }
-    int idelta = inv ? (int)floor((double)delta) : (int)ceil((double)delta);
     dim3 grd(cdiv(W, 256), H);
     k_at_rows<<<grd, 256, 0, st>>>(src, H, W, block, kbuf.as<float>(), method == 1 ? tmp.as<float>() : nullptr,
                                    method == 1 ? nullptr : tmp.as<int>());
