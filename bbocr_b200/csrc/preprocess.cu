@@ -296,6 +296,9 @@ static CubicTables cubic_tables(Handle* h, int sH, int sW, int dH, int dW, int m
         void* dev = nullptr;
         CUDA_CHECK(cudaMalloc(&dev, host.size() * 4));
         CUDA_CHECK(cudaMemcpy(dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+        // a pageable-memory cudaMemcpy may return while the DMA is still in flight, and the lanes' streams are non-blocking
+        // (no implicit ordering against the legacy stream): make sure the tables have landed before any kernel reads them
+        CUDA_CHECK(cudaDeviceSynchronize());
         it = h->cubic_cache.emplace(key, std::make_pair(dev, (tiled ? 1 : 0) | (fused ? 2 : 0))).first;
     }
     const size_t nx = (size_t)dW * 4, ny = (size_t)dH * 4;
@@ -377,6 +380,30 @@ __global__ void k_gaussian3(const uint8_t* __restrict__ src, uint8_t* __restrict
 // bytes are identical; the gray plane and the resized plane never go to HBM.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int FT_W = 128, FT_H = 32, FR_W = FT_W + 2, FR_P = 136, FR_H = FT_H + 2, FS_W = 100, FS_H = 30;
+
+// one resized pixel from its four horizontally-filtered rows (mode 0: OpenCV's float32 vector path / integer tail; mode 1: T2)
+__device__ __forceinline__ uint32_t cubic_vertical(int a0, int a1, int a2, int a3, const float4& b, const int4& by, int mode, bool vec) {
+    int v;
+    if (mode == 0) {
+        if (vec) {
+            float acc = __fmul_rn((float)a3, b.w);
+            acc = __fadd_rn(__fmul_rn((float)a2, b.z), acc);
+            acc = __fadd_rn(__fmul_rn((float)a1, b.y), acc);
+            acc = __fadd_rn(__fmul_rn((float)a0, b.x), acc);
+            v = __float2int_rn(acc);
+        } else {
+            v = (a0 * by.x + a1 * by.y + a2 * by.z + a3 * by.w + (1 << 21)) >> 22;
+        }
+    } else {
+        float a = __fmul_rn(__int_as_float(a0), b.x);
+        a = __fadd_rn(a, __fmul_rn(__int_as_float(a1), b.y));
+        a = __fadd_rn(a, __fmul_rn(__int_as_float(a2), b.z));
+        a = __fadd_rn(a, __fmul_rn(__int_as_float(a3), b.w));
+        v = __float2int_rn(a);
+    }
+    return (uint32_t)min(max(v, 0), 255);
+}
+
 __global__ void __launch_bounds__(256) k_gray_resize_gauss(const uint8_t* __restrict__ src, int channels, int stride, int sH, int sW,
                                                            uint8_t* __restrict__ dst, int dH, int dW,
                                                            const int32_t* __restrict__ xidx, const int32_t* __restrict__ xci,
@@ -384,88 +411,93 @@ __global__ void __launch_bounds__(256) k_gray_resize_gauss(const uint8_t* __rest
                                                            const int32_t* __restrict__ yci, const float* __restrict__ ycf, int mode,
                                                            int k0, int k1, unsigned long long* __restrict__ sum_out) {
     __shared__ uint8_t s_src[FS_H][FS_W];
-    __shared__ int4 s_xi[FR_W], s_xc[FR_W];
+    __shared__ int4 s_yi[FR_H], s_yq[FR_H];
+    __shared__ float4 s_yf[FR_H];
     __shared__ __align__(16) int s_h[FS_H][FR_P];
     __shared__ __align__(16) uint8_t s_r[FR_H][FR_P];
     __shared__ unsigned int wsum[8];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
     const int xa = max(x0 - 1, 0), xb = min(x0 + FT_W, dW - 1), ya = max(y0 - 1, 0), yb = min(y0 + FT_H, dH - 1);
     const int sx_lo = __ldg(xidx + 4 * xa), sx_hi = __ldg(xidx + 4 * xb + 3);
     const int sy_lo = __ldg(yidx + 4 * ya), sy_hi = __ldg(yidx + 4 * yb + 3);
     const int sw = sx_hi - sx_lo + 1, sh = sy_hi - sy_lo + 1;
-    for (int i = tid; i < sh * sw; i += 256) {
-        const int r = i / sw, c = i - r * sw;
-        const uint8_t* p = src + (int64_t)(sy_lo + r) * stride + (int64_t)(sx_lo + c) * channels;
-        s_src[r][c] = channels == 3 ? (uint8_t)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15) : p[0];
+    // phase 0: source patch (gray-converted on the way in), one warp per row; vertical taps of the 34 tile rows
+    for (int r = warp; r < sh; r += 8) {
+        const uint8_t* rowp = src + (int64_t)(sy_lo + r) * stride + (int64_t)sx_lo * channels;
+        if (channels == 3) {
+            for (int c = lane; c < sw; c += 32) {
+                const uint8_t* p = rowp + 3 * c;
+                s_src[r][c] = (uint8_t)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15);
+            }
+        } else {
+            for (int c = lane; c < sw; c += 32) s_src[r][c] = rowp[c];
+        }
     }
-    if (tid < FR_W) {
-        const int X = reflect101(min(x0 - 1 + tid, dW), dW);          // columns past the halo are never used
-        int4 xi = __ldg(reinterpret_cast<const int4*>(xidx) + X);
-        xi.x -= sx_lo; xi.y -= sx_lo; xi.z -= sx_lo; xi.w -= sx_lo;
-        s_xi[tid] = xi;
-        s_xc[tid] = mode == 0 ? __ldg(reinterpret_cast<const int4*>(xci) + X) : __ldg(reinterpret_cast<const int4*>(xcf) + X);
+    if (tid < FR_H) {
+        const int Y = reflect101(min(y0 - 1 + tid, dH), dH);              // rows past the halo are never used
+        int4 yi = __ldg(reinterpret_cast<const int4*>(yidx) + Y);
+        yi.x -= sy_lo; yi.y -= sy_lo; yi.z -= sy_lo; yi.w -= sy_lo;
+        s_yi[tid] = yi;
+        s_yq[tid] = __ldg(reinterpret_cast<const int4*>(yci) + Y);
+        s_yf[tid] = __ldg(reinterpret_cast<const float4*>(ycf) + Y);
     }
     __syncthreads();
-    for (int it = tid; it < sh * FR_W; it += 256) {
-        const int r = it / FR_W, c = it - r * FR_W;
-        const int4 xi = s_xi[c], xc = s_xc[c];
-        const uint8_t* p = s_src[r];
+    // phase 1: horizontal pass, thread = one tile column (taps in registers) walking down the patch rows
+    for (int c = tid & 127; c < FR_W; c += 128) {
+        if (c >= 128 && (tid & 127) >= FR_W - 128) break;
+        const int X = reflect101(min(x0 - 1 + c, dW), dW);                // columns past the halo are never used
+        int4 xi = __ldg(reinterpret_cast<const int4*>(xidx) + X);
+        xi.x -= sx_lo; xi.y -= sx_lo; xi.z -= sx_lo; xi.w -= sx_lo;
         if (mode == 0) {
-            s_h[r][c] = p[xi.x] * xc.x + p[xi.y] * xc.y + p[xi.z] * xc.z + p[xi.w] * xc.w;
+            const int4 xc = __ldg(reinterpret_cast<const int4*>(xci) + X);
+            for (int r = tid >> 7; r < sh; r += 2) {
+                const uint8_t* p = s_src[r];
+                s_h[r][c] = p[xi.x] * xc.x + p[xi.y] * xc.y + p[xi.z] * xc.z + p[xi.w] * xc.w;
+            }
         } else {
-            float a = __fmul_rn((float)p[xi.x], __int_as_float(xc.x));
-            a = __fadd_rn(a, __fmul_rn((float)p[xi.y], __int_as_float(xc.y)));
-            a = __fadd_rn(a, __fmul_rn((float)p[xi.z], __int_as_float(xc.z)));
-            a = __fadd_rn(a, __fmul_rn((float)p[xi.w], __int_as_float(xc.w)));
-            s_h[r][c] = __float_as_int(a);
+            const float4 xc = __ldg(reinterpret_cast<const float4*>(xcf) + X);
+            for (int r = tid >> 7; r < sh; r += 2) {
+                const uint8_t* p = s_src[r];
+                float a = __fmul_rn((float)p[xi.x], xc.x);
+                a = __fadd_rn(a, __fmul_rn((float)p[xi.y], xc.y));
+                a = __fadd_rn(a, __fmul_rn((float)p[xi.z], xc.z));
+                a = __fadd_rn(a, __fmul_rn((float)p[xi.w], xc.w));
+                s_h[r][c] = __float_as_int(a);
+            }
         }
     }
     __syncthreads();
+    // phase 2: vertical pass -> the 34 x 130 resized pixels the Gaussian needs, four per thread
     const int xvec_end = (dW / 8) * 8;
+    const bool all_vec = x0 + FT_W + 1 <= xvec_end;                        // no column of this tile is in OpenCV's scalar tail
     for (int it = tid; it < FR_H * (FR_P / 4 - 1); it += 256) {          // 34 rows x 33 groups of four columns (0..131)
         const int ry = it / (FR_P / 4 - 1), gq = it - ry * (FR_P / 4 - 1);
-        const int Y = reflect101(min(y0 - 1 + ry, dH), dH);
-        const int4 yi = __ldg(reinterpret_cast<const int4*>(yidx) + Y);
-        const int4 S0 = *reinterpret_cast<const int4*>(&s_h[yi.x - sy_lo][4 * gq]);
-        const int4 S1 = *reinterpret_cast<const int4*>(&s_h[yi.y - sy_lo][4 * gq]);
-        const int4 S2 = *reinterpret_cast<const int4*>(&s_h[yi.z - sy_lo][4 * gq]);
-        const int4 S3 = *reinterpret_cast<const int4*>(&s_h[yi.w - sy_lo][4 * gq]);
-        const int a0[4] = {S0.x, S0.y, S0.z, S0.w}, a1[4] = {S1.x, S1.y, S1.z, S1.w};
-        const int a2[4] = {S2.x, S2.y, S2.z, S2.w}, a3[4] = {S3.x, S3.y, S3.z, S3.w};
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ycf) + Y);
-        const int4 by = __ldg(reinterpret_cast<const int4*>(yci) + Y);
-        uint32_t packed = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            int v;
-            if (mode == 0) {
-                const int X = reflect101(min(x0 - 1 + 4 * gq + c, dW), dW);
-                if (X < xvec_end) {
-                    float acc = __fmul_rn((float)a3[c], b.w);
-                    acc = __fadd_rn(__fmul_rn((float)a2[c], b.z), acc);
-                    acc = __fadd_rn(__fmul_rn((float)a1[c], b.y), acc);
-                    acc = __fadd_rn(__fmul_rn((float)a0[c], b.x), acc);
-                    v = __float2int_rn(acc);
-                } else {
-                    v = (a0[c] * by.x + a1[c] * by.y + a2[c] * by.z + a3[c] * by.w + (1 << 21)) >> 22;
-                }
-            } else {
-                float a = __fmul_rn(__int_as_float(a0[c]), b.x);
-                a = __fadd_rn(a, __fmul_rn(__int_as_float(a1[c]), b.y));
-                a = __fadd_rn(a, __fmul_rn(__int_as_float(a2[c]), b.z));
-                a = __fadd_rn(a, __fmul_rn(__int_as_float(a3[c]), b.w));
-                v = __float2int_rn(a);
-            }
-            packed |= (uint32_t)min(max(v, 0), 255) << (8 * c);
+        const int4 yi = s_yi[ry], by = s_yq[ry];
+        const float4 b = s_yf[ry];
+        const int4 S0 = *reinterpret_cast<const int4*>(&s_h[yi.x][4 * gq]);
+        const int4 S1 = *reinterpret_cast<const int4*>(&s_h[yi.y][4 * gq]);
+        const int4 S2 = *reinterpret_cast<const int4*>(&s_h[yi.z][4 * gq]);
+        const int4 S3 = *reinterpret_cast<const int4*>(&s_h[yi.w][4 * gq]);
+        uint32_t packed;
+        if (all_vec || mode != 0) {
+            packed = cubic_vertical(S0.x, S1.x, S2.x, S3.x, b, by, mode, true) | (cubic_vertical(S0.y, S1.y, S2.y, S3.y, b, by, mode, true) << 8) |
+                     (cubic_vertical(S0.z, S1.z, S2.z, S3.z, b, by, mode, true) << 16) | (cubic_vertical(S0.w, S1.w, S2.w, S3.w, b, by, mode, true) << 24);
+        } else {
+            const int xc0 = x0 - 1 + 4 * gq;
+            packed = cubic_vertical(S0.x, S1.x, S2.x, S3.x, b, by, 0, reflect101(min(xc0, dW), dW) < xvec_end) |
+                     (cubic_vertical(S0.y, S1.y, S2.y, S3.y, b, by, 0, reflect101(min(xc0 + 1, dW), dW) < xvec_end) << 8) |
+                     (cubic_vertical(S0.z, S1.z, S2.z, S3.z, b, by, 0, reflect101(min(xc0 + 2, dW), dW) < xvec_end) << 16) |
+                     (cubic_vertical(S0.w, S1.w, S2.w, S3.w, b, by, 0, reflect101(min(xc0 + 3, dW), dW) < xvec_end) << 24);
         }
         reinterpret_cast<uint32_t*>(s_r[ry])[gq] = packed;
     }
     __syncthreads();
+    // phase 3: 3x3 Gaussian of the resized tile, four pixels per thread, + the global sum of the output
     unsigned int local = 0;
-    const int j = tid & 31;
+    const int j = lane;
     const bool st_vec = (dW & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
-    for (int oy = tid >> 5; oy < FT_H; oy += 8) {
+    for (int oy = warp; oy < FT_H; oy += 8) {
         const int y = y0 + oy, x = x0 + 4 * j;
         if (y >= dH || x >= dW) continue;
         int hsum[3][4];
@@ -475,12 +507,12 @@ __global__ void __launch_bounds__(256) k_gray_resize_gauss(const uint8_t* __rest
             const int p[6] = {(int)(w0 & 255u), (int)((w0 >> 8) & 255u), (int)((w0 >> 16) & 255u), (int)(w0 >> 24),
                               (int)(w1 & 255u), (int)((w1 >> 8) & 255u)};
 #pragma unroll
-            for (int c = 0; c < 4; ++c) hsum[r][c] = p[c] * k0 + p[c + 1] * k1 + p[c + 2] * k0;
+            for (int c = 0; c < 4; ++c) hsum[r][c] = (p[c] + p[c + 2]) * k0 + p[c + 1] * k1;
         }
         uint32_t packed = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int v = (hsum[0][c] * k0 + hsum[1][c] * k1 + hsum[2][c] * k0 + (1 << 15)) >> 16;
+            const int v = ((hsum[0][c] + hsum[2][c]) * k0 + hsum[1][c] * k1 + (1 << 15)) >> 16;
             packed |= (uint32_t)v << (8 * c);
             if (x + c < dW) local += v;
         }
@@ -493,7 +525,7 @@ __global__ void __launch_bounds__(256) k_gray_resize_gauss(const uint8_t* __rest
     }
     if (sum_out) {
         for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-        if ((tid & 31) == 0) wsum[tid >> 5] = local;
+        if (lane == 0) wsum[warp] = local;
         __syncthreads();
         if (tid == 0) {
             unsigned long long s = 0;

@@ -221,6 +221,7 @@ void load_craft(Handle* h, const bbocr_tensor* t, int n) {
         e.w_f32 = to_device(h, wf);
         c.c1_1_tc = e;
     }
+    CUDA_CHECK(cudaDeviceSynchronize());      // pageable cudaMemcpy may return before its DMA lands; the lanes' streams are non-blocking
     h->craft_loaded = true;
 }
 
@@ -240,6 +241,7 @@ void load_crnn(Handle* h, const bbocr_tensor* t, int n) {
     c.pred = make_linear(h, {d.get("Prediction.weight")}, {{d.get("Prediction.bias")}});
     c.num_class = c.pred.cout;
     ARG_CHECK(c.c0.cin == 1 && c.c0.cout == 32 && c.c6.kh == 2 && c.pred.cin == 256, "CRNN: unexpected shapes");
+    CUDA_CHECK(cudaDeviceSynchronize());
     h->crnn_loaded = true;
 }
 

@@ -175,3 +175,22 @@ def test_format_tail_detail_and_output_formats():
     assert r._format(raw, output_format="dict", paragraph=True)[0] == {"boxes": para[0][0], "text": "Red Men"}
     with pytest.raises(NotImplementedError):
         r._format(raw, output_format="free_merge")
+
+
+def test_central_edge_crop_matches_the_reference_fixtures():
+    """_central_edge_crop (enhanced_extractor.py:374-397) is pure host slicing: product vs the rectangles recorded from the
+    reference's own function (tests/golden/make_golden_autocrop.py)."""
+    import glob
+    from bbocr_b200 import extractor
+    paths = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "autocrop_*.npz")))
+    assert len(paths) >= 8
+    for path in paths:
+        z = np.load(path)
+        bgr = z["bgr"]
+        for pc, *want in z["edge"]:
+            got = extractor.central_edge_crop(bgr, float(pc))
+            if want[0] < 0:
+                assert got is None
+            else:
+                x0, y0, x1, y1 = (int(v) for v in want)
+                assert got.shape == (y1 - y0, x1 - x0, 3) and np.shares_memory(got, bgr) and np.array_equal(got, bgr[y0:y1, x0:x1])
