@@ -60,7 +60,7 @@ _lock = threading.Lock()
 # every symbol include/bbocr.h declares (tests check the export table against this list)
 SYMBOLS = [
     "bbocr_create", "bbocr_destroy", "bbocr_last_error", "bbocr_version", "bbocr_load_craft", "bbocr_load_crnn",
-    "bbocr_set_precision", "bbocr_get_precision", "bbocr_preprocess_u8", "bbocr_preprocess_batch_u8", "bbocr_preprocess_launches_per_image",
+    "bbocr_set_precision", "bbocr_get_precision", "bbocr_preprocess_u8", "bbocr_preprocess_batch_u8", "bbocr_preprocess_scan_u8", "bbocr_preprocess_launches_per_image",
     "bbocr_pp_gray", "bbocr_pp_resize_cubic", "bbocr_pp_gaussian3", "bbocr_pp_contrast", "bbocr_pp_brightness",
     "bbocr_pp_clahe", "bbocr_pp_unsharp", "bbocr_pp_adaptive_threshold", "bbocr_pp_deskew", "bbocr_craft_forward",
     "bbocr_det_boxes", "bbocr_min_area_box", "bbocr_group_boxes", "bbocr_crop_horizontal", "bbocr_crop_free",
@@ -217,6 +217,24 @@ class Handle:
                                                C.byref(oh), C.byref(ow)))
         assert (oh.value, ow.value) == (dH, dW)
         return out
+
+    def preprocess_scan(self, bgr, clahe_clip=2.0, block=11, delta=2.0, max_deg=5.0):
+        """BASELINE config[2] chain on a host BGR image: gray -> CLAHE -> deskew -> gentle_threshold.  -> (binary image, angle)."""
+        s, sp = _u8(bgr)
+        H, W = s.shape[:2]
+        out = np.empty((H, W), np.uint8)
+        ang = C.c_float()
+        self._check(self.L.bbocr_preprocess_scan_u8(self._h, sp, C.c_int(H), C.c_int(W), C.c_int(W * 3), C.c_int(0),
+                                                    C.c_float(clahe_clip), C.c_int(block), C.c_float(delta), C.c_float(max_deg),
+                                                    out.ctypes.data_as(C.c_void_p), C.c_int(0), C.byref(ang)))
+        return out, float(ang.value)
+
+    def preprocess_scan_dev(self, bgr_ptr: int, H: int, W: int, out_ptr: int, clahe_clip=2.0, block=11, delta=2.0, max_deg=5.0):
+        ang = C.c_float()
+        self._check(self.L.bbocr_preprocess_scan_u8(self._h, C.c_void_p(bgr_ptr), C.c_int(H), C.c_int(W), C.c_int(W * 3), C.c_int(1),
+                                                    C.c_float(clahe_clip), C.c_int(block), C.c_float(delta), C.c_float(max_deg),
+                                                    C.c_void_p(out_ptr), C.c_int(1), C.byref(ang)))
+        return float(ang.value)
 
     def preprocess_batch(self, images, params: PPParams):
         """The chain over a list of same-size host BGR images (bbocr_preprocess_batch_u8) -> list of host gray images."""

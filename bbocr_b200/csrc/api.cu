@@ -301,6 +301,33 @@ int bbocr_pp_deskew(bbocr_handle* h, const uint8_t* src, int H, int W, float max
     });
 }
 
+int bbocr_preprocess_scan_u8(bbocr_handle* h, const uint8_t* bgr, int H, int W, int stride, int in_on_device, float clahe_clip,
+                             int block, float delta, float max_deg, uint8_t* out, int out_on_device, float* angle_out) {
+    return guarded(h, [&] {
+        ARG_CHECK(bgr && out && H > 0 && W > 0 && stride >= W * 3, "bad arguments");
+        Lane& lane = h->lanes[0];
+        cudaStream_t st = lane.stream;
+        const size_t n = (size_t)H * W;
+        DevBuf din, dout;
+        const uint8_t* src = bgr;
+        if (!in_on_device) { upload(lane, din, bgr, (size_t)H * stride); src = din.as<uint8_t>(); }
+        uint8_t* dst = out;
+        if (!out_on_device) { dout.alloc(n, st); dst = dout.as<uint8_t>(); }
+        DevBuf gray(n, st), eq(n, st), rot(n, st), small(64 * 256 * 4 + 64 * 256, st);
+        unsigned int* hist = small.as<unsigned int>();
+        uint8_t* luts = small.as<uint8_t>() + 64 * 256 * 4;
+        pp_gray(h, st, src, H, W, stride, gray.as<uint8_t>());
+        pp_clahe_luts(h, st, gray.as<uint8_t>(), H, W, clahe_clip, nullptr, hist, luts);
+        pp_clahe_apply(h, st, gray.as<uint8_t>(), eq.as<uint8_t>(), H, W, nullptr, luts);
+        const float a = pp_deskew(h, st, eq.as<uint8_t>(), rot.as<uint8_t>(), H, W, max_deg);
+        if (angle_out) *angle_out = a;
+        pp_adaptive_threshold(h, st, rot.as<uint8_t>(), dst, H, W, 1, 0, block, delta);
+        if (!out_on_device) download(lane, out, dst, n);
+        else CUDA_CHECK(cudaStreamSynchronize(st));
+        lane.in_busy = false;
+    });
+}
+
 // ---- extractor glue ------------------------------------------------------------------------------------
 // PIL.Image.thumbnail((m, m)) size rule (Image.py::thumbnail, default BICUBIC, reducing_gap = 2.0):
 // aspect-preserving, never enlarges; round_aspect picks floor/ceil by the smaller aspect error (floor on ties), at least 1.

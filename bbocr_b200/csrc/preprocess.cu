@@ -1315,6 +1315,82 @@ __global__ void k_deskew_hist(const uint8_t* __restrict__ fg, int H, int W, cons
     }
 }
 
+// Banded variant (the default): a block owns DK_ROWS image rows and DK_ANG angles.  The ink pixels of a band land, for one
+// angle, in a window of at most DK_ROWS + W |sin| + 4 consecutive bins, so the block counts in shared memory and adds its
+// non-empty bins to the global profile once; per ink pixel that is DK_ANG shared atomics instead of n_ang global ones.
+// The bin of a pixel is computed exactly as above, so the profiles (integers) are identical.
+constexpr int DK_ROWS = 32, DK_ANG = 16;
+__global__ void __launch_bounds__(256) k_deskew_hist_band(const uint8_t* __restrict__ fg, int H, int W, const double* __restrict__ cs,
+                                                          int n_ang, int NR, int R0, double cx, double cy, int win,
+                                                          unsigned int* __restrict__ bins) {
+    extern __shared__ unsigned int s_bins[];             // [DK_ANG][win]
+    __shared__ int s_lo[DK_ANG];
+    __shared__ double s_c[DK_ANG], s_s[DK_ANG];
+    const int tid = threadIdx.x;
+    const int y0 = blockIdx.x * DK_ROWS, y1 = min(y0 + DK_ROWS, H);
+    const int a0 = blockIdx.y * DK_ANG, na = min(DK_ANG, n_ang - a0);
+    for (int i = tid; i < DK_ANG * win; i += 256) s_bins[i] = 0;
+    if (tid < na) {
+        const double c = cs[2 * (a0 + tid)], s = cs[2 * (a0 + tid) + 1];
+        s_c[tid] = c;
+        s_s[tid] = s;
+        // smallest projection over the band: rows y0..y1-1, columns 0..W-1 (c > 0 for |angle| <= 45 degrees)
+        const double dy_lo = (double)y0 - cy, dx_far = s >= 0.0 ? (double)(W - 1) - cx : -cx;
+        s_lo[tid] = (int)floor(dy_lo * c - dx_far * s) - 2 + R0;
+    }
+    __syncthreads();
+    // a thread takes four consecutive even columns (8 pixels of a row); the projection is monotone along the row, so equal
+    // bins are neighbours and are merged before the shared atomic
+    const int wq = (W + 7) / 8;
+    for (int i = tid; i < (y1 - y0) * wq; i += 256) {
+        const int ry = i / wq, xq = i - ry * wq;
+        const int y = y0 + ry, x = 8 * xq;
+        const uint8_t* row = fg + (int64_t)y * W;
+        bool ink[4];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ink[j] = x + 2 * j < W && row[x + 2 * j] != 0;
+            any |= ink[j];
+        }
+        if (!any) continue;
+        const double dy = (double)y - cy;
+        for (int k = 0; k < na; ++k) {
+            const double c = s_c[k], sn = s_s[k], dyc = __dmul_rn(dy, c);
+            const int lo = s_lo[k];
+            int prev = -1, cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!ink[j]) continue;
+                const double dx = (double)(x + 2 * j) - cx;
+                int r = (int)floor(__dsub_rn(dyc, __dmul_rn(dx, sn))) + R0;
+                r = min(max(r, 0), NR - 1);
+                if (r == prev) { ++cnt; continue; }
+                if (cnt) {
+                    const int idx = prev - lo;
+                    if (idx >= 0 && idx < win) atomicAdd(&s_bins[k * win + idx], (unsigned)cnt);
+                    else atomicAdd(&bins[(int64_t)(a0 + k) * NR + prev], (unsigned)cnt);
+                }
+                prev = r;
+                cnt = 1;
+            }
+            if (cnt) {
+                const int idx = prev - lo;
+                if (idx >= 0 && idx < win) atomicAdd(&s_bins[k * win + idx], (unsigned)cnt);
+                else atomicAdd(&bins[(int64_t)(a0 + k) * NR + prev], (unsigned)cnt);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < na * win; i += 256) {
+        const unsigned int v = s_bins[i];
+        if (v) {
+            const int k = i / win, r = s_lo[k] + (i - k * win);
+            atomicAdd(&bins[(int64_t)(a0 + k) * NR + r], v);
+        }
+    }
+}
+
 __global__ void k_deskew_score(const unsigned int* __restrict__ bins, int NR, unsigned long long* __restrict__ score) {
     unsigned long long acc = 0;
     for (int r = threadIdx.x; r < NR; r += blockDim.x) {
@@ -1371,8 +1447,14 @@ float pp_deskew(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, in
     pp_adaptive_threshold(h, st, src, fg.as<uint8_t>(), H, W, 1, 1, 31, 5.0f);
     CUDA_CHECK(cudaMemcpyAsync(dcs.p, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemsetAsync(bins.p, 0, (size_t)n_ang * NR * 4, st));
-    k_deskew_hist<<<dim3(cdiv(cdiv(W, 2), 128), H), 128, 0, st>>>(fg.as<uint8_t>(), H, W, dcs.as<double>(), n_ang, NR, R0,
-                                                                       cx, cy, bins.as<unsigned int>());
+    const int win = DK_ROWS + (int)ceil((double)W * sin((double)max_deg * 3.141592653589793 / 180.0)) + 8;
+    if ((size_t)DK_ANG * win * 4 <= 46 * 1024) {
+        k_deskew_hist_band<<<dim3(cdiv(H, DK_ROWS), cdiv(n_ang, DK_ANG)), 256, (size_t)DK_ANG * win * 4, st>>>(
+            fg.as<uint8_t>(), H, W, dcs.as<double>(), n_ang, NR, R0, cx, cy, win, bins.as<unsigned int>());
+    } else {
+        k_deskew_hist<<<dim3(cdiv(cdiv(W, 2), 128), H), 128, 0, st>>>(fg.as<uint8_t>(), H, W, dcs.as<double>(), n_ang, NR, R0,
+                                                                           cx, cy, bins.as<unsigned int>());
+    }
     k_deskew_score<<<n_ang, 256, 0, st>>>(bins.as<unsigned int>(), NR, score.as<unsigned long long>());
     std::vector<unsigned long long> hs(n_ang);
     CUDA_CHECK(cudaMemcpyAsync(hs.data(), score.p, (size_t)n_ang * 8, cudaMemcpyDeviceToHost, st));

@@ -99,6 +99,14 @@ int bbocr_pp_adaptive_threshold(bbocr_handle* h, const uint8_t* src, int H, int 
  * bilinear replicate-border rotation about the centre.  angle_out (degrees, may be NULL). */
 int bbocr_pp_deskew(bbocr_handle* h, const uint8_t* src, int H, int W, float max_deg, uint8_t* out, float* angle_out);
 
+/* BASELINE.json config[2] as one device-resident chain ("gray, CLAHE, adaptive threshold, deskew" on phone photos), composed of
+ * the steps above in the order a scan pipeline applies them: BGR -> gray (:25-30) -> CLAHE(clahe_clip) (:48-56) -> deskew
+ * (max_deg; this repository's definition, see bbocr_pp_deskew) -> gentle_threshold(block, delta) (:58-68).  out: HxW u8 in
+ * {0, 255}; angle_out (degrees, may be NULL). */
+int bbocr_preprocess_scan_u8(bbocr_handle* h, const uint8_t* bgr, int H, int W, int stride_bytes, int in_on_device,
+                             float clahe_clip, int block, float delta, float max_deg, uint8_t* out, int out_on_device,
+                             float* angle_out);
+
 /* ---- stage 2: detector (easyocr/detection.py, craft.py, imgproc.py) -------------------------------------------------- */
 /* test_net up to the score maps: resize_aspect_ratio(canvas_size, INTER_LINEAR, mag_ratio) -> normalizeMeanVariance
  * -> CRAFT.forward.  img is HxWx3 u8 in the channel order EasyOCR feeds the net.  score_text/score_link: host float

@@ -98,3 +98,23 @@ def test_deskew_matches_oracle_and_recovers_angle(handle):
         got, ga = handle.pp_deskew(rot, 5.0)
         assert abs(ga - float(wa)) < 1e-6 and abs(ga - ang) <= 0.15
         assert np.array_equal(got, want)
+
+
+def test_config3_scan_chain(handle):
+    """BASELINE config[2] (gray, CLAHE, adaptive threshold, deskew) as one chain: bit-exact against the composed oracles on a
+    reduced photo, and at the full 4032x3024 size determinism, a binary result and agreement of the estimated angle."""
+    import cv2
+    bgr = synth.phone_photo(3005, 1008, 756)
+    M = cv2.getRotationMatrix2D((503.5, 377.5), 1.8, 1.0)
+    bgr = cv2.warpAffine(bgr, M, (1008, 756), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+    got, ang = handle.preprocess_scan(bgr, 2.0, 11, 2.0, 5.0)
+    eq = P.clahe(P.bgr2gray(bgr), 2.0)
+    rot, want_ang = P.deskew(eq, 5.0)
+    want = P.adaptive_threshold(rot, 255, "gaussian", False, 11, 2)
+    assert abs(ang - float(want_ang)) < 1e-6
+    assert np.array_equal(got, want)
+    big = synth.phone_photo(3001)
+    a, ang_a = handle.preprocess_scan(big)
+    b, ang_b = handle.preprocess_scan(big)
+    assert a.shape == (3024, 4032) and set(np.unique(a).tolist()) <= {0, 255} and np.array_equal(a, b) and ang_a == ang_b
+    assert abs(ang_a) <= 5.0

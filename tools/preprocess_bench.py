@@ -71,6 +71,14 @@ def timed(fn):
 peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) if os.path.exists(
     os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {}
 hbm = float(peaks.get("hbm_gbs", 6557.4))
+scan_out = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+
+
+def scan(i):
+    h.preprocess_scan_dev(photos[i].data_ptr(), H, W, scan_out.data_ptr())
+
+
+t_scan = timed(scan)
 t_chain = timed(chain)
 chain_batch()
 torch.cuda.synchronize()
@@ -95,6 +103,9 @@ print(json.dumps({
     "preprocess_chain_batched": {"ms_per_photo": t_batch * 1e3, "photos_per_s": 1 / t_batch,
                                  "algorithmic_GBps": 12 * px / t_batch / 1e9, "frac_of_hbm_peak": 12 * px / t_batch / 1e9 / hbm,
                                  "api": "bbocr_preprocess_batch_u8, device pointers, photos spread over 8 streams"},
+    "scan_chain": {"what": "BASELINE config[2] literally: gray -> CLAHE -> deskew -> adaptive threshold (bbocr_preprocess_scan_u8); "
+                           "8 B per pixel algorithmic (SURVEY.md 8d)", "ms_per_photo": t_scan * 1e3, "photos_per_s": 1 / t_scan,
+                   "algorithmic_GBps": 8 * px / t_scan / 1e9, "frac_of_hbm_peak": 8 * px / t_scan / 1e9 / hbm},
     "autocrop": {"ms_per_photo": t_crop * 1e3, "photos_per_s": 1 / t_crop, "algorithmic_GBps": 10 * px / t_crop / 1e9,
                  "frac_of_hbm_peak": 10 * px / t_crop / 1e9 / hbm},
     "hbm_peak_GBps": hbm}))
