@@ -329,10 +329,12 @@ void pp_resize_cubic(Handle* h, cudaStream_t st, const uint8_t* src, int sH, int
 // A4  cv2.GaussianBlur((3,3), sigma): fixed-point [k0,k1,k0]/256 both ways, BORDER_REFLECT_101, one rounding
 //     (v + 2^15) >> 16.  Optionally accumulates the global pixel sum of the OUTPUT (Pillow Contrast's mean).
 // ------------------------------------------------------------------------------------------------------------------
+// cv2 borderInterpolate(BORDER_REFLECT_101): reflect until inside.  One reflection is the common case; tile loaders at
+// the image edge ask for columns far outside small images (their values are never used, but the index must stay legal),
+// and CLAHE pads an 8-pixel-wide image by 8.
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
-    if (i < 0) i = -i;
-    if (i >= n) i = 2 * n - 2 - i;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
     return i;
 }
 
