@@ -118,3 +118,24 @@ def test_config3_scan_chain(handle):
     b, ang_b = handle.preprocess_scan(big)
     assert a.shape == (3024, 4032) and set(np.unique(a).tolist()) <= {0, 255} and np.array_equal(a, b) and ang_a == ang_b
     assert abs(ang_a) <= 5.0
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_chain_fuzz_odd_sizes(handle, mode):
+    """The fused chain kernels on ragged geometries (widths not divisible by 4 or 8, tiles with one row / column, images
+    smaller than a tile): bit-exact against the oracle, and the batched entry gives the same bytes as the single one."""
+    rng = np.random.default_rng(90 + mode)
+    sizes = [(9, 9), (11, 86), (86, 11), (22, 171), (171, 22), (86, 87), (129, 257), (341, 343)] + \
+            [(int(rng.integers(8, 300)), int(rng.integers(8, 400))) for _ in range(10)]
+    for (hh, ww) in sizes:
+        bgr = rng.integers(0, 256, (hh, ww, 3), dtype=np.uint8)
+        if hh > 40:
+            bgr = synth.phone_photo(hh * 1000 + ww, ww, hh)
+        for cfg, pcfg in ((CURRENT, P.CURRENT), (LEGACY, P.LEGACY)):
+            got = preprocess_array(bgr, cfg, mode)
+            want = P.preprocess_chain(bgr, pcfg, "T1" if mode == 0 else "T2")
+            assert got.shape == want.shape and np.array_equal(got, want), (hh, ww, mode)
+    same = [rng.integers(0, 256, (37, 53, 3), dtype=np.uint8) for _ in range(11)]
+    outs = handle.preprocess_batch(same, pp_params(CURRENT, mode))
+    for im, o in zip(same, outs):
+        assert np.array_equal(o, preprocess_array(im, CURRENT, mode))
