@@ -218,6 +218,16 @@ class Handle:
         assert (oh.value, ow.value) == (dH, dW)
         return out
 
+    def dbg_deskew_scores(self, gray, max_deg: float, variant: int) -> np.ndarray:
+        """Test hook: per-angle projection scores from one of the three deskew histogram kernels (0 / 1 / 2)."""
+        g, gp = _u8(gray.copy())
+        H, W = g.shape
+        sc = np.zeros(1024, np.uint64)
+        n = C.c_int()
+        self._check(self.L.bbocr_dbg_deskew_scores(self._h, gp, C.c_int(H), C.c_int(W), C.c_float(max_deg), C.c_int(variant),
+                                                   sc.ctypes.data_as(C.c_void_p), C.c_int(1024), C.byref(n)))
+        return sc[:n.value].copy()
+
     def preprocess_scan(self, bgr, clahe_clip=2.0, block=11, delta=2.0, max_deg=5.0):
         """BASELINE config[2] chain on a host BGR image: gray -> CLAHE -> deskew -> gentle_threshold.  -> (binary image, angle)."""
         s, sp = _u8(bgr)

@@ -475,6 +475,18 @@ int bbocr_min_area_box(const int32_t* xy, int npoints, float* out8) {
     return BBOCR_OK;
 }
 
+// test hook: the per-angle projection scores of bbocr_pp_deskew computed by one of its three histogram kernels
+// (0 = one global atomic per ink pixel and angle, 1 = banded shared-memory counts, 2 = run-based prefix differences)
+int bbocr_dbg_deskew_scores(bbocr_handle* h, const uint8_t* src, int H, int W, float max_deg, int variant, uint64_t* scores,
+                            int cap, int* n_out) {
+    return pp_step(h, src, (size_t)H * W, const_cast<uint8_t*>(src), (size_t)H * W, [&](cudaStream_t st, const uint8_t* s, uint8_t* d) {
+        std::vector<unsigned long long> sc;
+        pp_deskew(h, st, s, d, H, W, max_deg, variant, &sc);
+        if (n_out) *n_out = (int)sc.size();
+        for (int i = 0; i < (int)sc.size() && i < cap; ++i) scores[i] = sc[i];
+    });
+}
+
 int bbocr_dbg_convex_hull(const int32_t* xy, int n, int clockwise, int32_t* out, int* nout) {
     std::vector<int> hull;
     debug_convex_hull(xy, n, clockwise, hull);

@@ -80,7 +80,8 @@ void pp_adaptive_threshold(Handle*, cudaStream_t, const uint8_t* src, uint8_t* d
 void preprocess_chain_dev(Handle*, cudaStream_t, const uint8_t* bgr, int H, int W, int stride, const bbocr_pp_params&,
                           uint8_t* out, int* outH, int* outW);
 int preprocess_launches_per_image();
-float pp_deskew(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int H, int W, float max_deg);
+float pp_deskew(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int H, int W, float max_deg, int variant = -1,
+                std::vector<unsigned long long>* scores_out = nullptr);
 
 // ---- autocrop.cu (enhanced_extractor.py:239-372) ---------------------------------------------------------
 struct AutoCropDebug {             // optional parity outputs (host memory)

@@ -1393,6 +1393,102 @@ __global__ void __launch_bounds__(256) k_deskew_hist_band(const uint8_t* __restr
     }
 }
 
+// Run-based variant (the default).  Along a row the bin floor(dy c - dx s) is monotone in x, so for one (row, angle) the ink
+// pixels of a bin are those of one interval of columns: with a per-row prefix count of the ink pixels (even columns) a thread
+// walks the intervals of its (row, angle) -- next boundary from the real-valued estimate, then corrected with the EXACT
+// per-pixel expression so that every pixel is counted in the bin the definition gives it -- and adds prefix differences.
+// ~W |sin| intervals per (row, angle) instead of W/2 pixels, and no per-pixel atomics.
+__global__ void __launch_bounds__(256) k_ink_prefix(const uint8_t* __restrict__ fg, int H, int W, int We, uint16_t* __restrict__ P) {
+    __shared__ int s_part[256];
+    const int y = blockIdx.x, tid = threadIdx.x;
+    const uint8_t* row = fg + (int64_t)y * W;
+    const int per = (We + 255) / 256, e0 = tid * per, e1 = min(e0 + per, We);
+    int cnt = 0;
+    for (int e = e0; e < e1; ++e) cnt += row[2 * e] != 0;
+    s_part[tid] = cnt;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        int add = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += add;
+        __syncthreads();
+    }
+    int run = s_part[tid] - cnt;                          // exclusive prefix of this thread's chunk
+    uint16_t* out = P + (int64_t)y * (We + 1);
+    for (int e = e0; e < e1; ++e) {
+        out[e] = (uint16_t)run;
+        run += row[2 * e] != 0;
+    }
+    if (e1 == We && e0 < We) out[We] = (uint16_t)run;
+    if (We == 0 && tid == 0) out[0] = 0;
+}
+
+__device__ __forceinline__ int deskew_bin(double dyc, int e, double cx, double sn) {
+    const double dx = (double)(2 * e) - cx;
+    return (int)floor(__dsub_rn(dyc, __dmul_rn(dx, sn)));
+}
+
+__global__ void __launch_bounds__(256) k_deskew_prof(const uint16_t* __restrict__ P, int H, int W, int We,
+                                                     const double* __restrict__ cs, int n_ang, int NR, int R0, double cx, double cy,
+                                                     int win, unsigned int* __restrict__ bins) {
+    extern __shared__ unsigned int s_bins[];             // [8][win]
+    __shared__ int s_lo[8];
+    const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;       // warp = one angle, lanes = the 32 rows of the band
+    const int y0 = blockIdx.x * 32, a0 = blockIdx.y * 8;
+    const int ai = a0 + k, y = y0 + lane;
+    const bool live = ai < n_ang;
+    for (int i = tid; i < 8 * win; i += 256) s_bins[i] = 0;
+    double c = 1.0, sn = 0.0;
+    if (live) { c = cs[2 * ai]; sn = cs[2 * ai + 1]; }
+    if (lane == 0) {
+        const double dy_lo = (double)y0 - cy, dx_far = sn >= 0.0 ? (double)(W - 1) - cx : -cx;
+        s_lo[k] = (int)floor(dy_lo * c - dx_far * sn) - 2 + R0;
+    }
+    __syncthreads();
+    if (live && y < H && We > 0) {
+        const uint16_t* pr = P + (int64_t)y * (We + 1);
+        const double dyc = __dmul_rn((double)y - cy, c);
+        const double inv = sn != 0.0 ? 1.0 / sn : 0.0;
+        const int lo = s_lo[k];
+        int e = 0;
+        int r = deskew_bin(dyc, 0, cx, sn);
+        unsigned before = pr[0];
+        while (e < We) {
+            int en;
+            if (sn == 0.0) {
+                en = We;
+            } else {
+                // real-valued crossing of the bin edge (r for a falling profile, r + 1 for a rising one), then exact correction
+                const double edge = sn > 0.0 ? (double)r : (double)(r + 1);
+                const double xe = ((dyc - edge) * inv + cx) * 0.5;
+                en = (int)floor(xe) + 1;
+                en = min(max(en, e + 1), We);
+                while (en > e + 1 && deskew_bin(dyc, en - 1, cx, sn) != r) --en;
+                while (en < We && deskew_bin(dyc, en, cx, sn) == r) ++en;
+            }
+            const unsigned after = pr[en];
+            const unsigned cnt = after - before;
+            if (cnt) {
+                const int rb = min(max(r + R0, 0), NR - 1);
+                const int idx = rb - lo;
+                if (idx >= 0 && idx < win) atomicAdd(&s_bins[k * win + idx], cnt);
+                else atomicAdd(&bins[(int64_t)ai * NR + rb], cnt);
+            }
+            before = after;
+            e = en;
+            if (e < We) r = deskew_bin(dyc, e, cx, sn);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 8 * win; i += 256) {
+        const unsigned int v = s_bins[i];
+        if (v) {
+            const int kk = i / win;
+            atomicAdd(&bins[(int64_t)(a0 + kk) * NR + s_lo[kk] + (i - kk * win)], v);
+        }
+    }
+}
+
 __global__ void k_deskew_score(const unsigned int* __restrict__ bins, int NR, unsigned long long* __restrict__ score) {
     unsigned long long acc = 0;
     for (int r = threadIdx.x; r < NR; r += blockDim.x) {
@@ -1432,7 +1528,8 @@ __global__ void k_rotate_bilinear(const uint8_t* __restrict__ src, uint8_t* __re
     dst[(int64_t)y * W + x] = (uint8_t)min(max(q, 0), 255);
 }
 
-float pp_deskew(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, int H, int W, float max_deg) {
+float pp_deskew(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, int H, int W, float max_deg, int variant,
+                std::vector<unsigned long long>* scores_out) {
     ARG_CHECK(max_deg >= 0.f && max_deg <= 45.f, "deskew: max_deg out of range");
     const int half = (int)lrint((double)max_deg / 0.1);
     const int n_ang = 2 * half + 1;
@@ -1450,7 +1547,15 @@ float pp_deskew(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, in
     CUDA_CHECK(cudaMemcpyAsync(dcs.p, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemsetAsync(bins.p, 0, (size_t)n_ang * NR * 4, st));
     const int win = DK_ROWS + (int)ceil((double)W * sin((double)max_deg * 3.141592653589793 / 180.0)) + 8;
-    if ((size_t)DK_ANG * win * 4 <= 46 * 1024) {
+    const int We = (W + 1) / 2;
+    // variant: -1 = fastest that fits (default); 0 = per-pixel global atomics, 1 = banded shared atomics, 2 = run-based (test hook)
+    if ((variant < 0 || variant == 2) && (size_t)8 * win * 4 <= 46 * 1024 && We < 65536) {
+        DevBuf prefix((size_t)H * (We + 1) * 2, st);
+        k_ink_prefix<<<H, 256, 0, st>>>(fg.as<uint8_t>(), H, W, We, prefix.as<uint16_t>());
+        k_deskew_prof<<<dim3(cdiv(H, 32), cdiv(n_ang, 8)), 256, (size_t)8 * win * 4, st>>>(
+            prefix.as<uint16_t>(), H, W, We, dcs.as<double>(), n_ang, NR, R0, cx, cy, win, bins.as<unsigned int>());
+        count_launch(h);
+    } else if ((variant < 0 || variant == 1) && (size_t)DK_ANG * win * 4 <= 46 * 1024) {
         k_deskew_hist_band<<<dim3(cdiv(H, DK_ROWS), cdiv(n_ang, DK_ANG)), 256, (size_t)DK_ANG * win * 4, st>>>(
             fg.as<uint8_t>(), H, W, dcs.as<double>(), n_ang, NR, R0, cx, cy, win, bins.as<unsigned int>());
     } else {
@@ -1461,6 +1566,7 @@ float pp_deskew(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, in
     std::vector<unsigned long long> hs(n_ang);
     CUDA_CHECK(cudaMemcpyAsync(hs.data(), score.p, (size_t)n_ang * 8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    if (scores_out) *scores_out = hs;
     int best = 0;
     for (int i = 1; i < n_ang; ++i)
         if (hs[i] > hs[best]) best = i;

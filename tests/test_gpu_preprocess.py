@@ -139,3 +139,31 @@ def test_chain_fuzz_odd_sizes(handle, mode):
     outs = handle.preprocess_batch(same, pp_params(CURRENT, mode))
     for im, o in zip(same, outs):
         assert np.array_equal(o, preprocess_array(im, CURRENT, mode))
+
+
+def test_deskew_histogram_kernels_agree(handle):
+    """The three projection-profile kernels (per-pixel atomics = the definition, banded, run-based) give identical scores
+    for every angle, including steep ranges where consecutive even columns skip bins, and equal the NumPy definition."""
+    import cv2
+    import math
+    rng = np.random.default_rng(12)
+    imgs = [cv2.cvtColor(synth.title_page(6, 801, 603), cv2.COLOR_RGB2GRAY), cv2.cvtColor(synth.phone_photo(7, 1000, 750), cv2.COLOR_BGR2GRAY),
+            rng.integers(0, 256, (97, 131), dtype=np.uint8), rng.integers(0, 256, (64, 1), dtype=np.uint8)]
+    for g in imgs:
+        for max_deg in (5.0, 40.0, 0.0):
+            ref = handle.dbg_deskew_scores(g, max_deg, 0)
+            assert len(ref) == 2 * int(round(max_deg / 0.1)) + 1
+            for variant in (1, 2):
+                assert np.array_equal(handle.dbg_deskew_scores(g, max_deg, variant), ref), (g.shape, max_deg, variant)
+    g = imgs[0]
+    H, W = g.shape
+    fg = P.adaptive_threshold(g, 255, "gaussian", True, 31, 5)
+    ys, xs = np.nonzero(fg[:, ::2])
+    dx, dy = xs.astype(np.float64) * 2 - (W - 1) * 0.5, ys.astype(np.float64) - (H - 1) * 0.5
+    NR = int(math.ceil(math.sqrt(float(H) * H + float(W) * W))) + 3
+    got = handle.dbg_deskew_scores(g, 5.0, 2)
+    for i in (0, 17, 50, 100):
+        rad = float(i - 50) * 0.1 * 3.141592653589793 / 180.0
+        r = np.clip(np.floor(dy * math.cos(rad) - dx * math.sin(rad)).astype(np.int64) + NR // 2, 0, NR - 1)
+        cnt = np.bincount(r, minlength=NR).astype(np.uint64)
+        assert int((cnt * cnt).sum()) == int(got[i])
