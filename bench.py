@@ -179,6 +179,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: bbocr_b200 has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import bbocr_b200
