@@ -120,6 +120,30 @@ __global__ void k_ac_mask(const uint8_t* __restrict__ thr_mean, const uint8_t* _
     if ((threadIdx.x & 31) == 0 && (x >> 5) < Ww) bits[(int64_t)y * Ww + (x >> 5)] = m;
 }
 
+// four pixels per thread (32-bit loads of the four planes), nibbles OR-reduced over 8 lanes into one word; needs W % 4 == 0
+__global__ void __launch_bounds__(256) k_ac_mask4(const uint32_t* __restrict__ thr_mean, const uint32_t* __restrict__ thr_gaus,
+                                                  const uint32_t* __restrict__ eq, const uint32_t* __restrict__ grad,
+                                                  const int* __restrict__ thr, int H, int W, int Ww, uint32_t* __restrict__ bits) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, lane = threadIdx.x & 31;
+    const int W4 = W >> 2;
+    uint32_t nib = 0;
+    if (g < W4) {
+        const int64_t i = (int64_t)y * W4 + g;
+        const uint32_t m = __ldg(thr_mean + i) | __ldg(thr_gaus + i), e = __ldg(eq + i), gr = __ldg(grad + i);
+        const int t0 = thr[0], t1 = thr[1];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const bool on = ((m >> (8 * c)) & 255u) || (int)((e >> (8 * c)) & 255u) <= t0 || (int)((gr >> (8 * c)) & 255u) > t1;
+            nib |= (on ? 1u : 0u) << c;
+        }
+    }
+    uint32_t v = nib << (4 * (lane & 7));
+    v |= __shfl_xor_sync(0xffffffffu, v, 1);
+    v |= __shfl_xor_sync(0xffffffffu, v, 2);
+    v |= __shfl_xor_sync(0xffffffffu, v, 4);
+    if ((lane & 7) == 0 && (g >> 3) < Ww) bits[(int64_t)y * Ww + (g >> 3)] = v;
+}
+
 __global__ void k_ac_pack(const uint8_t* __restrict__ src, int H, int W, int Ww, uint32_t* __restrict__ bits) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     bool on = x < W && src[(int64_t)y * W + x] != 0;
@@ -147,14 +171,23 @@ __global__ void k_bit_dilate(const uint32_t* __restrict__ a, const uint32_t* __r
         if (jj == Ww - 1) v &= tail;
         return v;
     };
-    uint32_t acc = 0;
+    // rows first (plain OR of words), then ONE horizontal spread of the 96-bit window by shift doubling: a value that already
+    // holds the OR of shifts 0..k extends to 0..k+s with one more shift by s <= k+1, so rx = 15 costs 4 steps per side
+    uint32_t p = 0, c = 0, n = 0;
     int ya = max(y - ry, 0), yb = min(y + ry, H - 1);
     for (int yy = ya; yy <= yb; ++yy) {
-        uint32_t p = load(yy, j - 1), c = load(yy, j), n = load(yy, j + 1);
-        uint32_t r = c;
-        for (int d = 1; d <= rx; ++d) r |= __funnelshift_l(p, c, d) | __funnelshift_r(c, n, d);
-        acc |= r;
+        p |= load(yy, j - 1);
+        c |= load(yy, j);
+        n |= load(yy, j + 1);
     }
+    uint64_t L = ((uint64_t)c << 32) | p, R = ((uint64_t)n << 32) | c;
+    for (int cover = 0; cover < rx;) {
+        const int step = min(cover + 1, rx - cover);
+        L |= L << step;
+        R |= R >> step;
+        cover += step;
+    }
+    uint32_t acc = (uint32_t)(L >> 32) | (uint32_t)R;
     if (inv_out) acc = ~acc;
     if (j == Ww - 1) acc &= tail;
     dst[(int64_t)y * Ww + j] = acc;
@@ -352,8 +385,12 @@ bool autocrop_dev(Handle* h, cudaStream_t st, const uint8_t* bgr, int H, int W, 
     k_ac_otsu<<<1, 32, 0, st>>>(hist, (double)n, thr);
     DevBuf mask(nb, st), a1(nb, st), a2(nb, st), b1(nb, st), b2(nb, st), merged(nb, st);
     dim3 grd(cdiv(W, 256), H);
-    k_ac_mask<<<grd, 256, 0, st>>>(tmean.as<uint8_t>(), tgaus.as<uint8_t>(), eq.as<uint8_t>(), grad.as<uint8_t>(), thr, H, W, Ww,
-                                   mask.as<uint32_t>());
+    if ((W & 3) == 0)
+        k_ac_mask4<<<dim3(cdiv(Ww * 8, 256), H), 256, 0, st>>>(tmean.as<uint32_t>(), tgaus.as<uint32_t>(), eq.as<uint32_t>(),
+                                                               grad.as<uint32_t>(), thr, H, W, Ww, mask.as<uint32_t>());
+    else
+        k_ac_mask<<<grd, 256, 0, st>>>(tmean.as<uint8_t>(), tgaus.as<uint8_t>(), eq.as<uint8_t>(), grad.as<uint8_t>(), thr, H, W, Ww,
+                                       mask.as<uint32_t>());
     count_launch(h, 3);
     bit_dilate(h, st, mask.as<uint32_t>(), nullptr, H, W, Ww, 17, 5, false, a1.as<uint32_t>());
     bit_dilate(h, st, a1.as<uint32_t>(), nullptr, H, W, Ww, 19, 7, true, a2.as<uint32_t>());

@@ -782,64 +782,8 @@ __global__ void k_clahe_apply(const uint8_t* __restrict__ src, uint8_t* __restri
 // Fused with the CLAHE application (tone LUT -> CLAHE LUT blend -> unsharp) when `luts_g` != nullptr so the chain
 // reads its input once and writes its output once.
 // ------------------------------------------------------------------------------------------------------------------
-#define US_T 32
-#define US_H 3
-#define US_S (US_T + 2 * US_H)      // 38
+#define US_H 3      // halo of the three box passes per direction
 
-__global__ void k_unsharp(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, unsigned ww,
-                          unsigned fw, int percent, int threshold, ClaheGeom g, const uint8_t* __restrict__ tone,
-                          const uint8_t* __restrict__ luts_g) {
-    __shared__ uint8_t a[US_S][US_S + 2], b[US_S][US_S + 2], orig[US_T][US_T];
-    const int bx = blockIdx.x * US_T - US_H, by = blockIdx.y * US_T - US_H;
-    for (int i = threadIdx.x; i < US_S * US_S; i += blockDim.x) {
-        int ty = i / US_S, tx = i % US_S;
-        int gy = by + ty, gx = bx + tx;
-        uint8_t v = 0;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            v = src[(int64_t)gy * W + gx];
-            if (luts_g) {
-                if (tone) v = tone[v];
-                v = clahe_px(luts_g, v, gx, gy, g);
-            }
-        }
-        a[ty][tx] = v;
-        if (ty >= US_H && ty < US_H + US_T && tx >= US_H && tx < US_H + US_T) orig[ty - US_H][tx - US_H] = v;
-    }
-    __syncthreads();
-    // tile-coordinate clamps that implement image-border replication
-    const int cx0 = max(0, -bx), cx1 = min(US_S - 1, W - 1 - bx);
-    const int cy0 = max(0, -by), cy1 = min(US_S - 1, H - 1 - by);
-    uint8_t(*in)[US_S + 2] = a;
-    uint8_t(*out)[US_S + 2] = b;
-    for (int pass = 0; pass < 6; ++pass) {
-        for (int i = threadIdx.x; i < US_S * US_S; i += blockDim.x) {
-            int ty = i / US_S, tx = i % US_S;
-            unsigned c = in[ty][tx], l, r;
-            if (pass < 3) {
-                l = in[ty][min(max(tx - 1, cx0), cx1)];
-                r = in[ty][min(max(tx + 1, cx0), cx1)];
-            } else {
-                l = in[min(max(ty - 1, cy0), cy1)][tx];
-                r = in[min(max(ty + 1, cy0), cy1)][tx];
-            }
-            out[ty][tx] = (uint8_t)((c * ww + (l + r) * fw + (1u << 23)) >> 24);
-        }
-        __syncthreads();
-        uint8_t(*t)[US_S + 2] = in; in = out; out = t;
-    }
-    for (int i = threadIdx.x; i < US_T * US_T; i += blockDim.x) {
-        int ty = i / US_T, tx = i % US_T;
-        int gy = by + US_H + ty, gx = bx + US_H + tx;
-        if (gy < H && gx < W) {
-            int s = orig[ty][tx], bl = in[ty + US_H][tx + US_H];
-            int d = s - bl, o = s;
-            if (abs(d) > threshold) o = min(max(s + d * percent / 100, 0), 255);
-            dst[(int64_t)gy * W + gx] = (uint8_t)o;
-        }
-    }
-}
-
-// Tiled variant used by pp_unsharp (k_unsharp above is kept as the plain restatement the tile kernel was checked against).
 // 128 x 32 output pixels per block, four pixels per thread in every phase:
 //   0. per-column / per-row CLAHE interpolation terms of the tile (they only depend on x or on y)
 //   1. tone LUT + CLAHE blend of the tile and its halo into shared memory: one aligned 32-bit load per four pixels and ONE
