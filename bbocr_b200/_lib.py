@@ -369,6 +369,22 @@ class Handle:
                                               out.ctypes.data_as(C.c_void_p), C.c_int(0), C.byref(oh), C.byref(ow)))
         return out
 
+    def thumbnail_dev(self, gray_ptr: int, H: int, W: int, max_dim: int, out_ptr: int | None = None):
+        """Device-resident bbocr_thumbnail_u8: with out_ptr None only the output size (oh, ow) is computed."""
+        oh, ow = C.c_int(), C.c_int()
+        self._check(self.L.bbocr_thumbnail_u8(self._h, C.c_void_p(gray_ptr), C.c_int(H), C.c_int(W), C.c_int(1), C.c_int(int(max_dim)),
+                                              C.c_void_p(out_ptr) if out_ptr else None, C.c_int(1), C.byref(oh), C.byref(ow)))
+        return oh.value, ow.value
+
+    def autocrop_rect_dev(self, ptr: int, H: int, W: int, channels: int, margin: int = 0):
+        """bbocr_autocrop_rect on a device-resident packed image (channels 1 or 3) -> (x0, y0, x1, y1) or None."""
+        rect = (C.c_int32 * 4)()
+        found = C.c_int()
+        self._check(self.L.bbocr_autocrop_rect(self._h, C.c_void_p(ptr), C.c_int(H), C.c_int(W), C.c_int(channels), C.c_int(W * channels),
+                                               C.c_int(1), C.c_int(int(margin)), rect, C.byref(found), None, None, None, C.c_int(0),
+                                               None, None))
+        return tuple(int(v) for v in rect) if found.value else None
+
     def autocrop_rect(self, bgr, margin: int = 0, debug: bool = False):
         """_auto_crop_text_region up to the slice (bbocr_autocrop_rect): (x0, y0, x1, y1) or None.  With debug=True also a
         dict with the reference's `mask`, `merged`, the external-contour boxes and the two Otsu thresholds."""

@@ -31,6 +31,14 @@ def ocr_input_image(reader, gray: np.ndarray, image_index=None) -> np.ndarray:
     return reader.handle.thumbnail(gray, m)
 
 
+def _torch_cuda_available() -> bool:
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:                                        # noqa: BLE001 -- torch is optional: the host-buffer path needs none
+        return False
+
+
 def central_edge_crop(img: np.ndarray, percent: float):
     """_central_edge_crop (:374-397) in memory: the centred view with `percent` removed from each edge, or None when the
     reference returns None (percent <= 0, or the rest would be under max(16 px, 20 %) of a side)."""
@@ -56,12 +64,54 @@ def auto_crop_text_region(reader, img: np.ndarray, margin: int):
     return img[y0:y1, x0:x1]
 
 
+def _extract_device_resident(reader, bgr, image_index, edge_crop_percent, crop_for_ocr, crop_margin):
+    """The same steps with the planes kept in HBM between them (one upload of the photo, results down): torch only owns the
+    device buffers (allocation, slicing, the gray -> 3-channel copy readtext's detector input needs); every pixel operation
+    is a libbbocr call on raw device pointers, so the bytes are those of the host-buffer path."""
+    import torch
+    h = reader.handle
+    dev = torch.device(reader.device)
+    src = torch.from_numpy(np.ascontiguousarray(bgr)).to(dev)
+    H, W = bgr.shape[:2]
+    p = pp_params(CURRENT, 0)
+    gray = torch.empty((int(H * p.scale), int(W * p.scale)), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize(dev)
+    with reader._lock:
+        h.preprocess_dev(src.data_ptr(), H, W, p, gray.data_ptr())
+        if edge_crop_percent > 0.0:
+            central = central_edge_crop(gray, edge_crop_percent)          # pure slicing: works on the tensor as on an array
+            if central is not None:
+                gray = central.contiguous()
+                torch.cuda.synchronize(dev)
+        if crop_for_ocr:
+            try:
+                rect = h.autocrop_rect_dev(gray.data_ptr(), gray.shape[0], gray.shape[1], 1, int(crop_margin))
+                if rect is not None:
+                    gray = gray[rect[1]:rect[3], rect[0]:rect[2]].contiguous()
+                    torch.cuda.synchronize(dev)
+            except Exception as e:                           # noqa: BLE001 -- :483-484
+                print(f"    Auto-cropping failed: {e}")
+        m = ocr_max_dim(image_index)
+        if max(gray.shape) > m:
+            oh, ow = h.thumbnail_dev(gray.data_ptr(), gray.shape[0], gray.shape[1], m)
+            small = torch.empty((oh, ow), dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize(dev)
+            h.thumbnail_dev(gray.data_ptr(), gray.shape[0], gray.shape[1], m, small.data_ptr())
+            gray = small
+        color = gray.unsqueeze(-1).expand(-1, -1, 3).contiguous()         # reformat_input: GRAY2BGR of a 2-D input
+        torch.cuda.synchronize(dev)
+        params, _keep = reader._params({})
+        raw = h.readtext_raw([(color.data_ptr(), gray.data_ptr(), gray.shape[0], gray.shape[1])], params, on_device=True)
+    return reader._format(raw[0][0])
+
+
 def extract_text_with_ocr(reader, image, *, use_preprocessing=True, image_index=None, return_results=False,
-                          edge_crop_percent=0.0, crop_for_ocr=False, crop_margin=16):
+                          edge_crop_percent=0.0, crop_for_ocr=False, crop_margin=16, device_resident=None):
     """extract_text_with_ocr (:413-561) in memory: [preprocess_for_book_cover] -> [edge crop] -> [auto crop] -> OCR-input
     cap -> readtext -> joined text.  `image`: path or BGR / gray uint8 array.  edge_crop_percent / crop_for_ocr /
     crop_margin are the extractor's attributes of the same names (:452-484; a failing crop keeps the current image, like
-    there).  Errors are swallowed into "" exactly like :529-531."""
+    there).  device_resident (default: whenever torch sees the GPU) keeps the planes in HBM between the steps instead of
+    bouncing them through host arrays; the results are identical.  Errors are swallowed into "" exactly like :529-531."""
     try:
         if isinstance(image, str):
             bgr = cv2.imread(image)
@@ -74,6 +124,12 @@ def extract_text_with_ocr(reader, image, *, use_preprocessing=True, image_index=
                 raise ValueError("preprocessing expects a BGR image")
             if bgr.dtype != np.uint8 or bgr.shape[2] != 3:
                 raise ValueError("expected an HxWx3 uint8 BGR image")
+            if device_resident is None:
+                device_resident = _torch_cuda_available()
+            if device_resident:
+                results = _extract_device_resident(reader, bgr, image_index, edge_crop_percent, crop_for_ocr, crop_margin)
+                text = " ".join([r[1] for r in results])
+                return (text, results) if return_results else text
             gray = reader.handle.preprocess(bgr, pp_params(CURRENT, 0))        # same handle (and device) as the reader
         else:
             gray = bgr if bgr.ndim == 2 else cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)

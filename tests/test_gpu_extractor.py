@@ -41,4 +41,13 @@ def test_extract_text_with_ocr_in_memory(gpu_reader, oracle_reader):
     assert np.array_equal(extractor.ocr_input_image(gpu_reader, pre, 0), cap)
     want = gpu_reader.readtext(cap, paragraph=False, batch_size=1, workers=0)
     assert results == want and text == " ".join(r[1] for r in want)
+    # host-buffer glue == device-resident glue, with and without the optional crops
+    for kw in ({}, {"edge_crop_percent": 3.0}, {"crop_for_ocr": True, "crop_margin": 16}, {"edge_crop_percent": 2.0, "crop_for_ocr": True}):
+        a = extractor.extract_text_with_ocr(gpu_reader, bgr, image_index=0, return_results=True, device_resident=False, **kw)
+        b = extractor.extract_text_with_ocr(gpu_reader, bgr, image_index=0, return_results=True, device_resident=True, **kw)
+        assert a == b and len(a[1]) > 0, kw
+    big = synth.phone_photo(3002)                            # 4032x3024 -> x1.5 -> cap 1600: the extractor's real geometry
+    a = extractor.extract_text_with_ocr(gpu_reader, big, image_index=0, return_results=True, device_resident=False)
+    b = extractor.extract_text_with_ocr(gpu_reader, big, image_index=0, return_results=True, device_resident=True)
+    assert a == b
     assert extractor.extract_text_with_ocr(gpu_reader, "/nonexistent.png") == ""      # errors become "" (:529-531)
