@@ -228,3 +228,28 @@ def test_detect_then_recognize_equals_readtext(gpu_reader):
     assert [r[0] for r in res] == [[[b[0], b[2]], [b[1], b[2]], [b[1], b[3]], [b[0], b[3]]] for b in boxes]
     single = [gpu_reader.recognize(page, [b], [])[0] for b in boxes]
     assert res == single                                    # batching crops never changes a crop's result
+
+
+def test_readtext_options_through_the_reader(gpu_reader):
+    """The remaining readtext keyword arguments BB-OCR's legacy callers may pass: paragraph mode, detail=0,
+    dict / json output, allowlist / blocklist, and the ones that are not implemented raise NotImplementedError."""
+    import json
+    from bbocr_b200.reader import get_paragraph
+    gpu_reader.set_precision("fp32")
+    img = synth.title_page(96, 800, 608)
+    std = gpu_reader.readtext(img)
+    assert len(std) > 3
+    assert gpu_reader.readtext(img, detail=0) == [t for _, t, _ in std]
+    assert gpu_reader.readtext(img, output_format="dict") == [{"boxes": b, "text": t, "confident": c} for b, t, c in std]
+    assert [json.loads(s)["text"] for s in gpu_reader.readtext(img, output_format="json")] == [t for _, t, _ in std]
+    para = gpu_reader.readtext(img, paragraph=True, x_ths=1.0, y_ths=0.5)
+    assert para == get_paragraph(std, 1.0, 0.5) and 0 < len(para) <= len(std)
+    assert gpu_reader.readtext(img, paragraph=True, detail=0) == [t for _, t in para]
+    digits = gpu_reader.readtext(img, allowlist="0123456789")
+    assert len(digits) == len(std) and all(set(t) <= set("0123456789") for _, t, _ in digits)
+    assert [b for b, _, _ in digits] == [b for b, _, _ in std]               # the detector does not depend on the lists
+    no_e = gpu_reader.readtext(img, blocklist="eE")
+    assert all("e" not in t and "E" not in t for _, t, _ in no_e)
+    for kw in ({"decoder": "beamsearch"}, {"rotation_info": [90]}, {"output_format": "free_merge"}):
+        with pytest.raises(NotImplementedError):
+            gpu_reader.readtext(img, **kw)
