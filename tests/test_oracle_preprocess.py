@@ -77,3 +77,20 @@ def test_step_strings():
     assert P.steps_list(P.CURRENT) == ["original", "grayscale", "resize(scale_factor=1.5)", "denoise(strength=3)",
                                        "increase_contrast(factor=1.9)", "increase_brightness(factor=1.2)",
                                        "clahe(clip_limit=2.5)", "sharpen(amount=0.3)"]
+
+
+def test_pillow_box_pass_closed_form():
+    """Closed form behind a cheaper device box pass: for UnsharpMask(radius=1) Pillow's pass
+    (c*ww + (l+r)*fw + 2^23) >> 24 with ww = 11184811 = 4 fw + 3 and 6 fw = 2^24 - 4 is round-half-up of (4c + l + r) / 6 except
+    that the exact ties t = 6k + 3 round DOWN unless 3c >= 4k + 2 (the weights sit a hair below 2/3 and 1/6); and
+    x // 6 == (x * 10923) >> 16 on the range, i.e. 11-bit arithmetic."""
+    edge_a, ww, fw = P._pil_box_params(1.0)
+    assert (edge_a, ww, fw) == (0, 11184811, 2796202) and ww == 4 * fw + 3 and 6 * fw == (1 << 24) - 4
+    c = np.arange(256, dtype=np.int64)[:, None]
+    s = np.arange(511, dtype=np.int64)[None, :]
+    pillow = (c * ww + s * fw + (1 << 23)) >> 24
+    t = 4 * c + s
+    tie_down = ((t % 6) == 3) & (3 * c < 4 * ((t - 3) // 6) + 2)
+    assert np.array_equal(pillow, (t + 3) // 6 - tie_down)
+    assert np.array_equal((t + 3) // 6, ((t + 3) * 10923) >> 16)
+    assert int(tie_down.sum()) > 0                              # the plain (t + 3) // 6 is NOT Pillow: 14.5 % of the triples differ
