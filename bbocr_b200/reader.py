@@ -23,6 +23,14 @@ SYMBOLS = "0123456789!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~ €"
 CHARACTERS = SYMBOLS + "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz"
 
 
+def _is_pil_image(obj) -> bool:
+    try:
+        from PIL import Image
+        return isinstance(obj, Image.Image)
+    except Exception:                                        # noqa: BLE001 -- Pillow is optional for the OCR stage
+        return False
+
+
 def reformat_input(image):
     """easyocr/utils.py::reformat_input -> (img HxWx3 as fed to the detector, img_cv_grey HxW).  Host-side decode;
     JPEG/PNG decoding stays on the host."""
@@ -54,6 +62,10 @@ def reformat_input(image):
             img_cv_grey = None
         else:
             raise ValueError("Invalid input type. Supporting format = string(file path or url), bytes, numpy array")
+    elif _is_pil_image(image):
+        # upstream handles PIL JPEG objects: np.array(image) (RGB) -> RGB2BGR for the detector, BGR2GRAY of that for the crops
+        img = cv2.cvtColor(np.array(image.convert("RGB")), cv2.COLOR_RGB2BGR)
+        img_cv_grey = None                                    # derived on the device with the BGR2GRAY fixed-point formula
     else:
         raise ValueError("Invalid input type. Supporting format = string(file path or url), bytes, numpy array")
     if img.dtype != np.uint8:

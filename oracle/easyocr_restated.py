@@ -198,6 +198,10 @@ def reformat_input(image):
             img_cv_grey = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
         else:
             raise ValueError("Invalid input type")
+    elif hasattr(image, "convert") and hasattr(image, "size"):          # PIL image (upstream: JpegImageFile)
+        image_array = np.array(image.convert("RGB"))
+        img = cv2.cvtColor(image_array, cv2.COLOR_RGB2BGR)
+        img_cv_grey = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
     else:
         raise ValueError("Invalid input type. Supporting format = string(file path or url), bytes, numpy array")
     return img, img_cv_grey

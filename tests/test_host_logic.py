@@ -194,3 +194,29 @@ def test_central_edge_crop_matches_the_reference_fixtures():
             else:
                 x0, y0, x1, y1 = (int(v) for v in want)
                 assert got.shape == (y1 - y0, x1 - x0, 3) and np.shares_memory(got, bgr) and np.array_equal(got, bgr[y0:y1, x0:x1])
+
+
+def test_reformat_input_kinds_match_the_oracle(tmp_path):
+    """easyocr/utils.py::reformat_input: every input kind gives the detector image and gray page of the restated upstream
+    (the product leaves the gray of 3-/4-channel arrays to the device: same fixed-point BGR2GRAY formula)."""
+    from PIL import Image
+    from bbocr_b200.reader import reformat_input
+    from oracle import preprocess_np as P
+    rng = np.random.default_rng(3)
+    rgb = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    png = str(tmp_path / "p.png")
+    cv2.imwrite(png, rgb)
+    kinds = [png, open(png, "rb").read(), rgb, rgb[:, :, 0].copy(), rgb[:, :, :1].copy(),
+             np.concatenate([rgb, rgb[:, :, :1]], axis=2), Image.fromarray(rgb)]
+    for k in kinds:
+        img, grey = reformat_input(k)
+        oimg, ogrey = E.reformat_input(k)
+        assert img.dtype == np.uint8 and np.array_equal(img, oimg)
+        if grey is None:
+            grey = P.bgr2gray(img)                           # what the device derives
+        assert np.array_equal(grey, ogrey)
+    for bad in (3.5, None, np.zeros((2, 2, 2), np.uint8), np.zeros((4, 4), np.float32)):
+        with pytest.raises(ValueError):
+            reformat_input(bad)
+    with pytest.raises(ValueError):
+        reformat_input(str(tmp_path / "missing.png"))
