@@ -123,7 +123,20 @@ def stage1_preprocess(h, peak_gbs, n_photos=16, reps=3):
         dt = (time.perf_counter() - t0) / n_photos
         best = dt if best is None or dt < best else best
     gbs = 12.0 * H * W / best / 1e9
-    return {"workload": f"{n_photos} synthetic 4032x3024 phone photos resident in HBM (BASELINE config[2]), reference chain "
+    cpu = None
+    try:                                                      # the CPU arm of the same chain: the reference's own cv2 + Pillow calls
+        import cv2
+        from oracle import preprocess_cv as CV
+        host = base[0].cpu().numpy()
+        CV.preprocess_for_book_cover_cv(host[:756, :1008].copy())          # first-use costs
+        t0 = time.perf_counter()
+        CV.preprocess_for_book_cover_cv(host)
+        dt = time.perf_counter() - t0
+        cpu = {"ms_per_photo": dt * 1e3, "photos_per_s": 1.0 / dt, "cores": cv2.getNumThreads(), "kind": "reference",
+               "sample": "1 of the photos, the reference chain's own OpenCV + Pillow calls (oracle/preprocess_cv.py; Pillow steps are single-threaded)"}
+    except Exception as e:                                    # noqa: BLE001 -- a reported baseline must never break the bench line
+        cpu = {"unavailable": str(e)[:200]}
+    return {"cpu_baseline": cpu, "workload": f"{n_photos} synthetic 4032x3024 phone photos resident in HBM (BASELINE config[2]), reference chain "
                         "gray -> x1.5 cubic -> Gaussian -> contrast -> brightness -> CLAHE -> unsharp, bit-exact (T1)",
             "photos_per_s": 1.0 / best, "ms_per_photo": best * 1e3, "bound": "hbm", "achieved": gbs, "peak": peak_gbs,
             "unit": "GB/s", "frac": gbs / peak_gbs, "algorithmic_bytes_per_photo": 12 * H * W,

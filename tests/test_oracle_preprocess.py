@@ -94,3 +94,19 @@ def test_pillow_box_pass_closed_form():
     assert np.array_equal(pillow, (t + 3) // 6 - tie_down)
     assert np.array_equal((t + 3) // 6, ((t + 3) * 10923) >> 16)
     assert int(tie_down.sum()) > 0                              # the plain (t + 3) // 6 is NOT Pillow: 14.5 % of the triples differ
+
+
+def test_library_call_chain_equals_the_numpy_oracle():
+    """oracle/preprocess_cv.py (the reference's own cv2 + Pillow calls, used to time the CPU arm of stage 1) gives the bytes
+    of the NumPy restatement when OpenCV's IPP paths are off (mode T1), and stays within the documented T1/T2 gap with IPP on."""
+    from oracle import preprocess_cv as CV
+    from bbocr_b200 import synth
+    bgr = synth.phone_photo(3009, 640, 480)
+    want = P.preprocess_chain(bgr, P.CURRENT, "T1")
+    try:
+        cv2.ipp.setUseIPP(False)
+        assert np.array_equal(CV.preprocess_for_book_cover_cv(bgr), want)
+    finally:
+        cv2.ipp.setUseIPP(True)
+    got = CV.preprocess_for_book_cover_cv(bgr)
+    assert got.shape == want.shape and np.abs(got.astype(int) - want.astype(int)).max() <= 12
