@@ -179,11 +179,15 @@ int bbocr_load_crnn(bbocr_handle* h, const bbocr_tensor* t, int n) {
 }
 int bbocr_set_precision(bbocr_handle* h, int prec) {
     return guarded(h, [&] {
-        ARG_CHECK(prec == BBOCR_PREC_FP32 || prec == BBOCR_PREC_BF16, "unknown precision %d", prec);
-        h->precision = prec;
+        ARG_CHECK(prec == BBOCR_PREC_FP32 || prec == BBOCR_PREC_BF16 || prec == BBOCR_PREC_BF16X3, "unknown precision %d", prec);
+        h->precision = prec == BBOCR_PREC_FP32 ? BBOCR_PREC_FP32 : BBOCR_PREC_BF16;      // kernel family: CUDA cores / tcgen05
+        h->det_split = prec == BBOCR_PREC_BF16X3;
     });
 }
-int bbocr_get_precision(const bbocr_handle* h) { return h ? h->precision : BBOCR_E_ARG; }
+int bbocr_get_precision(const bbocr_handle* h) {
+    if (!h) return BBOCR_E_ARG;
+    return h->det_split ? BBOCR_PREC_BF16X3 : h->precision;
+}
 
 // ---- preprocessing ---------------------------------------------------------------------------------------------------
 int bbocr_preprocess_launches_per_image(void) { return preprocess_launches_per_image(); }

@@ -102,7 +102,7 @@ struct ConvW {
     int cout_pad = 0;                 // cout rounded up to 16 (BF16 weight rows)
     float* w_f32 = nullptr;           // [kh*kw][cin][cout]          (FP32 path; cout contiguous)
     __nv_bfloat16* w_bf16 = nullptr;  // [kh*kw][cout_pad][cin]      (tcgen05 path; K-major rows)
-    __nv_bfloat16* w_split = nullptr; // [kh*kw][cout_pad][3*cin] = [w_hi | w_hi | w_lo]  (split-precision recogniser)
+    __nv_bfloat16* w_split = nullptr; // [kh*kw][cout_pad][2*cin] = [w_hi | w_lo]  (split precision: w = bf16 hi + bf16 lo)
     float* scale = nullptr;           // [cout_pad]
     float* bias = nullptr;            // [cout_pad]
 };

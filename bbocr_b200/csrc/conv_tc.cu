@@ -25,7 +25,8 @@ namespace {
 constexpr int BM = 128;
 
 struct TcParams {
-    int C1, C2, C3;             // channels of the input segments (C2, C3 may be 0); split precision: [x_hi | x_lo | x_hi]
+    int C1, C2;                 // channels of the two concatenated inputs (C2 may be 0)
+    int w_lo_off;               // PAIR: K offset of the w_lo half inside a weight row [w_hi (cin) | w_lo (cin)]
     int taps_w, taps;           // kw, kh*kw
     int pad, dil;
     int TW, TH, tiles_x, tiles_y;
@@ -191,10 +192,16 @@ __device__ __forceinline__ void store_split(void* hi_base, void* lo_base, int64_
     store16(reinterpret_cast<__nv_bfloat16*>(lo_base) + off, lo, nbase, cout);
 }
 
-template <int BK>
+// PAIR = 1: split-precision operands.  A pipeline stage holds the hi AND lo halves of the activation tile and of the
+// weight tile (four TMA boxes), and every K = 16 step issues three MMAs into the same accumulator:
+//     x_hi * w_hi  +  x_lo * w_hi  +  x_hi * w_lo        (the dropped x_lo * w_lo term is 2^-16-class)
+// so the operand stream through L2 -> SM is 2x the single-precision stream for 3x the tensor work.
+// Maps: PAIR = 0: tmA1 = in1, tmA2 = in2 (channel concat).  PAIR = 1: tmA1/tmA2 = in1 hi/lo, tmA3/tmA4 = in2 hi/lo.
+template <int BK, int PAIR>
 __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtensorMap tmA1,
                                                  const __grid_constant__ CUtensorMap tmA2,
                                                  const __grid_constant__ CUtensorMap tmA3,
+                                                 const __grid_constant__ CUtensorMap tmA4,
                                                  const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
@@ -202,10 +209,10 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int A_BYTES = BM * BK * 2;
     const int B_BYTES = p.BN * BK * 2;
-    const int STAGE_BYTES = A_BYTES + B_BYTES;
+    const int STAGE_BYTES = (PAIR ? 2 : 1) * (A_BYTES + B_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kb1 = p.C1 / BK, kb2 = p.C2 / BK, kb3 = p.C3 / BK;
-    const int kiters = p.taps * (kb1 + kb2 + kb3);
+    const int kb1 = p.C1 / BK, kb2 = p.C2 / BK;
+    const int kiters = p.taps * (kb1 + kb2);
     uint32_t ncols = 32;
     while ((int)ncols < 2 * p.BN) ncols <<= 1;
 
@@ -236,19 +243,34 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             for (int tap = 0; tap < p.taps; ++tap) {
                 const int ky = tap / p.taps_w, kx = tap - ky * p.taps_w;
                 const int cx = tc.x0 - p.pad + kx * p.dil, cy = tc.y0 - p.pad + ky * p.dil;
-                for (int kb = 0; kb < kb1 + kb2 + kb3; ++kb, ++it) {
+                for (int kb = 0; kb < kb1 + kb2; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
                     mbar_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
-                    const int seg = kb < kb1 ? 0 : (kb < kb1 + kb2 ? 1 : 2);
-                    const CUtensorMap* tma = seg == 0 ? &tmA1 : (seg == 1 ? &tmA2 : &tmA3);
-                    const int c0 = (seg == 0 ? kb : (seg == 1 ? kb - kb1 : kb - kb1 - kb2)) * BK;
-                    if (p.flat) tma_load_2d(sa, tma, &full_bar[s], c0, (int)tc.m0);
-                    else tma_load_4d(sa, tma, &full_bar[s], c0, cx, cy, tc.img);
-                    tma_load_3d(sb, &tmB, &full_bar[s], kb * BK, tc.n0, tap);
+                    const int seg = kb < kb1 ? 0 : 1;
+                    const int c0 = (seg == 0 ? kb : kb - kb1) * BK;
+                    if (PAIR) {
+                        const CUtensorMap* th = seg == 0 ? &tmA1 : &tmA3;
+                        const CUtensorMap* tl = seg == 0 ? &tmA2 : &tmA4;
+                        uint8_t* sb = sa + 2 * A_BYTES;
+                        if (p.flat) {
+                            tma_load_2d(sa, th, &full_bar[s], c0, (int)tc.m0);
+                            tma_load_2d(sa + A_BYTES, tl, &full_bar[s], c0, (int)tc.m0);
+                        } else {
+                            tma_load_4d(sa, th, &full_bar[s], c0, cx, cy, tc.img);
+                            tma_load_4d(sa + A_BYTES, tl, &full_bar[s], c0, cx, cy, tc.img);
+                        }
+                        tma_load_3d(sb, &tmB, &full_bar[s], kb * BK, tc.n0, tap);
+                        tma_load_3d(sb + B_BYTES, &tmB, &full_bar[s], p.w_lo_off + kb * BK, tc.n0, tap);
+                    } else {
+                        const CUtensorMap* tma = seg == 0 ? &tmA1 : &tmA2;
+                        uint8_t* sb = sa + A_BYTES;
+                        if (p.flat) tma_load_2d(sa, tma, &full_bar[s], c0, (int)tc.m0);
+                        else tma_load_4d(sa, tma, &full_bar[s], c0, cx, cy, tc.img);
+                        tma_load_3d(sb, &tmB, &full_bar[s], kb * BK, tc.n0, tap);
+                    }
                 }
             }
         }
@@ -269,10 +291,21 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                 mbar_wait(&full_bar[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                const uint64_t adesc = umma_desc<BK>(sa), bdesc = umma_desc<BK>(sa + A_BYTES);
+                if (PAIR) {
+                    const uint64_t ahi = umma_desc<BK>(sa), alo = umma_desc<BK>(sa + A_BYTES);
+                    const uint64_t bhi = umma_desc<BK>(sa + 2 * A_BYTES), blo = umma_desc<BK>(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < BK / 16; ++kk)      // +32 bytes (2 x 16 B units) per UMMA_K = 16 step inside the swizzle atom
-                    umma_bf16(tmem_acc, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        umma_bf16(tmem_acc, ahi + 2 * kk, bhi + 2 * kk, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+                        umma_bf16(tmem_acc, alo + 2 * kk, bhi + 2 * kk, idesc, 1u);
+                        umma_bf16(tmem_acc, ahi + 2 * kk, blo + 2 * kk, idesc, 1u);
+                    }
+                } else {
+                    const uint64_t adesc = umma_desc<BK>(sa), bdesc = umma_desc<BK>(sa + A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk)      // +32 bytes (2 x 16 B units) per UMMA_K = 16 step inside the swizzle atom
+                        umma_bf16(tmem_acc, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+                }
                 umma_commit(&empty_bar[s]);
             }
             umma_commit(&tfull_bar[as]);
@@ -409,13 +442,14 @@ bool conv_tc_supported(const ConvW& cw, const Act& in1, const Act& in2) {
 // out.p may be null together with a pooled output when only the pooled tensor is needed.
 void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, const Act& in2, Act& out, int flags,
                      Act* pooled, const uint8_t* colmask) {
-    const int bk = pick_bk(cw, in1, in2);
+    int bk = pick_bk(cw, in1, in2);
     const bool split_in = in1.lo != nullptr;
     if (split_in) {
-        ARG_CHECK(in2.C == 0 && cw.w_split, "split-precision convolution needs split weights and a single input");
+        ARG_CHECK(cw.w_split && (in2.C == 0 || in2.lo), "split-precision convolution needs split weights and split inputs");
     }
     TcParams p;
-    p.C1 = in1.C; p.C2 = split_in ? in1.C : in2.C; p.C3 = split_in ? in1.C : 0;
+    p.C1 = in1.C; p.C2 = in2.C;
+    p.w_lo_off = cw.cin;
     p.split_out = out.lo != nullptr ? 1 : 0;
     p.out_lo = out.lo;
     p.out2_lo = nullptr;
@@ -466,10 +500,13 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
         p.m_tiles = p.tiles_x * p.tiles_y * out.N;
     }
     p.total_tiles = p.m_tiles * p.n_tiles;
-    const int stage_bytes = BM * bk * 2 + p.BN * bk * 2;
     static const int smem_budget_kb = getenv("BBOCR_TC_SMEM_KB") ? atoi(getenv("BBOCR_TC_SMEM_KB")) : 100;
     static const int ctas_per_sm = getenv("BBOCR_TC_CTAS") ? atoi(getenv("BBOCR_TC_CTAS")) : 2;
-    p.stages = std::min(8, std::max(2, ((p.BN > 128 ? 200 : smem_budget_kb) * 1024) / stage_bytes));
+    const int budget = (p.BN > 128 ? 200 : smem_budget_kb) * 1024;
+    // a paired (hi + lo) stage is twice as large: fall back to 32-channel k-blocks when fewer than three 64-channel stages fit
+    if (split_in && bk == 64 && budget / (2 * (BM * 64 * 2 + p.BN * 64 * 2)) < 3) bk = 32;
+    const int stage_bytes = (split_in ? 2 : 1) * (BM * bk * 2 + p.BN * bk * 2);
+    p.stages = std::min(8, std::max(2, budget / stage_bytes));
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
 
     auto act_map = [&](const Act& a) {
@@ -486,13 +523,19 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     };
     CUtensorMap mA1 = act_map(in1);
     CUtensorMap mA2 = in2.C > 0 ? act_map(in2) : mA1;
-    CUtensorMap mA3 = mA1;
+    CUtensorMap mA3 = mA1, mA4 = mA1;
     if (split_in) {
         Act lo = in1;
         lo.p = in1.lo;
         mA2 = act_map(lo);
+        if (in2.C > 0) {
+            mA3 = act_map(in2);
+            Act lo2 = in2;
+            lo2.p = in2.lo;
+            mA4 = act_map(lo2);
+        }
     }
-    const uint64_t wcin = split_in ? (uint64_t)cw.cin * 3 : (uint64_t)cw.cin;
+    const uint64_t wcin = split_in ? (uint64_t)cw.cin * 2 : (uint64_t)cw.cin;
     uint64_t wd[3] = {wcin, (uint64_t)cw.cout_pad, (uint64_t)p.taps};
     uint64_t ws[2] = {wcin * 2, (uint64_t)cw.cout_pad * wcin * 2};
     uint32_t wb[3] = {(uint32_t)bk, (uint32_t)p.BN, 1};
@@ -501,12 +544,19 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     // persistent grid: a multiple of the SM count (148 on B200), never more CTAs than tiles
     const unsigned grid = (unsigned)std::min<int64_t>(p.total_tiles, (int64_t)h->sm_count * (p.BN > 128 ? 1 : ctas_per_sm));
     if (!h->tc_attr_set) {          // per device (one handle = one device)
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         h->tc_attr_set = true;
     }
-    if (bk == 64) k_conv_tc<64><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mB, p);
-    else k_conv_tc<32><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mB, p);
+    if (split_in) {
+        if (bk == 64) k_conv_tc<64, 1><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        else k_conv_tc<32, 1><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+    } else {
+        if (bk == 64) k_conv_tc<64, 0><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        else k_conv_tc<32, 0><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+    }
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 }

@@ -97,6 +97,54 @@ __global__ void __launch_bounds__(128) k_im2col_rgb(const uint8_t* __restrict__ 
     o[3] = make_uint4(w[12], w[13], w[14], w[15]);
 }
 
+// bf16x3 mode: the same gather, every normalised value as bf16 hi + bf16 lo (two [px][32] tensors)
+__global__ void __launch_bounds__(128) k_im2col_rgb_split(const uint8_t* __restrict__ img, int th, int tw, __nv_bfloat16* __restrict__ ohi,
+                                                          __nv_bfloat16* __restrict__ olo, int H32, int W32, float m0, float m1, float m2,
+                                                          float s0, float s1, float s2) {
+    __shared__ uint32_t lut[3][256];          // hi | lo << 16
+    {
+        const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+            const int c = i >> 8, v = i & 255;
+            const float f = __fdiv_rn(__fsub_rn((float)v, mean[c]), sd[c]);
+            const __nv_bfloat16 hb = __float2bfloat16_rn(f);
+            const __nv_bfloat16 lb = __float2bfloat16_rn(f - __bfloat162float(hb));
+            lut[c][v] = (uint32_t)*reinterpret_cast<const uint16_t*>(&hb) | ((uint32_t)*reinterpret_cast<const uint16_t*>(&lb) << 16);
+        }
+    }
+    __syncthreads();
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W32) return;
+    uint32_t v[32];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+        const bool in_canvas = yy >= 0 && yy < H32 && xx >= 0 && xx < W32;
+        const bool in_img = in_canvas && yy < th && xx < tw;
+        const uint8_t* p = img + ((int64_t)yy * tw + xx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int px = in_img ? (int)__ldg(p + c) : 0;
+            v[t * 3 + c] = in_canvas ? lut[c][px] : 0u;
+        }
+    }
+#pragma unroll
+    for (int i = 27; i < 32; ++i) v[i] = 0;
+    uint32_t wh[16], wl[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        wh[i] = (v[2 * i] & 0xffffu) | (v[2 * i + 1] << 16);
+        wl[i] = (v[2 * i] >> 16) | (v[2 * i + 1] & 0xffff0000u);
+    }
+    uint4* oh = reinterpret_cast<uint4*>(ohi + ((int64_t)y * W32 + x) * 32);
+    uint4* ol = reinterpret_cast<uint4*>(olo + ((int64_t)y * W32 + x) * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        oh[q] = make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3]);
+        ol[q] = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+    }
+}
+
 extern thread_local int g_conv_scope;
 
 void craft_forward_dev(Handle* h, cudaStream_t st, const uint8_t* img_dev, const CanvasGeom& g, float* text, float* link) {
@@ -116,8 +164,10 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     const float m0 = (float)(0.485 * 255.0), m1 = (float)(0.456 * 255.0), m2 = (float)(0.406 * 255.0);
     const float s0 = (float)(0.229 * 255.0), s1 = (float)(0.224 * 255.0), s2 = (float)(0.225 * 255.0);
     const bool tc_first = h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv;
+    const bool split = tc_first && h->det_split;        // bf16x3: every activation tensor is a hi/lo pair
     const size_t canvas_px_bytes = tc_first ? 64 : 16;
-    DevBuf canvas((size_t)nimg * H * W * canvas_px_bytes, st), resized;
+    const size_t canvas_plane = (((size_t)nimg * H * W * canvas_px_bytes) + 255) & ~(size_t)255;
+    DevBuf canvas(canvas_plane * (split ? 2 : 1), st), resized;
     const bool need_resize = g.th != g.H || g.tw != g.W;
     if (need_resize) resized.alloc((size_t)g.th * g.tw * 3, st);
     for (int i = 0; i < nimg; ++i) {
@@ -127,7 +177,10 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
             src = resized.as<uint8_t>();
         }
         uint8_t* dst = canvas.as<uint8_t>() + (size_t)i * H * W * canvas_px_bytes;
-        if (tc_first)
+        if (split)
+            k_im2col_rgb_split<<<dim3(cdiv(W, 128), H), 128, 0, st>>>(src, g.th, g.tw, reinterpret_cast<__nv_bfloat16*>(dst),
+                                                                      reinterpret_cast<__nv_bfloat16*>(dst + canvas_plane), H, W, m0, m1, m2, s0, s1, s2);
+        else if (tc_first)
             k_im2col_rgb<<<dim3(cdiv(W, 128), H), 128, 0, st>>>(src, g.th, g.tw, reinterpret_cast<__nv_bfloat16*>(dst), H, W, m0, m1, m2, s0, s1, s2);
         else
             k_canvas<<<dim3(cdiv(W, 256), H), 256, 0, st>>>(src, g.th, g.tw, reinterpret_cast<float*>(dst), H, W, m0, m1, m2, s0, s1, s2);
@@ -136,27 +189,26 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     CUDA_CHECK(cudaGetLastError());
 
     const Act none;
+    auto alloc = [&](DevBuf& buf, int n, int hh, int ww, int c) {
+        return split ? act_alloc_split(h, st, buf, n, hh, ww, c) : act_alloc(h, st, buf, n, hh, ww, c);
+    };
     auto conv = [&](const ConvW& cw, const Act& a, const Act& b, DevBuf& buf, int flags) {
-        Act o = act_alloc(h, st, buf, a.N, a.H + 2 * cw.pad - cw.dil * (cw.kh - 1), a.W + 2 * cw.pad - cw.dil * (cw.kw - 1), cw.cout);
+        Act o = alloc(buf, a.N, a.H + 2 * cw.pad - cw.dil * (cw.kh - 1), a.W + 2 * cw.pad - cw.dil * (cw.kw - 1), cw.cout);
         conv_forward(h, st, cw, a, b, o, flags);
         return o;
     };
-    auto pool2 = [&](const Act& a, DevBuf& buf) {
-        Act o = act_alloc(h, st, buf, a.N, a.H / 2, a.W / 2, a.C);
-        maxpool(h, st, a, o, 2, 2, 2, 2, 0, 0);
-        return o;
-    };
     auto up2 = [&](const Act& a, DevBuf& buf) {
-        Act o = act_alloc(h, st, buf, a.N, a.H * 2, a.W * 2, a.C);
-        upsample2x(h, st, a, o);
+        Act o = alloc(buf, a.N, a.H * 2, a.W * 2, a.C);
+        if (split) upsample2x_split(h, st, a, o);
+        else upsample2x(h, st, a, o);
         return o;
     };
     // conv + ReLU + MaxPool2d(2,2) in one launch; keep_full also materialises the un-pooled tensor (skip connection)
     auto conv_pool = [&](const ConvW& cw, const Act& a, DevBuf* full_buf, DevBuf& pool_buf, Act* full_out) {
         Act full;
         full.N = a.N; full.H = a.H; full.W = a.W; full.C = cw.cout; full.p = nullptr;
-        if (full_buf) full = act_alloc(h, st, *full_buf, a.N, a.H, a.W, cw.cout);
-        Act pooled = act_alloc(h, st, pool_buf, a.N, a.H / 2, a.W / 2, cw.cout);
+        if (full_buf) full = alloc(*full_buf, a.N, a.H, a.W, cw.cout);
+        Act pooled = alloc(pool_buf, a.N, a.H / 2, a.W / 2, cw.cout);
         conv_forward(h, st, cw, a, none, full, CONV_RELU | CONV_POOL22, &pooled);
         if (full_out) *full_out = full;
         return pooled;
@@ -164,10 +216,11 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     const int R = CONV_RELU;
     DevBuf b0, b1, b_r22, b_r32, b_r43, b_r53;
     // slice1
-    Act a = act_alloc(h, st, b0, nimg, H, W, 64);
+    Act a = alloc(b0, nimg, H, W, 64);
     if (tc_first) {
         Act x32;
         x32.N = nimg; x32.H = H; x32.W = W; x32.C = 32; x32.p = canvas.p;
+        if (split) x32.lo = canvas.as<uint8_t>() + canvas_plane;
         conv_forward(h, st, w.c1_1_tc, x32, none, a, R);
     } else {
         conv_first(h, st, w.c1_1, canvas.as<float>(), nimg, H, W, 4, a, R);
@@ -190,8 +243,9 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     a = conv(w.c5_1, a, none, b0, R);
     Act r53 = conv(w.c5_2, a, none, b_r53, 0);        // followed by MaxPool, not ReLU: stays the raw BN output
     // slice5
-    a = act_alloc(h, st, b0, nimg, r53.H, r53.W, 512);
-    maxpool(h, st, r53, a, 3, 3, 1, 1, 1, 1);
+    a = alloc(b0, nimg, r53.H, r53.W, 512);
+    if (split) maxpool_split(h, st, r53, a, 3, 3, 1, 1, 1, 1);
+    else maxpool(h, st, r53, a, 3, 3, 1, 1, 1, 1);
     a = conv(w.fc6, a, none, b1, 0);
     Act fc7 = conv(w.fc7, a, none, b0, 0);
     // decoder
@@ -212,7 +266,7 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     b_r22.release();
     a = conv(w.cls0, a, none, b0, R);
     a = conv(w.cls1, a, none, b1, R);
-    if (h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && conv_res_cls_tail_supported(w.cls2, w.cls3, w.cls4, a)) {
+    if (h->precision == BBOCR_PREC_BF16 && !split && !h->force_generic_conv && conv_res_cls_tail_supported(w.cls2, w.cls3, w.cls4, a)) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;            // counted with the detector convolutions (bench.py roofline)
         if (h->conv_timing) { CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventRecord(e0, st)); }
         conv_res_cls_tail(h, st, w.cls2, w.cls3, w.cls4, a, text, link);      // conv_cls[4] + the 1x1 tail in one launch
@@ -223,6 +277,12 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
             h->conv_flops += 2.0 * (double)a.N * a.H * a.W * (16.0 * 32 * 9 + 16 * 16 + 16 * 2);
             h->conv_launches += 1;
         }
+        return;
+    }
+    if (split) {                                       // conv_cls[4] to an FP32 tensor, then the FP32 1x1 tail
+        Act o = act_alloc(h, st, b0, a.N, a.H, a.W, w.cls2.cout, true);
+        conv_forward(h, st, w.cls2, a, none, o, R | CONV_OUT_F32);
+        cls_tail_f32(h, st, w.cls3, w.cls4, o, text, link);
         return;
     }
     a = conv(w.cls2, a, none, b0, R);

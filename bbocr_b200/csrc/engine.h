@@ -33,6 +33,7 @@ struct Handle {
     int device = 0;
     int sm_count = 148;
     int precision = BBOCR_PREC_FP32;
+    bool det_split = false;         // BBOCR_PREC_BF16X3: the detector runs in split precision as well (3 x bf16 products ~ FP32)
     std::string err;
     std::mutex mu;                  // one public call at a time per handle (Reader is shared between threads:
                                     // batch_processor_enhanced.py:215-216 + enhanced_extractor.py:97-98)
@@ -110,6 +111,10 @@ void maxpool(Handle*, cudaStream_t, const Act& in, Act& out, int kh, int kw, int
 void upsample2x(Handle*, cudaStream_t, const Act& in, Act& out);          // bilinear, align_corners=False
 void mean_rows(Handle*, cudaStream_t, const Act& in, Act& out);           // AdaptiveAvgPool2d((None,1)) after permute
 void cls_tail(Handle*, cudaStream_t, const ConvW& c3, const ConvW& c4, const Act& in, float* text, float* link);
+// split-precision (hi + lo bf16) glue of the detector in bf16x3 mode
+void maxpool_split(Handle*, cudaStream_t, const Act& in, Act& out, int kh, int kw, int sh, int sw, int ph, int pw);
+void upsample2x_split(Handle*, cudaStream_t, const Act& in, Act& out);
+void cls_tail_f32(Handle*, cudaStream_t, const ConvW& c3, const ConvW& c4, const Act& in, float* text, float* link);
 
 Act act_alloc_split(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C);
 void maxpool_f32_to_split(Handle*, cudaStream_t, const Act& in, Act& out, int kh, int kw, const uint8_t* colmask = nullptr);

@@ -171,16 +171,19 @@ void conv_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1, c
     } else {
         DevBuf tmp;
         Act full = out;
+        const bool split = pooled && pooled->lo;                        // split-precision tensors (bf16x3 detector)
         if (pooled && !full.p) {                                        // caller only wants the pooled tensor
             bool f32 = (flags & CONV_OUT_F32) != 0;
-            full = act_alloc(h, st, tmp, out.N, out.H, out.W, out.C, f32);
+            full = split ? act_alloc_split(h, st, tmp, out.N, out.H, out.W, out.C) : act_alloc(h, st, tmp, out.N, out.H, out.W, out.C, f32);
         }
         ARG_CHECK(!colmask, "conv: column mask with an unfused pool is not supported");
+        ARG_CHECK(tc || !in1.lo, "conv: split-precision tensors need the tcgen05 path");
         if (tc) conv_tc_forward(h, st, cw, in1, in2, full, flags, nullptr);
         else conv_generic(h, st, cw, in1, in2, full, flags);
         if (pooled) {
-            if (flags & CONV_POOL22) maxpool(h, st, full, *pooled, 2, 2, 2, 2, 0, 0);
-            else maxpool(h, st, full, *pooled, 2, 1, 2, 1, 0, 0);
+            const int kh = 2, kw = (flags & CONV_POOL22) ? 2 : 1;
+            if (split) maxpool_split(h, st, full, *pooled, kh, kw, kh, kw, 0, 0);
+            else maxpool(h, st, full, *pooled, kh, kw, kh, kw, 0, 0);
         }
     }
     if (timed) {
@@ -686,6 +689,107 @@ void mean_rows_split_ragged(Handle* h, cudaStream_t st, const Act& in, const Act
     if (n_crops == 0) return;
     k_mean_rows_split_ragged<<<dim3(cdiv(t_max * in.C, 256), n_crops), 256, 0, st>>>(
         (const __nv_bfloat16*)in.p, (const __nv_bfloat16*)in.lo, (__nv_bfloat16*)out.p, (__nv_bfloat16*)out.lo, in.H, in.W, in.C, meta_dev);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ---- split-precision glue of the detector (precision mode bf16x3): values are hi + lo, evaluated in FP32 and re-split --
+__device__ __forceinline__ void load4_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float v[4]) {
+    float a[4], b[4];
+    load4(hi, a);
+    load4(lo, b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = a[j] + b[j];
+}
+
+__global__ void k_maxpool_split(const __nv_bfloat16* __restrict__ ihi, const __nv_bfloat16* __restrict__ ilo,
+                                __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo, int N, int H, int W, int C, int OH,
+                                int OW, int kh, int kw, int sh, int sw, int ph, int pw) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int C4 = C >> 2;
+    int64_t total = (int64_t)N * OH * OW * C4;
+    if (idx >= total) return;
+    int c = (int)(idx % C4) * 4;
+    int64_t p = idx / C4;
+    int ox = (int)(p % OW);
+    p /= OW;
+    int oy = (int)(p % OH);
+    int n = (int)(p / OH);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int ky = 0; ky < kh; ++ky) {
+        int iy = oy * sh - ph + ky;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < kw; ++kx) {
+            int ix = ox * sw - pw + kx;
+            if (ix < 0 || ix >= W) continue;
+            float v[4];
+            const int64_t i = (((int64_t)n * H + iy) * W + ix) * C + c;
+            load4_split(ihi + i, ilo + i, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], v[j]);
+        }
+    }
+    const int64_t o = (((int64_t)n * OH + oy) * OW + ox) * C + c;
+    split_store4(ohi + o, olo + o, best);
+}
+
+void maxpool_split(Handle* h, cudaStream_t st, const Act& in, Act& out, int kh, int kw, int sh, int sw, int ph, int pw) {
+    ARG_CHECK(in.C % 4 == 0 && out.C == in.C && in.lo && out.lo, "maxpool_split: channels / split tensors");
+    int64_t total = (int64_t)out.N * out.H * out.W * (in.C / 4);
+    k_maxpool_split<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>((const __nv_bfloat16*)in.p, (const __nv_bfloat16*)in.lo, (__nv_bfloat16*)out.p,
+                                                                  (__nv_bfloat16*)out.lo, in.N, in.H, in.W, in.C, out.H, out.W, kh, kw, sh, sw, ph, pw);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// F.interpolate(bilinear, align_corners=False) x2 on a split tensor: same expression as k_upsample on hi + lo
+__global__ void k_upsample_split(const __nv_bfloat16* __restrict__ ihi, const __nv_bfloat16* __restrict__ ilo,
+                                 __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo, int N, int H, int W, int C, int OH,
+                                 int OW, float sy, float sx) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int C4 = C >> 2;
+    int64_t total = (int64_t)N * OH * OW * C4;
+    if (idx >= total) return;
+    int c = (int)(idx % C4) * 4;
+    int64_t p = idx / C4;
+    int ox = (int)(p % OW);
+    p /= OW;
+    int oy = (int)(p % OH);
+    int n = (int)(p / OH);
+    float fy = fmaxf(sy * ((float)oy + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)ox + 0.5f) - 0.5f, 0.f);
+    int y0 = (int)fy, x0 = (int)fx;
+    int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    float a[4], b[4], cc[4], d[4], o[4];
+    const int64_t base = (int64_t)n * H * W * C + c;
+    const int64_t i00 = base + ((int64_t)y0 * W + x0) * C, i01 = base + ((int64_t)y0 * W + x1) * C;
+    const int64_t i10 = base + ((int64_t)y1 * W + x0) * C, i11 = base + ((int64_t)y1 * W + x1) * C;
+    load4_split(ihi + i00, ilo + i00, a);
+    load4_split(ihi + i01, ilo + i01, b);
+    load4_split(ihi + i10, ilo + i10, cc);
+    load4_split(ihi + i11, ilo + i11, d);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = hy * (hx * a[j] + lx * b[j]) + ly * (hx * cc[j] + lx * d[j]);
+    const int64_t oo = (((int64_t)n * OH + oy) * OW + ox) * C + c;
+    split_store4(ohi + oo, olo + oo, o);
+}
+
+void upsample2x_split(Handle* h, cudaStream_t st, const Act& in, Act& out) {
+    ARG_CHECK(in.C % 4 == 0 && out.C == in.C && in.lo && out.lo, "upsample_split: channels / split tensors");
+    int64_t total = (int64_t)out.N * out.H * out.W * (in.C / 4);
+    float sy = (float)in.H / (float)out.H, sx = (float)in.W / (float)out.W;
+    k_upsample_split<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>((const __nv_bfloat16*)in.p, (const __nv_bfloat16*)in.lo, (__nv_bfloat16*)out.p,
+                                                                   (__nv_bfloat16*)out.lo, in.N, in.H, in.W, in.C, out.H, out.W, sy, sx);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// conv_cls tail on an FP32 16-channel tensor regardless of the precision mode (bf16x3 detector)
+void cls_tail_f32(Handle* h, cudaStream_t st, const ConvW& c3, const ConvW& c4, const Act& in, float* text, float* link) {
+    ARG_CHECK(in.C == 16 && c3.cin == 16 && c3.cout == 16 && c4.cin == 16 && c4.cout == 2, "cls_tail: shapes");
+    int64_t M = (int64_t)in.N * in.H * in.W;
+    k_cls_tail<<<(unsigned)cdiv64(M, 256), 256, 0, st>>>((const float*)in.p, M, c3.w_f32, c3.cout_pad, c3.bias, c4.w_f32, c4.cout_pad, c4.bias,
+                                                         text, link);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 }

@@ -80,17 +80,16 @@ ConvW make_conv(Handle* h, const Dict& d, const std::string& conv, const std::st
     c.w_bf16 = to_device(h, wb);
     c.scale = to_device(h, scale);
     c.bias = to_device(h, bias);
-    if (split) {      // [tap][cout_pad][hi(cin) | hi(cin) | lo(cin)] : pairs with activations [x_hi | x_lo | x_hi]
-        std::vector<__nv_bfloat16> ws((size_t)taps * c.cout_pad * 3 * c.cin, __float2bfloat16(0.f));
+    if (split) {      // [tap][cout_pad][hi(cin) | lo(cin)] : w = bf16 hi + bf16 lo (conv_tc.cu, PAIR stages)
+        std::vector<__nv_bfloat16> ws((size_t)taps * c.cout_pad * 2 * c.cin, __float2bfloat16(0.f));
         for (int o = 0; o < c.cout; ++o)
             for (int i = 0; i < c.cin; ++i)
                 for (int t = 0; t < taps; ++t) {
                     float v = w->data[((int64_t)o * c.cin + i) * taps + t];
                     __nv_bfloat16 hi = __float2bfloat16(v), lo = __float2bfloat16(v - __bfloat162float(hi));
-                    size_t base = ((size_t)t * c.cout_pad + o) * 3 * c.cin;
+                    size_t base = ((size_t)t * c.cout_pad + o) * 2 * c.cin;
                     ws[base + i] = hi;
-                    ws[base + c.cin + i] = hi;
-                    ws[base + 2 * c.cin + i] = lo;
+                    ws[base + c.cin + i] = lo;
                 }
         c.w_split = to_device(h, ws);
     }
@@ -112,7 +111,7 @@ ConvW make_linear(Handle* h, const std::vector<const bbocr_tensor*>& mats, const
     std::vector<float> scale(c.cout_pad, 0.f), bias(c.cout_pad, 0.f);
     std::vector<float> wf((size_t)c.cin * c.cout_pad, 0.f);
     std::vector<__nv_bfloat16> wb((size_t)c.cout_pad * c.cin, __float2bfloat16(0.f));
-    std::vector<__nv_bfloat16> ws(split ? (size_t)c.cout_pad * 3 * c.cin : 0, __float2bfloat16(0.f));
+    std::vector<__nv_bfloat16> ws(split ? (size_t)c.cout_pad * 2 * c.cin : 0, __float2bfloat16(0.f));
     int o0 = 0;
     for (size_t mi = 0; mi < mats.size(); ++mi) {
         const bbocr_tensor* m = mats[mi];
@@ -128,10 +127,9 @@ ConvW make_linear(Handle* h, const std::vector<const bbocr_tensor*>& mats, const
                 wb[(size_t)(o0 + o) * c.cin + i] = __float2bfloat16(v);
                 if (split) {
                     __nv_bfloat16 hi = __float2bfloat16(v), lo = __float2bfloat16(v - __bfloat162float(hi));
-                    size_t base = (size_t)(o0 + o) * 3 * c.cin;
+                    size_t base = (size_t)(o0 + o) * 2 * c.cin;
                     ws[base + i] = hi;
-                    ws[base + c.cin + i] = hi;
-                    ws[base + 2 * c.cin + i] = lo;
+                    ws[base + c.cin + i] = lo;
                 }
             }
         }
@@ -182,23 +180,23 @@ void load_craft(Handle* h, const bbocr_tensor* t, int n) {
     CraftW& c = h->craft;
     auto vgg = [&](int slice_conv, int idx, int slice_bn) {
         return make_conv(h, d, "basenet.slice" + std::to_string(slice_conv) + "." + std::to_string(idx),
-                         "basenet.slice" + std::to_string(slice_bn) + "." + std::to_string(idx + 1), 1, 1);
+                         "basenet.slice" + std::to_string(slice_bn) + "." + std::to_string(idx + 1), 1, 1, true);
     };
     c.c1_1 = vgg(1, 0, 1);  c.c1_2 = vgg(1, 3, 1);  c.c2_1 = vgg(1, 7, 1);  c.c2_2 = vgg(1, 10, 1);
     c.c3_1 = vgg(2, 14, 2); c.c3_2 = vgg(2, 17, 2);
     c.c3_3 = vgg(3, 20, 3); c.c4_1 = vgg(3, 24, 3); c.c4_2 = vgg(3, 27, 3);
     c.c4_3 = vgg(4, 30, 4); c.c5_1 = vgg(4, 34, 4); c.c5_2 = vgg(4, 37, 4);
-    c.fc6 = make_conv(h, d, "basenet.slice5.1", "", 6, 6);
-    c.fc7 = make_conv(h, d, "basenet.slice5.2", "", 0, 1);
+    c.fc6 = make_conv(h, d, "basenet.slice5.1", "", 6, 6, true);
+    c.fc7 = make_conv(h, d, "basenet.slice5.2", "", 0, 1, true);
     ConvW* ups[4][2] = {{&c.up1a, &c.up1b}, {&c.up2a, &c.up2b}, {&c.up3a, &c.up3b}, {&c.up4a, &c.up4b}};
     for (int i = 0; i < 4; ++i) {
         std::string p = "upconv" + std::to_string(i + 1) + ".conv.";
-        *ups[i][0] = make_conv(h, d, p + "0", p + "1", 0, 1);
-        *ups[i][1] = make_conv(h, d, p + "3", p + "4", 1, 1);
+        *ups[i][0] = make_conv(h, d, p + "0", p + "1", 0, 1, true);
+        *ups[i][1] = make_conv(h, d, p + "3", p + "4", 1, 1, true);
     }
-    c.cls0 = make_conv(h, d, "conv_cls.0", "", 1, 1);
-    c.cls1 = make_conv(h, d, "conv_cls.2", "", 1, 1);
-    c.cls2 = make_conv(h, d, "conv_cls.4", "", 1, 1);
+    c.cls0 = make_conv(h, d, "conv_cls.0", "", 1, 1, true);
+    c.cls1 = make_conv(h, d, "conv_cls.2", "", 1, 1, true);
+    c.cls2 = make_conv(h, d, "conv_cls.4", "", 1, 1, true);
     c.cls3 = make_conv(h, d, "conv_cls.6", "", 0, 1);
     c.cls4 = make_conv(h, d, "conv_cls.8", "", 0, 1);
     ARG_CHECK(c.c1_1.cin == 3 && c.c1_1.cout == 64 && c.cls4.cout == 2, "CRAFT: unexpected shapes");
@@ -206,18 +204,22 @@ void load_craft(Handle* h, const bbocr_tensor* t, int n) {
         // conv1_1 for the tensor-core path: the 3x3x3 neighbourhood is gathered into 32 channels (27 + 5 zeros) by
         // k_im2col_rgb, which turns the layer into a 1x1 convolution with Cin = 32: W32[o][tap*3 + c] = w[o][c][tap]
         const bbocr_tensor* w = d.get("basenet.slice1.0.weight");
-        std::vector<__nv_bfloat16> wb((size_t)64 * 32, __float2bfloat16(0.f));
+        std::vector<__nv_bfloat16> wb((size_t)64 * 32, __float2bfloat16(0.f)), ws((size_t)64 * 64, __float2bfloat16(0.f));
         std::vector<float> wf((size_t)32 * 64, 0.f);
         for (int o = 0; o < 64; ++o)
             for (int ci = 0; ci < 3; ++ci)
                 for (int t = 0; t < 9; ++t) {
                     float v = w->data[((int64_t)o * 3 + ci) * 9 + t];
-                    wb[(size_t)o * 32 + t * 3 + ci] = __float2bfloat16(v);
+                    __nv_bfloat16 hi = __float2bfloat16(v);
+                    wb[(size_t)o * 32 + t * 3 + ci] = hi;
+                    ws[(size_t)o * 64 + t * 3 + ci] = hi;
+                    ws[(size_t)o * 64 + 32 + t * 3 + ci] = __float2bfloat16(v - __bfloat162float(hi));
                     wf[(size_t)(t * 3 + ci) * 64 + o] = v;
                 }
         ConvW e = c.c1_1;
         e.cin = 32; e.kh = e.kw = 1; e.pad = 0; e.dil = 1;
         e.w_bf16 = to_device(h, wb);
+        e.w_split = to_device(h, ws);
         e.w_f32 = to_device(h, wf);
         c.c1_1_tc = e;
     }

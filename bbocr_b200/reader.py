@@ -171,7 +171,7 @@ class Reader:
 
     # ------------------------------------------------------------------------------------------------------------
     def set_precision(self, precision: str):
-        self._h.set_precision({"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision])
+        self._h.set_precision({"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3}[precision])
         self.precision = precision
 
     def _params(self, kw, allowlist=None, blocklist=None):

@@ -30,7 +30,11 @@ extern "C" {
 #define BBOCR_E_UNSUPPORTED (-5)
 
 #define BBOCR_PREC_FP32 0     /* CUDA-core FP32 implicit GEMM: the <=1e-3 parity mode */
-#define BBOCR_PREC_BF16 1     /* tcgen05 BF16 operands, FP32 accumulation in TMEM: the throughput mode */
+#define BBOCR_PREC_BF16 1     /* tcgen05, detector in plain BF16 operands (FP32 accumulation in TMEM), recogniser in split
+                                 precision: fastest mode; score maps within a stated 6e-2, boxes may move by a pixel */
+#define BBOCR_PREC_BF16X3 2   /* tcgen05, detector AND recogniser in split precision: every operand is bf16 hi + bf16 lo and
+                                 every product x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulates in FP32 (TMEM): FP32-class score
+                                 maps and logits on the tensor cores -- the parity-grade throughput mode */
 
 typedef struct bbocr_handle bbocr_handle;
 
