@@ -358,18 +358,29 @@ extern "C" int bbocr_thumbnail_u8(bbocr_handle* h, const uint8_t* src, int H, in
         *outW = ow; *outH = oh;
         if (!out) return;                                   // size query
         ARG_CHECK(src, "null image");
-        // Image.resize(reducing_gap = 2.0) inserts an integer box-reduce pass once an axis shrinks by >= 4x
-        if ((int)((double)W / ow / 2.0) > 1 || (int)((double)H / oh / 2.0) > 1)
-            fail(BBOCR_E_UNSUPPORTED, "thumbnail: %dx%d -> %dx%d shrinks by >= 4x (Pillow's reduce() pre-pass is not implemented)", W, H, ow, oh);
+        // Image.resize(reducing_gap = 2.0): once an axis shrinks by >= 4x, factor = int(src / dst / 2.0) > 1 and the image is
+        // box-reduced first (Image.reduce; the safe box of a full-image box is the full image), then the bicubic pass samples
+        // the reduced image through the fractional box (0, 0, W / fx, H / fy) -- single-precision floats on Pillow's C side
+        int fx = (int)((double)W / ow / 2.0), fy = (int)((double)H / oh / 2.0);
+        fx = std::max(fx, 1); fy = std::max(fy, 1);
         Lane& lane = h->lanes[0];
         cudaStream_t st = lane.stream;
-        DevBuf din, dout, scratch((size_t)H * std::max(ow, W) + 16, st);
+        DevBuf din, dout, scratch((size_t)H * std::max(ow, W) + 16, st), reduced;
         const uint8_t* s = src;
         if (!in_on_device) { upload(lane, din, src, (size_t)H * W); s = din.as<uint8_t>(); }
         uint8_t* d = out;
         if (!out_on_device) { dout.alloc((size_t)oh * ow, st); d = dout.as<uint8_t>(); }
-        if (ow == W && oh == H) CUDA_CHECK(cudaMemcpyAsync(d, s, (size_t)H * W, cudaMemcpyDeviceToDevice, st));
-        else pil_resize_bicubic_dev(h, st, s, H, W, d, oh, ow, scratch.as<uint8_t>());
+        int sH = H, sW = W;
+        float box_w = 0.f, box_h = 0.f;
+        if (fx > 1 || fy > 1) {
+            sW = (W + fx - 1) / fx; sH = (H + fy - 1) / fy;
+            reduced.alloc((size_t)sH * sW + 16, st);
+            pil_reduce_dev(h, st, s, H, W, fx, fy, reduced.as<uint8_t>());
+            s = reduced.as<uint8_t>();
+            box_w = (float)((double)W / fx); box_h = (float)((double)H / fy);
+        }
+        if (ow == sW && oh == sH && box_w == 0.f) CUDA_CHECK(cudaMemcpyAsync(d, s, (size_t)H * W, cudaMemcpyDeviceToDevice, st));
+        else pil_resize_bicubic_dev(h, st, s, sH, sW, d, oh, ow, scratch.as<uint8_t>(), box_w, box_h);
         if (!out_on_device) download(lane, out, d, (size_t)oh * ow);
         else CUDA_CHECK(cudaStreamSynchronize(st));
     });

@@ -194,7 +194,8 @@ void crop_hist_dev(Handle*, cudaStream_t, const uint8_t* crops, const CropDesc* 
 void crop_contrast_dev(Handle*, cudaStream_t, const uint8_t* crops, const CropDesc* descs_dev, int n, const double* low,
                        const double* ratio, const int* apply, uint8_t* out);
 void pil_resize_bicubic_dev(Handle*, cudaStream_t, const uint8_t* src, int sH, int sW, uint8_t* dst, int dH, int dW,
-                            uint8_t* scratch);
+                            uint8_t* scratch, float box_w = 0.f, float box_h = 0.f);
+void pil_reduce_dev(Handle*, cudaStream_t, const uint8_t* src, int sH, int sW, int fx, int fy, uint8_t* dst);   // Image.reduce
 void crops_to_input_dev(Handle*, cudaStream_t, const uint8_t* aligned, const CropDesc* descs_dev, int n, int max_model_w,
                         float* inputs);
 struct SeqDesc {                   // one crop's feature sequence inside the flat [rows][channels] tensors

@@ -156,8 +156,9 @@ static double pil_bicubic(double x) {
     return 0.0;
 }
 
-static int pil_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk) {
-    double scale = (double)in_size / out_size, filterscale = scale;
+// in1: right/bottom edge of the source box (Resample.c receives the box as single-precision floats; in0 = 0 here)
+static int pil_coeffs(int in_size, float in1, int out_size, std::vector<int>& bounds, std::vector<int>& kk) {
+    double scale = (double)(in1 - 0.0f) / out_size, filterscale = scale;
     if (filterscale < 1.0) filterscale = 1.0;
     double support = 2.0 * filterscale;
     int ksize = (int)ceil(support) * 2 + 1;
@@ -186,11 +187,47 @@ static int pil_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::
     return ksize;
 }
 
-// src (sH x sW) -> dst (dH x dW); scratch must hold sH*dW bytes
+// Image.reduce((fx, fy)) for mode L (libImaging/Reduce.c): out = ((count / 2 + sum of the fx x fy block clipped to the image) *
+// mult[count]) >> 24; mult = division_UINT32(count, 8) comes from the host (float division); the four possible counts are
+// full block, right edge, bottom edge, corner.
+__global__ void k_pil_reduce(const uint8_t* __restrict__ src, int sW, int sH, uint8_t* __restrict__ dst, int dW, int dH, int fx, int fy,
+                             uint32_t m_full, uint32_t m_right, uint32_t m_bottom, uint32_t m_corner) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dW) return;
+    const int x0 = x * fx, y0 = y * fy, x1 = min(x0 + fx, sW), y1 = min(y0 + fy, sH);
+    uint32_t ss = 0;
+    for (int yy = y0; yy < y1; ++yy)
+        for (int xx = x0; xx < x1; ++xx) ss += src[(int64_t)yy * sW + xx];
+    const bool pr = x1 - x0 < fx, pb = y1 - y0 < fy;
+    const uint32_t cnt = (uint32_t)((x1 - x0) * (y1 - y0));
+    const uint32_t mult = pr ? (pb ? m_corner : m_right) : (pb ? m_bottom : m_full);
+    dst[(int64_t)y * dW + x] = (uint8_t)(((ss + cnt / 2) * mult) >> 24);
+}
+
+static uint32_t pil_division_u32(int divider) {           // Reduce.c::division_UINT32(divider, 8)
+    const uint32_t max_dividend = (1u << 8) * (uint32_t)divider;
+    const float max_int = (float)(1 << 30) * 4.0f;
+    return (uint32_t)(max_int / (float)max_dividend);
+}
+
+void pil_reduce_dev(Handle* h, cudaStream_t st, const uint8_t* src, int sH, int sW, int fx, int fy, uint8_t* dst) {
+    const int dW = (sW + fx - 1) / fx, dH = (sH + fy - 1) / fy;
+    const int rx = sW % fx, ry = sH % fy;
+    k_pil_reduce<<<dim3(cdiv(dW, 128), dH), 128, 0, st>>>(src, sW, sH, dst, dW, dH, fx, fy, pil_division_u32(fx * fy),
+                                                         pil_division_u32(std::max(rx, 1) * fy), pil_division_u32(fx * std::max(ry, 1)),
+                                                         pil_division_u32(std::max(rx, 1) * std::max(ry, 1)));
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// src (sH x sW) -> dst (dH x dW); scratch must hold sH*dW bytes.  box_w / box_h: the source box (0, 0, box_w, box_h) the
+// bicubic pass samples (the whole image unless a reduce() pre-pass left a fractional extent).
 void pil_resize_bicubic_dev(Handle* h, cudaStream_t st, const uint8_t* src, int sH, int sW, uint8_t* dst, int dH, int dW,
-                            uint8_t* scratch) {
+                            uint8_t* scratch, float box_w, float box_h) {
+    if (box_w <= 0.f) box_w = (float)sW;
+    if (box_h <= 0.f) box_h = (float)sH;
     std::vector<int> bx, kx, by, ky;
-    int ksx = pil_coeffs(sW, dW, bx, kx), ksy = pil_coeffs(sH, dH, by, ky);
+    int ksx = pil_coeffs(sW, box_w, dW, bx, kx), ksy = pil_coeffs(sH, box_h, dH, by, ky);
     std::vector<int> all;
     all.insert(all.end(), bx.begin(), bx.end());
     all.insert(all.end(), kx.begin(), kx.end());
@@ -201,12 +238,12 @@ void pil_resize_bicubic_dev(Handle* h, cudaStream_t st, const uint8_t* src, int 
     CUDA_CHECK(cudaStreamSynchronize(st));
     int* t = tab.as<int>();
     const uint8_t* hsrc = src;
-    if (dW != sW) {
+    if (dW != sW || box_w != (float)dW) {                  // Resample.c: need_horizontal = xsize != in.xsize || box[2] != xsize
         k_pil_pass<<<dim3(cdiv(dW, 64), sH), 64, 0, st>>>(src, sW, sH, scratch, dW, sH, t, t + bx.size(), ksx, 0);
         count_launch(h);
         hsrc = scratch;
     }
-    if (dH != sH) {
+    if (dH != sH || box_h != (float)dH) {
         k_pil_pass<<<dim3(cdiv(dW, 64), dH), 64, 0, st>>>(hsrc, dW, sH, dst, dW, dH, t + bx.size() + kx.size(),
                                                          t + bx.size() + kx.size() + by.size(), ksy, 1);
         count_launch(h);

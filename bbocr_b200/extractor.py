@@ -105,13 +105,26 @@ def _extract_device_resident(reader, bgr, image_index, edge_crop_percent, crop_f
     return reader._format(raw[0][0])
 
 
+def ocr_input_color(reader, bgr: np.ndarray, image_index=None) -> np.ndarray:
+    """The cap for a colour page (preprocessing off, :486-497): `img.convert("RGB"); img.thumbnail((m, m))` resamples every
+    channel independently, so the device thumbnail runs once per plane."""
+    m = ocr_max_dim(image_index)
+    if max(bgr.shape[:2]) <= m:
+        return bgr
+    planes = [reader.handle.thumbnail(np.ascontiguousarray(bgr[:, :, c]), m) for c in range(3)]
+    return np.ascontiguousarray(np.stack(planes, axis=-1))
+
+
 def extract_text_with_ocr(reader, image, *, use_preprocessing=True, image_index=None, return_results=False,
                           edge_crop_percent=0.0, crop_for_ocr=False, crop_margin=16, device_resident=None):
     """extract_text_with_ocr (:413-561) in memory: [preprocess_for_book_cover] -> [edge crop] -> [auto crop] -> OCR-input
     cap -> readtext -> joined text.  `image`: path or BGR / gray uint8 array.  edge_crop_percent / crop_for_ocr /
     crop_margin are the extractor's attributes of the same names (:452-484; a failing crop keeps the current image, like
-    there).  device_resident (default: whenever torch sees the GPU) keeps the planes in HBM between the steps instead of
-    bouncing them through host arrays; the results are identical.  Errors are swallowed into "" exactly like :529-531."""
+    there).  With use_preprocessing=False -- or when preprocessing raises (:441-443) -- the ORIGINAL COLOUR page goes on
+    (:418, :446-447): the detector sees it in RGB order (upstream reads the file with skimage) and the crops come from its
+    BGR2GRAY plane (cv2.imread(IMREAD_GRAYSCALE)).  device_resident (default: whenever torch sees the GPU) keeps the planes
+    in HBM between the steps instead of bouncing them through host arrays; the results are identical.  OCR errors are
+    swallowed into "" exactly like :529-531."""
     try:
         if isinstance(image, str):
             bgr = cv2.imread(image)
@@ -119,33 +132,42 @@ def extract_text_with_ocr(reader, image, *, use_preprocessing=True, image_index=
                 raise ValueError(f"Could not load image from {image}")
         else:
             bgr = image
+        if bgr.dtype != np.uint8 or bgr.ndim not in (2, 3) or (bgr.ndim == 3 and bgr.shape[2] != 3):
+            raise ValueError("expected an HxWx3 BGR or HxW gray uint8 image")
+        page = None                                          # gray plane (preprocessed) or the colour page
         if use_preprocessing:
-            if bgr.ndim != 3:
-                raise ValueError("preprocessing expects a BGR image")
-            if bgr.dtype != np.uint8 or bgr.shape[2] != 3:
-                raise ValueError("expected an HxWx3 uint8 BGR image")
-            if device_resident is None:
-                device_resident = _torch_cuda_available()
-            if device_resident:
-                results = _extract_device_resident(reader, bgr, image_index, edge_crop_percent, crop_for_ocr, crop_margin)
-                text = " ".join([r[1] for r in results])
-                return (text, results) if return_results else text
-            gray = reader.handle.preprocess(bgr, pp_params(CURRENT, 0))        # same handle (and device) as the reader
-        else:
-            gray = bgr if bgr.ndim == 2 else cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+            try:
+                if bgr.ndim != 3:
+                    raise ValueError("preprocessing expects a BGR image")
+                if device_resident is None:
+                    device_resident = _torch_cuda_available()
+                if device_resident:
+                    results = _extract_device_resident(reader, bgr, image_index, edge_crop_percent, crop_for_ocr, crop_margin)
+                    text = " ".join([r[1] for r in results])
+                    return (text, results) if return_results else text
+                page = reader.handle.preprocess(bgr, pp_params(CURRENT, 0))    # same handle (and device) as the reader
+            except Exception as e:                           # noqa: BLE001 -- :441-443: fall back to the original image
+                print(f"    Preprocessing failed: {e}")
+                page = None
+        if page is None:
+            page = bgr
         if edge_crop_percent > 0.0:
-            central = central_edge_crop(gray, edge_crop_percent)
+            central = central_edge_crop(page, edge_crop_percent)
             if central is not None:
-                gray = np.ascontiguousarray(central)
+                page = np.ascontiguousarray(central)
         if crop_for_ocr:
             try:
-                cropped = auto_crop_text_region(reader, gray, crop_margin)
+                cropped = auto_crop_text_region(reader, page, crop_margin)
                 if cropped is not None:
-                    gray = np.ascontiguousarray(cropped)
+                    page = np.ascontiguousarray(cropped)
             except Exception as e:                           # noqa: BLE001 -- :483-484
                 print(f"    Auto-cropping failed: {e}")
-        ocr_in = ocr_input_image(reader, gray, image_index)
-        results = reader.readtext(ocr_in, paragraph=False, batch_size=1, workers=0)
+        if page.ndim == 2:
+            ocr_in = ocr_input_image(reader, page, image_index)
+            results = reader.readtext(ocr_in, paragraph=False, batch_size=1, workers=0)
+        else:
+            ocr_in = ocr_input_color(reader, page, image_index)
+            results = reader.readtext_pair(cv2.cvtColor(ocr_in, cv2.COLOR_BGR2RGB), cv2.cvtColor(ocr_in, cv2.COLOR_BGR2GRAY))
         text = " ".join([r[1] for r in results])
     except Exception as e:                                   # noqa: BLE001 -- mirrors the reference's blanket handler
         print(f"    OCR failed: {e}")

@@ -260,6 +260,17 @@ class Reader:
             return res, [s for _, s in raw]
         return res
 
+    def readtext_pair(self, img, img_cv_grey, **kw):
+        """readtext on the two arrays upstream's reformat_input derives from a FILE: `img` (HxWx3, RGB as skimage reads it)
+        feeds the detector, `img_cv_grey` (HxW, cv2.imread(IMREAD_GRAYSCALE)) feeds the crops.  Used by the in-memory
+        extractor glue when preprocessing is off (enhanced_extractor.py:446-447, :520)."""
+        if img.ndim != 3 or img.shape[2] != 3 or img_cv_grey.shape != img.shape[:2] or img.dtype != np.uint8 or img_cv_grey.dtype != np.uint8:
+            raise ValueError("readtext_pair expects an HxWx3 uint8 image and its HxW uint8 gray plane")
+        p, keep = self._params(kw)
+        with self._lock:
+            raw = self._h.readtext_raw([(np.ascontiguousarray(img), np.ascontiguousarray(img_cv_grey), img.shape[0], img.shape[1])], p)
+        return self._format(raw[0][0])
+
     def readtext_device(self, color_ptrs, H, W, **kw):
         """Pages already resident in HBM: `color_ptrs` are raw device pointers to HxWx3 u8 images."""
         p, keep = self._params(kw)

@@ -204,7 +204,8 @@ void bbocr_results_free(bbocr_results* r);
 /* The OCR-input cap of extract_text_with_ocr (pipeline_demo/extractor/enhanced_extractor.py:486-512): PIL
  * Image.thumbnail((max_dim, max_dim)) = aspect-preserving BICUBIC down-scale (Pillow's fixed-point two-pass convolution),
  * for one gray u8 plane, without the lossy JPEG round trip the reference adds.  out == NULL: size query only.  Shrinks
- * by 4x or more (where Pillow inserts reduce()) return BBOCR_E_UNSUPPORTED. */
+ * by 4x or more (the reference's 5712x4284 photos: x1.5 -> 8568x6426 -> 1600) take Pillow's Image.reduce() box pre-pass
+ * followed by the bicubic pass over the fractional box, bit-exact like the plain regime. */
 int bbocr_thumbnail_u8(bbocr_handle* h, const uint8_t* src, int H, int W, int in_on_device, int max_dim, uint8_t* out,
                        int out_on_device, int* outH, int* outW);
 
