@@ -1236,6 +1236,15 @@ int bbocr_readtext_batch(bbocr_handle* h, int n, const bbocr_image* imgs, const 
         const int nd = std::min<int>(h->n_det_lanes, cdiv(n, h->det_batch));
         const int nr = std::min<int>((int)h->lanes.size() - h->n_det_lanes, std::max(1, cdiv(n, h->rec_group)));
         std::vector<PageWork> work(n);
+        // processing order: pages grouped by size, largest first (stable), so that same-size pages of a MIXED batch are
+        // neighbours for the detector's pair batching and the long pages start first; results stay indexed by input position
+        std::vector<int> order(n);
+        for (int i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const int64_t pa = (int64_t)imgs[a].H * imgs[a].W, pb = (int64_t)imgs[b].H * imgs[b].W;
+            if (pa != pb) return pa > pb;
+            return imgs[a].W > imgs[b].W;
+        });
         std::atomic<int> next{0};
         std::mutex qmu;
         std::condition_variable qcv;
@@ -1263,17 +1272,19 @@ int bbocr_readtext_batch(bbocr_handle* h, int n, const bbocr_image* imgs, const 
                         for (int j = 0; j < kmax;) {
                             // consecutive pages of identical size go through the detector network as one batch
                             int k = 1;
-                            while (j + k < kmax && imgs[i0 + j + k].H == imgs[i0 + j].H && imgs[i0 + j + k].W == imgs[i0 + j].W) ++k;
+                            while (j + k < kmax && imgs[order[i0 + j + k]].H == imgs[order[i0 + j]].H &&
+                                   imgs[order[i0 + j + k]].W == imgs[order[i0 + j]].W) ++k;
                             const bbocr_image* ip[16];
                             PageWork* pp[16];
                             for (int q = 0; q < k; ++q) {
-                                work[i0 + j + q].index = i0 + j + q;
-                                ip[q] = &imgs[i0 + j + q];
-                                pp[q] = &work[i0 + j + q];
+                                const int idx = order[i0 + j + q];
+                                work[idx].index = idx;
+                                ip[q] = &imgs[idx];
+                                pp[q] = &work[idx];
                             }
                             detect_pages(h, h->lanes[l], ip, k, *p, pp);
                             std::lock_guard<std::mutex> g(qmu);
-                            for (int q = 0; q < k; ++q) ready.push_back(i0 + j + q);
+                            for (int q = 0; q < k; ++q) ready.push_back(order[i0 + j + q]);
                             det_done += k;
                             qcv.notify_all();
                             j += k;
@@ -1303,8 +1314,11 @@ int bbocr_readtext_batch(bbocr_handle* h, int n, const bbocr_image* imgs, const 
                             for (int k = 0; k < take; ++k) group.push_back(&work[ready[k]]);
                             ready.erase(ready.begin(), ready.begin() + take);
                         }
-                        static const bool skip_rec = getenv("BBOCR_DIAG_SKIP_REC") != nullptr;     // diagnostics: detector-only throughput
-                        if (!skip_rec) recognize_group(h, lane, group, *p);
+#ifdef BBOCR_DIAG          // diagnostics build only (make DIAG=1): detector-only throughput; never in the shipped library
+                        static const bool skip_rec = getenv("BBOCR_DIAG_SKIP_REC") != nullptr;
+                        if (!skip_rec)
+#endif
+                        recognize_group(h, lane, group, *p);
                         for (PageWork* pw : group) {
                             out[pw->index] = assemble_page(*pw);
                             pw->dcrops.release();

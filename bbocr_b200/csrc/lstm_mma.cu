@@ -299,8 +299,10 @@ void lstm_sequences_mma(Handle* h, Lane& lane, const float* gates_in, const floa
                         const int* groups_dev, int n_groups, void* out, void* out_lo, int out_mode) {
     cudaStream_t st = lane.stream;
     if (n_seq == 0 || n_groups == 0) return;
-    static const bool diag_skip = getenv("BBOCR_DIAG_SKIP_LSTM") != nullptr;      // diagnostics only: results are garbage
+#ifdef BBOCR_DIAG              // diagnostics build only (make DIAG=1): results are garbage; never in the shipped library
+    static const bool diag_skip = getenv("BBOCR_DIAG_SKIP_LSTM") != nullptr;
     if (diag_skip) return;
+#endif
     const size_t smem = (size_t)H_BYTES + W_BYTES + 1024;
     // staging: [group][dir][parity][hi|lo][128 crops][256 units] bf16 (256 KiB per (group, direction); lives in L2)
     const uint64_t stage_rows = (uint64_t)n_groups * 2 * 4 * MB;

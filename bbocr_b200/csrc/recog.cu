@@ -310,10 +310,13 @@ void crops_to_strip_dev(Handle* h, cudaStream_t st, const uint8_t* aligned, cons
 // Throughput mode keeps the recogniser at FP32-class accuracy on the tensor cores: activations are carried as a pair of
 // bf16 tensors (hi + lo) and every convolution / Linear is three bf16 GEMM segments x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
 // accumulated in FP32 (conv_tc.cu).  The recogniser is <5 % of the page's FLOPs, so the 3x costs little, and greedy CTC
-// strings then match the FP32 oracle (tests/test_gpu_recognizer.py).  BBOCR_CRNN_BF16=1 selects plain bf16 instead.
+// strings then match the FP32 oracle (tests/test_gpu_recognizer.py).
 bool crnn_split(const Handle* h) {
+#ifdef BBOCR_DIAG              // diagnostics build only (make DIAG=1): plain bf16 recogniser for A/B timing
     static const bool plain = getenv("BBOCR_CRNN_BF16") != nullptr;
-    return h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv && !plain;
+    if (plain) return false;
+#endif
+    return h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv;
 }
 
 Act crnn_alloc_seq(Handle* h, cudaStream_t st, DevBuf& buf, int rows) {

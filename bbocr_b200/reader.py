@@ -278,6 +278,13 @@ class Reader:
             raw = self._h.readtext_raw([(ptr, None, H, W) for ptr in color_ptrs], p, on_device=True)
         return [self._format(r) for r, _ in raw], [s for _, s in raw]
 
+    def readtext_device_pages(self, pages, **kw):
+        """Pages of any sizes already resident in HBM: `pages` = [(color_ptr, gray_ptr | None, H, W), ...] raw device pointers."""
+        p, keep = self._params(kw)
+        with self._lock:
+            raw = self._h.readtext_raw(list(pages), p, on_device=True)
+        return [self._format(r) for r, _ in raw], [s for _, s in raw]
+
     # stage boundaries (upstream signatures, reduced to the arguments that change arithmetic)
     def detect(self, img, min_size=20, text_threshold=0.7, low_text=0.4, link_threshold=0.4, canvas_size=2560,
                mag_ratio=1.0, slope_ths=0.1, ycenter_ths=0.5, height_ths=0.5, width_ths=0.5, add_margin=0.1,
