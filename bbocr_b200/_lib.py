@@ -62,7 +62,7 @@ SYMBOLS = [
     "bbocr_create", "bbocr_destroy", "bbocr_last_error", "bbocr_version", "bbocr_load_craft", "bbocr_load_crnn",
     "bbocr_set_precision", "bbocr_get_precision", "bbocr_preprocess_u8", "bbocr_preprocess_batch_u8", "bbocr_preprocess_scan_u8", "bbocr_preprocess_launches_per_image",
     "bbocr_pp_gray", "bbocr_pp_resize_cubic", "bbocr_pp_gaussian3", "bbocr_pp_contrast", "bbocr_pp_brightness",
-    "bbocr_pp_clahe", "bbocr_pp_unsharp", "bbocr_pp_adaptive_threshold", "bbocr_pp_deskew", "bbocr_craft_forward",
+    "bbocr_pp_clahe", "bbocr_pp_equalize_hist", "bbocr_pp_unsharp", "bbocr_pp_adaptive_threshold", "bbocr_pp_deskew", "bbocr_craft_forward",
     "bbocr_det_boxes", "bbocr_min_area_box", "bbocr_group_boxes", "bbocr_crop_horizontal", "bbocr_crop_free",
     "bbocr_crnn_forward", "bbocr_ctc_decode", "bbocr_default_params", "bbocr_readtext", "bbocr_readtext_batch",
     "bbocr_recognize", "bbocr_thumbnail_u8", "bbocr_autocrop_rect", "bbocr_external_boxes", "bbocr_rect_morph", "bbocr_results_free", "bbocr_launch_count", "bbocr_reset_launch_count", "bbocr_conv_stats",
@@ -98,7 +98,10 @@ def lib():
 
 
 def _u8(a):
-    a = np.ascontiguousarray(a, dtype=np.uint8)
+    a = np.asarray(a)
+    if a.dtype != np.uint8:                                  # never cast silently: float / int16 pixels would wrap
+        raise ValueError(f"expected a uint8 image, got dtype {a.dtype}")
+    a = np.ascontiguousarray(a)
     return a, a.ctypes.data_as(C.c_void_p)
 
 
@@ -163,6 +166,8 @@ class Handle:
         return out
 
     def pp_gray(self, bgr):
+        if getattr(bgr, "ndim", 0) != 3 or bgr.shape[2] != 3:
+            raise ValueError("to_grayscale expects an HxWx3 BGR image (cv2.cvtColor raises for other layouts as well)")
         H, W = bgr.shape[:2]
         return self._step(self.L.bbocr_pp_gray, bgr, (H, W), C.c_int(H), C.c_int(W))
 
@@ -170,6 +175,10 @@ class Handle:
         H, W = src.shape
         return self._step(self.L.bbocr_pp_resize_cubic, src, (dH, dW), C.c_int(H), C.c_int(W), C.c_int(dH), C.c_int(dW),
                           C.c_int(mode))
+
+    def pp_equalize_hist(self, src):
+        H, W = src.shape
+        return self._step(self.L.bbocr_pp_equalize_hist, src, (H, W), C.c_int(H), C.c_int(W))
 
     def pp_gaussian3(self, src, sigma):
         H, W = src.shape

@@ -53,7 +53,7 @@ int guarded(bbocr_handle* h, F&& f) {
 // host -> device through the lane's pinned staging buffer
 void* staging(Lane& lane, size_t bytes) {          // pinned H2D staging; waits for the previous copy out of it
     if (lane.in_busy) {
-        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        CUDA_CHECK(stream_sync(lane.stream));
         lane.in_busy = false;
     }
     return lane.pin_in.get(bytes);
@@ -70,7 +70,7 @@ void upload(Lane& lane, DevBuf& dst, const void* src, size_t bytes) {
 void download(Lane& lane, void* dst, const void* src_dev, size_t bytes) {
     void* pin = lane.pin_out.get(bytes);
     CUDA_CHECK(cudaMemcpyAsync(pin, src_dev, bytes, cudaMemcpyDeviceToHost, lane.stream));
-    CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+    CUDA_CHECK(stream_sync(lane.stream));
     lane.in_busy = false;
     memcpy(dst, pin, bytes);
 }
@@ -143,7 +143,7 @@ int bbocr_create(int device, bbocr_handle** out) {
                 cudaStream_t s0 = h->lanes[0].stream;
                 if (cudaMallocAsync(&p, want, s0) == cudaSuccess) cudaFreeAsync(p, s0);
                 else cudaGetLastError();
-                CUDA_CHECK(cudaStreamSynchronize(s0));
+                CUDA_CHECK(stream_sync(s0));
             }
         }
         *out = h.release();
@@ -212,7 +212,7 @@ int bbocr_preprocess_u8(bbocr_handle* h, const uint8_t* bgr, int H, int W, int s
         }
         preprocess_chain_dev(h, lane.stream, src, H, W, stride, *p, dst, outH, outW);
         if (!out_on_device) download(lane, out, dst, (size_t)dH * dW);
-        else CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        else CUDA_CHECK(stream_sync(lane.stream));
     });
 }
 
@@ -243,7 +243,7 @@ int bbocr_preprocess_batch_u8(bbocr_handle* h, int n, const uint8_t* const* bgr,
             for (int k = 0; k < m; ++k) {
                 Lane& lane = h->lanes[k];
                 if (!out_on_device) download(lane, out[base + k], dout[k].p, out_bytes);
-                else CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+                else CUDA_CHECK(stream_sync(lane.stream));
                 lane.in_busy = false;
             }
         }
@@ -287,6 +287,11 @@ int bbocr_pp_clahe(bbocr_handle* h, const uint8_t* src, int H, int W, float clip
         pp_clahe_apply(h, st, s, d, H, W, nullptr, luts);
     });
 }
+int bbocr_pp_equalize_hist(bbocr_handle* h, const uint8_t* src, int H, int W, uint8_t* out) {
+    if (H <= 0 || W <= 0 || (int64_t)H * W > INT32_MAX) return BBOCR_E_ARG;
+    return pp_step(h, src, (size_t)H * W, out, (size_t)H * W,
+                   [&](cudaStream_t st, const uint8_t* s, uint8_t* d) { pp_equalize_hist(h, st, s, d, H, W); });
+}
 int bbocr_pp_unsharp(bbocr_handle* h, const uint8_t* src, int H, int W, int percent, int threshold, uint8_t* out) {
     return pp_step(h, src, (size_t)H * W, out, (size_t)H * W, [&](cudaStream_t st, const uint8_t* s, uint8_t* d) {
         pp_unsharp(h, st, s, d, H, W, percent, threshold, nullptr, nullptr);
@@ -327,7 +332,7 @@ int bbocr_preprocess_scan_u8(bbocr_handle* h, const uint8_t* bgr, int H, int W, 
         if (angle_out) *angle_out = a;
         pp_adaptive_threshold(h, st, rot.as<uint8_t>(), dst, H, W, 1, 0, block, delta);
         if (!out_on_device) download(lane, out, dst, n);
-        else CUDA_CHECK(cudaStreamSynchronize(st));
+        else CUDA_CHECK(stream_sync(st));
         lane.in_busy = false;
     });
 }
@@ -382,7 +387,7 @@ extern "C" int bbocr_thumbnail_u8(bbocr_handle* h, const uint8_t* src, int H, in
         if (ow == sW && oh == sH && box_w == 0.f) CUDA_CHECK(cudaMemcpyAsync(d, s, (size_t)H * W, cudaMemcpyDeviceToDevice, st));
         else pil_resize_bicubic_dev(h, st, s, sH, sW, d, oh, ow, scratch.as<uint8_t>(), box_w, box_h);
         if (!out_on_device) download(lane, out, d, (size_t)oh * ow);
-        else CUDA_CHECK(cudaStreamSynchronize(st));
+        else CUDA_CHECK(stream_sync(st));
     });
 }
 
@@ -403,7 +408,7 @@ extern "C" int bbocr_autocrop_rect(bbocr_handle* h, const uint8_t* bgr, int H, i
         dbg.merged = merged_out;
         rect[0] = rect[1] = rect[2] = rect[3] = -1;
         *found = autocrop_dev(h, lane.stream, src, H, W, channels, stride, margin, rect, want_dbg ? &dbg : nullptr) ? 1 : 0;
-        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        CUDA_CHECK(stream_sync(lane.stream));
         lane.in_busy = false;
         if (nboxes) *nboxes = (int)(dbg.boxes.size() / 4);
         if (boxes_out) memcpy(boxes_out, dbg.boxes.data(), std::min((size_t)std::max(boxes_cap, 0) * 16, dbg.boxes.size() * 4));
@@ -420,7 +425,7 @@ extern "C" int bbocr_external_boxes(bbocr_handle* h, const uint8_t* binary, int 
         upload(lane, din, binary, (size_t)H * W);
         std::vector<int32_t> boxes;
         external_boxes_dev(h, lane.stream, din.as<uint8_t>(), H, W, boxes);
-        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        CUDA_CHECK(stream_sync(lane.stream));
         lane.in_busy = false;
         *nboxes = (int)(boxes.size() / 4);
         if (boxes_out) memcpy(boxes_out, boxes.data(), std::min((size_t)std::max(boxes_cap, 0) * 16, boxes.size() * 4));
@@ -466,7 +471,7 @@ int bbocr_det_boxes(bbocr_handle* h, const float* textmap, const float* linkmap,
         size_t np = (size_t)mapH * mapW;
         DevBuf dt, dl;
         upload(lane, dt, textmap, np * 4);
-        CUDA_CHECK(cudaStreamSynchronize(lane.stream));      // pin_in is reused by the next upload
+        CUDA_CHECK(stream_sync(lane.stream));      // pin_in is reused by the next upload
         upload(lane, dl, linkmap, np * 4);
         DetComponents dc;
         det_components_dev(h, lane, dt.as<float>(), dl.as<float>(), mapH, mapW, (float)text_threshold,
@@ -965,7 +970,7 @@ void build_crops(Handle* h, Lane& lane, const uint8_t* gray, int H, int W, const
         pw.dcrops.alloc(crops_bytes + 16, st);
         upload(lane, ddesc, descs.data(), descs.size() * sizeof(CropDesc));
         if (!mats.empty()) {
-            CUDA_CHECK(cudaStreamSynchronize(st));
+            CUDA_CHECK(stream_sync(st));
             upload(lane, dmats, mats.data(), mats.size() * 8);
         }
         crops_dev(h, st, gray, H, W, ddesc.as<CropDesc>(), n, descs.data(), dmats.as<double>(), dscratch.as<uint8_t>(),
@@ -1042,7 +1047,7 @@ void detect_pages(Handle* h, Lane& lane, const bbocr_image* const* imgs, int k, 
         build_crops(h, lane, gray[i], H, W, hlist, flist, *pws[i]);
     }
     tm.reset();
-    CUDA_CHECK(cudaStreamSynchronize(st));                 // the pages' crops are complete; pinned staging is free again
+    CUDA_CHECK(stream_sync(st));                 // the pages' crops are complete; pinned staging is free again
     lane.in_busy = false;
 }
 
@@ -1077,7 +1082,7 @@ void recognize_group(Handle* h, Lane& lane, const std::vector<PageWork*>& pages,
     const uint8_t* ignore_dev = nullptr;
     if (p.ignore) {
         upload(lane, dignore, p.ignore, h->crnn.num_class);
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_sync(st));
         lane.in_busy = false;
         ignore_dev = dignore.as<uint8_t>();
     }
@@ -1102,7 +1107,7 @@ void recognize_group(Handle* h, Lane& lane, const std::vector<PageWork*>& pages,
         std::vector<CropDesc> ldesc(nl);
         for (int k = 0; k < nl; ++k) ldesc[k] = jobs[low[k]].d;
         DevBuf dl, dhist((size_t)nl * 256 * 4, st), dadj(crops_bytes + 16, st);
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_sync(st));
         upload(lane, dl, ldesc.data(), ldesc.size() * sizeof(CropDesc));
         crop_hist_dev(h, st, dcrops.as<uint8_t>(), dl.as<CropDesc>(), nl, dhist.as<unsigned int>());
         std::vector<unsigned int> hist((size_t)nl * 256);
@@ -1120,11 +1125,11 @@ void recognize_group(Handle* h, Lane& lane, const std::vector<PageWork*>& pages,
         }
         DevBuf dpar, dapply;
         upload(lane, dpar, par.data(), par.size() * 8);
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_sync(st));
         upload(lane, dapply, apply.data(), (size_t)nl * 4);
         crop_contrast_dev(h, st, dcrops.as<uint8_t>(), dl.as<CropDesc>(), nl, dpar.as<double>(), dpar.as<double>() + nl,
                           dapply.as<int>(), dadj.as<uint8_t>());
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_sync(st));
         std::vector<Recognized> rec2;
         recognize_pass(h, lane, jobs, low, dadj.as<uint8_t>(), crops_bytes, ignore_dev, rec2);
         for (int k = 0; k < nl; ++k) {
@@ -1216,7 +1221,7 @@ int bbocr_recognize(bbocr_handle* h, const uint8_t* gray, int H, int W, int on_d
         std::vector<int32_t> hl(hlist, hlist + (size_t)nh * 4);
         std::vector<double> fl(flist, flist + (size_t)nf * 8);
         build_crops(h, lane, g, H, W, hl, fl, pw);
-        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        CUDA_CHECK(stream_sync(lane.stream));
         lane.in_busy = false;
         std::vector<PageWork*> one{&pw};
         recognize_group(h, lane, one, *p);
@@ -1352,7 +1357,7 @@ int bbocr_crop_horizontal(bbocr_handle* h, const uint8_t* gray, int H, int W, co
         j.d.off = 0;
         DevBuf dg, dd, dc((size_t)j.d.ow * j.d.oh + 16, lane.stream);
         upload(lane, dg, gray, (size_t)H * W);
-        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        CUDA_CHECK(stream_sync(lane.stream));
         upload(lane, dd, &j.d, sizeof(CropDesc));
         crops_dev(h, lane.stream, dg.as<uint8_t>(), H, W, dd.as<CropDesc>(), 1, &j.d, nullptr, nullptr, dc.as<uint8_t>());
         download(lane, out, dc.p, (size_t)j.d.ow * j.d.oh);
@@ -1376,9 +1381,9 @@ int bbocr_crop_free(bbocr_handle* h, const uint8_t* gray, int H, int W, const do
         j.d.off = 0;
         DevBuf dg, dd, dm, ds((size_t)mwid * mhei + 16, lane.stream), dc((size_t)j.d.ow * j.d.oh + 16, lane.stream);
         upload(lane, dg, gray, (size_t)H * W);
-        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        CUDA_CHECK(stream_sync(lane.stream));
         upload(lane, dd, &j.d, sizeof(CropDesc));
-        CUDA_CHECK(cudaStreamSynchronize(lane.stream));
+        CUDA_CHECK(stream_sync(lane.stream));
         upload(lane, dm, M, 72);
         crops_dev(h, lane.stream, dg.as<uint8_t>(), H, W, dd.as<CropDesc>(), 1, &j.d, dm.as<double>(), ds.as<uint8_t>(),
                   dc.as<uint8_t>());
@@ -1408,7 +1413,7 @@ int bbocr_ctc_decode(bbocr_handle* h, const float* logits, int N, int T, int C, 
         DevBuf dlg, dig;
         upload(lane, dlg, logits, (size_t)N * T * C * 4);
         if (ignore) {
-            CUDA_CHECK(cudaStreamSynchronize(st));
+            CUDA_CHECK(stream_sync(st));
             upload(lane, dig, ignore, C);
         }
         size_t se = (size_t)N * T;
@@ -1420,7 +1425,7 @@ int bbocr_ctc_decode(bbocr_handle* h, const float* logits, int N, int T, int C, 
         std::vector<SeqDesc> seqs(N);
         for (int i = 0; i < N; ++i) { seqs[i].row0 = i * T; seqs[i].T = T; }
         DevBuf dseq;
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_sync(st));
         upload(lane, dseq, seqs.data(), seqs.size() * sizeof(SeqDesc));
         ctc_decode_dev(h, st, dlg.as<float>(), N * T, C, ignore ? dig.as<uint8_t>() : nullptr, dseq.as<SeqDesc>(), N, d_text,
                        d_len, d_prob, d_sidx);

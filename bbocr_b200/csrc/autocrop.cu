@@ -314,7 +314,7 @@ static void external_boxes_bits(Handle* h, cudaStream_t st, const uint32_t* bits
     CUDA_CHECK(cudaGetLastError());
     int ncomp = 0;
     CUDA_CHECK(cudaMemcpyAsync(&ncomp, cnt.p, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(stream_sync(st));
     if (ncomp == 0) return;
     DevBuf box((size_t)ncomp * 20, st);
     k_cc_box_init<<<cdiv(ncomp, 256), 256, 0, st>>>(ncomp, box.as<int>());
@@ -323,7 +323,7 @@ static void external_boxes_bits(Handle* h, cudaStream_t st, const uint32_t* bits
     CUDA_CHECK(cudaGetLastError());
     std::vector<int> hb((size_t)ncomp * 5);
     CUDA_CHECK(cudaMemcpyAsync(hb.data(), box.p, (size_t)ncomp * 20, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(stream_sync(st));
     std::vector<std::array<int32_t, 4>> rows;
     for (int k = 0; k < ncomp; ++k)
         if (hb[5 * k + 4]) rows.push_back({hb[5 * k + 1], hb[5 * k + 0], hb[5 * k + 2] - hb[5 * k + 0] + 1, hb[5 * k + 3] - hb[5 * k + 1] + 1});
@@ -409,9 +409,9 @@ bool autocrop_dev(Handle* h, cudaStream_t st, const uint8_t* bgr, int H, int W, 
             if (!dst) continue;
             k_ac_unpack<<<grd, 256, 0, st>>>((which ? merged : mask).as<uint32_t>(), H, W, Ww, u8.as<uint8_t>());
             CUDA_CHECK(cudaMemcpyAsync(dst, u8.p, n, cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(cudaStreamSynchronize(st));
+            CUDA_CHECK(stream_sync(st));
         }
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_sync(st));
     }
     return crop_rect_from_boxes(boxes, H, W, margin, rect);
 }

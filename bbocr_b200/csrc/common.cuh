@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -41,6 +42,41 @@ struct Error : std::runtime_error {
     do {                                                       \
         if (!(cond)) ::bbocr::fail(BBOCR_E_ARG, __VA_ARGS__);  \
     } while (0)
+
+// Host wait for a stream WITHOUT spinning: record an event created with cudaEventBlockingSync and sleep on it.
+// cudaStreamSynchronize spins by default (cudaDeviceScheduleSpin on an otherwise idle context), and a handle keeps ~10 lane
+// threads waiting on their streams; with one process per GPU on a shared host (8 ranks x 10 threads on 32 cores) the spinning
+// waiters starve the threads that have launches to issue -- the 1 -> 8 GPU efficiency loss measured in round 1.
+inline cudaError_t stream_sync(cudaStream_t st) {
+    static const bool spin = getenv("BBOCR_SPIN_SYNC") != nullptr;          // A/B: the old spinning wait
+    if (spin) return cudaStreamSynchronize(st);
+    // one blocking event per stream (the lanes' streams live as long as their handle), created on first use
+    static std::mutex mu;
+    static std::map<cudaStream_t, std::pair<int, cudaEvent_t>> events;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t ev = nullptr;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = events.find(st);
+        if (it != events.end() && it->second.first != dev) {                // a recycled stream handle on another device
+            cudaEventDestroy(it->second.second);
+            events.erase(it);
+            it = events.end();
+        }
+        if (it == events.end()) {
+            e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+            events[st] = std::make_pair(dev, ev);
+        } else {
+            ev = it->second.second;
+        }
+    }
+    e = cudaEventRecord(ev, st);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev);
+}
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -672,7 +672,7 @@ void conv_res_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in
     if (want_trace) {
         long long t[8];
         CUDA_CHECK(cudaMemcpyAsync(t, p.trace, 64, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_sync(st));
         const double n = t[3] > 0 ? (double)t[3] : 1.0;
         fprintf(stderr, "[conv_res trace] %dx%d k%d cin %d cout %d BN %d MT %d stages %d b-stages %d grid %d | CTA0: %lld tiles; per tile: mma wait-tmem %.0f "
                         "wait-patch %.0f issue %.0f | epilogue wait %.0f work %.0f cycles\n",

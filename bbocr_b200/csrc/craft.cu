@@ -165,9 +165,13 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     const float s0 = (float)(0.229 * 255.0), s1 = (float)(0.224 * 255.0), s2 = (float)(0.225 * 255.0);
     const bool tc_first = h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv;
     const bool split = tc_first && h->det_split;        // bf16x3: every activation tensor is a hi/lo pair
-    const size_t canvas_px_bytes = tc_first ? 64 : 16;
+    // bf16x3 stem: the 27-tap conv1_1 runs on the CUDA cores straight from the FP32 canvas (exact FP32 products) and writes
+    // the split tensor; the gathered 32-channel stem would cost a 354 MB round trip per page for 1.5 % of the FLOPs
+    static const bool stem_gather_x3 = getenv("BBOCR_X3_STEM_GATHER") != nullptr;      // A/B: tensor-core stem as in bf16 mode
+    const bool gather = tc_first && (!split || stem_gather_x3);
+    const size_t canvas_px_bytes = gather ? 64 : 16;
     const size_t canvas_plane = (((size_t)nimg * H * W * canvas_px_bytes) + 255) & ~(size_t)255;
-    DevBuf canvas(canvas_plane * (split ? 2 : 1), st), resized;
+    DevBuf canvas(canvas_plane * (split && gather ? 2 : 1), st), resized;
     const bool need_resize = g.th != g.H || g.tw != g.W;
     if (need_resize) resized.alloc((size_t)g.th * g.tw * 3, st);
     for (int i = 0; i < nimg; ++i) {
@@ -177,10 +181,10 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
             src = resized.as<uint8_t>();
         }
         uint8_t* dst = canvas.as<uint8_t>() + (size_t)i * H * W * canvas_px_bytes;
-        if (split)
+        if (split && gather)
             k_im2col_rgb_split<<<dim3(cdiv(W, 128), H), 128, 0, st>>>(src, g.th, g.tw, reinterpret_cast<__nv_bfloat16*>(dst),
                                                                       reinterpret_cast<__nv_bfloat16*>(dst + canvas_plane), H, W, m0, m1, m2, s0, s1, s2);
-        else if (tc_first)
+        else if (gather)
             k_im2col_rgb<<<dim3(cdiv(W, 128), H), 128, 0, st>>>(src, g.th, g.tw, reinterpret_cast<__nv_bfloat16*>(dst), H, W, m0, m1, m2, s0, s1, s2);
         else
             k_canvas<<<dim3(cdiv(W, 256), H), 256, 0, st>>>(src, g.th, g.tw, reinterpret_cast<float*>(dst), H, W, m0, m1, m2, s0, s1, s2);
@@ -217,7 +221,7 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     DevBuf b0, b1, b_r22, b_r32, b_r43, b_r53;
     // slice1
     Act a = alloc(b0, nimg, H, W, 64);
-    if (tc_first) {
+    if (gather) {
         Act x32;
         x32.N = nimg; x32.H = H; x32.W = W; x32.C = 32; x32.p = canvas.p;
         if (split) x32.lo = canvas.as<uint8_t>() + canvas_plane;

@@ -70,6 +70,7 @@ void pp_sum(Handle*, cudaStream_t, const uint8_t* src, int64_t n, unsigned long 
 void pp_tone_lut(Handle*, cudaStream_t, const unsigned long long* sum, int64_t npix, float contrast, float brightness,
                  uint8_t* lut);
 void pp_apply_lut(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int64_t n, const uint8_t* lut);
+void pp_equalize_hist(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int H, int W);      // cv2.equalizeHist
 void pp_clahe_luts(Handle*, cudaStream_t, const uint8_t* src, int H, int W, float clip, const uint8_t* tone,
                    unsigned int* hist, uint8_t* luts);
 void pp_clahe_apply(Handle*, cudaStream_t, const uint8_t* src, uint8_t* dst, int H, int W, const uint8_t* tone,

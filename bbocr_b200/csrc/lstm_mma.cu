@@ -343,7 +343,7 @@ void lstm_sequences_mma(Handle* h, Lane& lane, const float* gates_in, const floa
     if (want_trace) {           // diagnostic: per-phase cycles of CTA 0, averaged over steps 8..39
         std::vector<long long> t(64 * 8);
         CUDA_CHECK(cudaMemcpyAsync(t.data(), trace, t.size() * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_sync(st));
         double acc[8] = {0};
         int cnt = 0;
         for (int s = 8; s < 40; ++s) {

@@ -38,6 +38,18 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, const float v[4]) {
     t.y = *reinterpret_cast<uint32_t*>(&b);
     *reinterpret_cast<uint2*>(p) = t;
 }
+// split-precision store: hi = bf16(v), lo = bf16(v - hi)
+__device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* lo, const float v[4]) {
+    float h4[4], l4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h4[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+        l4[j] = v[j] - h4[j];
+    }
+    store4(hi, h4);
+    store4(lo, l4);
+}
+__device__ __forceinline__ void split_store4(float*, float*, const float*) {}      // FP32 tensors are never split
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
@@ -202,7 +214,8 @@ template <int COUT, typename TO>
 __global__ void __launch_bounds__(128) k_conv_first(const float* __restrict__ in, int N, int H, int W, int cs, int cin,
                                                    const float* __restrict__ w /*[9][cin][cout_pad]*/,
                                                    int cout_pad, const float* __restrict__ scale,
-                                                   const float* __restrict__ bias, TO* __restrict__ out, int relu) {
+                                                   const float* __restrict__ bias, TO* __restrict__ out, TO* __restrict__ out_lo,
+                                                   int relu) {
     __shared__ float sw[9 * 3 * COUT];
     __shared__ float ss[COUT], sb[COUT];
     for (int i = threadIdx.x; i < 9 * cin * COUT; i += blockDim.x) {
@@ -244,7 +257,8 @@ __global__ void __launch_bounds__(128) k_conv_first(const float* __restrict__ in
             v[j] = fmaf(acc[c + j], ss[c + j], sb[c + j]);
             if (relu) v[j] = fmaxf(v[j], 0.f);
         }
-        store4(o + c, v);
+        if (out_lo) split_store4(o + c, out_lo + m * COUT + c, v);      // split-precision tensor (bf16x3 detector stem)
+        else store4(o + c, v);
     }
 }
 
@@ -257,8 +271,9 @@ void conv_first(Handle* h, cudaStream_t st, const ConvW& cw, const float* in, in
     unsigned grd = (unsigned)cdiv64(M, 128);
     int relu = (flags & CONV_RELU) ? 1 : 0;
     const bool bf = h->precision == BBOCR_PREC_BF16 && !force_f32;
+    ARG_CHECK(!out.lo || bf, "conv_first: split output needs the bf16 element type");
 #define LAUNCH(CO, TO) \
-    k_conv_first<CO, TO><<<grd, 128, 0, st>>>(in, N, H, W, cstride, cw.cin, cw.w_f32, cw.cout_pad, cw.scale, cw.bias, (TO*)out.p, relu)
+    k_conv_first<CO, TO><<<grd, 128, 0, st>>>(in, N, H, W, cstride, cw.cin, cw.w_f32, cw.cout_pad, cw.scale, cw.bias, (TO*)out.p, (TO*)out.lo, relu)
     if (cw.cout == 64) { if (bf) LAUNCH(64, __nv_bfloat16); else LAUNCH(64, float); }
     else { if (bf) LAUNCH(32, __nv_bfloat16); else LAUNCH(32, float); }
 #undef LAUNCH
@@ -345,8 +360,11 @@ __global__ void k_upsample(const T* __restrict__ in, T* __restrict__ out, int N,
 
 // bf16, exact x2: one thread per INPUT pixel and 8 channels produces the 2x2 output quad from the clamped 3x3 input
 // neighbourhood (9 x 16-byte loads for 4 x 16-byte stores instead of 16 x 8-byte loads).  Every output is evaluated with the
-// same expression and the same operands as k_upsample, so the two kernels are bit-identical.
-__global__ void __launch_bounds__(256) k_upsample2x_bf16(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N,
+// same expression and the same operands as k_upsample, so the two kernels are bit-identical.  SPLIT: the tensors are hi/lo
+// pairs (bf16x3 detector): values are hi + lo, the result is re-split.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) k_upsample2x_bf16(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ in_lo,
+                                                         __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, int N,
                                                          int H, int W, int C) {
     const int C8 = C >> 3;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,18 +375,29 @@ __global__ void __launch_bounds__(256) k_upsample2x_bf16(const __nv_bfloat16* __
     const int OH = 2 * H, OW = 2 * W;
     const int rows[3] = {max(i - 1, 0), i, min(i + 1, H - 1)}, cols[3] = {max(j - 1, 0), j, min(j + 1, W - 1)};
     float v[3][3][8];
-    const __nv_bfloat16* base = in + (size_t)n * H * W * C + c;
+    const size_t base = (size_t)n * H * W * C + c;
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)rows[a] * W + cols[b]) * C));
+            const size_t off = base + ((size_t)rows[a] * W + cols[b]) * C;
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + off));
             const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
                 v[a][b][2 * k] = __low2float(t);
                 v[a][b][2 * k + 1] = __high2float(t);
+            }
+            if (SPLIT) {
+                const uint4 ql = __ldg(reinterpret_cast<const uint4*>(in_lo + off));
+                const uint32_t wl[4] = {ql.x, ql.y, ql.z, ql.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&wl[k]);
+                    v[a][b][2 * k] += __low2float(t);
+                    v[a][b][2 * k + 1] += __high2float(t);
+                }
             }
         }
 #pragma unroll
@@ -386,7 +415,7 @@ __global__ void __launch_bounds__(256) k_upsample2x_bf16(const __nv_bfloat16* __
             const int x0 = (int)fx;
             const float lx = fx - (float)x0, hx = 1.f - lx;
             const bool left = dx == 0 && j >= 1;
-            uint32_t w[4];
+            uint32_t w[4], wl[4];
 #pragma unroll
             for (int k = 0; k < 8; k += 2) {
                 float o[2];
@@ -400,16 +429,22 @@ __global__ void __launch_bounds__(256) k_upsample2x_bf16(const __nv_bfloat16* __
                 }
                 const __nv_bfloat162 t = __floats2bfloat162_rn(o[0], o[1]);
                 w[k >> 1] = *reinterpret_cast<const uint32_t*>(&t);
+                if (SPLIT) {
+                    const __nv_bfloat162 tl = __floats2bfloat162_rn(o[0] - __low2float(t), o[1] - __high2float(t));
+                    wl[k >> 1] = *reinterpret_cast<const uint32_t*>(&tl);
+                }
             }
-            *reinterpret_cast<uint4*>(out + (((size_t)n * OH + oy) * OW + ox) * C + c) = make_uint4(w[0], w[1], w[2], w[3]);
+            const size_t oo = (((size_t)n * OH + oy) * OW + ox) * C + c;
+            *reinterpret_cast<uint4*>(out + oo) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (SPLIT) *reinterpret_cast<uint4*>(out_lo + oo) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
         }
     }
 }
 
 void upsample2x(Handle* h, cudaStream_t st, const Act& in, Act& out) {
     if (h->precision == BBOCR_PREC_BF16 && in.C % 8 == 0 && out.H == 2 * in.H && out.W == 2 * in.W && out.C == in.C) {
-        k_upsample2x_bf16<<<dim3(cdiv(in.W * (in.C / 8), 256), in.H, in.N), 256, 0, st>>>(
-            (const __nv_bfloat16*)in.p, (__nv_bfloat16*)out.p, in.N, in.H, in.W, in.C);
+        k_upsample2x_bf16<false><<<dim3(cdiv(in.W * (in.C / 8), 256), in.H, in.N), 256, 0, st>>>(
+            (const __nv_bfloat16*)in.p, nullptr, (__nv_bfloat16*)out.p, nullptr, in.N, in.H, in.W, in.C);
         count_launch(h);
         CUDA_CHECK(cudaGetLastError());
         return;
@@ -515,17 +550,6 @@ Act act_alloc_split(Handle* h, cudaStream_t st, DevBuf& buf, int N, int H, int W
     a.p = buf.p;
     a.lo = (uint8_t*)buf.p + half;
     return a;
-}
-
-__device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* lo, const float v[4]) {
-    float h4[4], l4[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        h4[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-        l4[j] = v[j] - h4[j];
-    }
-    store4(hi, h4);
-    store4(lo, l4);
 }
 
 // MaxPool2d on an FP32 tensor, output split
@@ -776,6 +800,13 @@ __global__ void k_upsample_split(const __nv_bfloat16* __restrict__ ihi, const __
 
 void upsample2x_split(Handle* h, cudaStream_t st, const Act& in, Act& out) {
     ARG_CHECK(in.C % 4 == 0 && out.C == in.C && in.lo && out.lo, "upsample_split: channels / split tensors");
+    if (in.C % 8 == 0 && out.H == 2 * in.H && out.W == 2 * in.W) {
+        k_upsample2x_bf16<true><<<dim3(cdiv(in.W * (in.C / 8), 256), in.H, in.N), 256, 0, st>>>(
+            (const __nv_bfloat16*)in.p, (const __nv_bfloat16*)in.lo, (__nv_bfloat16*)out.p, (__nv_bfloat16*)out.lo, in.N, in.H, in.W, in.C);
+        count_launch(h);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     int64_t total = (int64_t)out.N * out.H * out.W * (in.C / 4);
     float sy = (float)in.H / (float)out.H, sx = (float)in.W / (float)out.W;
     k_upsample_split<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>((const __nv_bfloat16*)in.p, (const __nv_bfloat16*)in.lo, (__nv_bfloat16*)out.p,

@@ -244,7 +244,7 @@ void det_components_dev(Handle* h, Lane& lane, const float* text, const float* l
     count_launch(h, 6);
     int hdr[2] = {0, 0};
     CUDA_CHECK(cudaMemcpyAsync(hdr, bhdr.p, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(stream_sync(st));
     const int ncomp = hdr[0];
     out = DetComponents();
     out.n_labels = ncomp;
@@ -266,7 +266,7 @@ void det_components_dev(Handle* h, Lane& lane, const float* text, const float* l
     CUDA_CHECK(cudaMemcpyAsync(pin + 16, stats, (size_t)ncomp * sizeof(CompStats), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(pin + 16 + (size_t)ncomp * sizeof(CompStats), browoff.p, (size_t)ncomp * 4,
                                cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(stream_sync(st));
     const int total_rows = ((int*)pin)[1];
     std::vector<CompStats> hs(ncomp);
     std::vector<int> hoff(ncomp);
@@ -278,7 +278,7 @@ void det_components_dev(Handle* h, Lane& lane, const float* text, const float* l
         int* pr = (int*)lane.pin_out.get((size_t)total_rows * 8);
         CUDA_CHECK(cudaMemcpyAsync(pr, brmin.p, (size_t)total_rows * 4, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaMemcpyAsync(pr + total_rows, brmax.p, (size_t)total_rows * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_sync(st));
         memcpy(out.row_min.data(), pr, (size_t)total_rows * 4);
         memcpy(out.row_max.data(), pr + total_rows, (size_t)total_rows * 4);
     }

@@ -636,6 +636,70 @@ __global__ void k_apply_lut(const uint8_t* __restrict__ src, uint8_t* __restrict
     }
 }
 
+// ---- cv2.equalizeHist (image_preprocessor.py:39-46): global 256-bin histogram -> LUT -> apply ------------------------------
+__global__ void k_hist256(const uint8_t* __restrict__ src, int64_t n, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[8][256];                      // one private histogram per warp
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    unsigned int* mine = sh[threadIdx.x >> 5];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < n; i += stride) {
+        if (i + 16 <= n) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                atomicAdd(&mine[w[q] & 255], 1u);
+                atomicAdd(&mine[(w[q] >> 8) & 255], 1u);
+                atomicAdd(&mine[(w[q] >> 16) & 255], 1u);
+                atomicAdd(&mine[w[q] >> 24], 1u);
+            }
+        } else {
+            for (int64_t j = i; j < n; ++j) atomicAdd(&mine[src[j]], 1u);
+        }
+    }
+    __syncthreads();
+    unsigned int t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+    if (t) atomicAdd(&hist[threadIdx.x], t);
+}
+
+// cv::equalizeHist's LUT: i0 = first non-empty bin; scale = 255.f / (total - hist[i0]); lut[i0] = 0;
+// lut[i] = saturate_cast<uchar>(sum_{i0 < j <= i} hist[j] * scale) with the int sum converted to float; a single-valued image
+// maps to itself (dst.setTo(i0)).
+__global__ void k_equalize_lut(const unsigned int* __restrict__ hist, int total, uint8_t* __restrict__ lut) {
+    if (threadIdx.x != 0) return;
+    int i = 0;
+    while (i < 255 && !hist[i]) ++i;
+    if ((int)hist[i] == total) {
+        for (int v = 0; v < 256; ++v) lut[v] = (uint8_t)i;
+        return;
+    }
+    const float scale = __fdiv_rn(255.f, (float)(total - (int)hist[i]));
+    for (int v = 0; v <= i; ++v) lut[v] = 0;
+    int sum = 0;
+    for (++i; i < 256; ++i) {
+        sum += (int)hist[i];
+        const int r = __float2int_rn(__fmul_rn((float)sum, scale));
+        lut[i] = (uint8_t)min(max(r, 0), 255);
+    }
+}
+
+void pp_equalize_hist(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, int H, int W) {
+    const int64_t n = (int64_t)H * W;
+    DevBuf tmp(256 * 4 + 256, st);
+    unsigned int* hist = tmp.as<unsigned int>();
+    uint8_t* lut = tmp.as<uint8_t>() + 1024;
+    CUDA_CHECK(cudaMemsetAsync(hist, 0, 1024, st));
+    const int blocks = (int)std::min<int64_t>(cdiv64(n, 256 * 16), 148 * 8);
+    k_hist256<<<blocks, 256, 0, st>>>(src, n, hist);
+    k_equalize_lut<<<1, 32, 0, st>>>(hist, (int)n, lut);
+    count_launch(h, 2);
+    pp_apply_lut(h, st, src, dst, n, lut);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 void pp_sum(Handle* h, cudaStream_t st, const uint8_t* src, int64_t n, unsigned long long* sum) {
     CUDA_CHECK(cudaMemsetAsync(sum, 0, 8, st));
     int blocks = (int)std::min<int64_t>(cdiv64(n, 256 * 16), 148 * 8);
@@ -1201,7 +1265,7 @@ void pp_adaptive_threshold(Handle* h, cudaStream_t st, const uint8_t* src, uint8
     DevBuf tmp((size_t)H * W * 4, st), kbuf(256 * 4, st);
     if (method == 1) {
         CUDA_CHECK(cudaMemcpyAsync(kbuf.p, kf.data(), block * 4, cudaMemcpyHostToDevice, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_sync(st));
     }
     dim3 grd(cdiv(W, 256), H);
     k_at_rows<<<grd, 256, 0, st>>>(src, H, W, block, kbuf.as<float>(), method == 1 ? tmp.as<float>() : nullptr,
@@ -1509,7 +1573,7 @@ float pp_deskew(Handle* h, cudaStream_t st, const uint8_t* src, uint8_t* dst, in
     k_deskew_score<<<n_ang, 256, 0, st>>>(bins.as<unsigned int>(), NR, score.as<unsigned long long>());
     std::vector<unsigned long long> hs(n_ang);
     CUDA_CHECK(cudaMemcpyAsync(hs.data(), score.p, (size_t)n_ang * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(stream_sync(st));
     if (scores_out) *scores_out = hs;
     int best = 0;
     for (int i = 1; i < n_ang; ++i)

@@ -12,16 +12,21 @@ namespace bbocr {
 // ------------------------------------------------------------------------------------------------------------------
 // cv2.warpPerspective(INTER_LINEAR, BORDER_CONSTANT 0) sample: fixed-point 5-bit sub-pixel, 15-bit weights
 __device__ __forceinline__ uint8_t warp_px(const uint8_t* __restrict__ src, int H, int W, const double* __restrict__ M,
-                                           int x, int y) {
-    // OpenCV evaluates X0 at the start of each 32-wide block and adds M[0]*x1 inside it (WarpPerspectiveInvoker)
-    const int xb = x & ~31, x1 = x - xb;
-    double X0 = M[0] * xb + M[1] * y + M[2];
-    double Y0 = M[3] * xb + M[4] * y + M[5];
-    double W0 = M[6] * xb + M[7] * y + M[8];
-    double Wd = W0 + M[6] * x1;
-    Wd = Wd ? 32.0 / Wd : 0;
-    double fX = fmax((double)INT_MIN, fmin((double)INT_MAX, (X0 + M[0] * x1) * Wd));
-    double fY = fmax((double)INT_MIN, fmin((double)INT_MAX, (Y0 + M[3] * x1) * Wd));
+                                           int x, int y, int dw, int dh) {
+    // OpenCV evaluates X0 at the start of each 32-wide block and adds M[0]*x1 inside it (WarpPerspectiveInvoker), in plain
+    // double multiplies and adds: every operation is written with the _rn intrinsics so that nvcc cannot contract a*b + c
+    // into an FMA (the contraction moved X by one 1/32-pixel step on ~2 % of the pixels in round 1)
+    // block width: BLOCK_SZ = 32; bh0 = min(16, rows); bw0 = min(32 * 32 / bh0, cols)  -> 64-pixel blocks for patches >= 16 rows
+    const int bw0 = min(1024 / min(16, dh), dw);
+    const int xb = (x / bw0) * bw0, x1 = x - xb;
+    const double dxb = (double)xb, dy = (double)y, dx1 = (double)x1;
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], dxb), __dmul_rn(M[1], dy)), M[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M[3], dxb), __dmul_rn(M[4], dy)), M[5]);
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M[6], dxb), __dmul_rn(M[7], dy)), M[8]);
+    double Wd = __dadd_rn(W0, __dmul_rn(M[6], dx1));
+    Wd = Wd ? __ddiv_rn(32.0, Wd) : 0;
+    double fX = fmax((double)INT_MIN, fmin((double)INT_MAX, __dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], dx1)), Wd)));
+    double fY = fmax((double)INT_MIN, fmin((double)INT_MAX, __dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], dx1)), Wd)));
     int X = __double2int_rn(fX), Y = __double2int_rn(fY);
     int sx = X >> 5, sy = Y >> 5;
     sx = max(-32768, min(32767, sx));
@@ -42,7 +47,7 @@ __global__ void k_warp(const uint8_t* __restrict__ gray, int H, int W, const Cro
     if (d.free_idx < 0) return;
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= d.w || y >= d.h) return;
-    scratch[(int64_t)d.x0 + (int64_t)y * d.w + x] = warp_px(gray, H, W, mats + d.free_idx * 9, x, y);
+    scratch[(int64_t)d.x0 + (int64_t)y * d.w + x] = warp_px(gray, H, W, mats + d.free_idx * 9, x, y, d.w, d.h);
 }
 
 // stage B: compute_ratio_and_resize (cv2.resize INTER_LINEAR) of the source rectangle into the packed crop buffer
@@ -235,7 +240,7 @@ void pil_resize_bicubic_dev(Handle* h, cudaStream_t st, const uint8_t* src, int 
     all.insert(all.end(), ky.begin(), ky.end());
     DevBuf tab(all.size() * 4, st);
     CUDA_CHECK(cudaMemcpyAsync(tab.p, all.data(), all.size() * 4, cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(stream_sync(st));
     int* t = tab.as<int>();
     const uint8_t* hsrc = src;
     if (dW != sW || box_w != (float)dW) {                  // Resample.c: need_horizontal = xsize != in.xsize || box[2] != xsize
@@ -435,7 +440,7 @@ void crnn_sequence_dev(Handle* h, Lane& lane, const Act& seq, const std::vector<
     for (int i = 0; i < n_seq; ++i) meta[(size_t)n_seq * 2 + i] = order[i];
     DevBuf dmeta(meta.size() * 4, st);
     {
-        if (lane.in_busy) { CUDA_CHECK(cudaStreamSynchronize(st)); lane.in_busy = false; }
+        if (lane.in_busy) { CUDA_CHECK(stream_sync(st)); lane.in_busy = false; }
         void* pin = lane.pin_in.get(meta.size() * 4);
         memcpy(pin, meta.data(), meta.size() * 4);
         CUDA_CHECK(cudaMemcpyAsync(dmeta.p, pin, meta.size() * 4, cudaMemcpyHostToDevice, st));

@@ -85,6 +85,13 @@ class ImagePreprocessor:
         self.steps_applied.append(f"denoise(strength={strength})")
         return self
 
+    def equalize_histogram(self):
+        h = self._need()
+        self._gray_first(h)
+        self.preprocessed_image = h.pp_equalize_hist(self.preprocessed_image)
+        self.steps_applied.append("equalize_histogram")
+        return self
+
     def clahe(self, clip_limit=2.0, tile_grid_size=(8, 8)):
         h = self._need()
         self._gray_first(h)

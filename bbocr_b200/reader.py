@@ -306,10 +306,10 @@ class Reader:
         With both lists None the whole image is one horizontal box, like upstream."""
         self._check_unsupported(decoder, rotation_info)
         if reformat:
-            _, img_cv_grey = reformat_input(img_cv_grey) if not (isinstance(img_cv_grey, np.ndarray) and img_cv_grey.ndim == 2) \
-                else (None, img_cv_grey)
-            if img_cv_grey is None:
-                raise ValueError("recognize needs a gray image (2-D array, path or bytes)")
+            if not (isinstance(img_cv_grey, np.ndarray) and img_cv_grey.ndim == 2):
+                img, img_cv_grey = reformat_input(img_cv_grey)
+                if img_cv_grey is None:                        # HxWx3 / HxWx4 / PIL input: upstream derives BGR2GRAY of `img`
+                    img_cv_grey = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
         if horizontal_list is None and free_list is None:
             y_max, x_max = img_cv_grey.shape
             horizontal_list, free_list = [[0, x_max, 0, y_max]], []

@@ -93,6 +93,7 @@ int bbocr_pp_gaussian3(bbocr_handle* h, const uint8_t* src, int H, int W, float 
 int bbocr_pp_contrast(bbocr_handle* h, const uint8_t* src, int H, int W, float factor, uint8_t* out);      /* :70-84  */
 int bbocr_pp_brightness(bbocr_handle* h, const uint8_t* src, int H, int W, float factor, uint8_t* out);    /* :86-100 */
 int bbocr_pp_clahe(bbocr_handle* h, const uint8_t* src, int H, int W, float clip, uint8_t* out);           /* :48-56  */
+int bbocr_pp_equalize_hist(bbocr_handle* h, const uint8_t* src, int H, int W, uint8_t* out);             /* :39-46  */
 int bbocr_pp_unsharp(bbocr_handle* h, const uint8_t* src, int H, int W, int percent, int threshold,
                      uint8_t* out);                                                                        /* :102-115 */
 /* gentle_threshold :58-68 and enhanced_extractor.py:258-259.  method 0 = MEAN_C, 1 = GAUSSIAN_C; inv = BINARY_INV */

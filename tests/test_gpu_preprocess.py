@@ -167,3 +167,30 @@ def test_deskew_histogram_kernels_agree(handle):
         r = np.clip(np.floor(dy * math.cos(rad) - dx * math.sin(rad)).astype(np.int64) + NR // 2, 0, NR - 1)
         cnt = np.bincount(r, minlength=NR).astype(np.uint64)
         assert int((cnt * cnt).sum()) == int(got[i])
+
+
+def test_equalize_histogram_bit_exact(handle):
+    """ImagePreprocessor.equalize_histogram (image_preprocessor.py:39-46) = cv2.equalizeHist."""
+    import cv2
+    from bbocr_b200.preprocess import ImagePreprocessor
+    rng = np.random.default_rng(9)
+    big = cv2.cvtColor(synth.phone_photo(3007, 4032, 3024), cv2.COLOR_BGR2GRAY)          # 12 MP: count sums beyond 2^24 are rare but legal
+    for g in [rng.integers(0, 256, (97, 131), dtype=np.uint8), rng.integers(40, 90, (300, 200), dtype=np.uint8),
+              np.full((20, 30), 77, np.uint8), big]:
+        assert np.array_equal(handle.pp_equalize_hist(g), cv2.equalizeHist(g))
+        assert np.array_equal(handle.pp_equalize_hist(g), P.equalize_hist(g))
+    pp = ImagePreprocessor().load_array(synth.phone_photo(3008, 640, 480)).equalize_histogram()
+    assert pp.get_steps_applied() == ["original", "grayscale", "equalize_histogram"]
+    assert np.array_equal(pp.get_image(), cv2.equalizeHist(cv2.cvtColor(synth.phone_photo(3008, 640, 480), cv2.COLOR_BGR2GRAY)))
+
+
+def test_input_validation_raises_instead_of_reading_out_of_bounds(handle):
+    """a 2-D array reaching bbocr_pp_gray was read as HxWx3; non-uint8 arrays were cast silently."""
+    from bbocr_b200.preprocess import ImagePreprocessor
+    gray = np.zeros((40, 50), np.uint8)
+    with pytest.raises(ValueError):
+        handle.pp_gray(gray)
+    with pytest.raises(ValueError):
+        ImagePreprocessor().load_array(gray).to_grayscale()
+    with pytest.raises(ValueError):
+        handle.pp_gaussian3(np.zeros((40, 50), np.float32), 3.0)

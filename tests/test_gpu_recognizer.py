@@ -23,24 +23,33 @@ def test_horizontal_crops_bit_exact(handle):
         assert gmw == mw and np.array_equal(crop, il[0][1]), b
 
 
-def test_free_crops_close_to_cv2(handle):
-    """four_point_transform: cv2.warpPerspective's SIMD path evaluates the homography block-wise; the kernel restates the
-    scalar formula.  Bit-exact on >= 99% of the pixels, never off by more than 1 level elsewhere... measured here."""
+def test_free_crops_bit_exact_vs_cv2(handle):
+    """four_point_transform: cv2.warpPerspective (INTER_LINEAR, fixed-point 5-bit sub-pixel table, block-wise evaluation of
+    the homography in unfused double arithmetic) restated on the device -- 0 differing pixels over a 1000-quad fuzz
+    (rotations up to +-35 deg, perspective skew, quads hanging over the page border)."""
     page = cv2.cvtColor(synth.book_cover(42, 960, 704), cv2.COLOR_RGB2GRAY)
     rng = np.random.default_rng(1)
-    worst = 0.0
-    for _ in range(20):
-        cx, cy = rng.uniform(200, 760), rng.uniform(150, 550)
-        w, h = rng.uniform(60, 300), rng.uniform(20, 60)
-        quad = cv2.boxPoints(((cx, cy), (w, h), float(rng.uniform(-20, 20)))).astype(np.float64)
+    total = bad = 0
+    for it in range(1000):
+        cx, cy = rng.uniform(-20, 980), rng.uniform(-20, 720)
+        w, h = rng.uniform(24, 420), rng.uniform(8, 90)
+        quad = cv2.boxPoints(((cx, cy), (w, h), float(rng.uniform(-35, 35)))).astype(np.float64)
         quad = np.roll(quad, 4 - quad.sum(1).argmin(), 0)
-        il, mw = E.get_image_list([], [quad.tolist()], page, model_height=64)
+        if it % 3 == 0:
+            quad += rng.uniform(-4, 4, quad.shape)              # not a rectangle any more: a real perspective map
+        try:
+            il, mw = E.get_image_list([], [quad.tolist()], page, model_height=64)
+        except Exception:                                        # noqa: BLE001 -- degenerate quad: upstream raises as well
+            continue
+        if not il:
+            continue
         crop, gmw = handle.crop_free(page, quad)
-        assert gmw == mw and crop.shape == il[0][1].shape
-        d = np.abs(crop.astype(int) - il[0][1].astype(int))
-        worst = max(worst, (d > 0).mean())
-        assert d.max() <= 2 and (d > 0).mean() < 0.02
-    print("free-crop mismatching pixel fraction (worst case)", worst)
+        assert gmw == mw and crop.shape == il[0][1].shape, (it, quad)
+        d = crop != il[0][1]
+        total += d.size
+        bad += int(d.sum())
+    print("free-form crops:", total, "pixels compared,", bad, "differ")
+    assert total > 1_000_000 and bad == 0
 
 
 def _inputs(n, wm, seed):

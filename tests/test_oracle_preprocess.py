@@ -110,3 +110,14 @@ def test_library_call_chain_equals_the_numpy_oracle():
         cv2.ipp.setUseIPP(True)
     got = CV.preprocess_for_book_cover_cv(bgr)
     assert got.shape == want.shape and np.abs(got.astype(int) - want.astype(int)).max() <= 12
+
+
+def test_equalize_hist_matches_cv2():
+    import cv2
+    from bbocr_b200 import synth
+    rng = np.random.default_rng(9)
+    imgs = [rng.integers(0, 256, (97, 131), dtype=np.uint8), rng.integers(40, 90, (300, 200), dtype=np.uint8),
+            np.full((20, 30), 77, np.uint8), cv2.cvtColor(synth.phone_photo(3007, 1008, 756), cv2.COLOR_BGR2GRAY),
+            (rng.random((512, 512)) ** 3 * 255).astype(np.uint8)]
+    for g in imgs:
+        assert np.array_equal(P.equalize_hist(g), cv2.equalizeHist(g))
