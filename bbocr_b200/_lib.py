@@ -307,16 +307,25 @@ class Handle:
                                                C.byref(ratio)))
         return text, link, ratio.value
 
-    def det_boxes(self, text, link, text_threshold=0.7, link_threshold=0.4, low_text=0.4, cap=65536):
+    def det_boxes(self, text, link, text_threshold=0.7, link_threshold=0.4, low_text=0.4, cap=65536, host_path=None):
+        """getDetBoxes_core on given maps.  host_path: None = the product path (bbocr_det_boxes: everything on the device);
+        True / False = the test hook, which also reports whether the device tail was used: -> (boxes, used_device)."""
         t = np.ascontiguousarray(text, np.float32)
         l = np.ascontiguousarray(link, np.float32)
         boxes = np.empty((cap, 4, 2), np.float32)
         n = C.c_int()
-        self._check(self.L.bbocr_det_boxes(self._h, t.ctypes.data_as(C.c_void_p), l.ctypes.data_as(C.c_void_p),
-                                           C.c_int(t.shape[0]), C.c_int(t.shape[1]), C.c_double(text_threshold),
-                                           C.c_double(link_threshold), C.c_double(low_text),
-                                           boxes.ctypes.data_as(C.c_void_p), C.c_int(cap), C.byref(n)))
-        return boxes[:n.value].copy()
+        if host_path is None:
+            self._check(self.L.bbocr_det_boxes(self._h, t.ctypes.data_as(C.c_void_p), l.ctypes.data_as(C.c_void_p),
+                                               C.c_int(t.shape[0]), C.c_int(t.shape[1]), C.c_double(text_threshold),
+                                               C.c_double(link_threshold), C.c_double(low_text),
+                                               boxes.ctypes.data_as(C.c_void_p), C.c_int(cap), C.byref(n)))
+            return boxes[:n.value].copy()
+        used = C.c_int()
+        self._check(self.L.bbocr_dbg_det_boxes(self._h, t.ctypes.data_as(C.c_void_p), l.ctypes.data_as(C.c_void_p),
+                                               C.c_int(t.shape[0]), C.c_int(t.shape[1]), C.c_double(text_threshold),
+                                               C.c_double(link_threshold), C.c_double(low_text), C.c_int(1 if host_path else 0),
+                                               boxes.ctypes.data_as(C.c_void_p), C.c_int(cap), C.byref(n), C.byref(used)))
+        return boxes[:n.value].copy(), bool(used.value)
 
     # ---- recogniser ------------------------------------------------------------------------------------------------
     def crop_horizontal(self, gray, box):

@@ -463,8 +463,10 @@ int bbocr_craft_forward(bbocr_handle* h, const uint8_t* img, int H, int W, int o
     });
 }
 
-int bbocr_det_boxes(bbocr_handle* h, const float* textmap, const float* linkmap, int mapH, int mapW,
-                    double text_threshold, double link_threshold, double low_text, float* boxes, int cap, int* n) {
+// test hook (not in include/bbocr.h): host_path != 0 runs the round-1 tail (row extents to the host, hull + calipers in
+// boxes.cpp) so that the device tail can be diffed against it; *used_device reports which one produced the boxes
+int bbocr_dbg_det_boxes(bbocr_handle* h, const float* textmap, const float* linkmap, int mapH, int mapW, double text_threshold,
+                        double link_threshold, double low_text, int host_path, float* boxes, int cap, int* n, int* used_device) {
     return guarded(h, [&] {
         ARG_CHECK(textmap && linkmap && boxes && n && mapH > 0 && mapW > 0, "bad arguments");
         Lane& lane = h->lanes[0];
@@ -473,16 +475,29 @@ int bbocr_det_boxes(bbocr_handle* h, const float* textmap, const float* linkmap,
         upload(lane, dt, textmap, np * 4);
         CUDA_CHECK(stream_sync(lane.stream));      // pin_in is reused by the next upload
         upload(lane, dl, linkmap, np * 4);
-        DetComponents dc;
-        det_components_dev(h, lane, dt.as<float>(), dl.as<float>(), mapH, mapW, (float)text_threshold,
-                           (float)link_threshold, (float)low_text, dc);
         std::vector<float> b;
-        boxes_from_components(dc, mapH, mapW, b);
+        static const bool env_host = getenv("BBOCR_HOST_BOXES") != nullptr;        // A/B: hull / calipers on the host
+        bool dev = false;
+        if (!host_path && !env_host)
+            dev = det_boxes_dev(h, lane, dt.as<float>(), dl.as<float>(), mapH, mapW, (float)text_threshold, (float)link_threshold,
+                                (float)low_text, b, nullptr);
+        if (!dev) {
+            DetComponents dc;
+            det_components_dev(h, lane, dt.as<float>(), dl.as<float>(), mapH, mapW, (float)text_threshold,
+                               (float)link_threshold, (float)low_text, dc);
+            boxes_from_components(dc, mapH, mapW, b);
+        }
+        if (used_device) *used_device = dev ? 1 : 0;
         int nb = (int)b.size() / 8;
         ARG_CHECK(nb <= cap, "box capacity %d too small for %d boxes", cap, nb);
         memcpy(boxes, b.data(), b.size() * 4);
         *n = nb;
     });
+}
+
+int bbocr_det_boxes(bbocr_handle* h, const float* textmap, const float* linkmap, int mapH, int mapW,
+                    double text_threshold, double link_threshold, double low_text, float* boxes, int cap, int* n) {
+    return bbocr_dbg_det_boxes(h, textmap, linkmap, mapH, mapW, text_threshold, link_threshold, low_text, 0, boxes, cap, n, nullptr);
 }
 
 int bbocr_min_area_box(const int32_t* xy, int npoints, float* out8) {
@@ -1033,13 +1048,19 @@ void detect_pages(Handle* h, Lane& lane, const bbocr_image* const* imgs, int k, 
     craft_forward_batch_dev(h, st, color.data(), k, g, text, link);
     for (int i = 0; i < k; ++i) {
         tm.reset(new StageTimer(h, 1));
-        DetComponents dc;
-        det_components_dev(h, lane, text + i * plane, link + i * plane, mh, mw, (float)p.text_threshold, (float)p.link_threshold,
-                           (float)p.low_text, dc);
-        pws[i]->n_labels = dc.n_labels;
-        tm.reset(new StageTimer(h, 2));
         std::vector<float> boxes;
-        boxes_from_components(dc, mh, mw, boxes);
+        static const bool host_boxes = getenv("BBOCR_HOST_BOXES") != nullptr;      // A/B: hull / calipers on the host (round 1)
+        int n_labels = 0;
+        if (host_boxes || !det_boxes_dev(h, lane, text + i * plane, link + i * plane, mh, mw, (float)p.text_threshold,
+                                         (float)p.link_threshold, (float)p.low_text, boxes, &n_labels)) {
+            DetComponents dc;
+            det_components_dev(h, lane, text + i * plane, link + i * plane, mh, mw, (float)p.text_threshold, (float)p.link_threshold,
+                               (float)p.low_text, dc);
+            n_labels = dc.n_labels;
+            boxes_from_components(dc, mh, mw, boxes);
+        }
+        pws[i]->n_labels = n_labels;
+        tm.reset(new StageTimer(h, 2));
         bbocr_group_params gp{p.slope_ths, p.ycenter_ths, p.height_ths, p.width_ths, p.add_margin, p.min_size};
         std::vector<int32_t> hlist;
         std::vector<double> flist;

@@ -14,323 +14,48 @@
 #include <vector>
 
 #include "engine.h"
+#include "geom.cuh"
 
 namespace bbocr {
 
 namespace {
 
-struct Pt { int x, y; };
-struct Pt2f { float x, y; };
+using geom::P2i;
+using geom::P2f;
 
-inline int sgn(int64_t v) { return (v > 0) - (v < 0); }
-
-// OpenCV convhull.cpp::Sklansky_<int,int64>
-int sklansky(const std::vector<const Pt*>& array, int start, int end, int* stack, int nsign, int sign2) {
-    int incr = end > start ? 1 : -1;
-    int pprev = start, pcur = pprev + incr, pnext = pcur + incr;
-    int stacksize = 3;
-    if (start == end || (array[start]->x == array[end]->x && array[start]->y == array[end]->y)) {
-        stack[0] = start;
-        return 1;
-    }
-    stack[0] = pprev;
-    stack[1] = pcur;
-    stack[2] = pnext;
-    end += incr;
-    while (pnext != end) {
-        int cury = array[pcur]->y;
-        int nexty = array[pnext]->y;
-        int by = nexty - cury;
-        if (sgn(by) != nsign) {
-            int ax = array[pcur]->x - array[pprev]->x;
-            int bx = array[pnext]->x - array[pcur]->x;
-            int ay = cury - array[pprev]->y;
-            int64_t convexity = (int64_t)ay * bx - (int64_t)ax * by;
-            if (sgn(convexity) == sign2 && (ax != 0 || ay != 0)) {
-                pprev = pcur;
-                pcur = pnext;
-                pnext += incr;
-                stack[stacksize] = pnext;
-                stacksize++;
-            } else {
-                if (pprev == start) {
-                    pcur = pnext;
-                    stack[1] = pcur;
-                    pnext += incr;
-                    stack[2] = pnext;
-                } else {
-                    stack[stacksize - 2] = pnext;
-                    pcur = pprev;
-                    pprev = stack[stacksize - 4];
-                    stacksize--;
-                }
-            }
-        } else {
-            pnext += incr;
-            stack[stacksize - 1] = pnext;
-        }
-    }
-    return --stacksize;
-}
-
-// cv::convexHull(points, hull, clockwise=false, returnPoints=true) for CV_32S points -> hull vertex indices
-void convex_hull(const Pt* data0, int total, std::vector<int>& hull, bool clockwise = false) {
-    hull.clear();
-    if (total == 0) return;
-    std::vector<const Pt*> pointer(total);
-    std::vector<int> stackv(total + 2), hullbuf(total);
-    int* stack = stackv.data();
-    for (int i = 0; i < total; ++i) pointer[i] = &data0[i];
-    std::sort(pointer.begin(), pointer.end(), [](const Pt* a, const Pt* b) {
-        if (a->x != b->x) return a->x < b->x;
-        if (a->y != b->y) return a->y < b->y;
+// sort order of cv::convexHull's pointer array: (x, y, original position)
+void sort_points(const P2i* pts, int n, std::vector<int>& sorted) {
+    sorted.resize(n);
+    for (int i = 0; i < n; ++i) sorted[i] = i;
+    std::sort(sorted.begin(), sorted.end(), [&](int a, int b) {
+        if (pts[a].x != pts[b].x) return pts[a].x < pts[b].x;
+        if (pts[a].y != pts[b].y) return pts[a].y < pts[b].y;
         return a < b;
     });
-    int miny_ind = 0, maxy_ind = 0, nout = 0;
-    for (int i = 1; i < total; ++i) {
-        int y = pointer[i]->y;
-        if (pointer[miny_ind]->y > y) miny_ind = i;
-        if (pointer[maxy_ind]->y < y) maxy_ind = i;
-    }
-    if (pointer[0]->x == pointer[total - 1]->x && pointer[0]->y == pointer[total - 1]->y) {
-        hullbuf[nout++] = 0;
-    } else {
-        int* tl_stack = stack;
-        int tl_count = sklansky(pointer, 0, maxy_ind, tl_stack, -1, 1);
-        int* tr_stack = stack + tl_count;
-        int tr_count = sklansky(pointer, total - 1, maxy_ind, tr_stack, -1, -1);
-        if (!clockwise) {
-            std::swap(tl_stack, tr_stack);
-            std::swap(tl_count, tr_count);
-        }
-        for (int i = 0; i < tl_count - 1; ++i) hullbuf[nout++] = (int)(pointer[tl_stack[i]] - data0);
-        for (int i = tr_count - 1; i > 0; --i) hullbuf[nout++] = (int)(pointer[tr_stack[i]] - data0);
-        int stop_idx = tr_count > 2 ? tr_stack[1] : tl_count > 2 ? tl_stack[tl_count - 2] : -1;
-
-        int* bl_stack = stack;
-        int bl_count = sklansky(pointer, 0, miny_ind, bl_stack, 1, -1);
-        int* br_stack = stack + bl_count;
-        int br_count = sklansky(pointer, total - 1, miny_ind, br_stack, 1, 1);
-        if (clockwise) {
-            std::swap(bl_stack, br_stack);
-            std::swap(bl_count, br_count);
-        }
-        if (stop_idx >= 0) {
-            int check_idx = bl_count > 2 ? bl_stack[1] : bl_count + br_count > 2 ? br_stack[2 - bl_count] : -1;
-            if (check_idx == stop_idx ||
-                (check_idx >= 0 && pointer[check_idx]->x == pointer[stop_idx]->x && pointer[check_idx]->y == pointer[stop_idx]->y)) {
-                bl_count = std::min(bl_count, 2);
-                br_count = std::min(br_count, 2);
-            }
-        }
-        for (int i = 0; i < bl_count - 1; ++i) hullbuf[nout++] = (int)(pointer[bl_stack[i]] - data0);
-        for (int i = br_count - 1; i > 0; --i) hullbuf[nout++] = (int)(pointer[br_stack[i]] - data0);
-
-        if (nout >= 3) {
-            int min_idx = 0, max_idx = 0, lt = 0, i;
-            for (i = 1; i < nout; ++i) {
-                int idx = hullbuf[i];
-                lt += hullbuf[i - 1] < idx;
-                if (lt > 1 && lt <= i - 2) break;
-                if (idx < hullbuf[min_idx]) min_idx = i;
-                if (idx > hullbuf[max_idx]) max_idx = i;
-            }
-            int mmdist = std::abs(max_idx - min_idx);
-            if ((mmdist == 1 || mmdist == nout - 1) && (lt <= 1 || lt >= nout - 2)) {
-                int ascending = (max_idx + 1) % nout == min_idx;
-                int i0 = ascending ? min_idx : max_idx, j = i0;
-                if (i0 > 0) {
-                    for (i = 0; i < nout; ++i) {
-                        int curr_idx = stack[i] = hullbuf[j];
-                        int next_j = j + 1 < nout ? j + 1 : 0;
-                        int next_idx = hullbuf[next_j];
-                        if (i < nout - 1 && (ascending != (curr_idx < next_idx))) break;
-                        j = next_j;
-                    }
-                    if (i == nout) memcpy(hullbuf.data(), stack, nout * sizeof(int));
-                }
-            }
-        }
-    }
-    hull.assign(hullbuf.begin(), hullbuf.begin() + nout);
-}
-
-inline void rot90cw(const Pt2f& in, Pt2f& out) { out.x = in.y; out.y = -in.x; }
-inline void rot90ccw(const Pt2f& in, Pt2f& out) { out.x = -in.y; out.y = in.x; }
-inline void rot180(const Pt2f& in, Pt2f& out) { out.x = -in.x; out.y = -in.y; }
-inline bool first_vec_is_right(const Pt2f& v1, const Pt2f& v2) {
-    Pt2f t;
-    rot90cw(v1, t);
-    return t.x * v2.x + t.y * v2.y < 0;
-}
-
-// OpenCV rotcalipers.cpp::rotatingCalipers(points, n, CALIPERS_MINAREARECT, out[6])
-void rotating_calipers(const Pt2f* points, int n, float* out) {
-    float minarea = FLT_MAX;
-    float buf[7] = {0, 0, 0, 0, 0, 0, 0};
-    int ibuf0 = 0, ibuf5 = 0;
-    std::vector<float> inv_vect_length(n);
-    std::vector<Pt2f> vect(n);
-    int left = 0, bottom = 0, right = 0, top = 0;
-    int seq[4] = {-1, -1, -1, -1};
-    Pt2f rot_vect[4];
-    float orientation = 0;
-    float base_a;
-    float base_b = 0;
-    float left_x, right_x, top_y, bottom_y;
-    Pt2f pt0 = points[0];
-    left_x = right_x = pt0.x;
-    top_y = bottom_y = pt0.y;
-    for (int i = 0; i < n; ++i) {
-        double dx, dy;
-        if (pt0.x < left_x) left_x = pt0.x, left = i;
-        if (pt0.x > right_x) right_x = pt0.x, right = i;
-        if (pt0.y > top_y) top_y = pt0.y, top = i;
-        if (pt0.y < bottom_y) bottom_y = pt0.y, bottom = i;
-        Pt2f pt = points[(i + 1) & (i + 1 < n ? -1 : 0)];
-        dx = pt.x - pt0.x;
-        dy = pt.y - pt0.y;
-        vect[i].x = (float)dx;
-        vect[i].y = (float)dy;
-        inv_vect_length[i] = (float)(1. / std::sqrt(dx * dx + dy * dy));
-        pt0 = pt;
-    }
-    {
-        double ax = vect[n - 1].x;
-        double ay = vect[n - 1].y;
-        for (int i = 0; i < n; ++i) {
-            double bx = vect[i].x;
-            double by = vect[i].y;
-            double convexity = ax * by - ay * bx;
-            if (convexity != 0) {
-                orientation = (convexity > 0) ? 1.f : (-1.f);
-                break;
-            }
-            ax = bx;
-            ay = by;
-        }
-    }
-    base_a = orientation;
-    seq[0] = bottom;
-    seq[1] = right;
-    seq[2] = top;
-    seq[3] = left;
-    for (int k = 0; k < n; ++k) {
-        int main_element = 0;
-        rot_vect[0] = vect[seq[0]];
-        rot90cw(vect[seq[1]], rot_vect[1]);
-        rot180(vect[seq[2]], rot_vect[2]);
-        rot90ccw(vect[seq[3]], rot_vect[3]);
-        for (int i = 1; i < 4; ++i)
-            if (first_vec_is_right(rot_vect[i], rot_vect[main_element])) main_element = i;
-        {
-            int pindex = seq[main_element];
-            float lead_x = vect[pindex].x * inv_vect_length[pindex];
-            float lead_y = vect[pindex].y * inv_vect_length[pindex];
-            switch (main_element) {
-                case 0: base_a = lead_x; base_b = lead_y; break;
-                case 1: base_a = lead_y; base_b = -lead_x; break;
-                case 2: base_a = -lead_x; base_b = -lead_y; break;
-                case 3: base_a = -lead_y; base_b = lead_x; break;
-            }
-        }
-        seq[main_element] += 1;
-        seq[main_element] = (seq[main_element] == n) ? 0 : seq[main_element];
-        {
-            float dx = points[seq[1]].x - points[seq[3]].x;
-            float dy = points[seq[1]].y - points[seq[3]].y;
-            float width = dx * base_a + dy * base_b;
-            dx = points[seq[2]].x - points[seq[0]].x;
-            dy = points[seq[2]].y - points[seq[0]].y;
-            float height = -dx * base_b + dy * base_a;
-            float area = width * height;
-            if (area <= minarea) {
-                minarea = area;
-                ibuf0 = seq[3];
-                buf[1] = base_a;
-                buf[2] = width;
-                buf[3] = base_b;
-                buf[4] = height;
-                ibuf5 = seq[0];
-                buf[6] = area;
-            }
-        }
-    }
-    float A1 = buf[1];
-    float B1 = buf[3];
-    float A2 = -buf[3];
-    float B2 = buf[1];
-    float C1 = A1 * points[ibuf0].x + points[ibuf0].y * B1;
-    float C2 = A2 * points[ibuf5].x + points[ibuf5].y * B2;
-    float idet = 1.f / (A1 * B2 - A2 * B1);
-    float px = (C1 * B2 - C2 * B1) * idet;
-    float py = (A1 * C2 - A2 * C1) * idet;
-    out[0] = px;
-    out[1] = py;
-    out[2] = A1 * buf[2];
-    out[3] = B1 * buf[2];
-    out[4] = A2 * buf[4];
-    out[5] = B2 * buf[4];
 }
 
 }  // namespace
 
 void debug_convex_hull(const int32_t* xy, int n, int clockwise, std::vector<int>& hull) {
-    std::vector<Pt> pts(n);
+    std::vector<P2i> pts(n);
     for (int i = 0; i < n; ++i) { pts[i].x = xy[2 * i]; pts[i].y = xy[2 * i + 1]; }
-    convex_hull(pts.data(), n, hull, clockwise != 0);
+    std::vector<int> sorted, stack(n + 2), hullbuf(std::max(n, 1));
+    sort_points(pts.data(), n, sorted);
+    const int hn = geom::convex_hull(pts.data(), sorted.data(), n, stack.data(), hullbuf.data(), clockwise != 0);
+    hull.assign(hullbuf.begin(), hullbuf.begin() + hn);
 }
 
-// cv2.boxPoints(cv2.minAreaRect(points)) for int32 (x,y) points
+// cv2.boxPoints(cv2.minAreaRect(points)) for int32 (x,y) points (the arithmetic lives in geom.cuh, shared with the device)
 void min_area_box(const int32_t* xy, int n, float* out8) {
-    std::vector<Pt> pts(n);
+    std::vector<P2i> pts(n);
     for (int i = 0; i < n; ++i) { pts[i].x = xy[2 * i]; pts[i].y = xy[2 * i + 1]; }
-    std::vector<int> hull;
-    convex_hull(pts.data(), n, hull, false);         // minAreaRect: convexHull(points, hull, clockwise=false, returnPoints=true)
-    int hn = (int)hull.size();
-    std::vector<Pt2f> hp(hn);
-    for (int i = 0; i < hn; ++i) { hp[i].x = (float)pts[hull[i]].x; hp[i].y = (float)pts[hull[i]].y; }
-    float cx = 0, cy = 0, bw = 0, bh = 0, angle = 0;
-    double ad = 0;
-    if (hn > 2) {
-        float o[6];
-        rotating_calipers(hp.data(), hn, o);
-        cx = o[0] + (o[2] + o[4]) * 0.5f;
-        cy = o[1] + (o[3] + o[5]) * 0.5f;
-        bw = (float)std::sqrt((double)o[2] * o[2] + (double)o[3] * o[3]);
-        bh = (float)std::sqrt((double)o[4] * o[4] + (double)o[5] * o[5]);
-        ad = atan2((double)o[3], (double)o[2]);
-    } else if (hn == 2) {
-        cx = (hp[0].x + hp[1].x) * 0.5f;
-        cy = (hp[0].y + hp[1].y) * 0.5f;
-        double dx = hp[1].x - hp[0].x;
-        double dy = hp[1].y - hp[0].y;
-        bw = (float)std::sqrt(dx * dx + dy * dy);
-        bh = 0;
-        ad = atan2(dy, dx);
-    } else if (hn == 1) {
-        cx = hp[0].x;
-        cy = hp[0].y;
-    }
-    // OpenCV >= 4.5.1 reports the angle in [-90, 0).  Measured against cv2 4.13: the caliper angle (degrees, kept in
-    // double) in [0, 90) is shifted by -90 with width/height exchanged; 90 becomes -90 without the exchange; the
-    // single cast to float happens after that.
-    ad = ad * 180 / 3.1415926535897932384626433832795;
-    if (hn >= 2) {
-        while (ad >= 0.0) { ad -= 90.0; std::swap(bw, bh); }
-        while (ad < -90.0) { ad += 90.0; std::swap(bw, bh); }
-    }
-    angle = (float)ad;
-    // RotatedRect::points
-    double _angle = angle * 3.1415926535897932384626433832795 / 180.;
-    float b = (float)cos(_angle) * 0.5f;
-    float a = (float)sin(_angle) * 0.5f;
-    float p0x = cx - a * bh - b * bw, p0y = cy + b * bh - a * bw;
-    float p1x = cx + a * bh - b * bw, p1y = cy - b * bh - a * bw;
-    out8[0] = p0x; out8[1] = p0y;
-    out8[2] = p1x; out8[3] = p1y;
-    out8[4] = 2 * cx - p0x; out8[5] = 2 * cy - p0y;
-    out8[6] = 2 * cx - p1x; out8[7] = 2 * cy - p1y;
+    std::vector<int> sorted, stack(n + 2), hullbuf(std::max(n, 1));
+    sort_points(pts.data(), n, sorted);
+    // minAreaRect: convexHull(points, hull, clockwise=false, returnPoints=true)
+    const int hn = geom::convex_hull(pts.data(), sorted.data(), n, stack.data(), hullbuf.data(), false);
+    std::vector<P2f> hp(std::max(hn, 1)), vect(std::max(hn, 1));
+    std::vector<float> inv_len(std::max(hn, 1));
+    geom::min_area_box_from_hull(pts.data(), hullbuf.data(), hn, hp.data(), inv_len.data(), vect.data(), out8);
 }
 
 // getDetBoxes_core per kept label, from the per-row extents of (label minus link-only pixels)
@@ -372,32 +97,16 @@ void boxes_from_components(const DetComponents& dc, int mh, int mw, std::vector<
             l = std::min(l, a); r_ = std::max(r_, e);
             t = std::min(t, yy); b = std::max(b, yy);
         }
-        float box[8];
+        float box[8], rolled[8];
         if (pts.empty()) {
             // cv2.minAreaRect on an empty point set returns a zero rect; upstream would then produce a zero box
             for (float& v : box) v = 0.f;
+            for (float& v : rolled) v = 0.f;
         } else {
             min_area_box(pts.data(), (int)pts.size() / 2, box);
-            float dx = box[0] - box[2], dy = box[1] - box[3];
-            float bw = std::sqrt(dx * dx + dy * dy);
-            dx = box[2] - box[4]; dy = box[3] - box[5];
-            float bh = std::sqrt(dx * dx + dy * dy);
-            float box_ratio = std::max(bw, bh) / (std::min(bw, bh) + 1e-5f);
-            if (std::fabs(1.f - box_ratio) <= 0.1f) {
-                box[0] = (float)l; box[1] = (float)t; box[2] = (float)r_; box[3] = (float)t;
-                box[4] = (float)r_; box[5] = (float)b; box[6] = (float)l; box[7] = (float)b;
-            }
+            geom::finish_det_box(box, l, t, r_, b, rolled);          // "diamond" rule + clockwise start
         }
-        int start = 0;
-        float best = box[0] + box[1];
-        for (int i = 1; i < 4; ++i) {
-            float s = box[2 * i] + box[2 * i + 1];
-            if (s < best) { best = s; start = i; }
-        }
-        for (int i = 0; i < 4; ++i) {                          // np.roll(box, 4 - start, 0): out[i] = box[(i + start) % 4]
-            boxes.push_back(box[2 * ((i + start) % 4)]);
-            boxes.push_back(box[2 * ((i + start) % 4) + 1]);
-        }
+        boxes.insert(boxes.end(), rolled, rolled + 8);
     }
 }
 
@@ -597,10 +306,13 @@ void free_box_transform(const double* quad, int* max_w, int* max_h, double* Minv
         r0[1] = r1[4] = sy;
         r0[2] = r1[5] = 1;
         r0[3] = r0[4] = r0[5] = r1[0] = r1[1] = r1[2] = 0;
-        r0[6] = -sx * dx;
-        r0[7] = -sy * dx;
-        r1[6] = -sx * dy;
-        r1[7] = -sy * dy;
+        // cv::getPerspectiveTransform multiplies the Point2f coordinates in FLOAT and widens the product:
+        // a[i][6] = -src[i].x*dst[i].x  (found by diffing against cv2: a double product moves M's low bits and, through a
+        // tie in cvRound, 1 pixel in ~10^6)
+        r0[6] = (double)(-r[2 * i] * dst[2 * i]);
+        r0[7] = (double)(-r[2 * i + 1] * dst[2 * i]);
+        r1[6] = (double)(-r[2 * i] * dst[2 * i + 1]);
+        r1[7] = (double)(-r[2 * i + 1] * dst[2 * i + 1]);
         b[i] = dx;
         b[i + 4] = dy;
     }

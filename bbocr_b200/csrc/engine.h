@@ -171,6 +171,9 @@ struct DetComponents {             // kept components of one page, host side
 void det_components_dev(Handle*, Lane&, const float* text, const float* link, int mh, int mw, float text_threshold,
                         float link_threshold, float low_text, DetComponents& out);
 void boxes_from_components(const DetComponents&, int mh, int mw, std::vector<float>& boxes /*n*8*/);
+// the same on the device incl. hull + min-area rectangle (one D2H of the finished boxes); false = capacity exceeded, use the two above
+bool det_boxes_dev(Handle*, Lane&, const float* text, const float* link, int mh, int mw, float text_threshold,
+                   float link_threshold, float low_text, std::vector<float>& boxes, int* n_labels);
 void min_area_box(const int32_t* xy, int n, float* out8);
 void debug_convex_hull(const int32_t* xy, int n, int clockwise, std::vector<int>& hull);
 void group_boxes(const float* boxes, int n, double ratio, const bbocr_group_params& p, std::vector<int32_t>& hlist,

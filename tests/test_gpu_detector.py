@@ -85,3 +85,54 @@ def test_detect_matches_oracle_given_same_maps(gpu_reader, oracle_reader):
     oh, of = oracle_reader.boxes_from_maps(ot, ol, ratio)
     assert [list(map(int, b)) for b in oh] == hl.tolist()
     assert len(of) == len(fl) and all(np.array_equal(np.array(a, np.float64), b) for a, b in zip(of, fl))
+
+
+def _shape_maps(seed, h, w, n_shapes):
+    """Score maps full of rotated rectangles, ellipses, thin strokes and touching blobs: many hull / caliper configurations."""
+    rng = np.random.default_rng(seed)
+    text = np.zeros((h, w), np.float32)
+    link = np.zeros((h, w), np.float32)
+    for _ in range(n_shapes):
+        cx, cy = int(rng.integers(0, w)), int(rng.integers(0, h))
+        kind = int(rng.integers(0, 4))
+        val = float(rng.uniform(0.5, 0.99))
+        if kind == 0:
+            box = cv2.boxPoints(((cx, cy), (float(rng.uniform(3, 120)), float(rng.uniform(2, 40))), float(rng.uniform(-90, 90))))
+            cv2.fillConvexPoly(text, box.astype(np.int32), val)
+        elif kind == 1:
+            cv2.ellipse(text, (cx, cy), (int(rng.integers(2, 60)), int(rng.integers(2, 25))), float(rng.uniform(0, 180)), 0, 360, val, -1)
+        elif kind == 2:
+            cv2.line(text, (cx, cy), (cx + int(rng.integers(-80, 80)), cy + int(rng.integers(-30, 30))), val, int(rng.integers(1, 4)))
+        else:
+            cv2.circle(text, (cx, cy), int(rng.integers(1, 12)), val, -1)
+            cv2.line(link, (cx, cy), (cx + int(rng.integers(5, 60)), cy), float(rng.uniform(0.45, 0.9)), int(rng.integers(1, 5)))
+    text += rng.normal(0, 0.004, text.shape).astype(np.float32)
+    return text, link
+
+
+@pytest.mark.parametrize("case", [(31, 480, 640, 400), (32, 720, 960, 800), (33, 333, 517, 300), (34, 1280, 960, 900), (35, 64, 96, 12)])
+def test_device_min_area_boxes_equal_host_tail_and_cv2(handle, case):
+    """getDetBoxes_core with hull + rotating calipers ON THE DEVICE (k_det_boxes, geom.cuh) vs the round-1 host tail (boxes.cpp,
+    same geom.cuh code on x86-64) vs cv2 itself: bitwise identical boxes, thousands of components of every shape."""
+    seed, h, w, n = case
+    t, l = _shape_maps(seed, h, w, n)
+    dev, used = handle.det_boxes(t, l, 0.7, 0.4, 0.4, host_path=False)
+    host, used_h = handle.det_boxes(t, l, 0.7, 0.4, 0.4, host_path=True)
+    assert used and not used_h, "the device tail must be the one that ran"
+    want, _, _ = E.get_det_boxes_core(t, l, 0.7, 0.4, 0.4)
+    assert len(dev) == len(host) == len(want) and len(want) > 0
+    assert np.array_equal(dev.view(np.uint32), host.view(np.uint32))
+    for a, b in zip(dev, want):
+        assert np.array_equal(a.view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
+    print(f"{len(want)} boxes identical (device == host == cv2)")
+
+
+def test_device_box_tail_overflow_falls_back_to_host(handle):
+    """A component taller than the per-block point budget (> 1024 score-map rows) is flagged and the page takes the host tail."""
+    t = np.zeros((1300, 200), np.float32)
+    l = np.zeros((1300, 200), np.float32)
+    t[20:1280, 90:110] = 0.9
+    boxes, used = handle.det_boxes(t, l, 0.7, 0.4, 0.4, host_path=False)
+    want, _, _ = E.get_det_boxes_core(t, l, 0.7, 0.4, 0.4)
+    assert not used and len(boxes) == len(want) == 1
+    assert np.array_equal(boxes[0].view(np.uint32), np.asarray(want[0], np.float32).view(np.uint32))
