@@ -110,7 +110,8 @@ def _shape_maps(seed, h, w, n_shapes):
     return text, link
 
 
-@pytest.mark.parametrize("case", [(31, 480, 640, 400), (32, 720, 960, 800), (33, 333, 517, 300), (34, 1280, 960, 900), (35, 64, 96, 12)])
+@pytest.mark.parametrize("case", [(31, 480, 640, 90), (32, 720, 960, 220), (33, 333, 517, 60), (34, 1280, 960, 400), (35, 64, 96, 4)] +
+                                 [(40 + i, 480, 640, 90) for i in range(24)])
 def test_device_min_area_boxes_equal_host_tail_and_cv2(handle, case):
     """getDetBoxes_core with hull + rotating calipers ON THE DEVICE (k_det_boxes, geom.cuh) vs the round-1 host tail (boxes.cpp,
     same geom.cuh code on x86-64) vs cv2 itself: bitwise identical boxes, thousands of components of every shape."""
