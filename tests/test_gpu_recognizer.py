@@ -262,3 +262,39 @@ def test_readtext_options_through_the_reader(gpu_reader):
     for kw in ({"decoder": "beamsearch"}, {"rotation_info": [90]}, {"output_format": "free_merge"}):
         with pytest.raises(NotImplementedError):
             gpu_reader.readtext(img, **kw)
+
+
+def test_one_reader_shared_by_two_threads(gpu_reader):
+    """batch_processor_enhanced.py:215-216 runs two books at a time over the class-level cached Reader
+    (enhanced_extractor.py:97-98, :151-154): two threads call readtext / readtext_batched on ONE Reader concurrently.  The
+    handle serialises its public calls (Handle::mu) and the Reader holds its own lock; results must equal the serial ones."""
+    import threading
+    pages = [synth.title_page(70 + i, 800, 608) for i in range(4)] + [synth.book_cover(80 + i, 640, 480) for i in range(4)]
+    gpu_reader.set_precision("bf16x3")
+    try:
+        serial = [gpu_reader.readtext(p) for p in pages]
+        out = [None] * len(pages)
+        errors = []
+
+        def worker(ids, batched):
+            try:
+                for rep in range(3):
+                    if batched:
+                        res = gpu_reader.readtext_batched([pages[i] for i in ids])
+                        for i, r in zip(ids, res):
+                            out[i] = r
+                    else:
+                        for i in ids:
+                            out[i] = gpu_reader.readtext(pages[i], paragraph=False, batch_size=1, workers=0)
+            except Exception as e:      # noqa: BLE001
+                errors.append(e)
+
+        ts = [threading.Thread(target=worker, args=([0, 2, 4, 6], False)), threading.Thread(target=worker, args=([1, 3, 5, 7], True))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not errors, errors
+        assert out == serial
+    finally:
+        gpu_reader.set_precision("fp32")
