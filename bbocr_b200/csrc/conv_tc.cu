@@ -47,6 +47,7 @@ struct TcParams {
     const float* bias;
     const uint8_t* colmask;     // optional [OW]: output columns with 0 are written as zeros (gaps between concatenated crops)
     int stages;
+    int p_stages, patch_al;     // halo-patch kernel: patch pipeline depth, bytes of one (1024-aligned) patch
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -192,6 +193,76 @@ __device__ __forceinline__ void store_split(void* hi_base, void* lo_base, int64_
     store16(reinterpret_cast<__nv_bfloat16*>(lo_base) + off, lo, nbase, cout);
 }
 
+// Epilogue warps (4..7) of both kernels: tcgen05.ld 32x32b -> folded-BN scale/bias (+ReLU) -> optional fused 2x2 / 2x1 max-pool
+// by warp shuffles -> bf16 / fp32 / split NHWC stores -> tempty[acc].  TMEM lane r = pixel (r / TW, r % TW) of the tile; with
+// TW in {8, 16} the 2x2 (2x1) pooling window lives in lanes {l, l^1, l^TW, l^TW^1} ({l, l^TW}).
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, int warp, int lane, uint64_t* tfull_bar,
+                                            uint64_t* tempty_bar) {
+        const int wq = warp & 3;
+        const int r = wq * 32 + lane;
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+            const TileCoord tc = tile_coord(p, tile);
+            const int as = ti & 1;
+            const uint32_t aph = (ti >> 1) & 1;
+            mbar_wait(&tfull_bar[as], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int64_t pix = -1, pix2 = -1;
+            bool colvalid = true;
+            if (p.flat) {
+                if (tc.m0 + r < p.M) pix = tc.m0 + r;
+            } else {
+                const int hl = r / p.TW, wl = r - hl * p.TW;
+                const int y = tc.y0 + hl, x = tc.x0 + wl;
+                if (y < p.OH && x < p.OW) pix = ((int64_t)tc.img * p.OH + y) * p.OW + x;
+                if (p.colmask && x < p.OW) colvalid = __ldg(p.colmask + x) != 0;
+                if (p.pool) {
+                    // lane = (hl % (32 / TW)) * TW + wl ; the 2x2 (2x1) window lives in lanes {l, l^1, l^TW, l^TW^1} ({l, l^TW})
+                    const int POH = p.OH >> 1, POW = p.pool == 1 ? p.OW >> 1 : p.OW;
+                    const int py = y >> 1, px = p.pool == 1 ? x >> 1 : x;
+                    const bool writer = (lane & p.TW) == 0 && (p.pool == 2 || (lane & 1) == 0);
+                    if (writer && py < POH && px < POW) pix2 = ((int64_t)tc.img * POH + py) * POW + px;
+                }
+            }
+            const uint32_t trow = tmem_base + (uint32_t)(as * p.BN) + ((uint32_t)(wq * 32) << 16);
+            for (int c = 0; c < p.BN; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + c, v);
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = tc.n0 + c + j;
+                    float a = fmaf(__uint_as_float(v[j]), __ldg(p.scale + n), __ldg(p.bias + n));   // padded to cout_pad
+                    f[j] = p.relu ? fmaxf(a, 0.f) : a;
+                    if (!colvalid) f[j] = 0.f;
+                }
+                const int nbase = tc.n0 + c;
+                if (pix >= 0 && (!p.pool || p.write_full)) {
+                    if (p.split_out) store_split(p.out, p.out_lo, pix * p.cout + nbase, f, nbase, p.cout);
+                    else if (p.out_f32) store16(reinterpret_cast<float*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
+                    else store16(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
+                }
+                if (p.pool) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float m = f[j];
+                        if (p.pool == 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, p.TW));
+                        f[j] = m;
+                    }
+                    if (pix2 >= 0) {
+                        if (p.split_out) store_split(p.out2, p.out2_lo, pix2 * p.cout + nbase, f, nbase, p.cout);
+                        else if (p.out_f32) store16(reinterpret_cast<float*>(p.out2) + pix2 * p.cout + nbase, f, nbase, p.cout);
+                        else store16(reinterpret_cast<__nv_bfloat16*>(p.out2) + pix2 * p.cout + nbase, f, nbase, p.cout);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
 // PAIR = 1: split-precision operands.  A pipeline stage holds the hi AND lo halves of the activation tile and of the
 // weight tile (four TMA boxes), and every K = 16 step issues three MMAs into the same accumulator:
 //     x_hi * w_hi  +  x_lo * w_hi  +  x_hi * w_lo        (the dropped x_lo * w_lo term is 2^-16-class)
@@ -311,70 +382,146 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             umma_commit(&tfull_bar[as]);
         }
     } else if (warp >= 4) {
-        // ---------------- epilogue ----------------
-        const int wq = warp & 3;
-        const int r = wq * 32 + lane;
-        int ti = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+        tc_epilogue(p, tmem_base, warp, lane, tfull_bar, tempty_bar);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// ---- halo-patch variant for split-precision 3x3 / pad 1 convolutions ------------------------------------------------------
+// k_conv_tc fetches one shifted 128-pixel A tile per filter tap: nine tiles (hi AND lo) per k-block for an output tile whose
+// taps overlap almost completely.  Here the input patch of an 8 x 16 output tile -- 10 x 18 pixels with the 1-px halo, TMA
+// out-of-bounds zero fill = the padding -- is loaded ONCE per k-block (hi + lo), and tap (ky, kx) is a shifted UMMA descriptor
+// into it: start = patch + (ky * 10 + kx) * PIX, stride between the 8-row groups (SBO) = one patch row (the trick of
+// conv_res.cu; SWIZZLE_128B / 64B are functions of absolute shared-memory address bits for the TMA write and the tensor-core
+// read alike).  Only the weight tiles (hi + lo per tap) stream through the ring.  A traffic per k-block: 2 x 23 KB instead of
+// 2 x 9 x 16 KB; the low-channel layers of the detector (Cout <= 128), where the A tile dominates the operand stream, leave
+// the L2 -> SM limit.  Three MMAs per K = 16 step as in k_conv_tc<.., PAIR = 1>.
+__device__ __forceinline__ uint64_t desc_kmajor_sbo(uint32_t saddr, uint32_t sbo_bytes, uint64_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
+template <int BK>
+__global__ void __launch_bounds__(256) k_conv_tc_patch(const __grid_constant__ CUtensorMap tmA1,
+                                                       const __grid_constant__ CUtensorMap tmA2,
+                                                       const __grid_constant__ CUtensorMap tmA3,
+                                                       const __grid_constant__ CUtensorMap tmA4,
+                                                       const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[8], empty_bar[8], pfull_bar[4], pempty_bar[4], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int PIX = BK * 2;                              // bytes per pixel row of the operand tiles
+    constexpr int PW = 10, PH = 18;                          // patch: 8 x 16 output pixels + halo
+    constexpr int PPITCH = PW * PIX;
+    constexpr int PATCH_BYTES = PH * PPITCH;
+    constexpr uint64_t LAYOUT = BK == 64 ? 2 : 4;
+    const int B_BYTES = p.BN * BK * 2;
+    const int PSTAGE = 2 * p.patch_al, RSTAGE = 2 * B_BYTES;
+    uint8_t* ring = smem + (size_t)p.p_stages * PSTAGE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb1 = p.C1 / BK, kb2 = p.C2 / BK;
+    uint32_t ncols = 32;
+    while ((int)ncols < 2 * p.BN) ncols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < p.p_stages; ++s) { mbar_init(&pfull_bar[s], 1); mbar_init(&pempty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer: one (hi, lo) patch per (tile, k-block), one (hi, lo) weight tile per tap ----------------
+        // The patch of item j + 1 is requested in the MIDDLE of item j's nine weight tiles: late enough that its stage has been
+        // released (the MMA issuer runs `stages` ring slots behind the producer, so item j - 1 has retired by tap `stages`),
+        // early enough to land before item j + 1 starts (requested after the nine tiles it stalled every tile switch).
+        const int nkb = kb1 + kb2;
+        const int my_tiles = blockIdx.x < p.total_tiles ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int items = my_tiles * nkb;
+        auto load_patch = [&](int j) {
+            const int tile = blockIdx.x + (j / nkb) * gridDim.x, kb = j % nkb;
             const TileCoord tc = tile_coord(p, tile);
-            const int as = ti & 1;
-            const uint32_t aph = (ti >> 1) & 1;
-            mbar_wait(&tfull_bar[as], aph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            int64_t pix = -1, pix2 = -1;
-            bool colvalid = true;
-            if (p.flat) {
-                if (tc.m0 + r < p.M) pix = tc.m0 + r;
-            } else {
-                const int hl = r / p.TW, wl = r - hl * p.TW;
-                const int y = tc.y0 + hl, x = tc.x0 + wl;
-                if (y < p.OH && x < p.OW) pix = ((int64_t)tc.img * p.OH + y) * p.OW + x;
-                if (p.colmask && x < p.OW) colvalid = __ldg(p.colmask + x) != 0;
-                if (p.pool) {
-                    // TW == 16: lane = (hl & 1) * 16 + wl ; the 2x2 (2x1) window lives in lanes {l, l^1, l^16, l^17} ({l, l^16})
-                    const int POH = p.OH >> 1, POW = p.pool == 1 ? p.OW >> 1 : p.OW;
-                    const int py = y >> 1, px = p.pool == 1 ? x >> 1 : x;
-                    const bool writer = (lane & 16) == 0 && (p.pool == 2 || (lane & 1) == 0);
-                    if (writer && py < POH && px < POW) pix2 = ((int64_t)tc.img * POH + py) * POW + px;
-                }
+            const int ps = j % p.p_stages;
+            mbar_wait(&pempty_bar[ps], ((j / p.p_stages) & 1) ^ 1);
+            const int seg = kb < kb1 ? 0 : 1;
+            const int c0 = (seg == 0 ? kb : kb - kb1) * BK;
+            uint8_t* pa = smem + (size_t)ps * PSTAGE;
+            mbar_expect_tx(&pfull_bar[ps], (uint32_t)(2 * PATCH_BYTES));
+            tma_load_4d(pa, seg == 0 ? &tmA1 : &tmA3, &pfull_bar[ps], c0, tc.x0 - 1, tc.y0 - 1, tc.img);
+            tma_load_4d(pa + p.patch_al, seg == 0 ? &tmA2 : &tmA4, &pfull_bar[ps], c0, tc.x0 - 1, tc.y0 - 1, tc.img);
+        };
+        int it = 0;
+        if (items > 0) load_patch(0);
+        const int tap_pf = p.stages < 8 ? p.stages : 8;
+        for (int j = 0; j < items; ++j) {
+            const int tile = blockIdx.x + (j / nkb) * gridDim.x, kb = j % nkb;
+            const int n0 = (tile % p.n_tiles) * p.BN;
+            for (int tap = 0; tap < 9; ++tap, ++it) {
+                const int s = it % p.stages;
+                mbar_wait(&empty_bar[s], ((it / p.stages) & 1) ^ 1);
+                uint8_t* sb = ring + (size_t)s * RSTAGE;
+                mbar_expect_tx(&full_bar[s], (uint32_t)RSTAGE);
+                tma_load_3d(sb, &tmB, &full_bar[s], kb * BK, n0, tap);
+                tma_load_3d(sb + B_BYTES, &tmB, &full_bar[s], p.w_lo_off + kb * BK, n0, tap);
+                if (tap == tap_pf && j + 1 < items) load_patch(j + 1);
             }
-            const uint32_t trow = tmem_base + (uint32_t)(as * p.BN) + ((uint32_t)(wq * 32) << 16);
-            for (int c = 0; c < p.BN; c += 16) {
-                uint32_t v[16];
-                tmem_ld16(trow + c, v);
-                float f[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = tc.n0 + c + j;
-                    float a = fmaf(__uint_as_float(v[j]), __ldg(p.scale + n), __ldg(p.bias + n));   // padded to cout_pad
-                    f[j] = p.relu ? fmaxf(a, 0.f) : a;
-                    if (!colvalid) f[j] = 0.f;
-                }
-                const int nbase = tc.n0 + c;
-                if (pix >= 0 && (!p.pool || p.write_full)) {
-                    if (p.split_out) store_split(p.out, p.out_lo, pix * p.cout + nbase, f, nbase, p.cout);
-                    else if (p.out_f32) store16(reinterpret_cast<float*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
-                    else store16(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
-                }
-                if (p.pool) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float m = f[j];
-                        if (p.pool == 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-                        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-                        f[j] = m;
-                    }
-                    if (pix2 >= 0) {
-                        if (p.split_out) store_split(p.out2, p.out2_lo, pix2 * p.cout + nbase, f, nbase, p.cout);
-                        else if (p.out_f32) store16(reinterpret_cast<float*>(p.out2) + pix2 * p.cout + nbase, f, nbase, p.cout);
-                        else store16(reinterpret_cast<__nv_bfloat16*>(p.out2) + pix2 * p.cout + nbase, f, nbase, p.cout);
-                    }
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        int it = 0, pit = 0, ti = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+            const int as = ti & 1;
+            mbar_wait(&tempty_bar[as], ((ti >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.BN);
+            for (int kb = 0; kb < kb1 + kb2; ++kb, ++pit) {
+                const int ps = pit % p.p_stages;
+                mbar_wait(&pfull_bar[ps], (pit / p.p_stages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t pa = smem_u32(smem + (size_t)ps * PSTAGE);
+                const uint64_t ahi0 = desc_kmajor_sbo(pa, PPITCH, LAYOUT), alo0 = desc_kmajor_sbo(pa + p.patch_al, PPITCH, LAYOUT);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap, ++it) {
+                    const int s = it % p.stages;
+                    mbar_wait(&full_bar[s], (it / p.stages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sb = smem_u32(ring + (size_t)s * RSTAGE);
+                    const uint64_t bhi = umma_desc<BK>(sb), blo = umma_desc<BK>(sb + B_BYTES);
+                    const int ky = tap / 3, kx = tap % 3;
+                    const uint64_t off = (uint64_t)(((ky * PW + kx) * PIX) >> 4);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        umma_bf16(tmem_acc, ahi0 + off + 2 * kk, bhi + 2 * kk, idesc, (kb > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                        umma_bf16(tmem_acc, alo0 + off + 2 * kk, bhi + 2 * kk, idesc, 1u);
+                        umma_bf16(tmem_acc, ahi0 + off + 2 * kk, blo + 2 * kk, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&pempty_bar[ps]);
+            }
+            umma_commit(&tfull_bar[as]);
+        }
+    } else if (warp >= 4) {
+        tc_epilogue(p, tmem_base, warp, lane, tfull_bar, tempty_bar);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -480,11 +627,15 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     p.scale = cw.scale;
     p.bias = cw.bias;
     p.colmask = colmask;
+    // halo-patch kernel: split-precision 3x3 / pad 1 layers with at least 16 output rows (BBOCR_TC_PATCH=0: A/B switch)
+    static const bool patch_on = !(getenv("BBOCR_TC_PATCH") && atoi(getenv("BBOCR_TC_PATCH")) == 0);
+    const bool patch = patch_on && split_in && !p.flat && cw.kh == 3 && cw.kw == 3 && cw.pad == 1 && cw.dil == 1 && out.H >= 16 && out.W >= 8;
     if (p.flat) { p.TW = 128; p.TH = 1; p.tiles_x = p.tiles_y = 1; }
+    else if (patch) { p.TW = 8; p.TH = 16; }
     else if (out.H >= 8) { p.TW = 16; p.TH = 8; }
     else { p.TW = 32; p.TH = 4; }
     if (pooled) {
-        ARG_CHECK(!p.flat && p.TW == 16, "fused pooling needs the 16x8 spatial tile");
+        ARG_CHECK(!p.flat && (p.TW == 16 || p.TW == 8), "fused pooling needs the 16x8 or 8x16 spatial tile");
         p.pool = (flags & CONV_POOL22) ? 1 : 2;
         ARG_CHECK(out.H % 2 == 0 && (p.pool == 2 || out.W % 2 == 0), "fused pooling needs even output dimensions");
         ARG_CHECK(pooled->H == out.H / 2 && pooled->W == (p.pool == 1 ? out.W / 2 : out.W) && pooled->C == out.C, "pooled geometry");
@@ -502,12 +653,49 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     p.total_tiles = p.m_tiles * p.n_tiles;
     static const int smem_budget_kb = getenv("BBOCR_TC_SMEM_KB") ? atoi(getenv("BBOCR_TC_SMEM_KB")) : 100;
     static const int ctas_per_sm = getenv("BBOCR_TC_CTAS") ? atoi(getenv("BBOCR_TC_CTAS")) : 2;
-    const int budget = (p.BN > 128 ? 200 : smem_budget_kb) * 1024;
-    // a paired (hi + lo) stage is twice as large: fall back to 32-channel k-blocks when fewer than three 64-channel stages fit
-    if (split_in && bk == 64 && budget / (2 * (BM * 64 * 2 + p.BN * 64 * 2)) < 3) bk = 32;
-    const int stage_bytes = (split_in ? 2 : 1) * (BM * bk * 2 + p.BN * bk * 2);
-    p.stages = std::min(8, std::max(2, budget / stage_bytes));
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    int budget = (p.BN > 128 ? 200 : smem_budget_kb) * 1024;
+    p.p_stages = 0;
+    p.patch_al = 0;
+    int stage_bytes;
+    size_t smem;
+    int ctas = p.BN > 128 ? 1 : ctas_per_sm;
+    if (patch) {
+        // patches: 2 stages of (hi, lo) 10 x 18 px; ring: (hi, lo) weight tiles, one per tap.  64-channel k-blocks when three
+        // ring stages still fit next to the patches, else 32-channel ones; two CTAs per SM when the whole CTA stays under 100 KB
+        auto plan = [&](int k, int& ring_stages, size_t& total) {
+            const int pal = ((18 * 10 * k * 2) + 1023) & ~1023;
+            const int rst = 2 * p.BN * k * 2;
+            const int avail = 200 * 1024 - 2 * 2 * pal;
+            ring_stages = std::min(8, avail / rst);
+            total = (size_t)2 * 2 * pal + (size_t)ring_stages * rst + 1024;
+            return pal;
+        };
+        int rs = 0;
+        size_t tot = 0;
+        int pal = plan(bk, rs, tot);
+        if (bk == 64 && rs < 3) { bk = 32; pal = plan(bk, rs, tot); }
+        ARG_CHECK(rs >= 2, "conv_tc patch: tile does not fit");
+        if (p.BN <= 64 && tot > 100 * 1024) {
+            // narrow layers (short MMAs, A-read bound): two CTAs per SM hide the tile switch and the barrier latencies better
+            // than one deep ring; 32-channel k-blocks halve the patches so that both fit
+            const int pal32 = ((18 * 10 * 32 * 2) + 1023) & ~1023, rst32 = 2 * p.BN * 32 * 2;
+            const int rs2 = std::min(8, (100 * 1024 - 1024 - 4 * pal32) / rst32);
+            if (rs2 >= 4) { bk = 32; pal = pal32; rs = rs2; tot = (size_t)4 * pal + (size_t)rs * rst32 + 1024; }
+        }
+        p.p_stages = 2;
+        p.patch_al = pal;
+        p.stages = rs;
+        stage_bytes = 2 * p.BN * bk * 2;
+        smem = tot;
+        ctas = tot <= 100 * 1024 ? 2 : 1;
+    } else {
+        // a paired (hi + lo) stage is twice as large: fall back to 32-channel k-blocks when fewer than three 64-channel stages fit
+        if (split_in && bk == 64 && budget / (2 * (BM * 64 * 2 + p.BN * 64 * 2)) < 3) bk = 32;
+        stage_bytes = (split_in ? 2 : 1) * (BM * bk * 2 + p.BN * bk * 2);
+        p.stages = std::min(8, std::max(2, budget / stage_bytes));
+        smem = (size_t)p.stages * stage_bytes + 1024;
+    }
+    (void)stage_bytes;
 
     auto act_map = [&](const Act& a) {
         if (p.flat) {
@@ -518,7 +706,7 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
         }
         uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
         uint64_t str[3] = {(uint64_t)a.C * 2, (uint64_t)a.W * a.C * 2, (uint64_t)a.H * a.W * a.C * 2};
-        uint32_t box[4] = {(uint32_t)bk, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        uint32_t box[4] = {(uint32_t)bk, (uint32_t)(patch ? 10 : p.TW), (uint32_t)(patch ? 18 : p.TH), 1};
         return make_map(a.p, 4, dims, str, box, bk);
     };
     CUtensorMap mA1 = act_map(in1);
@@ -542,15 +730,20 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     CUtensorMap mB = make_map(split_in ? cw.w_split : cw.w_bf16, 3, wd, ws, wb, bk);
 
     // persistent grid: a multiple of the SM count (148 on B200), never more CTAs than tiles
-    const unsigned grid = (unsigned)std::min<int64_t>(p.total_tiles, (int64_t)h->sm_count * (p.BN > 128 ? 1 : ctas_per_sm));
+    const unsigned grid = (unsigned)std::min<int64_t>(p.total_tiles, (int64_t)h->sm_count * ctas);
     if (!h->tc_attr_set) {          // per device (one handle = one device)
         CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc_patch<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc_patch<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         h->tc_attr_set = true;
     }
-    if (split_in) {
+    if (patch) {
+        if (bk == 64) k_conv_tc_patch<64><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        else k_conv_tc_patch<32><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+    } else if (split_in) {
         if (bk == 64) k_conv_tc<64, 1><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
         else k_conv_tc<32, 1><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
     } else {

@@ -165,10 +165,11 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     const float s0 = (float)(0.229 * 255.0), s1 = (float)(0.224 * 255.0), s2 = (float)(0.225 * 255.0);
     const bool tc_first = h->precision == BBOCR_PREC_BF16 && !h->force_generic_conv;
     const bool split = tc_first && h->det_split;        // bf16x3: every activation tensor is a hi/lo pair
-    // bf16x3 stem: the 27-tap conv1_1 runs on the CUDA cores straight from the FP32 canvas (exact FP32 products) and writes
-    // the split tensor; the gathered 32-channel stem would cost a 354 MB round trip per page for 1.5 % of the FLOPs
-    static const bool stem_gather_x3 = getenv("BBOCR_X3_STEM_GATHER") != nullptr;      // A/B: tensor-core stem as in bf16 mode
-    const bool gather = tc_first && (!split || stem_gather_x3);
+    // bf16x3 stem: the gathered 32-channel stem (hi + lo) on the tensor cores like bf16 mode: 553 us per 1920x1440 page.  The
+    // alternative -- the 27-tap conv1_1 on the CUDA cores straight from the FP32 canvas -- measured 827 us (its per-pixel 128-byte
+    // hi / lo stores are written 8 bytes per lane), kept behind BBOCR_X3_STEM_DIRECT for A/B.
+    static const bool stem_direct_x3 = getenv("BBOCR_X3_STEM_DIRECT") != nullptr;
+    const bool gather = tc_first && (!split || !stem_direct_x3);
     const size_t canvas_px_bytes = gather ? 64 : 16;
     const size_t canvas_plane = (((size_t)nimg * H * W * canvas_px_bytes) + 255) & ~(size_t)255;
     DevBuf canvas(canvas_plane * (split && gather ? 2 : 1), st), resized;
