@@ -395,7 +395,7 @@ def main():
         peak_burst, peak_sust, peak_gbs, peak_src = peaks()
         achieved = (iso_flops / 1e12) / (iso_ms / 1e3) if iso_ms > 0 else 0.0
         in_step = (conv_flops / 1e12) / (conv_ms / 1e3) if conv_ms > 0 else 0.0
-        step_tflops = flops_all / (ms / args.steps / 1e3) / 1e12
+        step_tflops = flops_all / world / (ms / args.steps / 1e3) / 1e12           # per GPU
         mma_factor = 3 if args.precision == "bf16x3" else 1
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r2_conv_traffic.json" if args.precision == "bf16x3" else "r1_conv_traffic.json")
@@ -432,7 +432,7 @@ def main():
                          "mma_flops_per_algorithmic_flop": mma_factor,
                          "tensor_pipe_frac": mma_factor * achieved / peak_burst if peak_burst else None,
                          "step_tflops": step_tflops, "step_frac_of_sustained": step_tflops / peak_sust,
-                         "step_frac_is": "algorithmic CRAFT FLOPs of the whole step / ms_per_step / SUSTAINED bf16 peak (kernels timed inside a long step)",
+                         "step_frac_is": "algorithmic CRAFT FLOPs of the step PER GPU / ms_per_step / SUSTAINED bf16 peak (kernels timed inside a long step)",
                          "achieved_in_step": in_step, "launches_in_step": int(conv_n),
                          "note": "algorithmic FLOPs = 2*M*Cout*Cin*taps per launch (711 440 per padded input pixel, 1.967 TFLOP per 1920x1440 page). In bf16x3 "
                                  "mode every algorithmic product costs three bf16 MMAs (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo): tensor_pipe_frac counts those. "
