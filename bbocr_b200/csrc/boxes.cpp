@@ -23,8 +23,8 @@ namespace {
 using geom::P2i;
 using geom::P2f;
 
-// sort order of cv::convexHull's pointer array: (x, y, original position)
-void sort_points(const P2i* pts, int n, std::vector<int>& sorted) {
+// sort order of cv::convexHull's pointer array: (x, y, original position); sp = the points in that order
+void sort_points(const P2i* pts, int n, std::vector<int>& sorted, std::vector<P2i>& sp) {
     sorted.resize(n);
     for (int i = 0; i < n; ++i) sorted[i] = i;
     std::sort(sorted.begin(), sorted.end(), [&](int a, int b) {
@@ -32,6 +32,8 @@ void sort_points(const P2i* pts, int n, std::vector<int>& sorted) {
         if (pts[a].y != pts[b].y) return pts[a].y < pts[b].y;
         return a < b;
     });
+    sp.resize(std::max(n, 1));
+    for (int i = 0; i < n; ++i) sp[i] = pts[sorted[i]];
 }
 
 }  // namespace
@@ -40,8 +42,9 @@ void debug_convex_hull(const int32_t* xy, int n, int clockwise, std::vector<int>
     std::vector<P2i> pts(n);
     for (int i = 0; i < n; ++i) { pts[i].x = xy[2 * i]; pts[i].y = xy[2 * i + 1]; }
     std::vector<int> sorted, stack(n + 2), hullbuf(std::max(n, 1));
-    sort_points(pts.data(), n, sorted);
-    const int hn = geom::convex_hull(pts.data(), sorted.data(), n, stack.data(), hullbuf.data(), clockwise != 0);
+    std::vector<P2i> sp;
+    sort_points(pts.data(), n, sorted, sp);
+    const int hn = geom::convex_hull(sp.data(), sorted.data(), n, stack.data(), hullbuf.data(), clockwise != 0);
     hull.assign(hullbuf.begin(), hullbuf.begin() + hn);
 }
 
@@ -50,9 +53,10 @@ void min_area_box(const int32_t* xy, int n, float* out8) {
     std::vector<P2i> pts(n);
     for (int i = 0; i < n; ++i) { pts[i].x = xy[2 * i]; pts[i].y = xy[2 * i + 1]; }
     std::vector<int> sorted, stack(n + 2), hullbuf(std::max(n, 1));
-    sort_points(pts.data(), n, sorted);
+    std::vector<P2i> sp;
+    sort_points(pts.data(), n, sorted, sp);
     // minAreaRect: convexHull(points, hull, clockwise=false, returnPoints=true)
-    const int hn = geom::convex_hull(pts.data(), sorted.data(), n, stack.data(), hullbuf.data(), false);
+    const int hn = geom::convex_hull(sp.data(), sorted.data(), n, stack.data(), hullbuf.data(), false);
     std::vector<P2f> hp(std::max(hn, 1)), vect(std::max(hn, 1));
     std::vector<float> inv_len(std::max(hn, 1));
     geom::min_area_box_from_hull(pts.data(), hullbuf.data(), hn, hp.data(), inv_len.data(), vect.data(), out8);

@@ -23,12 +23,14 @@ struct P2f { float x, y; };
 
 BB_HD int sgn64(int64_t v) { return (v > 0) - (v < 0); }
 
-// OpenCV convhull.cpp::Sklansky_<int, int64>.  `sorted[i]` = index (into pts) of the i-th point in (x, y, index) order.
-BB_HD int sklansky(const P2i* pts, const int* sorted, int start, int end, int* stack, int nsign, int sign2) {
+// OpenCV convhull.cpp::Sklansky_<int, int64>.  `sp[i]` = the i-th point in (x, y, index) order.  The three points of the
+// running triple live in registers (on the device the walk is one thread's dependent chain: a shared-memory round trip per
+// operand made a 1 400-point component cost ~0.4 ms).
+BB_HD int sklansky(const P2i* sp, int start, int end, int* stack, int nsign, int sign2) {
     int incr = end > start ? 1 : -1;
     int pprev = start, pcur = pprev + incr, pnext = pcur + incr;
     int stacksize = 3;
-    if (start == end || (pts[sorted[start]].x == pts[sorted[end]].x && pts[sorted[start]].y == pts[sorted[end]].y)) {
+    if (start == end || (sp[start].x == sp[end].x && sp[start].y == sp[end].y)) {
         stack[0] = start;
         return 1;
     }
@@ -36,36 +38,40 @@ BB_HD int sklansky(const P2i* pts, const int* sorted, int start, int end, int* s
     stack[1] = pcur;
     stack[2] = pnext;
     end += incr;
+    P2i Pprev = sp[pprev], Pcur = sp[pcur];
+    P2i Pnext = pnext != end ? sp[pnext] : Pcur;
     while (pnext != end) {
-        int cury = pts[sorted[pcur]].y;
-        int nexty = pts[sorted[pnext]].y;
-        int by = nexty - cury;
+        // the point after pnext is requested one iteration early (pnext either advances by incr or stays): on the device the
+        // walk is a single thread's dependent chain and this load's latency was the whole iteration
+        const P2i Pahead = (pnext + incr != end) ? sp[pnext + incr] : Pnext;
+        int by = Pnext.y - Pcur.y;
         if (sgn64(by) != nsign) {
-            int ax = pts[sorted[pcur]].x - pts[sorted[pprev]].x;
-            int bx = pts[sorted[pnext]].x - pts[sorted[pcur]].x;
-            int ay = cury - pts[sorted[pprev]].y;
+            int ax = Pcur.x - Pprev.x;
+            int bx = Pnext.x - Pcur.x;
+            int ay = Pcur.y - Pprev.y;
             int64_t convexity = (int64_t)ay * bx - (int64_t)ax * by;
             if (sgn64(convexity) == sign2 && (ax != 0 || ay != 0)) {
-                pprev = pcur;
-                pcur = pnext;
-                pnext += incr;
+                pprev = pcur; Pprev = Pcur;
+                pcur = pnext; Pcur = Pnext;
+                pnext += incr; Pnext = Pahead;
                 stack[stacksize] = pnext;
                 stacksize++;
             } else {
                 if (pprev == start) {
-                    pcur = pnext;
+                    pcur = pnext; Pcur = Pnext;
                     stack[1] = pcur;
-                    pnext += incr;
+                    pnext += incr; Pnext = Pahead;
                     stack[2] = pnext;
                 } else {
                     stack[stacksize - 2] = pnext;
-                    pcur = pprev;
+                    pcur = pprev; Pcur = Pprev;
                     pprev = stack[stacksize - 4];
+                    Pprev = sp[pprev];
                     stacksize--;
                 }
             }
         } else {
-            pnext += incr;
+            pnext += incr; Pnext = Pahead;
             stack[stacksize - 1] = pnext;
         }
     }
@@ -76,23 +82,27 @@ BB_HD void swap_ip(int*& a, int*& b) { int* t = a; a = b; b = t; }
 BB_HD void swap_i(int& a, int& b) { int t = a; a = b; b = t; }
 BB_HD void swap_f(float& a, float& b) { float t = a; a = b; b = t; }
 
-// cv::convexHull(points, hull, clockwise, returnPoints) for CV_32S points -> hull vertex indices (into pts) in hullbuf;
-// returns their number.  stack: total + 2 ints, hullbuf: total ints.
-BB_HD int convex_hull(const P2i* pts, const int* sorted, int total, int* stack, int* hullbuf, bool clockwise) {
+// cv::convexHull(points, hull, clockwise, returnPoints) for CV_32S points -> hull vertex indices (into the ORIGINAL point
+// array) in hullbuf; returns their number.  sp[i] = the i-th point in (x, y, index) order, sorted[i] = its original index.
+// stack: total + 2 ints, hullbuf: total ints.
+BB_HD int convex_hull(const P2i* sp, const int* sorted, int total, int* stack, int* hullbuf, bool clockwise) {
     if (total == 0) return 0;
     int miny_ind = 0, maxy_ind = 0, nout = 0;
-    for (int i = 1; i < total; ++i) {
-        int y = pts[sorted[i]].y;
-        if (pts[sorted[miny_ind]].y > y) miny_ind = i;
-        if (pts[sorted[maxy_ind]].y < y) maxy_ind = i;
+    {
+        int miny = sp[0].y, maxy = sp[0].y;
+        for (int i = 1; i < total; ++i) {
+            int y = sp[i].y;
+            if (miny > y) { miny = y; miny_ind = i; }
+            if (maxy < y) { maxy = y; maxy_ind = i; }
+        }
     }
-    if (pts[sorted[0]].x == pts[sorted[total - 1]].x && pts[sorted[0]].y == pts[sorted[total - 1]].y) {
+    if (sp[0].x == sp[total - 1].x && sp[0].y == sp[total - 1].y) {
         hullbuf[nout++] = 0;
     } else {
         int* tl_stack = stack;
-        int tl_count = sklansky(pts, sorted, 0, maxy_ind, tl_stack, -1, 1);
+        int tl_count = sklansky(sp, 0, maxy_ind, tl_stack, -1, 1);
         int* tr_stack = stack + tl_count;
-        int tr_count = sklansky(pts, sorted, total - 1, maxy_ind, tr_stack, -1, -1);
+        int tr_count = sklansky(sp, total - 1, maxy_ind, tr_stack, -1, -1);
         if (!clockwise) {
             swap_ip(tl_stack, tr_stack);
             swap_i(tl_count, tr_count);
@@ -102,17 +112,16 @@ BB_HD int convex_hull(const P2i* pts, const int* sorted, int total, int* stack, 
         int stop_idx = tr_count > 2 ? tr_stack[1] : tl_count > 2 ? tl_stack[tl_count - 2] : -1;
 
         int* bl_stack = stack;
-        int bl_count = sklansky(pts, sorted, 0, miny_ind, bl_stack, 1, -1);
+        int bl_count = sklansky(sp, 0, miny_ind, bl_stack, 1, -1);
         int* br_stack = stack + bl_count;
-        int br_count = sklansky(pts, sorted, total - 1, miny_ind, br_stack, 1, 1);
+        int br_count = sklansky(sp, total - 1, miny_ind, br_stack, 1, 1);
         if (clockwise) {
             swap_ip(bl_stack, br_stack);
             swap_i(bl_count, br_count);
         }
         if (stop_idx >= 0) {
             int check_idx = bl_count > 2 ? bl_stack[1] : bl_count + br_count > 2 ? br_stack[2 - bl_count] : -1;
-            if (check_idx == stop_idx || (check_idx >= 0 && pts[sorted[check_idx]].x == pts[sorted[stop_idx]].x &&
-                                          pts[sorted[check_idx]].y == pts[sorted[stop_idx]].y)) {
+            if (check_idx == stop_idx || (check_idx >= 0 && sp[check_idx].x == sp[stop_idx].x && sp[check_idx].y == sp[stop_idx].y)) {
                 bl_count = bl_count < 2 ? bl_count : 2;
                 br_count = br_count < 2 ? br_count : 2;
             }

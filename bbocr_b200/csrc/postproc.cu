@@ -278,6 +278,7 @@ constexpr int BOX_THREADS = 128;
 
 struct BoxSmem {
     geom::P2i pts[BOX_MAXPTS];
+    geom::P2i sp[BOX_MAXPTS];             // the points in cv::convexHull's sort order
     unsigned long long keys[BOX_MAXPTS];
     int sorted[BOX_MAXPTS];
     int stack[BOX_MAXPTS + 2];
@@ -378,10 +379,14 @@ __global__ void __launch_bounds__(BOX_THREADS) k_det_boxes(int* __restrict__ hea
                 }
                 __syncthreads();
             }
-        for (int i = tid; i < np; i += BOX_THREADS) S.sorted[i] = (int)(S.keys[i] & 0xfffffull);
+        for (int i = tid; i < np; i += BOX_THREADS) {
+            const int idx = (int)(S.keys[i] & 0xfffffull);
+            S.sorted[i] = idx;
+            S.sp[i] = S.pts[idx];
+        }
         __syncthreads();
         if (tid == 0) {
-            const int hn = geom::convex_hull(S.pts, S.sorted, np, S.stack, S.hullbuf, false);
+            const int hn = geom::convex_hull(S.sp, S.sorted, np, S.stack, S.hullbuf, false);
             float box[8], rolled[8];
             geom::min_area_box_from_hull(S.pts, S.hullbuf, hn, S.hp, S.inv_len, S.vect, box);
             geom::finish_det_box(box, S.l, S.t, S.r, S.b, rolled);
