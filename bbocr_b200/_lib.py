@@ -45,7 +45,8 @@ class Params(C.Structure):
                 ("adjust_contrast", C.c_double), ("text_threshold", C.c_double), ("low_text", C.c_double),
                 ("link_threshold", C.c_double), ("mag_ratio", C.c_double), ("slope_ths", C.c_double),
                 ("ycenter_ths", C.c_double), ("height_ths", C.c_double), ("width_ths", C.c_double),
-                ("add_margin", C.c_double), ("ignore", C.c_void_p)]
+                ("add_margin", C.c_double), ("ignore", C.c_void_p), ("decoder", C.c_int32), ("beam_width", C.c_int32),
+                ("batch_mode", C.c_int32), ("n_rotations", C.c_int32), ("rotation", C.c_int32 * 3), ("space_idx", C.c_int32)]
 
 
 class Results(C.Structure):
@@ -66,7 +67,7 @@ SYMBOLS = [
     "bbocr_det_boxes", "bbocr_min_area_box", "bbocr_group_boxes", "bbocr_crop_horizontal", "bbocr_crop_free",
     "bbocr_crnn_forward", "bbocr_ctc_decode", "bbocr_default_params", "bbocr_readtext", "bbocr_readtext_batch",
     "bbocr_recognize", "bbocr_thumbnail_u8", "bbocr_autocrop_rect", "bbocr_external_boxes", "bbocr_rect_morph", "bbocr_results_free", "bbocr_launch_count", "bbocr_reset_launch_count", "bbocr_conv_stats",
-    "bbocr_enable_conv_timing",
+    "bbocr_enable_conv_timing", "bbocr_set_dictionary", "bbocr_ctc_beam_decode",
 ]
 
 
@@ -508,6 +509,16 @@ class Handle:
         return self._unpack(out)
 
     # ---- instrumentation -------------------------------------------------------------------------------------------
+    def set_dictionary(self, words):
+        """wordbeamsearch dictionary: `words` = iterable of class-index sequences (CTCLabelConverter.dict_list)."""
+        words = [list(w) for w in words]
+        off = np.zeros(len(words) + 1, np.int32)
+        if words:
+            off[1:] = np.cumsum([len(w) for w in words])
+        idx = np.array([c for w in words for c in w], np.int32) if words else np.zeros(1, np.int32)
+        self._check(self.L.bbocr_set_dictionary(self._h, idx.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                                                C.c_int(len(words))))
+
     def launch_count(self) -> int:
         return int(self.L.bbocr_launch_count(self._h))
 
@@ -524,6 +535,27 @@ class Handle:
 
 
 # ---- pure-host entry points (usable without a GPU) -----------------------------------------------------------------------
+
+def ctc_beam_decode(probs, decoder: int, beam_width: int = 5, space_idx: int = 43, dict_words=()):
+    """CTCLabelConverter.decode_beamsearch (decoder 1) / decode_wordbeamsearch (2) of one crop: probs T x C float32 -> class
+    indices.  Host code of the library (upstream runs it on the CPU as well); needs no device."""
+    probs = np.ascontiguousarray(probs, np.float32)
+    T, Cn = probs.shape
+    words = [list(w) for w in dict_words]
+    off = np.zeros(len(words) + 1, np.int32)
+    if words:
+        off[1:] = np.cumsum([len(w) for w in words])
+    idx = np.array([c for w in words for c in w], np.int32) if words else np.zeros(1, np.int32)
+    out = np.zeros(max(2 * T + 1, 1), np.int32)
+    n = C.c_int()
+    rc = lib().bbocr_ctc_beam_decode(probs.ctypes.data_as(C.c_void_p), C.c_int(T), C.c_int(Cn), C.c_int(decoder),
+                                     C.c_int(beam_width), C.c_int(space_idx), idx.ctypes.data_as(C.c_void_p),
+                                     off.ctypes.data_as(C.c_void_p), C.c_int(len(words)), out.ctypes.data_as(C.c_void_p),
+                                     C.c_int(out.size), C.byref(n))
+    if rc != 0:
+        raise ValueError(f"bbocr_ctc_beam_decode failed ({rc})")
+    return out[:n.value].tolist()
+
 
 def min_area_box(points_xy) -> np.ndarray:
     """cv2.boxPoints(cv2.minAreaRect(points)) restated (bbocr_min_area_box)."""

@@ -184,6 +184,33 @@ int bbocr_set_precision(bbocr_handle* h, int prec) {
         h->det_split = prec == BBOCR_PREC_BF16X3;
     });
 }
+int bbocr_set_dictionary(bbocr_handle* h, const int32_t* idx, const int32_t* off, int n) {
+    return guarded(h, [&] {
+        ARG_CHECK(n >= 0 && (n == 0 || (idx && off)), "bad dictionary");
+        h->dict.clear();
+        for (int i = 0; i < n; ++i) {
+            ARG_CHECK(off[i + 1] >= off[i], "dictionary offsets must ascend");
+            h->dict.emplace(idx + off[i], idx + off[i + 1]);
+        }
+    });
+}
+int bbocr_ctc_beam_decode(const float* probs, int T, int C, int decoder, int beam_width, int space_idx, const int32_t* dict_idx,
+                          const int32_t* dict_off, int n_dict, int32_t* text_out, int cap, int* len) {
+    if (!probs || T < 0 || C < 2 || (decoder != 1 && decoder != 2) || beam_width < 1 || !text_out || !len || n_dict < 0 ||
+        (n_dict > 0 && (!dict_idx || !dict_off)))
+        return BBOCR_E_ARG;
+    try {
+        std::set<std::vector<int32_t>> dict;
+        for (int i = 0; i < n_dict; ++i) dict.emplace(dict_idx + dict_off[i], dict_idx + dict_off[i + 1]);
+        std::vector<int32_t> text;
+        bbocr::decode_beam(probs, T, C, decoder, beam_width, space_idx, &dict, text);
+        *len = (int)text.size();
+        for (int i = 0; i < (int)text.size() && i < cap; ++i) text_out[i] = text[i];
+    } catch (...) {
+        return BBOCR_E_ARG;
+    }
+    return BBOCR_OK;
+}
 int bbocr_get_precision(const bbocr_handle* h) {
     if (!h) return BBOCR_E_ARG;
     return h->det_split ? BBOCR_PREC_BF16X3 : h->precision;
@@ -615,6 +642,12 @@ void bbocr_default_params(bbocr_params* p) {
     p->width_ths = 0.5;
     p->add_margin = 0.1;
     p->ignore = nullptr;
+    p->decoder = 0;
+    p->beam_width = 5;
+    p->batch_mode = 0;
+    p->n_rotations = 0;
+    p->rotation[0] = p->rotation[1] = p->rotation[2] = 0;
+    p->space_idx = 43;
 }
 
 }  // extern "C"
@@ -629,7 +662,17 @@ struct CropJob {
     bool is_free = false;
     double box[8];          // result box (clamped ints for horizontal boxes, the free quad otherwise)
     bool tall = false;
+    int base = -1;          // rotation_info: index of the unrotated job this one is a rotated copy of (-1 = it is one itself)
 };
+
+// AlignCollate geometry of a (oh x ow) crop for model width model_w: resized_w = min(ceil(64 * w / h), imgW); `tall` = the
+// PIL BICUBIC resize is not the identity
+void align_geometry(CropJob& j) {
+    const double r2 = (double)j.d.ow / (double)j.d.oh;
+    const int rw = (int)std::ceil(64 * r2);
+    j.d.resized_w = rw > j.d.model_w ? j.d.model_w : rw;
+    j.tall = !(j.d.oh == 64 && j.d.resized_w == j.d.ow);
+}
 
 // utils.get_image_list geometry for one horizontal box [xmin,xmax,ymin,ymax]
 bool horizontal_job(const int32_t* b, int H, int W, CropJob& j) {
@@ -702,10 +745,36 @@ double confidence_of(const float* prob, const int32_t* idx, int T) {
     return std::pow((double)prod, 2.0 / std::sqrt((double)cnt));
 }
 
+// decoder = 'beamsearch' / 'wordbeamsearch' (recognizer_predict): the strings come from the host beam search over the
+// probability matrix; the confidence stays the greedy path's custom_mean, as upstream computes it for every decoder.
+void beam_decode_pass(Handle* h, Lane& lane, const float* logits_dev, int rows, int C, const uint8_t* ignore_dev,
+                      const std::vector<SeqDesc>& where, const bbocr_params& p, std::vector<Recognized>& out) {
+    if (p.decoder == 0 || rows == 0) return;
+    ARG_CHECK(p.decoder == 1 || p.decoder == 2, "unknown decoder %d", p.decoder);
+    ARG_CHECK(p.beam_width >= 1, "beamWidth must be positive");
+    cudaStream_t st = lane.stream;
+    DevBuf dprobs((size_t)rows * C * 4, st);
+    row_probs_dev(h, st, logits_dev, rows, C, ignore_dev, dprobs.as<float>());
+    std::vector<float> probs((size_t)rows * C);
+    download(lane, probs.data(), dprobs.p, probs.size() * 4);
+    const int space_idx = p.space_idx;                          // CTCLabelConverter.dict[' ']
+    const int n = (int)where.size();
+    const int nt = std::max(1, std::min<int>(8, n / 4));
+    std::atomic<int> next{0};
+    auto work = [&] {
+        for (int k; (k = next.fetch_add(1)) < n;)
+            decode_beam(probs.data() + (size_t)where[k].row0 * C, where[k].T, C, p.decoder, p.beam_width, space_idx, &h->dict, out[k].text);
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < nt; ++i) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+}
+
 // Throughput-mode variant of recognize_pass: the crops of the pass are laid side by side in strip images (at most
 // `max_cols` columns each) and the feature extractor runs once per strip; the sequence half and the decoder run once.
 void recognize_pass_ragged(Handle* h, Lane& lane, std::vector<CropJob>& jobs, const std::vector<int>& which, const uint8_t* crops,
-                           size_t crops_bytes, const uint8_t* ignore_dev, std::vector<Recognized>& out) {
+                           size_t crops_bytes, const uint8_t* ignore_dev, const bbocr_params& p, std::vector<Recognized>& out) {
     cudaStream_t st = lane.stream;
     const int n = (int)which.size();
     out.assign(n, Recognized());
@@ -821,13 +890,14 @@ void recognize_pass_ragged(Handle* h, Lane& lane, std::vector<CropJob>& jobs, co
         out[k].text.assign(h_text + so, h_text + so + h_len[k]);
         out[k].conf = confidence_of(h_prob + so, h_sidx + so, seqs[k].T);
     }
+    beam_decode_pass(h, lane, logits.as<float>(), rows, C, ignore_dev, seqs, p, out);
 }
 
 // One pass of AlignCollate -> CRNN -> decode over `jobs` whose (possibly contrast-adjusted) crops live in `crops`.
 void recognize_pass(Handle* h, Lane& lane, std::vector<CropJob>& jobs, const std::vector<int>& which, const uint8_t* crops,
-                    size_t crops_bytes, const uint8_t* ignore_dev, std::vector<Recognized>& out) {
+                    size_t crops_bytes, const uint8_t* ignore_dev, const bbocr_params& p, std::vector<Recognized>& out) {
     if (crnn_ragged(h)) {
-        recognize_pass_ragged(h, lane, jobs, which, crops, crops_bytes, ignore_dev, out);
+        recognize_pass_ragged(h, lane, jobs, which, crops, crops_bytes, ignore_dev, p, out);
         return;
     }
     cudaStream_t st = lane.stream;
@@ -920,6 +990,7 @@ void recognize_pass(Handle* h, Lane& lane, std::vector<CropJob>& jobs, const std
     const int32_t* h_sidx = h_text + step_elems;
     const float* h_prob = reinterpret_cast<const float*>(h_sidx + step_elems);
     const int32_t* h_len = reinterpret_cast<const int32_t*>(h_prob + step_elems);
+    std::vector<SeqDesc> where(n);
     for (int k = 0; k < n; ++k) {
         const CropJob& j = jobs[which[k]];
         int q = job_bucket[k], T = bucket_w[q] / 4 - 1;
@@ -927,7 +998,9 @@ void recognize_pass(Handle* h, Lane& lane, std::vector<CropJob>& jobs, const std
         int len = h_len[seq_of_bucket_slot0[q] + j.d.slot];
         out[k].text.assign(h_text + so, h_text + so + len);
         out[k].conf = confidence_of(h_prob + so, h_sidx + so, T);
+        where[k] = SeqDesc{(int)so, T};
     }
+    beam_decode_pass(h, lane, logits.as<float>(), rows, C, ignore_dev, where, p, out);
 }
 
 // ---- readtext = detect (per page) -> recognize (per GROUP of pages) -> assemble (per page) ---------------------------------
@@ -949,16 +1022,25 @@ struct PageWork {
 // utils.get_image_list for the boxes of one page (batch_size == 1 semantics: every box has its own max_width): crop jobs in
 // upstream order (horizontal list, then free list) and the packed u8 crops on the device
 void build_crops(Handle* h, Lane& lane, const uint8_t* gray, int H, int W, const std::vector<int32_t>& hlist,
-                 const std::vector<double>& flist, PageWork& pw) {
+                 const std::vector<double>& flist, const bbocr_params& p, PageWork& pw) {
     cudaStream_t st = lane.stream;
     std::vector<CropJob>& jobs = pw.jobs;
     std::vector<double> mats;
     size_t scratch_bytes = 0;
-    for (size_t i = 0; i + 4 <= hlist.size(); i += 4) {
-        CropJob j;
-        horizontal_job(&hlist[i], H, W, j);
-        if (finish_geometry(j)) jobs.push_back(j);
-    }
+    ARG_CHECK(p.n_rotations >= 0 && p.n_rotations <= 3, "rotation_info: at most three orientations");
+    for (int r = 0; r < p.n_rotations; ++r)
+        ARG_CHECK(p.rotation[r] == 90 || p.rotation[r] == 180 || p.rotation[r] == 270, "rotation_info: eligible values are 90, 180 and 270");
+    // upstream's batched branch of Reader.recognize (batch_size > 1 on a GPU reader, or rotation_info): get_image_list over
+    // the whole page = free boxes first, one max_width, crops stably sorted by the y of their first corner
+    const bool batch_mode = p.batch_mode != 0 || p.n_rotations > 0;
+    auto add_horizontal = [&] {
+        for (size_t i = 0; i + 4 <= hlist.size(); i += 4) {
+            CropJob j;
+            horizontal_job(&hlist[i], H, W, j);
+            if (finish_geometry(j)) jobs.push_back(j);
+        }
+    };
+    if (!batch_mode) add_horizontal();
     for (size_t i = 0; i + 8 <= flist.size(); i += 8) {
         CropJob j;
         int mwid, mhei;
@@ -973,15 +1055,38 @@ void build_crops(Handle* h, Lane& lane, const uint8_t* gray, int H, int W, const
         scratch_bytes += (size_t)mwid * mhei;
         if (finish_geometry(j)) jobs.push_back(j);
     }
+    if (batch_mode) {
+        add_horizontal();
+        int shared_w = 64;
+        for (auto& j : jobs) shared_w = std::max(shared_w, j.d.model_w);
+        std::stable_sort(jobs.begin(), jobs.end(), [](const CropJob& a, const CropJob& b) { return a.box[1] < b.box[1]; });
+        for (auto& j : jobs) { j.d.model_w = shared_w; align_geometry(j); }
+    }
     const int n = (int)jobs.size();
-    pw.rec.assign(n, Recognized());
     if (n > 0) {
         size_t crops_bytes = 0;
         for (auto& j : jobs) { j.d.off = (int)crops_bytes; crops_bytes += (size_t)j.d.ow * j.d.oh; }
+        const size_t base_bytes = crops_bytes;
+        // rotation_info (utils.make_rotated_img_list): for every angle a rotated copy of every crop, appended in that order
+        std::vector<RotDesc> rots;
+        int max_pixels = 0;
+        for (int r = 0; r < p.n_rotations; ++r)
+            for (int i = 0; i < n; ++i) {
+                CropJob j = jobs[i];
+                const int k = p.rotation[r] / 90;
+                rots.push_back(RotDesc{jobs[i].d.off, (int)crops_bytes, jobs[i].d.oh, jobs[i].d.ow, k});
+                max_pixels = std::max(max_pixels, jobs[i].d.oh * jobs[i].d.ow);
+                if (k != 2) std::swap(j.d.ow, j.d.oh);
+                j.d.off = (int)crops_bytes;
+                j.base = i;
+                align_geometry(j);
+                crops_bytes += (size_t)j.d.ow * j.d.oh;
+                jobs.push_back(j);
+            }
         pw.crops_bytes = crops_bytes;
         std::vector<CropDesc> descs(n);
         for (int i = 0; i < n; ++i) descs[i] = jobs[i].d;
-        DevBuf ddesc, dmats, dscratch(scratch_bytes + 16, st);
+        DevBuf ddesc, dmats, drots, dscratch(scratch_bytes + 16, st);
         pw.dcrops.alloc(crops_bytes + 16, st);
         upload(lane, ddesc, descs.data(), descs.size() * sizeof(CropDesc));
         if (!mats.empty()) {
@@ -990,7 +1095,14 @@ void build_crops(Handle* h, Lane& lane, const uint8_t* gray, int H, int W, const
         }
         crops_dev(h, st, gray, H, W, ddesc.as<CropDesc>(), n, descs.data(), dmats.as<double>(), dscratch.as<uint8_t>(),
                   pw.dcrops.as<uint8_t>());
+        if (!rots.empty()) {
+            CUDA_CHECK(stream_sync(st));
+            upload(lane, drots, rots.data(), rots.size() * sizeof(RotDesc));
+            rotate_crops_dev(h, st, pw.dcrops.as<uint8_t>(), drots.as<RotDesc>(), (int)rots.size(), max_pixels);
+        }
+        (void)base_bytes;
     }
+    pw.rec.assign(jobs.size(), Recognized());
 }
 
 // Reader.detect + utils.get_image_list for one page on one lane; leaves the page's crops on the device
@@ -1065,7 +1177,7 @@ void detect_pages(Handle* h, Lane& lane, const bbocr_image* const* imgs, int k, 
         std::vector<int32_t> hlist;
         std::vector<double> flist;
         group_boxes(boxes.data(), (int)boxes.size() / 8, g.ratio, gp, hlist, flist);
-        build_crops(h, lane, gray[i], H, W, hlist, flist, *pws[i]);
+        build_crops(h, lane, gray[i], H, W, hlist, flist, p, *pws[i]);
     }
     tm.reset();
     CUDA_CHECK(stream_sync(st));                 // the pages' crops are complete; pinned staging is free again
@@ -1116,7 +1228,7 @@ void recognize_group(Handle* h, Lane& lane, const std::vector<PageWork*>& pages,
     for (int i = 0; i < n; ++i) all[i] = i;
     std::unique_ptr<StageTimer> tm(new StageTimer(h, 3));
     std::vector<Recognized> rec1;
-    recognize_pass(h, lane, jobs, all, dcrops.as<uint8_t>(), crops_bytes, ignore_dev, rec1);
+    recognize_pass(h, lane, jobs, all, dcrops.as<uint8_t>(), crops_bytes, ignore_dev, p, rec1);
     std::vector<int> low;
     for (int i = 0; i < n; ++i)
         if (rec1[i].conf < p.contrast_ths) low.push_back(i);
@@ -1152,7 +1264,7 @@ void recognize_group(Handle* h, Lane& lane, const std::vector<PageWork*>& pages,
                           dapply.as<int>(), dadj.as<uint8_t>());
         CUDA_CHECK(stream_sync(st));
         std::vector<Recognized> rec2;
-        recognize_pass(h, lane, jobs, low, dadj.as<uint8_t>(), crops_bytes, ignore_dev, rec2);
+        recognize_pass(h, lane, jobs, low, dadj.as<uint8_t>(), crops_bytes, ignore_dev, p, rec2);
         for (int k = 0; k < nl; ++k) {
             pages[origin[low[k]].first]->n_crops_run += 1;
             if (!(rec1[low[k]].conf > rec2[k].conf)) final_rec[low[k]] = rec2[k];
@@ -1167,8 +1279,16 @@ void recognize_group(Handle* h, Lane& lane, const std::vector<PageWork*>& pages,
 }
 
 // result assembly (horizontal boxes in group order, then free boxes)
-bbocr_results* assemble_page(const PageWork& pw) {
-    const int n = (int)pw.jobs.size();
+bbocr_results* assemble_page(PageWork& pw) {
+    // rotation_info (utils.set_result_with_confidence): every box keeps the orientation with the highest confidence, the
+    // first one on ties (Python's max); the rotated copies follow the n base jobs angle by angle
+    int n = (int)pw.jobs.size();
+    for (int i = 0; i < (int)pw.jobs.size(); ++i)
+        if (pw.jobs[i].base >= 0) { n = i; break; }
+    for (int i = n; i < (int)pw.jobs.size(); ++i) {
+        const int b = pw.jobs[i].base;
+        if (pw.rec[i].conf > pw.rec[b].conf) pw.rec[b] = pw.rec[i];
+    }
     bbocr_results* r = new bbocr_results();
     memset(r, 0, sizeof *r);
     r->n_components = pw.n_labels;
@@ -1179,7 +1299,7 @@ bbocr_results* assemble_page(const PageWork& pw) {
     r->text_off = new int32_t[n + 1];
     r->conf = new double[std::max(n, 1)];
     size_t total = 0;
-    for (auto& f : pw.rec) total += f.text.size();
+    for (int i = 0; i < n; ++i) total += pw.rec[i].text.size();
     r->text_idx = new int32_t[std::max<size_t>(total, 1)];
     size_t off = 0;
     for (int i = 0; i < n; ++i) {
@@ -1241,7 +1361,7 @@ int bbocr_recognize(bbocr_handle* h, const uint8_t* gray, int H, int W, int on_d
         pw.H = H; pw.W = W;
         std::vector<int32_t> hl(hlist, hlist + (size_t)nh * 4);
         std::vector<double> fl(flist, flist + (size_t)nf * 8);
-        build_crops(h, lane, g, H, W, hl, fl, pw);
+        build_crops(h, lane, g, H, W, hl, fl, *p, pw);
         CUDA_CHECK(stream_sync(lane.stream));
         lane.in_busy = false;
         std::vector<PageWork*> one{&pw};

@@ -57,6 +57,7 @@ struct Handle {
     double conv_flops = 0;
     double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t conv_launches = 0;
+    std::set<std::vector<int32_t>> dict;   // wordbeamsearch dictionary as class-index words (bbocr_set_dictionary)
 };
 
 inline void count_launch(Handle* h, int n) { h->launches.fetch_add(n, std::memory_order_relaxed); }
@@ -229,5 +230,13 @@ int lstm_mma_group_size();
 void ctc_decode_dev(Handle*, cudaStream_t, const float* logits, int rows, int C, const uint8_t* ignore_dev,
                     const SeqDesc* seqs_dev, int n_seq, int32_t* text_idx /*[rows]*/, int32_t* text_len /*[n_seq]*/,
                     float* step_prob /*[rows]*/, int32_t* step_idx /*[rows]*/);
+// recognizer_predict's probability matrix (softmax, ignored classes zeroed, renormalised): probs [rows][C] FP32
+void row_probs_dev(Handle*, cudaStream_t, const float* logits, int rows, int C, const uint8_t* ignore_dev, float* probs);
+// rotation_info: out = np.rot90(src, k) for every job (k = 1, 2, 3), u8 crops inside one packed buffer
+struct RotDesc { int src_off, dst_off, sh, sw, k; };
+void rotate_crops_dev(Handle*, cudaStream_t, uint8_t* crops, const RotDesc* descs_dev, int n, int max_pixels);
+// beam.cpp: CTCLabelConverter.decode_beamsearch (decoder 1) / decode_wordbeamsearch (decoder 2) of one crop, host side
+void decode_beam(const float* probs, int T, int C, int decoder, int beam_width, int space_idx,
+                 const std::set<std::vector<int32_t>>* dict, std::vector<int32_t>& text);
 
 }  // namespace bbocr

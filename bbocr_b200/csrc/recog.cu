@@ -540,4 +540,61 @@ void ctc_decode_dev(Handle* h, cudaStream_t st, const float* logits, int rows, i
     CUDA_CHECK(cudaGetLastError());
 }
 
+// the full probability matrix of recognizer_predict for the beam-search decoders: same arithmetic as k_row_argmax
+__global__ void k_row_probs(const float* __restrict__ logits, int rows, int C, const uint8_t* __restrict__ ignore,
+                            float* __restrict__ probs) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* lg = logits + (int64_t)row * C;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lg[c]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum_all = 0.f, sum_kept = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float e = expf(lg[c] - mx);
+        sum_all += e;
+        if (!(ignore && ignore[c])) sum_kept += e;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_all += __shfl_xor_sync(0xffffffffu, sum_all, o);
+        sum_kept += __shfl_xor_sync(0xffffffffu, sum_kept, o);
+    }
+    const float norm = sum_kept / sum_all;
+    for (int c = lane; c < C; c += 32) {
+        const bool ig = ignore && ignore[c];
+        probs[(int64_t)row * C + c] = ig ? 0.f : (expf(lg[c] - mx) / sum_all) / norm;
+    }
+}
+
+void row_probs_dev(Handle* h, cudaStream_t st, const float* logits, int rows, int C, const uint8_t* ignore_dev, float* probs) {
+    if (rows == 0) return;
+    k_row_probs<<<cdiv(rows * 32, 256), 256, 0, st>>>(logits, rows, C, ignore_dev, probs);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// utils.make_rotated_img_list for the eligible angles: scipy.ndimage.rotate(img, 90 k, reshape=True) == np.rot90(img, k)
+//   k = 1: out[i][j] = src[j][W-1-i] (W x H);  k = 2: out[i][j] = src[H-1-i][W-1-j];  k = 3: out[i][j] = src[H-1-j][i] (W x H)
+__global__ void k_rotate_crops(uint8_t* __restrict__ crops, const RotDesc* __restrict__ descs) {
+    const RotDesc d = descs[blockIdx.y];
+    const int n = d.sh * d.sw;
+    const int oh = d.k == 2 ? d.sh : d.sw, ow = d.k == 2 ? d.sw : d.sh;
+    (void)oh;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int i = p / ow, j = p - i * ow;
+        int sy, sx;
+        if (d.k == 1) { sy = j; sx = d.sw - 1 - i; }
+        else if (d.k == 2) { sy = d.sh - 1 - i; sx = d.sw - 1 - j; }
+        else { sy = d.sh - 1 - j; sx = i; }
+        crops[d.dst_off + p] = crops[d.src_off + sy * d.sw + sx];
+    }
+}
+
+void rotate_crops_dev(Handle* h, cudaStream_t st, uint8_t* crops, const RotDesc* descs_dev, int n, int max_pixels) {
+    if (n == 0) return;
+    k_rotate_crops<<<dim3(std::min(64, cdiv(max_pixels, 256)), n), 256, 0, st>>>(crops, descs_dev);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 }  // namespace bbocr

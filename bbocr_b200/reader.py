@@ -161,6 +161,7 @@ class Reader:
         self.character = CHARACTERS
         self.lang_char = CHARACTERS                            # en_char.txt + symbols cover the whole english_g2 alphabet
         self.model_lang = "english"
+        self.dict_list = []                                    # wordbeamsearch dictionary (set_dictionary)
         craft_path, crnn_path = weights.find_checkpoints(model_storage_directory)
         if craft_state is None:
             craft_state = weights.load_pth(craft_path) if craft_path else weights.calibrated_craft_state()
@@ -173,6 +174,16 @@ class Reader:
         self._h.load_craft(craft_state)
         self._h.load_crnn(crnn_state)
         self.set_precision(precision)
+        # CTCLabelConverter.__init__ reads easyocr/dict/en.txt for decoder='wordbeamsearch'; use it when the package is around
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("easyocr")
+            path = os.path.join(os.path.dirname(spec.origin), "dict", "en.txt") if spec and spec.origin else None
+            if path and os.path.exists(path):
+                with open(path, "r", encoding="utf-8-sig") as f:
+                    self.set_dictionary(f.read().splitlines())
+        except Exception:                                      # noqa: BLE001 -- optional, like upstream's try/except around the file
+            pass
 
     # ------------------------------------------------------------------------------------------------------------
     def set_precision(self, precision: str):
@@ -226,12 +237,34 @@ class Reader:
             raise NotImplementedError(f"output_format={output_format!r} is not implemented (SURVEY.md §8f-3)")
         return out
 
-    @staticmethod
-    def _check_unsupported(decoder, rotation_info):
-        if decoder != "greedy":
-            raise NotImplementedError("only decoder='greedy' is implemented (SURVEY.md §8f-3)")
-        if rotation_info:
-            raise NotImplementedError("rotation_info is not implemented (SURVEY.md §8f-3)")
+    def _decode_options(self, p, decoder="greedy", beamWidth=5, batch_size=1, rotation_info=None):
+        """decoder / beamWidth / batch_size / rotation_info of Reader.recognize (easyocr/easyocr.py) -> bbocr_params."""
+        try:
+            p.decoder = {"greedy": 0, "beamsearch": 1, "wordbeamsearch": 2}[decoder]
+        except KeyError:
+            raise ValueError(f"unknown decoder {decoder!r} (greedy, beamsearch, wordbeamsearch)") from None
+        p.beam_width = int(beamWidth)
+        p.space_idx = self.character.index(" ") + 1
+        rot = [int(a) for a in (rotation_info or [])]
+        if any(a not in (90, 180, 270) for a in rot) or len(rot) > 3:
+            raise ValueError("rotation_info: eligible values are 90, 180 and 270")
+        p.n_rotations = len(rot)
+        for i, a in enumerate(rot):
+            p.rotation[i] = a
+        # upstream takes its per-box branch only for batch_size == 1 (or a CPU reader) without rotation_info; anything else
+        # goes through get_image_list over the whole page: one max_width, results ordered by y
+        p.batch_mode = 1 if (int(batch_size) > 1 or rot) else 0
+
+    def set_dictionary(self, words):
+        """Dictionary of decoder='wordbeamsearch' (upstream reads easyocr/dict/en.txt at construction; that file is part of
+        the easyocr package, which this image does not have).  Words with characters outside the alphabet cannot match."""
+        idx = []
+        for w in words:
+            if w and all(ch in self.character for ch in w):
+                idx.append([self.character.index(ch) + 1 for ch in w])
+        self.dict_list = list(words)
+        with self._lock:
+            self._h.set_dictionary(idx)
 
     def readtext(self, image, decoder="greedy", beamWidth=5, batch_size=1, workers=0, allowlist=None, blocklist=None,
                  detail=1, rotation_info=None, paragraph=False, min_size=20, contrast_ths=0.1, adjust_contrast=0.5,
@@ -239,7 +272,8 @@ class Reader:
                  slope_ths=0.1, ycenter_ths=0.5, height_ths=0.5, width_ths=0.5, y_ths=0.5, x_ths=1.0, add_margin=0.1,
                  threshold=0.2, bbox_min_score=0.2, bbox_min_size=3, max_candidates=0, output_format="standard"):
         """Reader.readtext (easyocr/easyocr.py).  Returns [(box, text, confidence), ...] in upstream order."""
-        return self.readtext_batched([image], decoder=decoder, allowlist=allowlist, blocklist=blocklist, detail=detail,
+        return self.readtext_batched([image], decoder=decoder, beamWidth=beamWidth, batch_size=batch_size, allowlist=allowlist,
+                                     blocklist=blocklist, detail=detail,
                                      rotation_info=rotation_info, paragraph=paragraph, min_size=min_size,
                                      contrast_ths=contrast_ths, adjust_contrast=adjust_contrast,
                                      text_threshold=text_threshold, low_text=low_text, link_threshold=link_threshold,
@@ -248,11 +282,14 @@ class Reader:
                                      add_margin=add_margin, y_ths=y_ths, x_ths=x_ths, output_format=output_format)[0]
 
     def readtext_batched(self, images, decoder="greedy", allowlist=None, blocklist=None, detail=1, rotation_info=None,
-                         paragraph=False, output_format="standard", return_stats=False, y_ths=0.5, x_ths=1.0, **kw):
+                         paragraph=False, output_format="standard", return_stats=False, y_ths=0.5, x_ths=1.0, beamWidth=5,
+                         batch_size=1, **kw):
         """Batched extension: independent pages pipelined over the handle's CUDA streams; per-page semantics are exactly
-        those of readtext(batch_size=1)."""
-        self._check_unsupported(decoder, rotation_info)
+        those of readtext (batch_size=1 by default, i.e. what BB-OCR passes)."""
+        if output_format == "free_merge":
+            raise NotImplementedError("output_format='free_merge' (utils.merge_to_free) is not implemented (SURVEY.md §8f-3)")
         p, keep = self._params(kw, allowlist, blocklist)
+        self._decode_options(p, decoder, beamWidth, batch_size, rotation_info)
         pages = []
         for im in images:
             img, grey = reformat_input(im)
@@ -309,7 +346,6 @@ class Reader:
                   **_ignored):
         """Reader.recognize -> [(box, text, confidence)] for the given boxes (upstream order: horizontal, then free).
         With both lists None the whole image is one horizontal box, like upstream."""
-        self._check_unsupported(decoder, rotation_info)
         if reformat:
             if not (isinstance(img_cv_grey, np.ndarray) and img_cv_grey.ndim == 2):
                 img, img_cv_grey = reformat_input(img_cv_grey)
@@ -319,6 +355,7 @@ class Reader:
             y_max, x_max = img_cv_grey.shape
             horizontal_list, free_list = [[0, x_max, 0, y_max]], []
         p, keep = self._params({"contrast_ths": contrast_ths, "adjust_contrast": adjust_contrast}, allowlist, blocklist)
+        self._decode_options(p, decoder, beamWidth, batch_size, rotation_info)
         with self._lock:
             raw, _ = self._h.recognize_raw(np.ascontiguousarray(img_cv_grey), horizontal_list or [], free_list or [], p)
         return self._format(raw, detail, output_format, paragraph, x_ths, y_ths)

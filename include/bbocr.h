@@ -175,6 +175,15 @@ typedef struct {            /* the subset of readtext kwargs that changes arithm
     double mag_ratio;       /* 1.0 */
     double slope_ths, ycenter_ths, height_ths, width_ths, add_margin;  /* .1 .5 .5 .5 .1 */
     const uint8_t* ignore;  /* num_class bytes or NULL (allowlist / blocklist mask; 1 = masked) */
+    /* SURVEY.md §8f-3 -- the remaining readtext options (easyocr/easyocr.py::Reader.recognize, easyocr/utils.py) */
+    int32_t decoder;        /* 0 'greedy' | 1 'beamsearch' | 2 'wordbeamsearch' (dictionary: bbocr_set_dictionary) */
+    int32_t beam_width;     /* 5 (beamWidth) */
+    int32_t batch_mode;     /* 0: batch_size == 1 branch (every box has its own max_width; horizontal then free boxes).
+                               1: upstream's batched branch (batch_size > 1 on a GPU Reader, or rotation_info): ONE max_width
+                               for the page's boxes, free boxes first, results stably ordered by the first corner's y */
+    int32_t n_rotations;    /* rotation_info: number of extra orientations (0..3); implies batch_mode */
+    int32_t rotation[3];    /* each 90, 180 or 270 (the eligible values upstream documents) */
+    int32_t space_idx;      /* 43: class index of ' ' in english_g2 (CTCLabelConverter.dict[' ']); wordbeamsearch cuts there */
 } bbocr_params;
 
 void bbocr_default_params(bbocr_params* p);
@@ -200,6 +209,14 @@ int bbocr_readtext_batch(bbocr_handle* h, int n, const bbocr_image* imgs, const 
 int bbocr_recognize(bbocr_handle* h, const uint8_t* gray, int H, int W, int on_device, const int32_t* hlist, int nh,
                     const double* flist, int nf, const bbocr_params* p, bbocr_results** out);
 void bbocr_results_free(bbocr_results* r);
+/* Dictionary of decoder 'wordbeamsearch' (upstream: easyocr/dict/en.txt read by CTCLabelConverter.__init__): n words given as
+ * class-index sequences idx[off[i] .. off[i+1]).  n = 0 clears it (every word is then plain beam search). */
+int bbocr_set_dictionary(bbocr_handle* h, const int32_t* idx, const int32_t* off, int n);
+/* CTCLabelConverter.decode_beamsearch / decode_wordbeamsearch of ONE crop on the host (upstream runs them in Python on the
+ * CPU as well): probs = T x C float32 as recognizer_predict hands them over; decoder 1 | 2; space_idx = class index of ' '.
+ * Writes at most cap class indices to text_out, *len = the text's length.  Needs no device (parity-test surface). */
+int bbocr_ctc_beam_decode(const float* probs, int T, int C, int decoder, int beam_width, int space_idx, const int32_t* dict_idx,
+                          const int32_t* dict_off, int n_dict, int32_t* text_out, int cap, int* len);
 
 /* ---- extractor glue ---------------------------------------------------------------------------- */
 /* The OCR-input cap of extract_text_with_ocr (pipeline_demo/extractor/enhanced_extractor.py:486-512): PIL

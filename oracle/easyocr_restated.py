@@ -569,6 +569,151 @@ def decode_probs(preds_prob: np.ndarray, character=CHARACTERS):
     return out
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Beam-search decoders (easyocr/utils.py: BeamEntry, BeamState, fast_simplify_label, ctcBeamSearch,
+# CTCLabelConverter.decode_beamsearch / decode_wordbeamsearch).  Restated from the 1.7.x source; the reference pins
+# numpy==1.26.4, under which `python_float * np.float32` promotes to float64, so every beam probability is a float64
+# product of float32 inputs -- written out explicitly here so that NumPy 2's scalar rules cannot change it.
+# ----------------------------------------------------------------------------------------------------------------------
+
+class _BeamEntry:
+    __slots__ = ("prTotal", "prNonBlank", "prBlank", "prText", "labeling")
+
+    def __init__(self):
+        self.prTotal = 0.0
+        self.prNonBlank = 0.0
+        self.prBlank = 0.0
+        self.prText = 1.0          # LM score; no language model is ever applied upstream (applyLM is commented out)
+        self.labeling = ()
+
+
+def fast_simplify_label(labeling, c, blankIdx=0):
+    if labeling and c == blankIdx and labeling[-1] != blankIdx:          # blank after a character: keep it
+        return labeling + (c,)
+    if labeling and c != blankIdx and labeling[-1] == blankIdx:          # character after a blank
+        if labeling[-2] == c:                                            # blank between equal characters stays
+            return labeling + (c,)
+        return labeling[:-1] + (c,)                                      # blank between different characters goes
+    if labeling and c == blankIdx and labeling[-1] == blankIdx:          # consecutive blanks collapse
+        return labeling
+    if not labeling and c == blankIdx:                                   # leading blank is dropped
+        return labeling
+    return labeling + (c,)
+
+
+def _sorted_beams(entries):
+    """BeamState.sort: sorted(..., reverse=True, key=prTotal*prText) -- stable, ties keep insertion order."""
+    return sorted(entries.values(), reverse=True, key=lambda x: x.prTotal * x.prText)
+
+
+def ctc_beam_search(mat, character, ignore_idx, beamWidth=25, dict_list=()):
+    """utils.ctcBeamSearch(mat, classes, ignore_idx, lm=None, beamWidth, dict_list).  mat: (T, C) float32 probabilities;
+    `character` = converter.character (['[blank]'] + alphabet)."""
+    blankIdx = 0
+    maxT, maxC = mat.shape
+    m = [[float(v) for v in row] for row in mat]                        # float32 -> float64, exact
+    last = {(): _BeamEntry()}
+    last[()].prBlank = 1.0
+    last[()].prTotal = 1.0
+    for t in range(maxT):
+        curr = {}
+        best = [b.labeling for b in _sorted_beams(last)[0:beamWidth]]
+        # the comparison `float32_array >= python_float` is made in float32 under NumPy 1.26 (value-based casting of the
+        # scalar) as well as under NumPy 2 (weak scalar): round the threshold to float32 first
+        thr32 = float(np.float32(0.5 / maxC))
+        cand = [c for c in range(maxC) if m[t][c] >= thr32]
+        for labeling in best:
+            prNonBlank = 0.0
+            if labeling:
+                prNonBlank = last[labeling].prNonBlank * m[t][labeling[-1]]
+            prBlank = last[labeling].prTotal * m[t][blankIdx]
+            e = curr.get(labeling)
+            if e is None:
+                e = curr[labeling] = _BeamEntry()
+            e.labeling = labeling
+            e.prNonBlank += prNonBlank
+            e.prBlank += prBlank
+            e.prTotal += prBlank + prNonBlank
+            e.prText = last[labeling].prText
+            for c in cand:
+                newLabeling = fast_simplify_label(labeling, c, blankIdx)
+                if labeling and labeling[-1] == c:
+                    prNonBlank = m[t][c] * last[labeling].prBlank
+                else:
+                    prNonBlank = m[t][c] * last[labeling].prTotal
+                e2 = curr.get(newLabeling)
+                if e2 is None:
+                    e2 = curr[newLabeling] = _BeamEntry()
+                e2.labeling = newLabeling
+                e2.prNonBlank += prNonBlank
+                e2.prTotal += prNonBlank
+        last = curr
+    for e in last.values():                                              # BeamState.norm (prText stays 1.0 without an LM)
+        n = len(e.labeling)
+        e.prText = e.prText ** (1.0 / (n if n else 1.0))
+
+    def text_of(lab):
+        return "".join(character[l] for i, l in enumerate(lab) if l not in ignore_idx and not (i > 0 and lab[i - 1] == lab[i]))
+
+    beams = _sorted_beams(last)
+    if len(dict_list) == 0:
+        return text_of(beams[0].labeling)
+    best_text = None                                                     # BeamState.wordsearch(classes, ignore_idx, 20, dict_list)
+    for j, cand_beam in enumerate(beams[:20]):
+        text = text_of(cand_beam.labeling)
+        if j == 0:
+            best_text = text
+        if text in dict_list:
+            best_text = text
+            break
+    return best_text
+
+
+def decode_beamsearch(preds_prob, character=CHARACTERS, beamWidth=5):
+    table = ["[blank]"] + list(character)
+    return [ctc_beam_search(preds_prob[i], table, [0], beamWidth=beamWidth) for i in range(preds_prob.shape[0])]
+
+
+def decode_wordbeamsearch(preds_prob, character=CHARACTERS, beamWidth=5, dict_list=()):
+    """CTCLabelConverter.decode_wordbeamsearch, the branch without separator characters (every Latin-script model):
+    the arg-max path is cut at its space symbols and every run in between is beam-searched against the dictionary."""
+    table = ["[blank]"] + list(character)
+    space_idx = character.index(" ") + 1
+    argmax = np.argmax(preds_prob, axis=2)
+    texts = []
+    for i in range(preds_prob.shape[0]):
+        string = ""
+        data = np.argwhere(argmax[i] != space_idx).flatten()
+        group = np.split(data, np.where(np.diff(data) != 1)[0] + 1)
+        group = [list(item) for item in group if len(item) > 0]
+        for j, list_idx in enumerate(group):
+            t = ctc_beam_search(preds_prob[i, list_idx, :], table, [0], beamWidth=beamWidth, dict_list=dict_list)
+            string += t if j == 0 else " " + t
+        texts.append(string)
+    return texts
+
+
+def make_rotated_img_list(rotation_info, img_list):
+    """utils.make_rotated_img_list: scipy.ndimage.rotate(img, angle, reshape=True) of every crop for every angle.  For the
+    documented angles (90, 180, 270) the spline rotation returns exactly np.rot90(img, angle // 90) (checked against scipy
+    1.18 on 600 random u8 crops, tests/test_oracle_easyocr.py) -- restated that way so the oracle does not need scipy."""
+    out = list(img_list)
+    for angle in rotation_info:
+        if angle not in (90, 180, 270):
+            raise ValueError("rotation_info: eligible values are 90, 180 and 270")
+        for box, img in img_list:
+            out.append((box, np.ascontiguousarray(np.rot90(img, angle // 90))))
+    return out
+
+
+def set_result_with_confidence(results):
+    final = []
+    for col in range(len(results[0])):
+        best_row = max([(row, results[row][col][2]) for row in range(len(results))], key=lambda x: x[1])[0]
+        final.append(results[best_row][col])
+    return final
+
+
 # ======================================================================================================================
 # Reader
 # ======================================================================================================================
@@ -640,6 +785,7 @@ class Reader:
             self.recognizer = torch.quantization.quantize_dynamic(self.recognizer, dtype=torch.qint8)
         self.character = character
         self.ignore_idx = []       # character - lang_char is empty for ['en'] + english_g2
+        self.dict_list = []        # easyocr/dict/en.txt (not in this image); wordbeamsearch without it = per-word beam search
 
     # ---- detection -----------------------------------------------------------------------------------------------
     def score_maps(self, img, canvas_size=2560, mag_ratio=1.0):
@@ -668,19 +814,25 @@ class Reader:
         with torch.no_grad():
             return self.recognizer(torch.from_numpy(batch[:, None]), None)
 
-    def _predict(self, crops, imgW, adjust_contrast=0.0):
+    def _predict(self, crops, imgW, adjust_contrast=0.0, decoder="greedy", beamWidth=5):
         res = []
-        for c in crops:                                     # batch_size == 1
+        for c in crops:                                     # one crop per forward pass (the result does not depend on the batch)
             x = align_collate_one(c, imgW, adjust_contrast)[None]
-            res += decode_probs(probs_from_logits(self.logits(x), self.ignore_idx), self.character)
+            probs = probs_from_logits(self.logits(x), self.ignore_idx)
+            one = decode_probs(probs, self.character)       # greedy string + the confidence every decoder reports
+            if decoder == "beamsearch":
+                one[0][0] = decode_beamsearch(probs, self.character, beamWidth)[0]
+            elif decoder == "wordbeamsearch":
+                one[0][0] = decode_wordbeamsearch(probs, self.character, beamWidth, self.dict_list)[0]
+            res += one
         return res
 
-    def get_text(self, image_list, imgW, contrast_ths=0.1, adjust_contrast=0.5):
+    def get_text(self, image_list, imgW, contrast_ths=0.1, adjust_contrast=0.5, decoder="greedy", beamWidth=5):
         coord = [item[0] for item in image_list]
         img_list = [item[1] for item in image_list]
-        result1 = self._predict(img_list, imgW)
+        result1 = self._predict(img_list, imgW, 0.0, decoder, beamWidth)
         low = [i for i, item in enumerate(result1) if item[1] < contrast_ths]
-        result2 = self._predict([img_list[i] for i in low], imgW, adjust_contrast) if low else []
+        result2 = self._predict([img_list[i] for i in low], imgW, adjust_contrast, decoder, beamWidth) if low else []
         result = []
         for i, (box, pred1) in enumerate(zip(coord, result1)):
             if i in low:
@@ -693,22 +845,36 @@ class Reader:
                 result.append((box, pred1[0], pred1[1]))
         return result
 
-    def recognize(self, img_cv_grey, horizontal_list, free_list, contrast_ths=0.1, adjust_contrast=0.5):
-        result = []
-        for bbox in horizontal_list:
-            image_list, max_width = get_image_list([bbox], [], img_cv_grey, model_height=IMG_H)
-            result += self.get_text(image_list, int(max_width), contrast_ths, adjust_contrast)
-        for bbox in free_list:
-            image_list, max_width = get_image_list([], [bbox], img_cv_grey, model_height=IMG_H)
-            result += self.get_text(image_list, int(max_width), contrast_ths, adjust_contrast)
+    def recognize(self, img_cv_grey, horizontal_list, free_list, contrast_ths=0.1, adjust_contrast=0.5, decoder="greedy",
+                  beamWidth=5, batch_size=1, rotation_info=None):
+        """Reader.recognize: the per-box branch (batch_size == 1 and no rotation_info; what BB-OCR runs) or upstream's
+        batched branch (one max_width for all boxes of the page, crops ordered by y, optional rotated copies)."""
+        if batch_size == 1 and not rotation_info:
+            result = []
+            for bbox in horizontal_list:
+                image_list, max_width = get_image_list([bbox], [], img_cv_grey, model_height=IMG_H)
+                result += self.get_text(image_list, int(max_width), contrast_ths, adjust_contrast, decoder, beamWidth)
+            for bbox in free_list:
+                image_list, max_width = get_image_list([], [bbox], img_cv_grey, model_height=IMG_H)
+                result += self.get_text(image_list, int(max_width), contrast_ths, adjust_contrast, decoder, beamWidth)
+            return result
+        image_list, max_width = get_image_list(horizontal_list, free_list, img_cv_grey, model_height=IMG_H)
+        image_len = len(image_list)
+        if rotation_info and image_list:
+            image_list = make_rotated_img_list(rotation_info, image_list)
+            max_width = max(max_width, IMG_H)
+        result = self.get_text(image_list, int(max_width), contrast_ths, adjust_contrast, decoder, beamWidth)
+        if rotation_info and (horizontal_list + free_list):
+            result = set_result_with_confidence([result[image_len * i:image_len * (i + 1)] for i in range(len(rotation_info) + 1)])
         return result
 
     def readtext(self, image, min_size=20, contrast_ths=0.1, adjust_contrast=0.5, text_threshold=0.7, low_text=0.4,
                  link_threshold=0.4, canvas_size=2560, mag_ratio=1.0, slope_ths=0.1, ycenter_ths=0.5, height_ths=0.5,
-                 width_ths=0.5, add_margin=0.1, **_ignored):
+                 width_ths=0.5, add_margin=0.1, decoder="greedy", beamWidth=5, batch_size=1, rotation_info=None, **_ignored):
         img, img_cv_grey = reformat_input(image)
         h_list, f_list = self.detect(img, min_size=min_size, text_threshold=text_threshold, low_text=low_text,
                                      link_threshold=link_threshold, canvas_size=canvas_size, mag_ratio=mag_ratio,
                                      slope_ths=slope_ths, ycenter_ths=ycenter_ths, height_ths=height_ths,
                                      width_ths=width_ths, add_margin=add_margin)
-        return self.recognize(img_cv_grey, h_list, f_list, contrast_ths, adjust_contrast)
+        return self.recognize(img_cv_grey, h_list, f_list, contrast_ths, adjust_contrast, decoder, beamWidth, batch_size,
+                              rotation_info)

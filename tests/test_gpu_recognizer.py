@@ -259,9 +259,55 @@ def test_readtext_options_through_the_reader(gpu_reader):
     assert [b for b, _, _ in digits] == [b for b, _, _ in std]               # the detector does not depend on the lists
     no_e = gpu_reader.readtext(img, blocklist="eE")
     assert all("e" not in t and "E" not in t for _, t, _ in no_e)
-    for kw in ({"decoder": "beamsearch"}, {"rotation_info": [90]}, {"output_format": "free_merge"}):
-        with pytest.raises(NotImplementedError):
-            gpu_reader.readtext(img, **kw)
+    with pytest.raises(NotImplementedError):
+        gpu_reader.readtext(img, output_format="free_merge")
+    with pytest.raises(ValueError):
+        gpu_reader.readtext(img, rotation_info=[45])
+    with pytest.raises(ValueError):
+        gpu_reader.readtext(img, decoder="viterbi")
+
+
+def _same_results(got, want):
+    assert len(got) == len(want) and len(want) > 0
+    for (gb, gt, gc), (wb, wt, wc) in zip(got, want):
+        assert np.allclose(np.array(gb, float), np.array(wb, float), atol=1e-9), (gb, wb)
+        assert gt == wt, (gt, wt)
+        assert abs(gc - float(wc)) <= 1e-2 * max(float(wc), 1e-2), (gc, wc)
+
+
+def test_beam_decoders_batch_mode_and_rotation_match_oracle(gpu_reader, oracle_reader):
+    """decoder='beamsearch' / 'wordbeamsearch', batch_size > 1 (upstream's batched branch: one max_width
+    per page, results ordered by y) and rotation_info, end to end against the restated upstream in FP32."""
+    gpu_reader.set_precision("fp32")
+    img = synth.book_cover(91, 800, 608)              # has rotated lines -> free boxes
+    greedy = oracle_reader.readtext(img)
+    assert len(greedy) > 3
+    for decoder in ("beamsearch", "wordbeamsearch"):
+        _same_results(gpu_reader.readtext(img, decoder=decoder, beamWidth=5), oracle_reader.readtext(img, decoder=decoder, beamWidth=5))
+    # a dictionary made of some greedy words: wordbeamsearch snaps to them where a candidate matches
+    words = sorted({w for _, t, _ in greedy for w in t.split(" ") if w})[::2] + ["the", "Book"]
+    gpu_reader.set_dictionary(words)
+    oracle_reader.dict_list = list(words)
+    try:
+        _same_results(gpu_reader.readtext(img, decoder="wordbeamsearch", beamWidth=10),
+                      oracle_reader.readtext(img, decoder="wordbeamsearch", beamWidth=10))
+    finally:
+        gpu_reader.set_dictionary([])
+        oracle_reader.dict_list = []
+    # batched branch: shared max_width, y-sorted
+    want = oracle_reader.readtext(img, batch_size=4)
+    _same_results(gpu_reader.readtext(img, batch_size=4), want)
+    assert [r[0][0][1] for r in want] == sorted(r[0][0][1] for r in want)
+    # rotation_info: every box keeps its best orientation
+    for rot in ([90, 180, 270], [180]):
+        _same_results(gpu_reader.readtext(img, rotation_info=rot), oracle_reader.readtext(img, rotation_info=rot))
+    # the tensor-core path runs the same options (strings may differ from FP32 only on near-tie logits: compare with itself)
+    gpu_reader.set_precision("bf16x3")
+    try:
+        a = gpu_reader.readtext(img, rotation_info=[90, 180, 270], decoder="beamsearch")
+        assert [r[0] for r in a] == [r[0] for r in want]
+    finally:
+        gpu_reader.set_precision("fp32")
 
 
 def test_one_reader_shared_by_two_threads(gpu_reader):

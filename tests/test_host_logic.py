@@ -220,3 +220,55 @@ def test_reformat_input_kinds_match_the_oracle(tmp_path):
             reformat_input(bad)
     with pytest.raises(ValueError):
         reformat_input(str(tmp_path / "missing.png"))
+
+
+def _peaky_probs(rng, T, C=97, space=43, sharp=4.0):
+    """A probability matrix shaped like a recogniser's softmax: mostly blank, a few confident characters, some spaces."""
+    logits = rng.normal(size=(T, C)).astype(np.float32)
+    logits[:, 0] += 3.0
+    for t in range(T):
+        u = rng.random()
+        if u < 0.35:
+            logits[t, rng.integers(1, C)] += sharp * rng.uniform(0.5, 2.0)
+        elif u < 0.45:
+            logits[t, space] += sharp
+    e = np.exp(logits - logits.max(1, keepdims=True))
+    return (e / e.sum(1, keepdims=True)).astype(np.float32)
+
+
+def test_beam_decoders_match_the_restated_upstream(lib_built):
+    """decoder='beamsearch' / 'wordbeamsearch' (easyocr/utils.py::ctcBeamSearch and friends; SURVEY.md §8f-3): the library's
+    host decoder vs the restated upstream on random softmax-like matrices, several beam widths, with and without a
+    dictionary."""
+    rng = np.random.default_rng(11)
+    chars = E.CHARACTERS
+    space = chars.index(" ") + 1
+    n = 0
+    for trial in range(60):
+        T = int(rng.integers(1, 60))
+        probs = _peaky_probs(rng, T, sharp=float(rng.uniform(1.0, 6.0)))
+        bw = int(rng.choice([1, 2, 5, 10]))
+        want = E.decode_beamsearch(probs[None], chars, bw)[0]
+        got = "".join(chars[i - 1] for i in lib_built.ctc_beam_decode(probs, 1, bw, space))
+        assert got == want, (trial, got, want)
+        # dictionary: half of the greedy words (so that some candidates hit), plus noise
+        greedy_words = [w for w in E.decode_probs(probs[None], chars)[0][0].split(" ") if w]
+        words = [w for k, w in enumerate(greedy_words) if k % 2 == 0] + ["the", "of", "Book"]
+        want = E.decode_wordbeamsearch(probs[None], chars, bw, words)[0]
+        enc = [[chars.index(ch) + 1 for ch in w] for w in words]
+        got = "".join(chars[i - 1] for i in lib_built.ctc_beam_decode(probs, 2, bw, space, enc))
+        assert got == want, (trial, got, want)
+        want = E.decode_wordbeamsearch(probs[None], chars, bw, [])[0]
+        got = "".join(chars[i - 1] for i in lib_built.ctc_beam_decode(probs, 2, bw, space, []))
+        assert got == want, (trial, got, want)
+        n += 3
+    assert n == 180
+    # a sharp matrix without repeated characters: every decoder returns the greedy string
+    probs = np.full((12, 97), 1e-4, np.float32)
+    for t, c in enumerate([0, 30, 0, 0, 31, 32, 0, space, 0, 50, 0, 0]):
+        probs[t, c] = 1.0
+    probs /= probs.sum(1, keepdims=True)
+    greedy = E.decode_probs(probs[None], chars)[0][0]
+    assert greedy == "".join(chars[c - 1] for c in (30, 31, 32, space, 50))
+    for dec in (1, 2):
+        assert "".join(chars[i - 1] for i in lib_built.ctc_beam_decode(probs, dec, 5, space)) == greedy

@@ -41,3 +41,23 @@ def test_group_text_box_known_answer():
     h, f = E.group_text_box(polys, 0.1, 0.5, 0.5, 0.5, 0.1, True)
     assert [list(map(int, b)) for b in h] == [[7, 203, 7, 45]]
     assert len(f) == 1
+
+
+def test_rotation_info_is_rot90():
+    """utils.make_rotated_img_list calls scipy.ndimage.rotate(img, angle, reshape=True); for the eligible angles the spline
+    rotation is exactly np.rot90 -- the form the oracle (and the device kernel) use."""
+    ndi = pytest.importorskip("scipy.ndimage")
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        h, w = int(rng.integers(1, 80)), int(rng.integers(1, 300))
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        for angle in (90, 180, 270):
+            assert np.array_equal(ndi.rotate(a, angle, reshape=True), np.rot90(a, angle // 90))
+    box = [[0, 0], [1, 0], [1, 1], [0, 1]]
+    out = E.make_rotated_img_list([90, 270], [(box, a)])
+    assert len(out) == 3 and np.array_equal(out[1][1], np.rot90(a, 1)) and np.array_equal(out[2][1], np.rot90(a, 3))
+
+
+def test_set_result_with_confidence_takes_the_first_maximum():
+    rows = [[("b0", "a", 0.5), ("b1", "x", 0.2)], [("b0", "b", 0.5), ("b1", "y", 0.9)], [("b0", "c", 0.1), ("b1", "z", 0.9)]]
+    assert E.set_result_with_confidence(rows) == [("b0", "a", 0.5), ("b1", "y", 0.9)]
