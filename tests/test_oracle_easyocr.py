@@ -1,5 +1,6 @@
 """CPU: structural pins of the restated EasyOCR oracle (parity unpinned: no easyocr / checkpoints in the image)."""
 import numpy as np
+import pytest
 import torch
 
 from bbocr_b200 import weights
