@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbbocr.so")
 
+E_UNSUPPORTED = -5
 PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 
 
@@ -68,6 +69,7 @@ SYMBOLS = [
     "bbocr_crnn_forward", "bbocr_ctc_decode", "bbocr_default_params", "bbocr_readtext", "bbocr_readtext_batch",
     "bbocr_recognize", "bbocr_thumbnail_u8", "bbocr_autocrop_rect", "bbocr_external_boxes", "bbocr_rect_morph", "bbocr_results_free", "bbocr_launch_count", "bbocr_reset_launch_count", "bbocr_conv_stats",
     "bbocr_enable_conv_timing", "bbocr_set_dictionary", "bbocr_ctc_beam_decode",
+    "bbocr_jpeg_info", "bbocr_jpeg_coefficients", "bbocr_jpeg_decode", "bbocr_jpeg_decode_batch",
 ]
 
 
@@ -508,6 +510,32 @@ class Handle:
                                            C.c_int(len(fl)), p, C.byref(out)))
         return self._unpack(out)
 
+    # ---- image decode -----------------------------------------------------------------------------
+    def jpeg_decode(self, data: bytes, color: bool = True, gray: bool = False, ignore_orientation: bool = False):
+        """cv2.imdecode of a baseline JPEG on the device -> (bgr HxWx3 | None, gray HxW | None) host arrays."""
+        buf = np.frombuffer(data, np.uint8)
+        H, W, ch, o = jpeg_info(data)
+        if ignore_orientation and o >= 5:
+            H, W = W, H
+        bgr = np.empty((H, W, 3), np.uint8) if color else None
+        g = np.empty((H, W), np.uint8) if gray else None
+        oh, ow = C.c_int(), C.c_int()
+        self._check(self.L.bbocr_jpeg_decode(self._h, buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size), C.c_int(int(ignore_orientation)),
+                                             bgr.ctypes.data_as(C.c_void_p) if color else None,
+                                             g.ctypes.data_as(C.c_void_p) if gray else None, C.c_int(0), C.byref(oh), C.byref(ow)))
+        assert (oh.value, ow.value) == (H, W)
+        return bgr, g
+
+    def jpeg_decode_batch_dev(self, datas, bgr_ptrs=None, gray_ptrs=None, ignore_orientation: bool = False):
+        """n JPEG byte strings -> n device images (raw device pointers sized from jpeg_info), pipelined over the lanes."""
+        n = len(datas)
+        bufs = [np.frombuffer(d, np.uint8) for d in datas]
+        dp = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sz = (C.c_size_t * n)(*[b.size for b in bufs])
+        bp = (C.c_void_p * n)(*[int(p) for p in bgr_ptrs]) if bgr_ptrs is not None else None
+        gp = (C.c_void_p * n)(*[int(p) for p in gray_ptrs]) if gray_ptrs is not None else None
+        self._check(self.L.bbocr_jpeg_decode_batch(self._h, C.c_int(n), dp, sz, C.c_int(int(ignore_orientation)), bp, gp))
+
     # ---- instrumentation -------------------------------------------------------------------------------------------
     def set_dictionary(self, words):
         """wordbeamsearch dictionary: `words` = iterable of class-index sequences (CTCLabelConverter.dict_list)."""
@@ -535,6 +563,31 @@ class Handle:
 
 
 # ---- pure-host entry points (usable without a GPU) -----------------------------------------------------------------------
+
+def jpeg_info(data: bytes):
+    """(H, W, channels, exif orientation) of a baseline JPEG as cv2.imread would return it (oriented); host only."""
+    buf = np.frombuffer(data, np.uint8)
+    H, W, ch, o = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    rc = lib().bbocr_jpeg_info(buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size), C.byref(H), C.byref(W), C.byref(ch), C.byref(o))
+    if rc != 0:
+        raise BbocrError(rc, "unsupported or malformed JPEG")
+    return H.value, W.value, ch.value, o.value
+
+
+def jpeg_coefficients(data: bytes) -> np.ndarray:
+    """Quantised DCT coefficients [n_blocks][64] int16 (all components, padded to whole MCUs) via the product's host code."""
+    buf = np.frombuffer(data, np.uint8)
+    nb = C.c_int64()
+    rc = lib().bbocr_jpeg_coefficients(buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size), None, C.c_int64(0), C.byref(nb))
+    if rc != 0:
+        raise BbocrError(rc, "unsupported or malformed JPEG")
+    out = np.zeros((nb.value, 64), np.int16)
+    rc = lib().bbocr_jpeg_coefficients(buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size), out.ctypes.data_as(C.c_void_p),
+                                       C.c_int64(nb.value), C.byref(nb))
+    if rc != 0:
+        raise BbocrError(rc, "unsupported or malformed JPEG")
+    return out
+
 
 def ctc_beam_decode(probs, decoder: int, beam_width: int = 5, space_idx: int = 43, dict_words=()):
     """CTCLabelConverter.decode_beamsearch (decoder 1) / decode_wordbeamsearch (2) of one crop: probs T x C float32 -> class

@@ -1485,6 +1485,76 @@ int bbocr_readtext_batch(bbocr_handle* h, int n, const bbocr_image* imgs, const 
     });
 }
 
+// ---- image decode ------------------------------------------------------------------------------------
+int bbocr_jpeg_info(const uint8_t* data, size_t n, int* H, int* W, int* channels, int* orientation) {
+    if (!data || !H || !W || !channels || !orientation) return BBOCR_E_ARG;
+    try {
+        bbocr::jpeg_info(data, n, H, W, channels, orientation);
+    } catch (const bbocr::Error& e) {
+        return e.code;
+    } catch (...) {
+        return BBOCR_E_ARG;
+    }
+    return BBOCR_OK;
+}
+
+int bbocr_jpeg_coefficients(const uint8_t* data, size_t n, int16_t* out, int64_t cap_blocks, int64_t* n_blocks) {
+    if (!data || !n_blocks) return BBOCR_E_ARG;
+    try {
+        *n_blocks = bbocr::jpeg_coefficients_host(data, n, out, cap_blocks);
+    } catch (const bbocr::Error& e) {
+        return e.code;
+    } catch (...) {
+        return BBOCR_E_ARG;
+    }
+    return BBOCR_OK;
+}
+
+int bbocr_jpeg_decode(bbocr_handle* h, const uint8_t* data, size_t n, int ignore_orientation, uint8_t* out_bgr, uint8_t* out_gray,
+                      int out_on_device, int* H, int* W) {
+    return guarded(h, [&] {
+        ARG_CHECK(data && n > 0 && H && W, "bad arguments");
+        Lane& lane = h->lanes[0];
+        if (out_on_device || (!out_bgr && !out_gray)) {
+            jpeg_decode_dev(h, lane, data, n, ignore_orientation, out_bgr, out_gray, H, W);
+            CUDA_CHECK(stream_sync(lane.stream));
+            lane.in_busy = false;
+            return;
+        }
+        int ch = 0, o = 0;
+        jpeg_info(data, n, H, W, &ch, &o);
+        if (ignore_orientation && o >= 5) std::swap(*H, *W);
+        const size_t px = (size_t)*H * *W;
+        DevBuf dbgr, dgray;
+        if (out_bgr) dbgr.alloc(px * 3, lane.stream);
+        if (out_gray) dgray.alloc(px, lane.stream);
+        jpeg_decode_dev(h, lane, data, n, ignore_orientation, out_bgr ? dbgr.as<uint8_t>() : nullptr,
+                        out_gray ? dgray.as<uint8_t>() : nullptr, H, W);
+        if (out_bgr) download(lane, out_bgr, dbgr.p, px * 3);
+        if (out_gray) download(lane, out_gray, dgray.p, px);
+        CUDA_CHECK(stream_sync(lane.stream));
+        lane.in_busy = false;
+    });
+}
+
+int bbocr_jpeg_decode_batch(bbocr_handle* h, int n, const uint8_t* const* data, const size_t* sizes, int ignore_orientation,
+                            uint8_t* const* out_bgr, uint8_t* const* out_gray) {
+    return guarded(h, [&] {
+        ARG_CHECK(n >= 0 && (n == 0 || (data && sizes)) && (out_bgr || out_gray), "bad arguments");
+        const int nl = std::max(1, std::min<int>((int)h->lanes.size(), 8));
+        for (int i = 0; i < n; ++i) {
+            ARG_CHECK(data[i] && sizes[i] > 0, "bad arguments");
+            int H = 0, W = 0;
+            jpeg_decode_dev(h, h->lanes[i % nl], data[i], sizes[i], ignore_orientation, out_bgr ? out_bgr[i] : nullptr,
+                            out_gray ? out_gray[i] : nullptr, &H, &W);
+        }
+        for (int l = 0; l < nl; ++l) {
+            CUDA_CHECK(stream_sync(h->lanes[l].stream));
+            h->lanes[l].in_busy = false;
+        }
+    });
+}
+
 // single-stage recogniser entry points (parity-test surface)
 int bbocr_crop_horizontal(bbocr_handle* h, const uint8_t* gray, int H, int W, const int32_t box[4], uint8_t* out, int cap,
                           int* outH, int* outW, int* model_w) {

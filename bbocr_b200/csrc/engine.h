@@ -235,6 +235,11 @@ void row_probs_dev(Handle*, cudaStream_t, const float* logits, int rows, int C, 
 // rotation_info: out = np.rot90(src, k) for every job (k = 1, 2, 3), u8 crops inside one packed buffer
 struct RotDesc { int src_off, dst_off, sh, sw, k; };
 void rotate_crops_dev(Handle*, cudaStream_t, uint8_t* crops, const RotDesc* descs_dev, int n, int max_pixels);
+// jpeg.cu: baseline JPEG -> BGR / luma planes on the device, bit-exact with cv2.imdecode (libjpeg-turbo defaults + EXIF orientation)
+void jpeg_info(const uint8_t* data, size_t n, int* H, int* W, int* channels, int* orientation);
+long long jpeg_coefficients_host(const uint8_t* data, size_t n, int16_t* out, long long cap_blocks);
+void jpeg_decode_dev(Handle*, Lane&, const uint8_t* data, size_t n, int ignore_orientation, uint8_t* out_bgr, uint8_t* out_gray,
+                     int* outH, int* outW);
 // beam.cpp: CTCLabelConverter.decode_beamsearch (decoder 1) / decode_wordbeamsearch (decoder 2) of one crop, host side
 void decode_beam(const float* probs, int T, int C, int decoder, int beam_width, int space_idx,
                  const std::set<std::vector<int32_t>>* dict, std::vector<int32_t>& text);

@@ -227,6 +227,28 @@ int bbocr_ctc_beam_decode(const float* probs, int T, int C, int decoder, int bea
 int bbocr_thumbnail_u8(bbocr_handle* h, const uint8_t* src, int H, int W, int in_on_device, int max_dim, uint8_t* out,
                        int out_on_device, int* outH, int* outW);
 
+/* ---- image decode in front of the path ------------------------------------------------------------- */
+/* cv2.imread / cv2.imdecode of a baseline JPEG (pipeline_demo/ocr_testing/preprocessing/image_preprocessor.py:18;
+ * easyocr/utils.py::reformat_input reads the file as IMREAD_GRAYSCALE and as colour), bit-exact with OpenCV's libjpeg-turbo
+ * (islow IDCT, fancy up-sampling, fixed-point YCbCr->BGR) including the EXIF orientation step.  Entropy decoding runs on the
+ * device with one thread per restart interval (phone cameras write one per MCU row); files without restart markers are
+ * Huffman-decoded by host threads and take the device from the IDCT on.  Progressive / arithmetic / 12-bit / CMYK /
+ * multi-scan files return BBOCR_E_UNSUPPORTED (callers keep their host decoder for those). */
+int bbocr_jpeg_info(const uint8_t* data, size_t n, int* H, int* W, int* channels, int* orientation);   /* oriented H, W; no device */
+/* Host only (parity-test surface): the quantised DCT coefficients (jdhuff.c output) of every block -- component after
+ * component, blocks in raster order padded to whole MCUs, 64 int16 each in natural order -- through the product's parser and
+ * entropy decoder.  out == NULL or cap_blocks too small: only *n_blocks is set. */
+int bbocr_jpeg_coefficients(const uint8_t* data, size_t n, int16_t* out, int64_t cap_blocks, int64_t* n_blocks);
+/* out_bgr: H x W x 3 (cv2.IMREAD_COLOR) and / or out_gray: H x W (cv2.IMREAD_GRAYSCALE = the luma plane); either may be NULL.
+ * out_on_device = 1: device pointers, the call returns once the work is enqueued and complete on return of
+ * bbocr_jpeg_decode_batch / any later synchronous call of the handle. */
+int bbocr_jpeg_decode(bbocr_handle* h, const uint8_t* data, size_t n, int ignore_orientation, uint8_t* out_bgr, uint8_t* out_gray,
+                      int out_on_device, int* H, int* W);
+/* n files -> n device images, pipelined over the handle's streams; returns when all are complete.  out_bgr[i] / out_gray[i]
+ * are device pointers (NULL entries or NULL arrays skip that output). */
+int bbocr_jpeg_decode_batch(bbocr_handle* h, int n, const uint8_t* const* data, const size_t* sizes, int ignore_orientation,
+                            uint8_t* const* out_bgr, uint8_t* const* out_gray);
+
 /* ---- page crops in front of the OCR stage ---------------------------------------------------------- */
 /* _auto_crop_text_region (pipeline_demo/extractor/enhanced_extractor.py:239-372) up to the slice it writes: the crop
  * rectangle rect = (x0, y0, x1, y1) of a page for the given margin; *found = 0 is the reference's `return None`
