@@ -6,7 +6,7 @@ when the in-tree library or a B200 is missing (there is no CPU fallback).
 from .reader import Reader, reformat_input, CHARACTERS                      # noqa: F401
 from .preprocess import ImagePreprocessor, preprocess_for_book_cover, preprocess_array   # noqa: F401
 from .extractor import extract_text_with_ocr, ocr_input_image              # noqa: F401
-from . import _lib, extractor, sharding, synth, weights                     # noqa: F401
+from . import _lib, decode, extractor, sharding, synth, weights                     # noqa: F401
 
 __all__ = ["Reader", "ImagePreprocessor", "preprocess_for_book_cover", "preprocess_array", "reformat_input",
            "extract_text_with_ocr", "ocr_input_image"]

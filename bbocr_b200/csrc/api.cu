@@ -163,6 +163,12 @@ void bbocr_destroy(bbocr_handle* h) {
     cudaDeviceSynchronize();
     for (auto& l : h->lanes)
         if (l.stream) cudaStreamDestroy(l.stream);
+    for (auto& l : h->jpeg_lanes)
+        if (l.stream) cudaStreamDestroy(l.stream);
+    for (auto* v : {&h->lanes, &h->jpeg_lanes})
+        for (auto& l : *v)
+            for (auto& sc : l.scr)
+                if (sc.p) cudaFree(sc.p);
     for (void* p : h->owned) cudaFree(p);
     for (auto& kv : h->cubic_cache) cudaFree(kv.second.first);
     for (auto& ev : h->conv_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -1541,17 +1547,57 @@ int bbocr_jpeg_decode_batch(bbocr_handle* h, int n, const uint8_t* const* data, 
                             uint8_t* const* out_bgr, uint8_t* const* out_gray) {
     return guarded(h, [&] {
         ARG_CHECK(n >= 0 && (n == 0 || (data && sizes)) && (out_bgr || out_gray), "bad arguments");
-        const int nl = std::max(1, std::min<int>((int)h->lanes.size(), 8));
-        for (int i = 0; i < n; ++i) {
-            ARG_CHECK(data[i] && sizes[i] > 0, "bad arguments");
-            int H = 0, W = 0;
-            jpeg_decode_dev(h, h->lanes[i % nl], data[i], sizes[i], ignore_orientation, out_bgr ? out_bgr[i] : nullptr,
-                            out_gray ? out_gray[i] : nullptr, &H, &W);
+        if (n == 0) return;
+        // Host threads parse / stage / launch GROUPS of files, each thread over its own two lanes (the staging of one group
+        // fills while the other group's work drains); a group's entropy decoding is ONE launch over all its restart intervals.
+        static const int kThreads = getenv("BBOCR_JPEG_THREADS") ? std::min(32, std::max(1, atoi(getenv("BBOCR_JPEG_THREADS")))) : 4;
+        static const int kGroup = getenv("BBOCR_JPEG_GROUP") ? std::min(64, std::max(1, atoi(getenv("BBOCR_JPEG_GROUP")))) : 8;
+        constexpr int kLanesPerThread = 2;
+        if (h->jpeg_lanes.empty()) {
+            h->jpeg_lanes.resize(kThreads * kLanesPerThread);
+            for (auto& l : h->jpeg_lanes) CUDA_CHECK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         }
-        for (int l = 0; l < nl; ++l) {
-            CUDA_CHECK(stream_sync(h->lanes[l].stream));
-            h->lanes[l].in_busy = false;
-        }
+        const int n_groups = cdiv(n, kGroup);
+        const int nt = std::min(kThreads, n_groups);
+        std::vector<int> codes(nt, 0);
+        std::vector<std::string> errs(nt);
+        std::atomic<int> next_group{0};
+        auto work = [&](int t) {
+            try {
+                CUDA_CHECK(cudaSetDevice(h->device));
+                std::vector<JpegJob> jobs;
+                int k = 0;
+                for (int gi; (gi = next_group.fetch_add(1)) < n_groups; ++k) {
+                    jobs.clear();
+                    for (int i = gi * kGroup; i < std::min(n, (gi + 1) * kGroup); ++i) {
+                        ARG_CHECK(data[i] && sizes[i] > 0, "bad arguments");
+                        jobs.push_back(JpegJob{data[i], sizes[i], out_bgr ? out_bgr[i] : nullptr, out_gray ? out_gray[i] : nullptr, 0, 0});
+                    }
+                    jpeg_decode_group_dev(h, h->jpeg_lanes[t * kLanesPerThread + k % kLanesPerThread], jobs.data(), (int)jobs.size(),
+                                          ignore_orientation);
+                }
+                for (int l = 0; l < kLanesPerThread; ++l) {
+                    Lane& lane = h->jpeg_lanes[t * kLanesPerThread + l];
+                    CUDA_CHECK(stream_sync(lane.stream));
+                    lane.in_busy = false;
+                }
+            } catch (const Error& e) {
+                codes[t] = e.code;
+                errs[t] = e.what();
+            } catch (const std::exception& e) {
+                codes[t] = BBOCR_E_ARG;
+                errs[t] = e.what();
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& t : th) t.join();
+        for (int t = 0; t < nt; ++t)
+            if (codes[t]) {
+                for (auto& l : h->jpeg_lanes) { cudaStreamSynchronize(l.stream); l.in_busy = false; }
+                throw Error(codes[t], errs[t]);
+            }
     });
 }
 

@@ -23,10 +23,26 @@ struct CrnnW {
     int num_class = 97;
 };
 
+struct LaneScratch {                // grow-only device buffer owned by ONE lane: reused in stream order, so it never creates the
+    void* p = nullptr;              // cross-stream reuse dependencies a shared cudaMallocAsync pool inserts between lanes
+    size_t cap = 0;
+    void* get(size_t n) {
+        if (n > cap) {
+            if (p) cudaFree(p);     // synchronises the device; happens only while the buffers grow to the working size
+            p = nullptr;
+            cap = n + n / 8 + 4096;
+            CUDA_CHECK(cudaMalloc(&p, cap));
+        }
+        return p;
+    }
+};
+
 struct Lane {                       // one in-flight page: a stream + its pinned staging
     cudaStream_t stream = nullptr;
     PinnedBuf pin_in, pin_out;
     bool in_busy = false;           // an async H2D copy out of pin_in may still be in flight
+    LaneScratch scr[3];             // jpeg.cu: coefficient blocks, sample planes, tables + entropy bytes
+    bool scr_dirty = false;         // jpeg.cu: scr[0] may hold coefficients of an image whose IDCT was never enqueued
 };
 
 struct Handle {
@@ -57,6 +73,7 @@ struct Handle {
     double conv_flops = 0;
     double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t conv_launches = 0;
+    std::vector<Lane> jpeg_lanes;          // streams + pinned staging of bbocr_jpeg_decode_batch (created on first use)
     std::set<std::vector<int32_t>> dict;   // wordbeamsearch dictionary as class-index words (bbocr_set_dictionary)
 };
 
@@ -238,6 +255,8 @@ void rotate_crops_dev(Handle*, cudaStream_t, uint8_t* crops, const RotDesc* desc
 // jpeg.cu: baseline JPEG -> BGR / luma planes on the device, bit-exact with cv2.imdecode (libjpeg-turbo defaults + EXIF orientation)
 void jpeg_info(const uint8_t* data, size_t n, int* H, int* W, int* channels, int* orientation);
 long long jpeg_coefficients_host(const uint8_t* data, size_t n, int16_t* out, long long cap_blocks);
+struct JpegJob { const uint8_t* data; size_t n; uint8_t* out_bgr; uint8_t* out_gray; int H, W; };   // H, W: set by the decoder
+void jpeg_decode_group_dev(Handle*, Lane&, JpegJob* jobs, int nj, int ignore_orientation);
 void jpeg_decode_dev(Handle*, Lane&, const uint8_t* data, size_t n, int ignore_orientation, uint8_t* out_bgr, uint8_t* out_gray,
                      int* outH, int* outW);
 // beam.cpp: CTCLabelConverter.decode_beamsearch (decoder 1) / decode_wordbeamsearch (decoder 2) of one crop, host side

@@ -31,6 +31,8 @@ struct HuffTab {                             // jdhuff.c::jpeg_make_d_derived_tb
     int32_t maxcode[18];                     // largest code of each length (-1 = none); [17] = sentinel
     int32_t valoff[18];
     uint8_t vals[256];
+    int16_t fast[1 << LA];                   // AC tables: (value << 8) | (run << 4) | (code + magnitude bits) when both fit into LA
+                                             // bits and the value into a signed byte, else 0 (the stb_image "fast AC" trick)
 };
 
 struct JpegComp {
@@ -82,6 +84,15 @@ void build_huff(const uint8_t* counts, const uint8_t* vals, int nvals, HuffTab& 
         code <<= 1;
     }
     t.maxcode[17] = 0x7fffffff;
+    for (int i = 0; i < (1 << LA); ++i) {
+        const int e = t.look[i];
+        if (!e) continue;
+        const int len = e >> 8, run = (e >> 4) & 15, mag = e & 15;
+        if (mag == 0 || len + mag > LA) continue;
+        int v = ((i << len) & ((1 << LA) - 1)) >> (LA - mag);
+        if (v < (1 << (mag - 1))) v += (int)((~0u) << mag) + 1;
+        if (v >= -128 && v <= 127) t.fast[i] = (int16_t)(v * 256 + run * 16 + len + mag);
+    }
 }
 
 int exif_orientation(const uint8_t* t, size_t n) {          // TIFF header of an APP1 "Exif\0\0" segment -> tag 0x0112 of IFD0
@@ -248,27 +259,75 @@ void find_segments(const uint8_t* d, const JpegInfo& J, std::vector<uint32_t>& b
 }
 
 // ---- entropy decoding: jdhuff.c::decode_mcu over the MCUs [mcu0, mcu1) of one restart interval ---------------------------
+// The bit reservoir of jdhuff.c (64 bits), fed from the interval's bytes with the stuffed zero after every 0xFF removed.
+// Host: byte by byte.  Device: a dependent chain of single-byte loads and branches per symbol is what a SIMT lane is worst at,
+// so the lane keeps 4-7 stream bytes in a register (aligned 32-bit loads) and moves FOUR bytes into the reservoir at once
+// whenever they contain no 0xFF (98.5 % of the time); only words with an 0xFF take the byte-wise path.
 struct BitReader {
-    const uint8_t* p;
-    const uint8_t* end;
+    uint32_t left;             // bytes of the interval not yet moved into the reservoir
     uint64_t acc;
     int n;
-    __host__ __device__ void fill() {
+#ifdef __CUDA_ARCH__
+    const uint32_t* wp;        // next aligned word
+    uint64_t word;             // stream bytes fetched but not yet consumed, lowest first
+    int wn;
+    __device__ BitReader(const uint8_t* begin, const uint8_t* end) : left((uint32_t)(end - begin)), acc(0), n(0) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(begin);
+        const int mis = (int)(a & 3);
+        wp = reinterpret_cast<const uint32_t*>(a - mis);       // the bytes in front of `begin` belong to the same upload
+        word = (uint64_t)(__ldg(wp++) >> (8 * mis));
+        wn = 4 - mis;
+    }
+    __device__ __forceinline__ uint32_t next_byte() {
+        if (left == 0) return 0;                               // past the interval: zeros, like libjpeg at a marker
+        --left;
+        if (wn == 0) { word = __ldg(wp++); wn = 4; }           // the upload is padded: whole words are readable
+        const uint32_t b = (uint32_t)(word & 0xff);
+        word >>= 8;
+        --wn;
+        return b;
+    }
+    __device__ __forceinline__ void fill() {
+        if (n > 32) return;
+        if (wn < 4) { word |= (uint64_t)__ldg(wp++) << (8 * wn); wn += 4; }
+        const uint32_t b4 = (uint32_t)word;
+        if (left >= 4 && !((~b4 - 0x01010101u) & b4 & 0x80808080u)) {      // no byte of b4 is 0xFF
+            acc |= (uint64_t)__byte_perm(b4, 0, 0x0123) << (32 - n);
+            n += 32;
+            word >>= 32;
+            wn -= 4;
+            left -= 4;
+            return;
+        }
         while (n <= 56) {
-            uint32_t b = 0;
-            if (p < end) {
-                b = *p++;
-                if (b == 0xFF && p < end) ++p;            // FF 00: the stuffed zero (a marker never lies inside an interval)
-            }
+            const uint32_t b = next_byte();
+            if (b == 0xFF) next_byte();                        // FF 00: the stuffed zero (a marker never lies inside an interval)
             acc |= (uint64_t)b << (56 - n);
             n += 8;
         }
     }
-    __host__ __device__ uint32_t peek(int k) const { return (uint32_t)(acc >> (64 - k)); }
-    __host__ __device__ void skip(int k) { acc <<= k; n -= k; }
+#else
+    const uint8_t* p;
+    BitReader(const uint8_t* begin, const uint8_t* end) : left((uint32_t)(end - begin)), acc(0), n(0), p(begin) {}
+    uint32_t next_byte() {
+        if (left == 0) return 0;
+        --left;
+        return *p++;
+    }
+    void fill() {
+        while (n <= 56) {
+            const uint32_t b = next_byte();
+            if (b == 0xFF) next_byte();
+            acc |= (uint64_t)b << (56 - n);
+            n += 8;
+        }
+    }
+#endif
+    __host__ __device__ __forceinline__ uint32_t peek(int k) const { return (uint32_t)(acc >> (64 - k)); }
+    __host__ __device__ __forceinline__ void skip(int k) { acc <<= k; n -= k; }
 };
 
-__host__ __device__ inline int huff_symbol(BitReader& br, const HuffTab& t) {
+__host__ __device__ __forceinline__ int huff_symbol(BitReader& br, const HuffTab& t) {
     const uint32_t e = t.look[br.peek(LA)];
     if (e) {
         br.skip((int)(e >> 8));
@@ -285,7 +344,7 @@ __host__ __device__ inline int huff_symbol(BitReader& br, const HuffTab& t) {
     return t.vals[(code + t.valoff[len]) & 255];
 }
 
-__host__ __device__ inline int receive_extend(BitReader& br, int s) {
+__host__ __device__ __forceinline__ int receive_extend(BitReader& br, int s) {
     if (s == 0) return 0;
     const int v = (int)br.peek(s);
     br.skip(s);
@@ -293,10 +352,10 @@ __host__ __device__ inline int receive_extend(BitReader& br, int s) {
 }
 
 template <typename ZZ>
-__host__ __device__ inline void decode_segment(const uint8_t* data, uint32_t begin, uint32_t end, const ScanDesc& S, const HuffTab* tabs,
+__host__ __device__ __forceinline__ void decode_segment(const uint8_t* data, uint32_t begin, uint32_t end, const ScanDesc& S, const HuffTab* tabs,
                                                int mcu0, int mcu1, int16_t* coef, ZZ zigzag) {
-    BitReader br{data + begin, data + end, 0, 0};
-    int pred[3] = {0, 0, 0};
+    BitReader br(data + begin, data + end);
+    int pred0 = 0, pred1 = 0, pred2 = 0;
     for (int m = mcu0; m < mcu1; ++m) {
         const int my = m / S.mcux, mx = m - my * S.mcux;
         for (int ci = 0; ci < S.ncomp; ++ci) {
@@ -304,19 +363,27 @@ __host__ __device__ inline void decode_segment(const uint8_t* data, uint32_t beg
             const HuffTab& act = tabs[4 + S.ac[ci]];
             for (int by = 0; by < S.v[ci]; ++by)
                 for (int bx = 0; bx < S.h[ci]; ++bx) {
+                    // the coefficient buffer was zeroed up front (one memset per image): only the non-zero values are stored
                     int16_t* blk = nullptr;
-                    if (S.store[ci]) {
-                        blk = coef + (S.coef_off[ci] + (long long)(my * S.v[ci] + by) * S.bx[ci] + (mx * S.h[ci] + bx)) * 64;
-                        int4* z = reinterpret_cast<int4*>(blk);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) z[i] = int4{0, 0, 0, 0};
-                    }
+                    if (S.store[ci]) blk = coef + (S.coef_off[ci] + (long long)(my * S.v[ci] + by) * S.bx[ci] + (mx * S.h[ci] + bx)) * 64;
                     br.fill();
                     int s = huff_symbol(br, dct);
-                    pred[ci] += receive_extend(br, s & 15);
-                    if (blk) blk[0] = (int16_t)pred[ci];
+                    const int diff = receive_extend(br, s & 15);
+                    int dcv;
+                    if (ci == 0) dcv = (pred0 += diff);
+                    else if (ci == 1) dcv = (pred1 += diff);
+                    else dcv = (pred2 += diff);
+                    if (blk) blk[0] = (int16_t)dcv;
                     for (int k = 1; k < 64;) {
                         br.fill();
+                        const int f = act.fast[br.peek(LA)];
+                        if (f) {                                   // short code + small value: one lookup
+                            k += (f >> 4) & 15;
+                            br.skip(f & 15);
+                            if (blk) blk[zigzag(k & 63)] = (int16_t)(f >> 8);
+                            ++k;
+                            continue;
+                        }
                         const int rs = huff_symbol(br, act);
                         const int r = rs >> 4;
                         s = rs & 15;
@@ -338,19 +405,10 @@ __host__ __device__ inline void decode_segment(const uint8_t* data, uint32_t beg
 struct ZigDev { __device__ int operator()(int k) const { return c_zigzag[k]; } };
 struct ZigHost { int operator()(int k) const { return h_zigzag[k]; } };
 
-__global__ void __launch_bounds__(64)
-    k_jpeg_huff(const uint8_t* __restrict__ data, const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ seg_end, int nseg,
-                ScanDesc S, const HuffTab* __restrict__ tabs_g, int16_t* __restrict__ coef) {
-    __shared__ HuffTab tabs[8];                                   // dc0..3 | ac0..3 (unused ones are zero)
-    for (int i = threadIdx.x; i < (int)(sizeof(HuffTab) * 8 / 4); i += blockDim.x)
-        reinterpret_cast<uint32_t*>(tabs)[i] = reinterpret_cast<const uint32_t*>(tabs_g)[i];
-    __syncthreads();
-    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
-    if (seg >= nseg) return;
-    const int mcu0 = S.restart > 0 ? seg * S.restart : 0;
-    const int mcu1 = S.restart > 0 ? min(S.nmcu, mcu0 + S.restart) : S.nmcu;
-    decode_segment(data, seg_begin[seg], seg_end[seg], S, tabs, mcu0, mcu1, coef, ZigDev());
-}
+// One thread per restart interval, `lpw` of them per warp: the threads of a warp walk different bit streams, so every
+// data-dependent branch (reservoir refill, end of block, long codes) serialises the warp; with few active lanes per warp the
+// intervals run close to their own latency chain, and the idle lanes cost nothing (a photo has ~200-270 intervals).
+// (kernel: k_jpeg_huff_group below)
 
 // ---- jidctint.c::jpeg_idct_islow: one thread per 8x8 block ----------------------------------------------------------------
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
@@ -383,17 +441,20 @@ __device__ __forceinline__ uint32_t range_limit(int x) {          // sample_rang
 }
 
 __global__ void __launch_bounds__(128)
-    k_jpeg_idct(const int16_t* __restrict__ coef, const uint16_t* __restrict__ qt /*[64]*/, int bx, int n_blocks, uint8_t* __restrict__ plane) {
+    k_jpeg_idct(int16_t* __restrict__ coef, const uint16_t* __restrict__ qt /*[64]*/, int bx, int n_blocks, uint8_t* __restrict__ plane) {
     __shared__ int q[64];
     if (threadIdx.x < 64) q[threadIdx.x] = qt[threadIdx.x];
     __syncthreads();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
     int v[64];
-    const int4* src = reinterpret_cast<const int4*>(coef + (size_t)b * 64);
+    // the block is handed back zeroed: the entropy decoder of the NEXT image on this lane stores only non-zero coefficients
+    // (a cudaMemsetAsync of the 36 MB buffer per photo runs at copy-engine speed and serialised the lanes)
+    int4* src = reinterpret_cast<int4*>(coef + (size_t)b * 64);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        const int4 w = __ldg(src + r);
+        const int4 w = src[r];
+        src[r] = int4{0, 0, 0, 0};
         const int wi[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -549,6 +610,7 @@ long long jpeg_coefficients_host(const uint8_t* data, size_t n, int16_t* out, lo
     }
     std::vector<int16_t> tmp((size_t)J.n_blocks * 64 + 8);
     int16_t* base = reinterpret_cast<int16_t*>(((uintptr_t)tmp.data() + 15) & ~(uintptr_t)15);
+    memset(base, 0, (size_t)J.n_blocks * 128);
     for (int sgi = 0; sgi < nseg; ++sgi) {
         const int mcu0 = J.restart > 0 ? sgi * J.restart : 0;
         const int mcu1 = J.restart > 0 ? std::min(S.nmcu, mcu0 + J.restart) : S.nmcu;
@@ -558,116 +620,213 @@ long long jpeg_coefficients_host(const uint8_t* data, size_t n, int16_t* out, lo
     return J.n_blocks;
 }
 
+// ---- a GROUP of files on one lane: one upload, ONE entropy-decoder launch over the restart intervals of all of them ----------
+// Entropy decoding is a latency chain per interval (~2 ms per 12 MP photo whatever else the GPU does), so the lane-level unit
+// of work is a group: 8 photos = ~1 500-2 100 intervals in one grid.  (Running one photo per stream instead needs 30+ streams
+// that really overlap, i.e. CUDA_DEVICE_MAX_CONNECTIONS = 32 -- which costs the detector lanes of readtext 8 %.)
+struct ImgDesc {                             // device-visible descriptor of one image of the group
+    ScanDesc S;
+    uint32_t tabs_off, seg_off, data_off;    // byte offsets into the group blob
+    int nseg;
+    long long coef_base;                     // first int16 of this image's blocks in the lane's coefficient buffer
+};
+
+__global__ void __launch_bounds__(128)
+    k_jpeg_huff_group(const uint8_t* __restrict__ blob, const ImgDesc* __restrict__ imgs, const int2* __restrict__ blockmap /*(image, first interval)*/,
+                      int16_t* __restrict__ coef, int lpw) {
+    __shared__ HuffTab tabs[8];                                   // dc0..3 | ac0..3 of this block's image
+    __shared__ ImgDesc I;
+    const int2 bm = blockmap[blockIdx.x];
+    if (threadIdx.x < (int)(sizeof(ImgDesc) / 4))
+        reinterpret_cast<uint32_t*>(&I)[threadIdx.x] = reinterpret_cast<const uint32_t*>(imgs + bm.x)[threadIdx.x];
+    __syncthreads();
+    const uint32_t* tg = reinterpret_cast<const uint32_t*>(blob + I.tabs_off);
+    for (int i = threadIdx.x; i < (int)(sizeof(HuffTab) * 8 / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(tabs)[i] = tg[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    if (lane >= lpw) return;
+    const int seg = bm.y + (threadIdx.x >> 5) * lpw + lane;
+    if (seg >= I.nseg) return;
+    const uint32_t* sg = reinterpret_cast<const uint32_t*>(blob + I.seg_off);
+    const int mcu0 = I.S.restart > 0 ? seg * I.S.restart : 0;
+    const int mcu1 = I.S.restart > 0 ? min(I.S.nmcu, mcu0 + I.S.restart) : I.S.nmcu;
+    decode_segment(blob + I.data_off, sg[seg], sg[I.nseg + seg], I.S, tabs, mcu0, mcu1, coef + I.coef_base, ZigDev());
+}
+
+struct GroupImage {
+    JpegInfo J;
+    std::vector<uint32_t> sb, se;
+    bool need_chroma = false, device_huffman = false;
+    long long n_blocks = 0, coef_base = 0, plane_base = 0;
+    size_t o_tabs = 0, o_q = 0, o_seg = 0, o_data = 0, o_end = 0, o_hostcoef = 0;
+};
+
+void jpeg_decode_group_dev(Handle* h, Lane& lane, JpegJob* jobs, int nj, int ignore_orientation) {
+    cudaStream_t st = lane.stream;
+    if (nj <= 0) return;
+    static const int lpw = getenv("BBOCR_JPEG_LPW") ? std::min(32, std::max(1, atoi(getenv("BBOCR_JPEG_LPW")))) : 2;
+    std::vector<GroupImage> g(nj);
+    long long coef_total = 0, plane_total = 0;
+    size_t blob = ((size_t)nj * sizeof(ImgDesc) + 15) & ~(size_t)15;
+    int total_blocks = 0;
+    for (int i = 0; i < nj; ++i) {
+        GroupImage& G = g[i];
+        JpegJob& jb = jobs[i];
+        parse_jpeg(jb.data, jb.n, G.J);
+        JpegInfo& J = G.J;
+        if (ignore_orientation) J.orientation = 1;
+        ARG_CHECK((long long)J.H * J.W <= (1ll << 30), "JPEG: image too large");
+        const bool swap = J.orientation >= 5;
+        jb.H = swap ? J.W : J.H;
+        jb.W = swap ? J.H : J.W;
+        if (!jb.out_bgr && !jb.out_gray) continue;
+        G.need_chroma = jb.out_bgr != nullptr && J.ncomp == 3;
+        find_segments(jb.data, J, G.sb, G.se);
+        const int nseg = (int)G.sb.size();
+        const int want_seg = J.restart > 0 ? cdiv(J.mcux * J.mcuy, J.restart) : 1;
+        if (nseg != want_seg) fail(BBOCR_E_ARG, "JPEG: %d restart intervals found, %d expected (corrupt stream)", nseg, want_seg);
+        G.device_huffman = J.restart > 0 && nseg >= 8;
+        G.n_blocks = G.need_chroma ? J.n_blocks : (long long)J.c[0].bx * J.c[0].by;
+        G.coef_base = coef_total * 64;
+        G.plane_base = plane_total;
+        coef_total += G.n_blocks;
+        plane_total += G.need_chroma ? J.plane_bytes : G.n_blocks * 64;
+        G.o_tabs = blob;
+        G.o_q = G.o_tabs + sizeof(HuffTab) * 8;
+        G.o_seg = G.o_q + 4 * 64 * 2;
+        G.o_data = (G.o_seg + (size_t)nseg * 8 + 15) & ~(size_t)15;
+        G.o_end = G.device_huffman ? ((G.o_data + (J.scan_end - J.scan_start) + 16 + 15) & ~(size_t)15) : G.o_data;
+        blob = G.o_end;
+        if (G.device_huffman) total_blocks += cdiv(nseg, 4 * lpw);
+    }
+    if (coef_total == 0) return;
+    const size_t o_map = blob;
+    blob = (o_map + (size_t)std::max(total_blocks, 1) * sizeof(int2) + 15) & ~(size_t)15;
+    const size_t blob_bytes = blob;
+    size_t pin_bytes = blob_bytes;
+    for (auto& G : g)
+        if (!G.device_huffman && G.n_blocks) { G.o_hostcoef = pin_bytes; pin_bytes += (size_t)G.n_blocks * 128; }
+
+    if (lane.in_busy) { CUDA_CHECK(stream_sync(st)); lane.in_busy = false; }   // also orders a cudaFree of a growing scratch buffer
+    // invariant: a lane's coefficient buffer is all zeros between groups (k_jpeg_idct clears what the decoder wrote)
+    const size_t coef_cap_before = lane.scr[0].cap;
+    int16_t* dcoef = reinterpret_cast<int16_t*>(lane.scr[0].get((size_t)coef_total * 128));
+    if (lane.scr[0].cap != coef_cap_before || lane.scr_dirty) CUDA_CHECK(cudaMemsetAsync(dcoef, 0, lane.scr[0].cap, st));
+    lane.scr_dirty = true;                                         // until every IDCT launch of the group is enqueued
+    uint8_t* dplanes = reinterpret_cast<uint8_t*>(lane.scr[1].get((size_t)plane_total));
+    uint8_t* dblob = reinterpret_cast<uint8_t*>(lane.scr[2].get(blob_bytes));
+    uint8_t* pin = (uint8_t*)lane.pin_in.get(pin_bytes);
+    ImgDesc* descs = reinterpret_cast<ImgDesc*>(pin);
+    int2* bmap = reinterpret_cast<int2*>(pin + o_map);
+    int nb_map = 0;
+    for (int i = 0; i < nj; ++i) {
+        GroupImage& G = g[i];
+        ImgDesc& D = descs[i];
+        memset(&D, 0, sizeof D);
+        if (!G.n_blocks) continue;
+        const JpegInfo& J = G.J;
+        ScanDesc& S = D.S;
+        S.ncomp = J.ncomp; S.mcux = J.mcux; S.nmcu = J.mcux * J.mcuy; S.restart = J.restart;
+        for (int k = 0; k < J.ncomp; ++k) {
+            S.h[k] = J.c[k].h; S.v[k] = J.c[k].v; S.bx[k] = J.c[k].bx; S.dc[k] = J.c[k].td; S.ac[k] = J.c[k].ta;
+            S.store[k] = (k == 0 || G.need_chroma) ? 1 : 0;
+            S.coef_off[k] = J.c[k].coef_off;
+        }
+        const int nseg = (int)G.sb.size();
+        D.tabs_off = (uint32_t)G.o_tabs; D.seg_off = (uint32_t)G.o_seg; D.data_off = (uint32_t)G.o_data;
+        D.nseg = nseg;
+        D.coef_base = G.coef_base;
+        HuffTab* tabs = reinterpret_cast<HuffTab*>(pin + G.o_tabs);
+        memset(tabs, 0, sizeof(HuffTab) * 8);
+        for (int k = 0; k < 4; ++k) {
+            if (J.has_dc[k]) tabs[k] = J.dc[k];
+            if (J.has_ac[k]) tabs[4 + k] = J.ac[k];
+        }
+        memcpy(pin + G.o_q, J.q, sizeof J.q);
+        if (G.device_huffman) {
+            uint32_t* segs = reinterpret_cast<uint32_t*>(pin + G.o_seg);
+            for (int q = 0; q < nseg; ++q) {
+                segs[q] = G.sb[q] - (uint32_t)J.scan_start;          // relative to the uploaded entropy bytes
+                segs[nseg + q] = G.se[q] - (uint32_t)J.scan_start;
+            }
+            memcpy(pin + G.o_data, jobs[i].data + J.scan_start, J.scan_end - J.scan_start);
+            for (int q = 0; q < nseg; q += 4 * lpw) bmap[nb_map++] = int2{i, q};
+        } else {
+            // no (or too few) restart intervals: the scan is one bit-serial chain -> the same routine on host threads
+            int16_t* hc = reinterpret_cast<int16_t*>(pin + G.o_hostcoef);
+            memset(hc, 0, (size_t)G.n_blocks * 128);
+            const int nt = std::max(1, std::min(nseg, 8));
+            std::vector<std::thread> th;
+            auto work = [&](int t) {
+                for (int sgi = t; sgi < nseg; sgi += nt) {
+                    const int mcu0 = J.restart > 0 ? sgi * J.restart : 0;
+                    const int mcu1 = J.restart > 0 ? std::min(S.nmcu, mcu0 + J.restart) : S.nmcu;
+                    decode_segment(jobs[i].data, G.sb[sgi], G.se[sgi], S, tabs, mcu0, mcu1, hc, ZigHost());
+                }
+            };
+            for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto& t : th) t.join();
+        }
+    }
+    if ((size_t)blob_bytes >= (1ull << 32)) fail(BBOCR_E_ARG, "JPEG: group too large");
+    CUDA_CHECK(cudaMemcpyAsync(dblob, pin, blob_bytes, cudaMemcpyHostToDevice, st));
+    for (auto& G : g)
+        if (!G.device_huffman && G.n_blocks)
+            CUDA_CHECK(cudaMemcpyAsync(dcoef + G.coef_base, pin + G.o_hostcoef, (size_t)G.n_blocks * 128, cudaMemcpyHostToDevice, st));
+    lane.in_busy = true;
+    if (nb_map > 0) {
+        k_jpeg_huff_group<<<nb_map, 128, 0, st>>>(dblob, reinterpret_cast<const ImgDesc*>(dblob), reinterpret_cast<const int2*>(dblob + o_map),
+                                                  dcoef, lpw);
+        count_launch(h);
+    }
+    for (int i = 0; i < nj; ++i) {
+        GroupImage& G = g[i];
+        if (!G.n_blocks) continue;
+        const JpegInfo& J = G.J;
+        const int ncomp_run = G.need_chroma ? J.ncomp : 1;
+        uint8_t* planes = dplanes + G.plane_base;
+        for (int k = 0; k < ncomp_run; ++k) {
+            const JpegComp& c = J.c[k];
+            const int nb = c.bx * c.by;
+            k_jpeg_idct<<<cdiv(nb, 128), 128, 0, st>>>(dcoef + G.coef_base + c.coef_off * 64,
+                                                       reinterpret_cast<const uint16_t*>(dblob + G.o_q) + c.tq * 64, c.bx, nb,
+                                                       planes + c.plane_off);
+            count_launch(h);
+        }
+        ColorDesc D{};
+        D.y = planes + J.c[0].plane_off;
+        D.ypitch = J.c[0].bx * 8;
+        D.ncomp = G.need_chroma ? 3 : 1;
+        D.hx = D.vx = 1;
+        if (G.need_chroma) {
+            D.cb = planes + J.c[1].plane_off;
+            D.cr = planes + J.c[2].plane_off;
+            D.cpitch = J.c[1].bx * 8;
+            D.cdw = J.c[1].dw;
+            D.cdh = J.c[1].dh;
+            D.hx = J.hmax / J.c[1].h;
+            D.vx = J.vmax / J.c[1].v;
+        }
+        D.H = J.H; D.W = J.W;
+        D.orientation = J.orientation;
+        D.bgr = jobs[i].out_bgr;
+        D.gray = jobs[i].out_gray;
+        k_jpeg_color<<<dim3(cdiv(J.W, 32), cdiv(J.H, 32)), 256, 0, st>>>(D);
+        count_launch(h);
+    }
+    lane.scr_dirty = false;
+    CUDA_CHECK(cudaGetLastError());
+}
+
 // Decode one JPEG on `lane`.  out_bgr / out_gray: device pointers (either may be null), sized for the oriented image.
 // Returns after enqueueing the work on the lane's stream (the pinned staging stays busy until the stream drains).
 void jpeg_decode_dev(Handle* h, Lane& lane, const uint8_t* data, size_t n, int ignore_orientation, uint8_t* out_bgr, uint8_t* out_gray,
                      int* outH, int* outW) {
-    cudaStream_t st = lane.stream;
-    JpegInfo J;
-    parse_jpeg(data, n, J);
-    if (ignore_orientation) J.orientation = 1;
-    ARG_CHECK((long long)J.H * J.W <= (1ll << 30), "JPEG: image too large");
-    const bool swap = J.orientation >= 5;
-    if (outH) *outH = swap ? J.W : J.H;
-    if (outW) *outW = swap ? J.H : J.W;
-    if (!out_bgr && !out_gray) return;
-    const bool need_chroma = out_bgr != nullptr && J.ncomp == 3;
-    ScanDesc S{};
-    S.ncomp = J.ncomp; S.mcux = J.mcux; S.nmcu = J.mcux * J.mcuy; S.restart = J.restart;
-    for (int k = 0; k < J.ncomp; ++k) {
-        S.h[k] = J.c[k].h; S.v[k] = J.c[k].v; S.bx[k] = J.c[k].bx; S.dc[k] = J.c[k].td; S.ac[k] = J.c[k].ta;
-        S.store[k] = (k == 0 || need_chroma) ? 1 : 0;
-        S.coef_off[k] = J.c[k].coef_off;
-    }
-    std::vector<uint32_t> sb, se;
-    find_segments(data, J, sb, se);
-    const int nseg = (int)sb.size();
-    const int want_seg = J.restart > 0 ? cdiv(S.nmcu, J.restart) : 1;
-    if (nseg != want_seg) fail(BBOCR_E_ARG, "JPEG: %d restart intervals found, %d expected (corrupt stream)", nseg, want_seg);
-
-    const long long n_blocks = need_chroma ? J.n_blocks : (long long)J.c[0].bx * J.c[0].by;
-    DevBuf dcoef((size_t)n_blocks * 128, st), dplanes((size_t)(need_chroma ? J.plane_bytes : n_blocks * 64), st);
-    // one pinned blob: tables | quantisation tables | segment offsets | entropy bytes  (or the host-decoded coefficients)
-    const bool device_huffman = J.restart > 0 && nseg >= 8;
-    const size_t o_tabs = 0, o_q = o_tabs + sizeof(HuffTab) * 8, o_seg = o_q + 4 * 64 * 2,
-                 o_data = (o_seg + (size_t)nseg * 8 + 15) & ~(size_t)15;
-    const size_t entropy_bytes = J.scan_end - J.scan_start;
-    const size_t blob_bytes = device_huffman ? o_data + entropy_bytes + 16 : o_data;
-    if (lane.in_busy) { CUDA_CHECK(stream_sync(st)); lane.in_busy = false; }
-    uint8_t* pin = (uint8_t*)lane.pin_in.get(blob_bytes + (device_huffman ? 0 : (size_t)n_blocks * 128));
-    HuffTab* tabs = reinterpret_cast<HuffTab*>(pin + o_tabs);
-    memset(tabs, 0, sizeof(HuffTab) * 8);
-    for (int k = 0; k < 4; ++k) {
-        if (J.has_dc[k]) tabs[k] = J.dc[k];
-        if (J.has_ac[k]) tabs[4 + k] = J.ac[k];
-    }
-    memcpy(pin + o_q, J.q, sizeof J.q);
-    uint32_t* segs = reinterpret_cast<uint32_t*>(pin + o_seg);
-    for (int i = 0; i < nseg; ++i) {
-        segs[i] = sb[i] - (uint32_t)J.scan_start;                  // relative to the uploaded entropy bytes
-        segs[nseg + i] = se[i] - (uint32_t)J.scan_start;
-    }
-    DevBuf dblob(blob_bytes, st);
-    if (device_huffman) {
-        memcpy(pin + o_data, data + J.scan_start, entropy_bytes);
-        CUDA_CHECK(cudaMemcpyAsync(dblob.p, pin, blob_bytes, cudaMemcpyHostToDevice, st));
-        lane.in_busy = true;
-        const uint8_t* db = dblob.as<uint8_t>();
-        k_jpeg_huff<<<cdiv(nseg, 64), 64, 0, st>>>(db + o_data, reinterpret_cast<const uint32_t*>(db + o_seg),
-                                                   reinterpret_cast<const uint32_t*>(db + o_seg) + nseg, nseg, S,
-                                                   reinterpret_cast<const HuffTab*>(db + o_tabs), dcoef.as<int16_t>());
-        count_launch(h);
-    } else {
-        // no (or too few) restart intervals: the scan is one bit-serial chain -> the same routine on the host, split over the
-        // intervals there are
-        int16_t* hc = reinterpret_cast<int16_t*>(pin + blob_bytes);
-        const int nt = std::max(1, std::min(nseg, 8));
-        std::vector<std::thread> th;
-        auto work = [&](int t) {
-            for (int sgi = t; sgi < nseg; sgi += nt) {
-                const int mcu0 = J.restart > 0 ? sgi * J.restart : 0;
-                const int mcu1 = J.restart > 0 ? std::min(S.nmcu, mcu0 + J.restart) : S.nmcu;
-                decode_segment(data, sb[sgi], se[sgi], S, tabs, mcu0, mcu1, hc, ZigHost());
-            }
-        };
-        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
-        work(0);
-        for (auto& t : th) t.join();
-        CUDA_CHECK(cudaMemcpyAsync(dblob.p, pin, blob_bytes, cudaMemcpyHostToDevice, st));
-        CUDA_CHECK(cudaMemcpyAsync(dcoef.p, hc, (size_t)n_blocks * 128, cudaMemcpyHostToDevice, st));
-        lane.in_busy = true;
-    }
-    const uint8_t* db = dblob.as<uint8_t>();
-    const int ncomp_run = need_chroma ? J.ncomp : 1;
-    for (int k = 0; k < ncomp_run; ++k) {
-        const JpegComp& c = J.c[k];
-        const int nb = c.bx * c.by;
-        k_jpeg_idct<<<cdiv(nb, 128), 128, 0, st>>>(dcoef.as<int16_t>() + c.coef_off * 64,
-                                                   reinterpret_cast<const uint16_t*>(db + o_q) + c.tq * 64, c.bx, nb,
-                                                   dplanes.as<uint8_t>() + c.plane_off);
-        count_launch(h);
-    }
-    ColorDesc D{};
-    D.y = dplanes.as<uint8_t>() + J.c[0].plane_off;
-    D.ypitch = J.c[0].bx * 8;
-    D.ncomp = need_chroma ? 3 : 1;
-    D.hx = D.vx = 1;
-    if (need_chroma) {
-        D.cb = dplanes.as<uint8_t>() + J.c[1].plane_off;
-        D.cr = dplanes.as<uint8_t>() + J.c[2].plane_off;
-        D.cpitch = J.c[1].bx * 8;
-        D.cdw = J.c[1].dw;
-        D.cdh = J.c[1].dh;
-        D.hx = J.hmax / J.c[1].h;
-        D.vx = J.vmax / J.c[1].v;
-    }
-    D.H = J.H; D.W = J.W;
-    D.orientation = J.orientation;
-    D.bgr = out_bgr;
-    D.gray = out_gray;
-    k_jpeg_color<<<dim3(cdiv(J.W, 32), cdiv(J.H, 32)), 256, 0, st>>>(D);
-    count_launch(h);
-    CUDA_CHECK(cudaGetLastError());
+    JpegJob jb{data, n, out_bgr, out_gray, 0, 0};
+    jpeg_decode_group_dev(h, lane, &jb, 1, ignore_orientation);
+    if (outH) *outH = jb.H;
+    if (outW) *outW = jb.W;
 }
 
 }  // namespace bbocr

@@ -36,9 +36,8 @@ def imdecode(handle: "_lib.Handle", buf, flags: int = cv2.IMREAD_COLOR):
             bgr, gray = handle.jpeg_decode(data, color=base == cv2.IMREAD_COLOR, gray=base == cv2.IMREAD_GRAYSCALE,
                                            ignore_orientation=bool(flags & cv2.IMREAD_IGNORE_ORIENTATION))
             return bgr if base == cv2.IMREAD_COLOR else gray
-        except _lib.BbocrError as e:
-            if e.code != _lib.E_UNSUPPORTED:
-                return None                                     # cv2 returns None for undecodable data
+        except _lib.BbocrError:                                 # unsupported layout or damaged stream: cv2 decides
+            pass
     return cv2.imdecode(np.frombuffer(data, np.uint8), flags)
 
 

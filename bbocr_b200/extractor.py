@@ -13,6 +13,7 @@ from __future__ import annotations
 import cv2
 import numpy as np
 
+from . import decode
 from .preprocess import CURRENT, pp_params
 
 
@@ -64,6 +65,24 @@ def auto_crop_text_region(reader, img: np.ndarray, margin: int):
     return img[y0:y1, x0:x1]
 
 
+def _decode_to_device(reader, path: str):
+    """A JPEG file straight into HBM (bbocr_jpeg_decode, bit-exact with cv2.imread): the photo never exists as a host array.
+    None when the file is not something the device decoder takes (the caller then reads it with cv2)."""
+    import torch
+    from . import _lib
+    try:
+        with open(path, "rb") as f:
+            data = f.read()
+        H, W, _ch, _o = _lib.jpeg_info(data)
+    except Exception:                                        # noqa: BLE001 -- not a baseline JPEG: host decode
+        return None
+    out = torch.empty((H, W, 3), dtype=torch.uint8, device=torch.device(reader.device))
+    torch.cuda.synchronize(out.device)
+    with reader._lock:
+        reader.handle.jpeg_decode_batch_dev([data], [out.data_ptr()], None)
+    return out
+
+
 def _extract_device_resident(reader, bgr, image_index, edge_crop_percent, crop_for_ocr, crop_margin):
     """The same steps with the planes kept in HBM between them (one upload of the photo, results down): torch only owns the
     device buffers (allocation, slicing, the gray -> 3-channel copy readtext's detector input needs); every pixel operation
@@ -71,7 +90,7 @@ def _extract_device_resident(reader, bgr, image_index, edge_crop_percent, crop_f
     import torch
     h = reader.handle
     dev = torch.device(reader.device)
-    src = torch.from_numpy(np.ascontiguousarray(bgr)).to(dev)
+    src = bgr if isinstance(bgr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bgr)).to(dev)
     H, W = bgr.shape[:2]
     p = pp_params(CURRENT, 0)
     gray = torch.empty((int(H * p.scale), int(W * p.scale)), dtype=torch.uint8, device=dev)
@@ -126,8 +145,23 @@ def extract_text_with_ocr(reader, image, *, use_preprocessing=True, image_index=
     in HBM between the steps instead of bouncing them through host arrays; the results are identical.  OCR errors are
     swallowed into "" exactly like :529-531."""
     try:
+        if device_resident is None:
+            device_resident = _torch_cuda_available()
         if isinstance(image, str):
-            bgr = cv2.imread(image)
+            bgr = None
+            if use_preprocessing and device_resident:        # file -> HBM -> text: decode on the device as well (§8f-4)
+                dev_bgr = _decode_to_device(reader, image)
+                if dev_bgr is not None:
+                    try:
+                        results = _extract_device_resident(reader, dev_bgr, image_index, edge_crop_percent, crop_for_ocr, crop_margin)
+                        text = " ".join([r[1] for r in results])
+                        return (text, results) if return_results else text
+                    except Exception as e:                   # noqa: BLE001 -- :441-443: fall back to the original image
+                        print(f"    Preprocessing failed: {e}")
+                        bgr = dev_bgr.cpu().numpy()
+                        use_preprocessing = False
+            if bgr is None:
+                bgr = decode.imread(reader.handle, image)
             if bgr is None:
                 raise ValueError(f"Could not load image from {image}")
         else:
@@ -139,8 +173,6 @@ def extract_text_with_ocr(reader, image, *, use_preprocessing=True, image_index=
             try:
                 if bgr.ndim != 3:
                     raise ValueError("preprocessing expects a BGR image")
-                if device_resident is None:
-                    device_resident = _torch_cuda_available()
                 if device_resident:
                     results = _extract_device_resident(reader, bgr, image_index, edge_crop_percent, crop_for_ocr, crop_margin)
                     text = " ".join([r[1] for r in results])

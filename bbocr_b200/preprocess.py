@@ -3,7 +3,8 @@
 Reference interface (same names, argument meaning, step strings and error behaviour):
     pipeline_demo/ocr_testing/preprocessing/image_preprocessor.py:7-145   class ImagePreprocessor (fluent steps)
     pipeline_demo/ocr_testing/preprocessing/image_preprocessor.py:147-160 preprocess_for_book_cover(image_path, output_path)
-File decode / encode (cv2.imread / cv2.imwrite) stays on the host; every pixel operation is a CUDA kernel.
+Baseline JPEG files decode on the device (decode.py, bit-exact with cv2.imread); other formats and cv2.imwrite stay on the
+host; every pixel operation is a CUDA kernel.
 """
 from __future__ import annotations
 
@@ -13,7 +14,7 @@ import threading
 import cv2
 import numpy as np
 
-from . import _lib
+from . import _lib, decode
 
 _handles = {}
 _hlock = threading.Lock()
@@ -55,7 +56,7 @@ class ImagePreprocessor:
             self.to_grayscale()
 
     def load_image(self, image_path):
-        img = cv2.imread(image_path)
+        img = decode.imread(_handle(self._device), image_path)        # cv2.imread; baseline JPEG decodes on the device (§8f-4)
         if img is None:
             raise ValueError(f"Could not load image from {image_path}")
         return self.load_array(img)
@@ -185,7 +186,7 @@ def preprocess_array(bgr: np.ndarray, cfg=CURRENT, resize_mode: int = 0, device:
 
 def preprocess_for_book_cover(image_path, output_path=None, *, resize_mode: int = 0, device: int = 0):
     """-> (preprocessed gray image, output_path, steps) exactly like the reference function."""
-    bgr = cv2.imread(image_path)
+    bgr = decode.imread(_handle(device), image_path)                  # cv2.imread; baseline JPEG decodes on the device (§8f-4)
     if bgr is None:
         raise ValueError(f"Could not load image from {image_path}")
     out = preprocess_array(bgr, CURRENT, resize_mode, device)

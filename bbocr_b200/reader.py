@@ -16,7 +16,7 @@ import threading
 import cv2
 import numpy as np
 
-from . import _lib, weights
+from . import _lib, decode, weights
 
 # easyocr/config.py : recognition_models['gen2']['english_g2']
 SYMBOLS = "0123456789!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~ €"
@@ -31,18 +31,31 @@ def _is_pil_image(obj) -> bool:
         return False
 
 
-def reformat_input(image):
-    """easyocr/utils.py::reformat_input -> (img HxWx3 as fed to the detector, img_cv_grey HxW).  Host-side decode;
-    JPEG/PNG decoding stays on the host."""
+def _read_file_both(path, handle):
+    """The two reads upstream makes of a file -- cv2.imread(path, IMREAD_GRAYSCALE) and a colour read -- from ONE device
+    decode when the file is a baseline JPEG (bit-exact with cv2), else from cv2 on the host."""
+    if handle is not None:
+        try:
+            with open(os.path.expanduser(path), "rb") as f:
+                data = f.read()
+            if decode._is_jpeg(data):
+                return decode.imdecode_both(handle, data)
+        except (OSError, _lib.BbocrError):
+            pass
+    return cv2.imread(os.path.expanduser(path), cv2.IMREAD_COLOR), cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+
+
+def reformat_input(image, handle=None):
+    """easyocr/utils.py::reformat_input -> (img HxWx3 as fed to the detector, img_cv_grey HxW).  With a `handle`, baseline
+    JPEG files / byte strings decode on the device (bbocr_jpeg_decode); everything else decodes on the host as before."""
     if isinstance(image, str):
-        img_cv_grey = cv2.imread(image, cv2.IMREAD_GRAYSCALE)
-        bgr = cv2.imread(os.path.expanduser(image), cv2.IMREAD_COLOR)
+        bgr, img_cv_grey = _read_file_both(image, handle)
         if bgr is None or img_cv_grey is None:
             raise ValueError(f"Invalid input: could not read {image}")
         img = cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB)          # upstream: skimage.io.imread (RGB)
     elif isinstance(image, bytes):
         nparr = np.frombuffer(image, np.uint8)
-        img = cv2.imdecode(nparr, cv2.IMREAD_COLOR)
+        img = decode.imdecode(handle, image, cv2.IMREAD_COLOR) if handle is not None else cv2.imdecode(nparr, cv2.IMREAD_COLOR)
         if img is None:
             raise ValueError("Invalid input: undecodable bytes")
         img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
@@ -292,7 +305,7 @@ class Reader:
         self._decode_options(p, decoder, beamWidth, batch_size, rotation_info)
         pages = []
         for im in images:
-            img, grey = reformat_input(im)
+            img, grey = reformat_input(im, self._h)
             pages.append((np.ascontiguousarray(img), None if grey is None else np.ascontiguousarray(grey),
                           img.shape[0], img.shape[1]))
         with self._lock:
@@ -333,7 +346,7 @@ class Reader:
                reformat=True, **_ignored):
         """Reader.detect -> ([horizontal_list], [free_list])"""
         if reformat:
-            img, _ = reformat_input(img)
+            img, _ = reformat_input(img, self._h)
         with self._lock:
             text, link, ratio = self._h.craft_forward(img, canvas_size, mag_ratio)
             boxes = self._h.det_boxes(text, link, text_threshold, link_threshold, low_text)
@@ -348,7 +361,7 @@ class Reader:
         With both lists None the whole image is one horizontal box, like upstream."""
         if reformat:
             if not (isinstance(img_cv_grey, np.ndarray) and img_cv_grey.ndim == 2):
-                img, img_cv_grey = reformat_input(img_cv_grey)
+                img, img_cv_grey = reformat_input(img_cv_grey, self._h)
                 if img_cv_grey is None:                        # HxWx3 / HxWx4 / PIL input: upstream derives BGR2GRAY of `img`
                     img_cv_grey = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
         if horizontal_list is None and free_list is None:

@@ -17,7 +17,7 @@ same comparison is repeated here on the benched batch and reported as config.ide
 detector mode is measured next to it (key `fast_mode`) with ITS parity numbers.
 
 Documented extra keys of the line (N = 1 only): `fast_mode`, `config0_cover_1280x960`, `stage1_preprocess` (config[2]),
-`recognition_only` (config[3]), `cpu_baseline_int8` (EasyOCR's default CPU path quantises the recogniser), `tesseract`.
+`recognition_only` (config[3]), `decode_jpeg` (file bytes -> BGR in HBM vs cv2.imdecode), `cpu_baseline_int8` (EasyOCR's default CPU path quantises the recogniser), `tesseract`.
 """
 import argparse
 import json
@@ -193,6 +193,63 @@ def stage1_preprocess(h, peak_gbs, n_photos=256, reps=2):
             "photos_per_s": 1.0 / best, "ms_per_photo": best * 1e3, "bound": "hbm", "achieved": gbs, "peak": peak_gbs,
             "unit": "GB/s", "frac": gbs / peak_gbs, "algorithmic_bytes_per_photo": 12 * H * W,
             "launches_per_photo": int(h.L.bbocr_preprocess_launches_per_image())}
+
+
+def decode_jpeg(h, peak_gbs, n_files=64, distinct=8, reps=3):
+    """SURVEY.md §8f-4 / image_preprocessor.py:18: cv2.imread of phone photos.  n_files JPEG files (4032x3024, 4:2:0, quality
+    90, one restart interval per MCU row, EXIF orientation 6 -- the layout of the reference's own books/*/IMG_*.JPG) held as
+    byte strings on the host -> BGR images in HBM through bbocr_jpeg_decode_batch (file bytes H2D inside the timed region),
+    next to cv2.imdecode of the same bytes on all host cores.  Algorithmic bytes per photo = coefficient blocks written +
+    read (2 B x 1.5 samples per pixel, twice) + sample planes written + read (1.5 B, twice) + BGR written (3 B) = 12 B / pixel."""
+    import io
+    from concurrent.futures import ThreadPoolExecutor
+    import cv2
+    import torch
+    from PIL import Image
+    from bbocr_b200 import synth
+    H, W = 3024, 4032
+    ex = Image.Exif()
+    ex[0x0112] = 6
+    files = []
+    for i in range(distinct):
+        b = io.BytesIO()
+        Image.fromarray(synth.phone_photo(3001 + i, W, H)[:, :, ::-1]).save(b, "JPEG", quality=90, exif=ex.tobytes(), restart_marker_rows=1)
+        files.append(b.getvalue())
+    datas = [files[i % distinct] for i in range(n_files)]
+    outs = [torch.empty((W, H, 3), dtype=torch.uint8, device="cuda") for _ in range(n_files)]        # orientation 6: rotated
+    ptrs = [t.data_ptr() for t in outs]
+    h.jpeg_decode_batch_dev(datas[:8], ptrs[:8])
+    torch.cuda.synchronize()
+    want = cv2.imdecode(np.frombuffer(datas[0], np.uint8), cv2.IMREAD_COLOR)
+    exact = bool(np.array_equal(outs[0].cpu().numpy(), want))
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        h.jpeg_decode_batch_dev(datas, ptrs)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_files
+        best = dt if best is None or dt < best else best
+    ncpu = os.cpu_count() or 1
+    cv2.setNumThreads(1)
+    sample = datas[:max(ncpu, 8)]
+    with ThreadPoolExecutor(ncpu) as ex_:
+        list(ex_.map(lambda d: cv2.imdecode(np.frombuffer(d, np.uint8), cv2.IMREAD_COLOR), sample[:ncpu]))
+        t0 = time.perf_counter()
+        list(ex_.map(lambda d: cv2.imdecode(np.frombuffer(d, np.uint8), cv2.IMREAD_COLOR), sample))
+        cpu_dt = (time.perf_counter() - t0) / len(sample)
+    t0 = time.perf_counter()
+    cv2.imdecode(np.frombuffer(datas[0], np.uint8), cv2.IMREAD_COLOR)
+    one = time.perf_counter() - t0
+    cv2.setNumThreads(-1)
+    del outs
+    torch.cuda.empty_cache()
+    gbs = 12.0 * H * W / best / 1e9
+    return {"workload": f"{n_files} JPEG files ({distinct} distinct synthetic phone photos 4032x3024, 4:2:0, q90, DRI = one MCU row, EXIF orientation 6; "
+                        f"{sum(len(d) for d in datas) / n_files / 1e6:.2f} MB each) as host byte strings -> BGR in HBM (cv2.imread semantics incl. orientation)",
+            "photos_per_s": 1.0 / best, "ms_per_photo": best * 1e3, "bit_exact_vs_cv2": exact, "bound": "hbm", "achieved": gbs, "peak": peak_gbs,
+            "unit": "GB/s", "frac": gbs / peak_gbs, "algorithmic_bytes_per_photo": 12 * H * W, "launches_per_photo": 5,
+            "cpu_baseline": {"photos_per_s": 1.0 / cpu_dt, "ms_per_photo_one_core": one * 1e3, "cores": ncpu, "kind": "reference",
+                             "sample": f"cv2.imdecode (the reference's cv2.imread, libjpeg-turbo) of {len(sample)} of the files, {ncpu} threads"}}
 
 
 def recognition_only(reader, peak_sustained, n_crops=100000, distinct=512, per_call=12500, reps=1):
@@ -478,6 +535,10 @@ def main():
             del dcov
             line["recognition_only"] = recognition_only(reader, peak_sust)
             line["stage1_preprocess"] = stage1_preprocess(h, peak_gbs)
+            try:
+                line["decode_jpeg"] = decode_jpeg(h, peak_gbs)
+            except Exception as e:                            # noqa: BLE001 -- an extra key must never break the bench line
+                line["decode_jpeg"] = {"unavailable": str(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pages, 1)
             if not args.no_extras:
