@@ -48,6 +48,11 @@ struct TcParams {
     const uint8_t* colmask;     // optional [OW]: output columns with 0 are written as zeros (gaps between concatenated crops)
     int stages;
     int p_stages, patch_al;     // halo-patch kernel: patch pipeline depth, bytes of one (1024-aligned) patch
+    int ncat;                   // split precision, BN <= 128: the w_hi and w_lo tiles sit back to back in shared memory and are
+                                // used as ONE B operand of 2*BN rows, so a K = 16 step is two MMAs instead of three:
+                                //   D[:, 0:2BN] += x_hi * [w_hi ; w_lo]      D[:, 0:BN] += x_lo * w_hi
+                                // (same products, one A-operand read less per step: the low-channel layers are bound by the
+                                // operand reads from shared memory, not by the math); the epilogue adds the two column halves
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -224,10 +229,16 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                     if (writer && py < POH && px < POW) pix2 = ((int64_t)tc.img * POH + py) * POW + px;
                 }
             }
-            const uint32_t trow = tmem_base + (uint32_t)(as * p.BN) + ((uint32_t)(wq * 32) << 16);
+            const uint32_t trow = tmem_base + (uint32_t)(as * (p.ncat ? 2 * p.BN : p.BN)) + ((uint32_t)(wq * 32) << 16);
             for (int c = 0; c < p.BN; c += 16) {
                 uint32_t v[16];
                 tmem_ld16(trow + c, v);
+                if (p.ncat) {                       // x_hi * w_lo accumulated in the second half of the stage
+                    uint32_t v2[16];
+                    tmem_ld16(trow + p.BN + c, v2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                }
                 float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -285,7 +296,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     const int kb1 = p.C1 / BK, kb2 = p.C2 / BK;
     const int kiters = p.taps * (kb1 + kb2);
     uint32_t ncols = 32;
-    while ((int)ncols < 2 * p.BN) ncols <<= 1;
+    while ((int)ncols < (p.ncat ? 4 : 2) * p.BN) ncols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -355,7 +366,8 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             const uint32_t aph = (ti >> 1) & 1;
             mbar_wait(&tempty_bar[as], aph ^ 1);                 // the epilogue has drained this accumulator stage
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.BN);
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * (p.ncat ? 2 * p.BN : p.BN));
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             for (int k = 0; k < kiters; ++k, ++it) {
                 const int s = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
@@ -367,9 +379,14 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                     const uint64_t bhi = umma_desc<BK>(sa + 2 * A_BYTES), blo = umma_desc<BK>(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
-                        umma_bf16(tmem_acc, ahi + 2 * kk, bhi + 2 * kk, idesc, (k > 0 || kk > 0) ? 1u : 0u);
-                        umma_bf16(tmem_acc, alo + 2 * kk, bhi + 2 * kk, idesc, 1u);
-                        umma_bf16(tmem_acc, ahi + 2 * kk, blo + 2 * kk, idesc, 1u);
+                        if (p.ncat) {
+                            umma_bf16(tmem_acc, ahi + 2 * kk, bhi + 2 * kk, idesc2, (k > 0 || kk > 0) ? 1u : 0u);
+                            umma_bf16(tmem_acc, alo + 2 * kk, bhi + 2 * kk, idesc, 1u);
+                        } else {
+                            umma_bf16(tmem_acc, ahi + 2 * kk, bhi + 2 * kk, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+                            umma_bf16(tmem_acc, alo + 2 * kk, bhi + 2 * kk, idesc, 1u);
+                            umma_bf16(tmem_acc, ahi + 2 * kk, blo + 2 * kk, idesc, 1u);
+                        }
                     }
                 } else {
                     const uint64_t adesc = umma_desc<BK>(sa), bdesc = umma_desc<BK>(sa + A_BYTES);
@@ -425,7 +442,7 @@ __global__ void __launch_bounds__(256) k_conv_tc_patch(const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb1 = p.C1 / BK, kb2 = p.C2 / BK;
     uint32_t ncols = 32;
-    while ((int)ncols < 2 * p.BN) ncols <<= 1;
+    while ((int)ncols < (p.ncat ? 4 : 2) * p.BN) ncols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -492,7 +509,8 @@ __global__ void __launch_bounds__(256) k_conv_tc_patch(const __grid_constant__ C
             const int as = ti & 1;
             mbar_wait(&tempty_bar[as], ((ti >> 1) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.BN);
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * (p.ncat ? 2 * p.BN : p.BN));
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             for (int kb = 0; kb < kb1 + kb2; ++kb, ++pit) {
                 const int ps = pit % p.p_stages;
                 mbar_wait(&pfull_bar[ps], (pit / p.p_stages) & 1);
@@ -510,9 +528,14 @@ __global__ void __launch_bounds__(256) k_conv_tc_patch(const __grid_constant__ C
                     const uint64_t off = (uint64_t)(((ky * PW + kx) * PIX) >> 4);
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
-                        umma_bf16(tmem_acc, ahi0 + off + 2 * kk, bhi + 2 * kk, idesc, (kb > 0 || tap > 0 || kk > 0) ? 1u : 0u);
-                        umma_bf16(tmem_acc, alo0 + off + 2 * kk, bhi + 2 * kk, idesc, 1u);
-                        umma_bf16(tmem_acc, ahi0 + off + 2 * kk, blo + 2 * kk, idesc, 1u);
+                        if (p.ncat) {
+                            umma_bf16(tmem_acc, ahi0 + off + 2 * kk, bhi + 2 * kk, idesc2, (kb > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                            umma_bf16(tmem_acc, alo0 + off + 2 * kk, bhi + 2 * kk, idesc, 1u);
+                        } else {
+                            umma_bf16(tmem_acc, ahi0 + off + 2 * kk, bhi + 2 * kk, idesc, (kb > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                            umma_bf16(tmem_acc, alo0 + off + 2 * kk, bhi + 2 * kk, idesc, 1u);
+                            umma_bf16(tmem_acc, ahi0 + off + 2 * kk, blo + 2 * kk, idesc, 1u);
+                        }
                     }
                     umma_commit(&empty_bar[s]);
                 }
@@ -696,6 +719,12 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
         smem = (size_t)p.stages * stage_bytes + 1024;
     }
     (void)stage_bytes;
+    // two-MMA scheme for split-precision layers with BN <= 128 and enough k-iterations for the MMA stream to matter
+    // (BBOCR_TC_NCAT=0: the three-MMA scheme everywhere, A/B switch)
+    static const bool ncat_on = !(getenv("BBOCR_TC_NCAT") && atoi(getenv("BBOCR_TC_NCAT")) == 0);
+    // cout_pad <= 128 (not BN <= 128): BN of the wider layers depends on the batch geometry, and the two schemes add the same
+    // products in a different order -- a layer must use ONE scheme whatever else shares its launch (batched == single, bit for bit)
+    p.ncat = (ncat_on && split_in && cw.cout_pad <= 128 && p.BN % 8 == 0 && p.taps * ((in1.C + in2.C) / bk) >= 4) ? 1 : 0;
 
     auto act_map = [&](const Act& a) {
         if (p.flat) {
