@@ -61,9 +61,38 @@ void* staging(Lane& lane, size_t bytes) {          // pinned H2D staging; waits 
 
 void upload(Lane& lane, DevBuf& dst, const void* src, size_t bytes) {
     dst.alloc(bytes, lane.stream);
-    void* pin = staging(lane, bytes);
-    memcpy(pin, src, bytes);
-    CUDA_CHECK(cudaMemcpyAsync(dst.p, pin, bytes, cudaMemcpyHostToDevice, lane.stream));
+    uint8_t* pin = (uint8_t*)staging(lane, bytes);
+    constexpr size_t kChunk = 16u << 20;
+    if (bytes <= 2 * kChunk) {
+        memcpy(pin, src, bytes);
+        CUDA_CHECK(cudaMemcpyAsync(dst.p, pin, bytes, cudaMemcpyHostToDevice, lane.stream));
+    } else {
+        // a large page (recognition-only pages are hundreds of MB): a single-threaded pageable -> pinned memcpy runs at ~6 GB/s
+        // and used to be 40 % of the call.  Four threads copy 16 MB chunks; every chunk's DMA is enqueued as soon as it is staged.
+        const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
+        std::atomic<size_t> next{0};
+        std::vector<std::atomic<int>> ready(n_chunks);
+        for (auto& r : ready) r.store(0);
+        auto work = [&] {
+            for (size_t c; (c = next.fetch_add(1)) < n_chunks;) {
+                const size_t o = c * kChunk, n = std::min(kChunk, bytes - o);
+                memcpy(pin + o, (const uint8_t*)src + o, n);
+                ready[c].store(1, std::memory_order_release);
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 0; t < 3; ++t) th.emplace_back(work);
+        std::thread last(work);
+        cudaError_t err = cudaSuccess;
+        for (size_t c = 0; c < n_chunks; ++c) {
+            while (!ready[c].load(std::memory_order_acquire)) std::this_thread::yield();
+            const size_t o = c * kChunk, n = std::min(kChunk, bytes - o);
+            if (err == cudaSuccess) err = cudaMemcpyAsync((uint8_t*)dst.p + o, pin + o, n, cudaMemcpyHostToDevice, lane.stream);
+        }
+        for (auto& t : th) t.join();
+        last.join();
+        CUDA_CHECK(err);
+    }
     lane.in_busy = true;
 }
 

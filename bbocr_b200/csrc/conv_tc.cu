@@ -157,11 +157,21 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
     return t;
 }
 
+// 256-bit global store (sm_100: STG.E.256): one 32-byte sector per request instead of two 16-byte halves
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* w) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
+
 template <typename TO>
 __device__ __forceinline__ void store16(TO* o, const float* f, int nbase, int cout);
 template <>
 __device__ __forceinline__ void store16<float>(float* o, const float* f, int nbase, int cout) {
-    if ((cout & 3) == 0 && nbase + 16 <= cout) {
+    if ((cout & 7) == 0 && nbase + 16 <= cout && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+        st_global_256(o, reinterpret_cast<const uint32_t*>(f));
+        st_global_256(o + 8, reinterpret_cast<const uint32_t*>(f) + 8);
+    } else if ((cout & 3) == 0 && nbase + 16 <= cout) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
     } else {
@@ -178,8 +188,12 @@ __device__ __forceinline__ void store16<__nv_bfloat16>(__nv_bfloat16* o, const f
             __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
             w[j] = *reinterpret_cast<uint32_t*>(&t);
         }
-        *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        if ((reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+            st_global_256(o, w);
+        } else {
+            *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
     } else {
         for (int j = 0; j < 16; ++j)
             if (nbase + j < cout) o[j] = __float2bfloat16_rn(f[j]);
@@ -201,6 +215,7 @@ __device__ __forceinline__ void store_split(void* hi_base, void* lo_base, int64_
 // Epilogue warps (4..7) of both kernels: tcgen05.ld 32x32b -> folded-BN scale/bias (+ReLU) -> optional fused 2x2 / 2x1 max-pool
 // by warp shuffles -> bf16 / fp32 / split NHWC stores -> tempty[acc].  TMEM lane r = pixel (r / TW, r % TW) of the tile; with
 // TW in {8, 16} the 2x2 (2x1) pooling window lives in lanes {l, l^1, l^TW, l^TW^1} ({l, l^TW}).
+template <bool NCAT>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, int warp, int lane, uint64_t* tfull_bar,
                                             uint64_t* tempty_bar) {
         const int wq = warp & 3;
@@ -229,11 +244,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                     if (writer && py < POH && px < POW) pix2 = ((int64_t)tc.img * POH + py) * POW + px;
                 }
             }
-            const uint32_t trow = tmem_base + (uint32_t)(as * (p.ncat ? 2 * p.BN : p.BN)) + ((uint32_t)(wq * 32) << 16);
+            const uint32_t trow = tmem_base + (uint32_t)(as * (NCAT ? 2 * p.BN : p.BN)) + ((uint32_t)(wq * 32) << 16);
             for (int c = 0; c < p.BN; c += 16) {
                 uint32_t v[16];
                 tmem_ld16(trow + c, v);
-                if (p.ncat) {                       // x_hi * w_lo accumulated in the second half of the stage
+                if (NCAT) {                         // x_hi * w_lo accumulated in the second half of the stage
                     uint32_t v2[16];
                     tmem_ld16(trow + p.BN + c, v2);
 #pragma unroll
@@ -279,7 +294,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
 //     x_hi * w_hi  +  x_lo * w_hi  +  x_hi * w_lo        (the dropped x_lo * w_lo term is 2^-16-class)
 // so the operand stream through L2 -> SM is 2x the single-precision stream for 3x the tensor work.
 // Maps: PAIR = 0: tmA1 = in1, tmA2 = in2 (channel concat).  PAIR = 1: tmA1/tmA2 = in1 hi/lo, tmA3/tmA4 = in2 hi/lo.
-template <int BK, int PAIR>
+template <int BK, int PAIR, bool NCAT>
 __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtensorMap tmA1,
                                                  const __grid_constant__ CUtensorMap tmA2,
                                                  const __grid_constant__ CUtensorMap tmA3,
@@ -296,7 +311,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     const int kb1 = p.C1 / BK, kb2 = p.C2 / BK;
     const int kiters = p.taps * (kb1 + kb2);
     uint32_t ncols = 32;
-    while ((int)ncols < (p.ncat ? 4 : 2) * p.BN) ncols <<= 1;
+    while ((int)ncols < (NCAT ? 4 : 2) * p.BN) ncols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -366,7 +381,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             const uint32_t aph = (ti >> 1) & 1;
             mbar_wait(&tempty_bar[as], aph ^ 1);                 // the epilogue has drained this accumulator stage
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * (p.ncat ? 2 * p.BN : p.BN));
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * (NCAT ? 2 * p.BN : p.BN));
             const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             for (int k = 0; k < kiters; ++k, ++it) {
                 const int s = it % p.stages;
@@ -379,7 +394,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                     const uint64_t bhi = umma_desc<BK>(sa + 2 * A_BYTES), blo = umma_desc<BK>(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
-                        if (p.ncat) {
+                        if (NCAT) {
                             umma_bf16(tmem_acc, ahi + 2 * kk, bhi + 2 * kk, idesc2, (k > 0 || kk > 0) ? 1u : 0u);
                             umma_bf16(tmem_acc, alo + 2 * kk, bhi + 2 * kk, idesc, 1u);
                         } else {
@@ -399,7 +414,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             umma_commit(&tfull_bar[as]);
         }
     } else if (warp >= 4) {
-        tc_epilogue(p, tmem_base, warp, lane, tfull_bar, tempty_bar);
+        tc_epilogue<NCAT>(p, tmem_base, warp, lane, tfull_bar, tempty_bar);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -421,7 +436,7 @@ __device__ __forceinline__ uint64_t desc_kmajor_sbo(uint32_t saddr, uint32_t sbo
     return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
-template <int BK>
+template <int BK, bool NCAT>
 __global__ void __launch_bounds__(256) k_conv_tc_patch(const __grid_constant__ CUtensorMap tmA1,
                                                        const __grid_constant__ CUtensorMap tmA2,
                                                        const __grid_constant__ CUtensorMap tmA3,
@@ -442,7 +457,7 @@ __global__ void __launch_bounds__(256) k_conv_tc_patch(const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb1 = p.C1 / BK, kb2 = p.C2 / BK;
     uint32_t ncols = 32;
-    while ((int)ncols < (p.ncat ? 4 : 2) * p.BN) ncols <<= 1;
+    while ((int)ncols < (NCAT ? 4 : 2) * p.BN) ncols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -509,7 +524,7 @@ __global__ void __launch_bounds__(256) k_conv_tc_patch(const __grid_constant__ C
             const int as = ti & 1;
             mbar_wait(&tempty_bar[as], ((ti >> 1) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * (p.ncat ? 2 * p.BN : p.BN));
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * (NCAT ? 2 * p.BN : p.BN));
             const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             for (int kb = 0; kb < kb1 + kb2; ++kb, ++pit) {
                 const int ps = pit % p.p_stages;
@@ -528,7 +543,7 @@ __global__ void __launch_bounds__(256) k_conv_tc_patch(const __grid_constant__ C
                     const uint64_t off = (uint64_t)(((ky * PW + kx) * PIX) >> 4);
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
-                        if (p.ncat) {
+                        if (NCAT) {
                             umma_bf16(tmem_acc, ahi0 + off + 2 * kk, bhi + 2 * kk, idesc2, (kb > 0 || tap > 0 || kk > 0) ? 1u : 0u);
                             umma_bf16(tmem_acc, alo0 + off + 2 * kk, bhi + 2 * kk, idesc, 1u);
                         } else {
@@ -544,7 +559,7 @@ __global__ void __launch_bounds__(256) k_conv_tc_patch(const __grid_constant__ C
             umma_commit(&tfull_bar[as]);
         }
     } else if (warp >= 4) {
-        tc_epilogue(p, tmem_base, warp, lane, tfull_bar, tempty_bar);
+        tc_epilogue<NCAT>(p, tmem_base, warp, lane, tfull_bar, tempty_bar);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -761,23 +776,30 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     // persistent grid: a multiple of the SM count (148 on B200), never more CTAs than tiles
     const unsigned grid = (unsigned)std::min<int64_t>(p.total_tiles, (int64_t)h->sm_count * ctas);
     if (!h->tc_attr_set) {          // per device (one handle = one device)
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc_patch<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc_patch<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+#define TC_SMEM(...) CUDA_CHECK(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024))
+        TC_SMEM(k_conv_tc<64, 0, false>); TC_SMEM(k_conv_tc<32, 0, false>);
+        TC_SMEM(k_conv_tc<64, 1, false>); TC_SMEM(k_conv_tc<32, 1, false>);
+        TC_SMEM(k_conv_tc<64, 1, true>); TC_SMEM(k_conv_tc<32, 1, true>);
+        TC_SMEM(k_conv_tc_patch<64, false>); TC_SMEM(k_conv_tc_patch<32, false>);
+        TC_SMEM(k_conv_tc_patch<64, true>); TC_SMEM(k_conv_tc_patch<32, true>);
+#undef TC_SMEM
         h->tc_attr_set = true;
     }
-    if (patch) {
-        if (bk == 64) k_conv_tc_patch<64><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
-        else k_conv_tc_patch<32><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+    if (patch && p.ncat) {
+        if (bk == 64) k_conv_tc_patch<64, true><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        else k_conv_tc_patch<32, true><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+    } else if (patch) {
+        if (bk == 64) k_conv_tc_patch<64, false><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        else k_conv_tc_patch<32, false><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+    } else if (split_in && p.ncat) {
+        if (bk == 64) k_conv_tc<64, 1, true><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        else k_conv_tc<32, 1, true><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
     } else if (split_in) {
-        if (bk == 64) k_conv_tc<64, 1><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
-        else k_conv_tc<32, 1><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        if (bk == 64) k_conv_tc<64, 1, false><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        else k_conv_tc<32, 1, false><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
     } else {
-        if (bk == 64) k_conv_tc<64, 0><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
-        else k_conv_tc<32, 0><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        if (bk == 64) k_conv_tc<64, 0, false><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        else k_conv_tc<32, 0, false><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
     }
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
