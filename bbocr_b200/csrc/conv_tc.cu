@@ -134,6 +134,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same load without the wait: the epilogue issues the load of column group c + 1 before it works on group c
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 struct TileCoord {
     int n0, img, x0, y0;
     int64_t m0;
@@ -245,15 +255,20 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                 }
             }
             const uint32_t trow = tmem_base + (uint32_t)(as * (NCAT ? 2 * p.BN : p.BN)) + ((uint32_t)(wq * 32) << 16);
+            uint32_t vn[16];
+            tmem_ld16_nowait(trow, vn);
             for (int c = 0; c < p.BN; c += 16) {
                 uint32_t v[16];
-                tmem_ld16(trow + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = vn[j];
                 if (NCAT) {                         // x_hi * w_lo accumulated in the second half of the stage
                     uint32_t v2[16];
                     tmem_ld16(trow + p.BN + c, v2);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
                 }
+                if (c + 16 < p.BN) tmem_ld16_nowait(trow + c + 16, vn);     // in flight while this group is scaled, split and stored
                 float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -295,7 +310,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
 // so the operand stream through L2 -> SM is 2x the single-precision stream for 3x the tensor work.
 // Maps: PAIR = 0: tmA1 = in1, tmA2 = in2 (channel concat).  PAIR = 1: tmA1/tmA2 = in1 hi/lo, tmA3/tmA4 = in2 hi/lo.
 template <int BK, int PAIR, bool NCAT>
-__global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtensorMap tmA1,
+__global__ void __launch_bounds__(256, 2) k_conv_tc(const __grid_constant__ CUtensorMap tmA1,
                                                  const __grid_constant__ CUtensorMap tmA2,
                                                  const __grid_constant__ CUtensorMap tmA3,
                                                  const __grid_constant__ CUtensorMap tmA4,
@@ -437,7 +452,7 @@ __device__ __forceinline__ uint64_t desc_kmajor_sbo(uint32_t saddr, uint32_t sbo
 }
 
 template <int BK, bool NCAT>
-__global__ void __launch_bounds__(256) k_conv_tc_patch(const __grid_constant__ CUtensorMap tmA1,
+__global__ void __launch_bounds__(256, 2) k_conv_tc_patch(const __grid_constant__ CUtensorMap tmA1,
                                                        const __grid_constant__ CUtensorMap tmA2,
                                                        const __grid_constant__ CUtensorMap tmA3,
                                                        const __grid_constant__ CUtensorMap tmA4,
