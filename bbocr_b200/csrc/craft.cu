@@ -136,12 +136,15 @@ __global__ void __launch_bounds__(128) k_im2col_rgb_split(const uint8_t* __restr
         wh[i] = (v[2 * i] & 0xffffu) | (v[2 * i + 1] << 16);
         wl[i] = (v[2 * i] >> 16) | (v[2 * i + 1] & 0xffff0000u);
     }
-    uint4* oh = reinterpret_cast<uint4*>(ohi + ((int64_t)y * W32 + x) * 32);
-    uint4* ol = reinterpret_cast<uint4*>(olo + ((int64_t)y * W32 + x) * 32);
+    // 64 bytes per pixel and tensor: two 256-bit stores each (one 32-byte sector per request)
+    __nv_bfloat16* oh = ohi + ((int64_t)y * W32 + x) * 32;
+    __nv_bfloat16* ol = olo + ((int64_t)y * W32 + x) * 32;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        oh[q] = make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3]);
-        ol[q] = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+    for (int q = 0; q < 2; ++q) {
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(oh + 16 * q), "r"(wh[8 * q]), "r"(wh[8 * q + 1]),
+                     "r"(wh[8 * q + 2]), "r"(wh[8 * q + 3]), "r"(wh[8 * q + 4]), "r"(wh[8 * q + 5]), "r"(wh[8 * q + 6]), "r"(wh[8 * q + 7]) : "memory");
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ol + 16 * q), "r"(wl[8 * q]), "r"(wl[8 * q + 1]),
+                     "r"(wl[8 * q + 2]), "r"(wl[8 * q + 3]), "r"(wl[8 * q + 4]), "r"(wl[8 * q + 5]), "r"(wl[8 * q + 6]), "r"(wl[8 * q + 7]) : "memory");
     }
 }
 
