@@ -520,11 +520,108 @@ __device__ __forceinline__ int chroma_at(const uint8_t* __restrict__ p, const Co
     return p[(size_t)y * D.cpitch + x];
 }
 
+__device__ __forceinline__ void ycc_bgr(int yy, int cb, int cr, int& b, int& g, int& r) {       // jdcolor.c tables, inlined
+    cb -= 128; cr -= 128;
+    r = min(max(yy + ((91881 * cr + 32768) >> 16), 0), 255);
+    g = min(max(yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16), 0), 255);
+    b = min(max(yy + ((116130 * cb + 32768) >> 16), 0), 255);
+}
+
+// h2v2_fancy_upsample for the four pixels x .. x+3 (x % 4 == 0) of row y: chroma columns c0 = x / 2 and c0 + 1, their outer
+// neighbours c0 - 1 and c0 + 2, from the nearer row r and the further row o (clamped reads; unused values are never selected)
+__device__ __forceinline__ void chroma4_h2v2(const uint8_t* __restrict__ p, const ColorDesc& D, int x, int y, int (&out)[4]) {
+    const int c0 = x >> 1, r = y >> 1;
+    const int o = (y & 1) ? min(r + 1, D.cdh - 1) : max(r - 1, 0);
+    const uint8_t* p0 = p + (size_t)r * D.cpitch;
+    const uint8_t* p1 = p + (size_t)o * D.cpitch;
+    int cs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = min(max(c0 - 1 + k, 0), D.cdw - 1);
+        cs[k] = 3 * p0[c] + p1[c];
+    }
+    out[0] = c0 == 0 ? (4 * cs[1] + 8) >> 4 : (3 * cs[1] + cs[0] + 8) >> 4;
+    out[1] = c0 == D.cdw - 1 ? (4 * cs[1] + 7) >> 4 : (3 * cs[1] + cs[2] + 7) >> 4;
+    out[2] = (3 * cs[2] + cs[1] + 8) >> 4;
+    out[3] = c0 + 1 == D.cdw - 1 ? (4 * cs[2] + 7) >> 4 : (3 * cs[2] + cs[3] + 7) >> 4;
+}
+
 __global__ void __launch_bounds__(256) k_jpeg_color(ColorDesc D) {
-    __shared__ uint8_t sb[32][32 * 3 + 4];
-    __shared__ uint8_t sg[32][32 + 4];
+    __shared__ __align__(16) uint8_t sb[32][32 * 3 + 4];      // full tiles: indexed in DESTINATION order [row][col * 3]
+    __shared__ __align__(16) uint8_t sg[32][32 + 4];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
     const bool want_bgr = D.bgr != nullptr, want_gray = D.gray != nullptr;
+    const int o = D.orientation;
+    const int dW = o < 5 ? D.W : D.H;
+    // ---- fast path: a full 32 x 32 tile whose destination rows are word-aligned: four pixels per thread in, 32-bit words out ----
+    if (x0 + 32 <= D.W && y0 + 32 <= D.H && (dW & 3) == 0 && ((D.ypitch | D.cpitch) & 3) == 0) {
+        const int ly = threadIdx.x >> 3, lx = (threadIdx.x & 7) * 4;
+        const int x = x0 + lx, y = y0 + ly;
+        const uint32_t y4 = *reinterpret_cast<const uint32_t*>(D.y + (size_t)y * D.ypitch + x);
+        int cb[4], cr[4];
+        if (want_bgr && D.ncomp == 3) {
+            if (D.hx == 2 && D.vx == 2 && D.cdw > 2) {
+                chroma4_h2v2(D.cb, D, x, y, cb);
+                chroma4_h2v2(D.cr, D, x, y, cr);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { cb[k] = chroma_at(D.cb, D, x + k, y); cr[k] = chroma_at(D.cr, D, x + k, y); }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int yy = (y4 >> (8 * k)) & 255;
+            const int sx = lx + k;
+            int drow, dcol;                                       // destination-local position of source pixel (sx, ly)
+            switch (o) {
+                case 2: drow = ly; dcol = 31 - sx; break;
+                case 3: drow = 31 - ly; dcol = 31 - sx; break;
+                case 4: drow = 31 - ly; dcol = sx; break;
+                case 5: drow = sx; dcol = ly; break;
+                case 6: drow = sx; dcol = 31 - ly; break;
+                case 7: drow = 31 - sx; dcol = 31 - ly; break;
+                case 8: drow = 31 - sx; dcol = ly; break;
+                default: drow = ly; dcol = sx; break;
+            }
+            sg[drow][dcol] = (uint8_t)yy;
+            if (want_bgr) {
+                int b = yy, g = yy, r = yy;
+                if (D.ncomp == 3) ycc_bgr(yy, cb[k], cr[k], b, g, r);
+                sb[drow][3 * dcol] = (uint8_t)b; sb[drow][3 * dcol + 1] = (uint8_t)g; sb[drow][3 * dcol + 2] = (uint8_t)r;
+            }
+        }
+        __syncthreads();
+        int dx0, dy0;                                             // destination origin of the tile
+        switch (o) {
+            case 2: dx0 = D.W - x0 - 32; dy0 = y0; break;
+            case 3: dx0 = D.W - x0 - 32; dy0 = D.H - y0 - 32; break;
+            case 4: dx0 = x0; dy0 = D.H - y0 - 32; break;
+            case 5: dx0 = y0; dy0 = x0; break;
+            case 6: dx0 = D.H - y0 - 32; dy0 = x0; break;
+            case 7: dx0 = D.H - y0 - 32; dy0 = D.W - x0 - 32; break;
+            case 8: dx0 = y0; dy0 = D.W - x0 - 32; break;
+            default: dx0 = x0; dy0 = y0; break;
+        }
+        if (want_bgr && (reinterpret_cast<uintptr_t>(D.bgr) & 3) == 0) {
+            for (int w = threadIdx.x; w < 32 * 24; w += 256) {    // 96 bytes = 24 words per destination row
+                const int row = w / 24, col = w - row * 24;
+                reinterpret_cast<uint32_t*>(D.bgr + ((size_t)(dy0 + row) * dW + dx0) * 3)[col] = reinterpret_cast<const uint32_t*>(sb[row])[col];
+            }
+        } else if (want_bgr) {
+            for (int i = threadIdx.x; i < 32 * 96; i += 256) {
+                const int row = i / 96, col = i - row * 96;
+                D.bgr[((size_t)(dy0 + row) * dW + dx0) * 3 + col] = sb[row][col];
+            }
+        }
+        if (want_gray && (reinterpret_cast<uintptr_t>(D.gray) & 3) == 0) {
+            const int row = threadIdx.x >> 3, col = threadIdx.x & 7;
+            reinterpret_cast<uint32_t*>(D.gray + (size_t)(dy0 + row) * dW + dx0)[col] = reinterpret_cast<const uint32_t*>(sg[row])[col];
+        } else if (want_gray) {
+            for (int i = threadIdx.x; i < 1024; i += 256) D.gray[(size_t)(dy0 + (i >> 5)) * dW + dx0 + (i & 31)] = sg[i >> 5][i & 31];
+        }
+        return;
+    }
+    // ---- general path (edge tiles, odd widths): pixel by pixel, source order in shared memory --------------------------------
     for (int i = threadIdx.x; i < 1024; i += 256) {
         const int ly = i >> 5, lx = i & 31;
         const int x = x0 + lx, y = y0 + ly;
@@ -533,19 +630,11 @@ __global__ void __launch_bounds__(256) k_jpeg_color(ColorDesc D) {
         sg[ly][lx] = (uint8_t)yy;
         if (want_bgr) {
             int b = yy, g = yy, r = yy;
-            if (D.ncomp == 3) {
-                const int cb = chroma_at(D.cb, D, x, y) - 128, cr = chroma_at(D.cr, D, x, y) - 128;
-                r = yy + ((91881 * cr + 32768) >> 16);
-                g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
-                b = yy + ((116130 * cb + 32768) >> 16);
-                r = min(max(r, 0), 255); g = min(max(g, 0), 255); b = min(max(b, 0), 255);
-            }
+            if (D.ncomp == 3) ycc_bgr(yy, chroma_at(D.cb, D, x, y), chroma_at(D.cr, D, x, y), b, g, r);
             sb[ly][3 * lx] = (uint8_t)b; sb[ly][3 * lx + 1] = (uint8_t)g; sb[ly][3 * lx + 2] = (uint8_t)r;
         }
     }
     __syncthreads();
-    const int o = D.orientation;
-    const int dW = o < 5 ? D.W : D.H;
     for (int i = threadIdx.x; i < 1024; i += 256) {
         // the fast index runs along the destination row: source x for orientations 1-4, source y for 5-8
         const int a = i >> 5, f = i & 31;
