@@ -78,3 +78,25 @@ def test_imread_surface_and_fallbacks(handle, tmp_path):
     prog = tmp_path / "c.jpg"
     Image.fromarray(img[:, :, ::-1]).save(str(prog), "JPEG", progressive=True)
     assert np.array_equal(decode.imread(handle, str(prog)), cv2.imread(str(prog)))
+
+
+def test_damaged_entropy_data_is_survivable(handle):
+    """Bit flips / truncation inside the entropy-coded segment (restart intervals -> device Huffman): the call decodes something
+    or raises, never faults; the device stays usable (a clean file decodes bit-exactly afterwards)."""
+    rng = np.random.default_rng(1)
+    img = synth.phone_photo(3003, 640, 480)
+    good = encode(img, 85, "420", 40)
+    sos = J.parse(good)["scan"]["start"]
+    for it in range(120):
+        d = bytearray(good)
+        if it % 3 == 0:
+            d = d[:int(rng.integers(sos + 1, len(d)))]
+        else:
+            for _ in range(int(rng.integers(1, 20))):
+                d[int(rng.integers(sos, len(d)))] = int(rng.integers(0, 256))
+        try:
+            bgr, gray = handle.jpeg_decode(bytes(d), color=True, gray=True)
+            assert bgr.shape == img.shape and gray.shape == img.shape[:2]
+        except Exception as e:      # noqa: BLE001
+            assert "libbbocr" in str(e)
+    _check(handle, good, oracle=False)

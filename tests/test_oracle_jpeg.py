@@ -65,3 +65,33 @@ def test_product_entropy_decoder_matches_the_oracle(lib_built):
     data = cv2.imencode(".jpg", g, [cv2.IMWRITE_JPEG_QUALITY, 80, cv2.IMWRITE_JPEG_RST_INTERVAL, 2])[1].tobytes()
     coefs, _ = J.decode_coefficients(data, J.parse(data))
     assert np.array_equal(lib_built.jpeg_coefficients(data), coefs[0].reshape(-1, 64))
+
+
+def test_damaged_files_never_crash_the_host_half(lib_built):
+    """Truncated, bit-flipped, spliced streams: the parser / restart-interval finder / entropy decoder either decode or
+    refuse with a BbocrError -- no out-of-bounds access (the same routines feed the device path their offsets)."""
+    rng = np.random.default_rng(0)
+    base = [encode(_photo(64, 80), 85, "420", 3), encode(_photo(33, 47), 60, "444", 0), with_orientation(_photo(40, 60), 6),
+            encode(_photo(120, 17), 30, "422", 1)]
+    decoded = 0
+    for it in range(1600):
+        d = bytearray(base[it % len(base)])
+        mode = it % 4
+        if mode == 0:
+            d = d[:int(rng.integers(0, len(d)))]
+        elif mode == 1:
+            for _ in range(int(rng.integers(1, 6))):
+                d[int(rng.integers(0, len(d)))] = int(rng.integers(0, 256))
+        elif mode == 2:
+            i = int(rng.integers(2, min(len(d), 700)))
+            d[i:i + int(rng.integers(1, 8))] = bytes(rng.integers(0, 256, int(rng.integers(1, 8)), dtype=np.uint8))
+        else:
+            i = int(rng.integers(0, len(d)))
+            d = d[:i] + bytes(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8)) + d[i:]
+        try:
+            lib_built.jpeg_info(bytes(d))
+            lib_built.jpeg_coefficients(bytes(d))
+            decoded += 1
+        except lib_built.BbocrError:
+            pass
+    assert decoded > 100                     # many damaged streams still decode (libjpeg is equally tolerant)
