@@ -583,6 +583,146 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc_patch(const __grid_constant_
     }
 }
 
+// ---- fused detector stem (bf16x3): gather + normalise + conv1_1 in ONE kernel ---------------------------------------------------
+// k_im2col_rgb_split wrote the gathered 32-channel stem (hi + lo: 354 MB per 1920x1440 page) and conv1_1 read it back through
+// TMA.  Here four producer warps build the A tiles in shared memory themselves: thread r of a tile looks the 27 neighbourhood
+// bytes of pixel m0 + r up in the (hi | lo) normalisation table -- the very words k_im2col_rgb_split stored -- and writes its
+// 64-byte hi and lo rows in the K-major SWIZZLE_64B layout the UMMA descriptor expects (16-byte chunk c of row r at chunk
+// c ^ ((r >> 1) & 3): the swizzle TMA would have applied).  The weight tile (w_hi | w_lo, 8 KB) is resident; MMAs and epilogue
+// are those of k_conv_tc<32, 1, false>, so the layer's output is bit-identical to the two-kernel path.
+struct StemParams {
+    const uint8_t* img[16];          // nimg images, th x tw x 3 u8 (after the canvas resize), placed top-left on the H32 x W32 canvas
+    int th, tw, H, W, nimg;
+    float mean[3], sd[3];
+};
+
+constexpr int STEM_STAGES = 4;
+
+__global__ void __launch_bounds__(384, 2) k_conv_stem(const __grid_constant__ CUtensorMap tmB, const TcParams p, const StemParams sp) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t afull_bar[STEM_STAGES], aempty_bar[STEM_STAGES], bfull_bar, tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ uint32_t lut[3][256];                                    // hi | lo << 16
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int BK = 32;
+    constexpr int A_BYTES = BM * BK * 2;                                // 8 KB per (hi or lo) tile
+    const int B_BYTES = p.BN * BK * 2;
+    uint8_t* sB = smem + (size_t)STEM_STAGES * 2 * A_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t ncols = 32;
+    while ((int)ncols < 2 * p.BN) ncols <<= 1;
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        const int c = i >> 8, v = i & 255;
+        const float f = __fdiv_rn(__fsub_rn((float)v, sp.mean[c]), sp.sd[c]);
+        const __nv_bfloat16 hb = __float2bfloat16_rn(f);
+        const __nv_bfloat16 lb = __float2bfloat16_rn(f - __bfloat162float(hb));
+        lut[c][v] = (uint32_t)*reinterpret_cast<const uint16_t*>(&hb) | ((uint32_t)*reinterpret_cast<const uint16_t*>(&lb) << 16);
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STEM_STAGES; ++s) { mbar_init(&afull_bar[s], 128); mbar_init(&aempty_bar[s], 1); }
+        mbar_init(&bfull_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // the resident weight tile: w_hi at sB, w_lo behind it
+        mbar_expect_tx(&bfull_bar, (uint32_t)(2 * B_BYTES));
+        tma_load_3d(sB, &tmB, &bfull_bar, 0, 0, 0);
+        tma_load_3d(sB + B_BYTES, &tmB, &bfull_bar, p.w_lo_off, 0, 0);
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        mbar_wait(&bfull_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t bhi = umma_desc<BK>(smem_u32(sB)), blo = umma_desc<BK>(smem_u32(sB + B_BYTES));
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+            const int as = ti & 1;
+            mbar_wait(&tempty_bar[as], ((ti >> 1) & 1) ^ 1);
+            const int s = ti % STEM_STAGES;
+            mbar_wait(&afull_bar[s], (ti / STEM_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.BN);
+            const uint32_t sa = smem_u32(smem + (size_t)s * 2 * A_BYTES);
+            const uint64_t ahi = umma_desc<BK>(sa), alo = umma_desc<BK>(sa + A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+                umma_bf16(tmem_acc, ahi + 2 * kk, bhi + 2 * kk, idesc, kk > 0 ? 1u : 0u);
+                umma_bf16(tmem_acc, alo + 2 * kk, bhi + 2 * kk, idesc, 1u);
+                umma_bf16(tmem_acc, ahi + 2 * kk, blo + 2 * kk, idesc, 1u);
+            }
+            umma_commit(&aempty_bar[s]);
+            umma_commit(&tfull_bar[as]);
+        }
+    } else if (warp >= 4 && warp < 8) {
+        tc_epilogue<false>(p, tmem_base, warp, lane, tfull_bar, tempty_bar);
+    } else if (warp >= 8) {
+        // ---------------- gather producers: thread r builds row r of the A tiles ----------------
+        const int r = threadIdx.x - 256;
+        const int64_t plane = (int64_t)sp.H * sp.W;
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+            const int s = ti % STEM_STAGES;
+            mbar_wait(&aempty_bar[s], ((ti / STEM_STAGES) & 1) ^ 1);
+            const int64_t m = (int64_t)tile * BM + r;
+            uint32_t v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0;
+            if (m < p.M) {
+                const int n_img = (int)(m / plane);
+                const int rem = (int)(m - (int64_t)n_img * plane);
+                const int y = rem / sp.W, x = rem - y * sp.W;
+                const uint8_t* img = sp.img[n_img];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+                    const bool in_canvas = yy >= 0 && yy < sp.H && xx >= 0 && xx < sp.W;
+                    const bool in_img = in_canvas && yy < sp.th && xx < sp.tw;
+                    const uint8_t* px = img + ((int64_t)yy * sp.tw + xx) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int pv = in_img ? (int)__ldg(px + c) : 0;
+                        v[t * 3 + c] = in_canvas ? lut[c][pv] : 0u;
+                    }
+                }
+            }
+            uint8_t* ahi = smem + (size_t)s * 2 * A_BYTES + (size_t)r * 64;
+            uint8_t* alo = ahi + A_BYTES;
+            const int sw = (r >> 1) & 3;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                              // 16-byte chunk c = channels 8c .. 8c+7
+                uint32_t wh[4], wl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t a = v[8 * c + 2 * j], b = v[8 * c + 2 * j + 1];
+                    wh[j] = (a & 0xffffu) | (b << 16);
+                    wl[j] = (a >> 16) | (b & 0xffff0000u);
+                }
+                *reinterpret_cast<uint4*>(ahi + ((c ^ sw) << 4)) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                *reinterpret_cast<uint4*>(alo + ((c ^ sw) << 4)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");            // generic-proxy writes -> visible to the tensor core
+            mbar_arrive(&afull_bar[s]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
 // ---- host side: tensor maps --------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -816,6 +956,57 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
         if (bk == 64) k_conv_tc<64, 0, false><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
         else k_conv_tc<32, 0, false><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
     }
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// conv1_1 of the bf16x3 detector straight from the u8 images (k_conv_stem): out = split NHWC [nimg][H][W][64]
+bool conv_stem_supported(const ConvW& cw, const Act& out) {
+    return cw.w_split && cw.cin == 32 && cw.cout_pad == 64 && cw.kh == 1 && cw.kw == 1 && out.lo != nullptr;
+}
+
+void conv_stem_forward(Handle* h, cudaStream_t st, const ConvW& cw, const uint8_t* const* imgs, int nimg, int th, int tw, Act& out,
+                       const float* mean, const float* sd, int flags) {
+    ARG_CHECK(conv_stem_supported(cw, out) && nimg >= 1 && nimg <= 16, "conv_stem: unsupported layer");
+    TcParams p{};
+    p.C1 = 32; p.C2 = 0;
+    p.w_lo_off = cw.cin;
+    p.split_out = 1;
+    p.out = out.p; p.out_lo = out.lo; p.out2 = nullptr; p.out2_lo = nullptr;
+    p.taps_w = 1; p.taps = 1; p.pad = 0; p.dil = 1;
+    p.OH = out.H; p.OW = out.W; p.NIMG = out.N;
+    p.M = (int64_t)out.N * out.H * out.W;
+    p.flat = 1;
+    p.cout = cw.cout; p.BN = cw.cout_pad; p.n_tiles = 1;
+    p.relu = (flags & CONV_RELU) ? 1 : 0;
+    p.out_f32 = 0; p.pool = 0; p.write_full = 1;
+    p.scale = cw.scale; p.bias = cw.bias; p.colmask = nullptr;
+    p.TW = 128; p.TH = 1; p.tiles_x = p.tiles_y = 1;
+    p.m_tiles = (int)cdiv64(p.M, BM);
+    p.total_tiles = p.m_tiles;
+    p.stages = STEM_STAGES; p.p_stages = 0; p.patch_al = 0; p.ncat = 0;
+    StemParams sp{};
+    for (int i = 0; i < nimg; ++i) sp.img[i] = imgs[i];
+    sp.th = th; sp.tw = tw; sp.H = out.H; sp.W = out.W; sp.nimg = nimg;
+    for (int c = 0; c < 3; ++c) { sp.mean[c] = mean[c]; sp.sd[c] = sd[c]; }
+    const uint64_t wcin = (uint64_t)cw.cin * 2;
+    uint64_t wd[3] = {wcin, (uint64_t)cw.cout_pad, 1};
+    uint64_t ws[2] = {wcin * 2, (uint64_t)cw.cout_pad * wcin * 2};
+    uint32_t wb[3] = {32, (uint32_t)p.BN, 1};
+    CUtensorMap mB = make_map(cw.w_split, 3, wd, ws, wb, 32);
+    const size_t smem = (size_t)STEM_STAGES * 2 * BM * 32 * 2 + (size_t)2 * p.BN * 32 * 2 + 1024;
+    static std::once_flag once;
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (!h->stem_attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(k_conv_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            h->stem_attr_set = true;
+        }
+    }
+    (void)once;
+    const unsigned grid = (unsigned)std::min<int64_t>(p.total_tiles, (int64_t)h->sm_count * 2);
+    k_conv_stem<<<grid, 384, smem, st>>>(mB, p, sp);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 }

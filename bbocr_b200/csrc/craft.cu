@@ -175,10 +175,14 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     const bool gather = tc_first && (!split || !stem_direct_x3);
     const size_t canvas_px_bytes = gather ? 64 : 16;
     const size_t canvas_plane = (((size_t)nimg * H * W * canvas_px_bytes) + 255) & ~(size_t)255;
-    DevBuf canvas(canvas_plane * (split && gather ? 2 : 1), st), resized;
+    // bf16x3: gather + conv1_1 fused (k_conv_stem builds the A tiles in shared memory; no 32-channel stem tensor in HBM).
+    // BBOCR_STEM_FUSED=0: the two-kernel path (k_im2col_rgb_split + k_conv_tc), A/B switch
+    static const bool stem_fused_on = !(getenv("BBOCR_STEM_FUSED") && atoi(getenv("BBOCR_STEM_FUSED")) == 0);
     const bool need_resize = g.th != g.H || g.tw != g.W;
+    const bool stem_fused = stem_fused_on && split && gather && !need_resize;
+    DevBuf canvas(stem_fused ? 16 : canvas_plane * (split && gather ? 2 : 1), st), resized;
     if (need_resize) resized.alloc((size_t)g.th * g.tw * 3, st);
-    for (int i = 0; i < nimg; ++i) {
+    for (int i = 0; i < nimg && !stem_fused; ++i) {
         const uint8_t* src = imgs_dev[i];
         if (need_resize) {
             resize_bilinear_u8(h, st, imgs_dev[i], g.H, g.W, g.W * 3, 3, resized.as<uint8_t>(), g.th, g.tw);
@@ -225,7 +229,11 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     DevBuf b0, b1, b_r22, b_r32, b_r43, b_r53;
     // slice1
     Act a = alloc(b0, nimg, H, W, 64);
-    if (gather) {
+    if (stem_fused && conv_stem_supported(w.c1_1_tc, a)) {
+        const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+        conv_stem_forward(h, st, w.c1_1_tc, imgs_dev, nimg, g.th, g.tw, a, mean, sd, R);
+    } else if (gather) {
+        ARG_CHECK(!stem_fused, "conv_stem: layer shape not supported");
         Act x32;
         x32.N = nimg; x32.H = H; x32.W = W; x32.C = 32; x32.p = canvas.p;
         if (split) x32.lo = canvas.as<uint8_t>() + canvas_plane;

@@ -65,7 +65,7 @@ struct Handle {
     // dominant-kernel instrumentation (bench.py roofline): CUDA events around every implicit-GEMM conv launch
     bool conv_timing = false;
     bool force_generic_conv = false; // test hook: route BF16-mode convolutions through the CUDA-core kernel
-    bool tc_attr_set = false, lstm_attr_set = false, lstm_mma_attr_set = false;
+    bool tc_attr_set = false, lstm_attr_set = false, lstm_mma_attr_set = false, stem_attr_set = false;
     std::mutex stat_mu;
     std::map<std::array<int, 5>, std::pair<void*, int>> cubic_cache;   // preprocess.cu: INTER_CUBIC tables per geometry
     std::set<int> res_attr_done;     // conv_res.cu kernel variants whose smem attribute is set on this device
@@ -149,6 +149,9 @@ Act act_alloc(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C, bo
 
 // ---- conv_tc.cu : tcgen05 implicit GEMM ------------------------------------------------------------------------------
 bool conv_tc_supported(const ConvW&, const Act& in1, const Act& in2);
+bool conv_stem_supported(const ConvW&, const Act& out);
+void conv_stem_forward(Handle*, cudaStream_t, const ConvW&, const uint8_t* const* imgs, int nimg, int th, int tw, Act& out,
+                       const float* mean, const float* sd, int flags);
 void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled,
                      const uint8_t* colmask = nullptr);
 

@@ -137,3 +137,23 @@ def test_device_box_tail_overflow_falls_back_to_host(handle):
     want, _, _ = E.get_det_boxes_core(t, l, 0.7, 0.4, 0.4)
     assert not used and len(boxes) == len(want) == 1
     assert np.array_equal(boxes[0].view(np.uint32), np.asarray(want[0], np.float32).view(np.uint32))
+
+
+def test_fused_stem_equals_two_kernel_path(tmp_path):
+    """k_conv_stem (bf16x3: gather + normalise + conv1_1 in one kernel, A tiles built in shared memory) against
+    k_im2col_rgb_split + k_conv_tc on the same pages: score maps and batched readtext results bitwise equal.  The switch is read
+    once per process, hence the two sub-processes (tools/stem_ab.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = []
+    for fused in ("1", "0"):
+        f = str(tmp_path / f"stem{fused}.npz")
+        env = dict(os.environ, BBOCR_STEM_FUSED=fused)
+        subprocess.run([sys.executable, os.path.join(root, "tools", "stem_ab.py"), f], check=True, env=env, timeout=600)
+        files.append(np.load(f))
+    a, b = files
+    assert set(a.files) == set(b.files) and len(a.files) >= 9
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k
