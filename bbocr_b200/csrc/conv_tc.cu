@@ -583,40 +583,72 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc_patch(const __grid_constant_
     }
 }
 
-// ---- fused detector stem (bf16x3): gather + normalise + conv1_1 in ONE kernel ---------------------------------------------------
+// ---- fused detector stem (bf16x3): gather + conv1_1 in ONE kernel -----------------------------------------------------------------
 // k_im2col_rgb_split wrote the gathered 32-channel stem (hi + lo: 354 MB per 1920x1440 page) and conv1_1 read it back through
-// TMA.  Here four producer warps build the A tiles in shared memory themselves: thread r of a tile looks the 27 neighbourhood
-// bytes of pixel m0 + r up in the (hi | lo) normalisation table -- the very words k_im2col_rgb_split stored -- and writes its
-// 64-byte hi and lo rows in the K-major SWIZZLE_64B layout the UMMA descriptor expects (16-byte chunk c of row r at chunk
+// TMA.  Here k_stem_norm writes the normalised canvas ONCE, 16 bytes per pixel ((hi | lo << 16) per channel: the very words
+// k_im2col_rgb_split stored, 44 MB per page, L2-resident), and four producer warps build the A tiles in shared memory
+// themselves: thread r of a tile fetches the nine neighbours of pixel m0 + r with one 128-bit load each and writes its 64-byte
+// hi and lo rows in the K-major SWIZZLE_64B layout the UMMA descriptor expects (16-byte chunk c of row r at chunk
 // c ^ ((r >> 1) & 3): the swizzle TMA would have applied).  The weight tile (w_hi | w_lo, 8 KB) is resident; MMAs and epilogue
 // are those of k_conv_tc<32, 1, false>, so the layer's output is bit-identical to the two-kernel path.
+// (First version: 27 byte loads + 27 table look-ups per pixel in the producer -- ~530 instructions per tile on one warp,
+// 10 k cycles per tile, 390 us per page, no faster than the two kernels it replaced.)
 struct StemParams {
-    const uint8_t* img[16];          // nimg images, th x tw x 3 u8 (after the canvas resize), placed top-left on the H32 x W32 canvas
-    int th, tw, H, W, nimg;
-    float mean[3], sd[3];
+    const uint4* norm;               // [nimg][H][W] normalised canvas, {c0, c1, c2, 0} with c = bf16 hi | bf16 lo << 16
+    int H, W;
 };
 
-constexpr int STEM_STAGES = 4;
+constexpr int STEM_STAGES = 2;
+constexpr int STEM_OUT_TILE = BM * 128;        // one staged output tile: 128 pixels x 64 channels bf16 (hi or lo)
 
-__global__ void __launch_bounds__(384, 2) k_conv_stem(const __grid_constant__ CUtensorMap tmB, const TcParams p, const StemParams sp) {
+// u8 image (th x tw x 3, placed top-left on the H x W canvas) -> normalised canvas; canvas pixels outside the image hold the
+// normalised value of 0 like upstream's zero-filled canvas (imgproc.resize_aspect_ratio + normalizeMeanVariance)
+__global__ void __launch_bounds__(256) k_stem_norm(const uint8_t* __restrict__ img, int th, int tw, uint4* __restrict__ out, int H, int W,
+                                                   float m0, float m1, float m2, float s0, float s1, float s2) {
+    __shared__ uint32_t lut[3][256];                                    // hi | lo << 16
+    {
+        const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+            const int c = i >> 8, v = i & 255;
+            const float f = __fdiv_rn(__fsub_rn((float)v, mean[c]), sd[c]);
+            const __nv_bfloat16 hb = __float2bfloat16_rn(f);
+            const __nv_bfloat16 lb = __float2bfloat16_rn(f - __bfloat162float(hb));
+            lut[c][v] = (uint32_t)*reinterpret_cast<const uint16_t*>(&hb) | ((uint32_t)*reinterpret_cast<const uint16_t*>(&lb) << 16);
+        }
+    }
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    uint32_t v[3];
+    const bool in_img = y < th && x < tw;
+    const uint8_t* px = img + ((int64_t)y * tw + x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = lut[c][in_img ? (int)__ldg(px + c) : 0];
+    out[(int64_t)y * W + x] = make_uint4(v[0], v[1], v[2], 0u);
+}
+
+// Epilogue (64 output channels, split hi / lo): the four epilogue warps stage the tile in shared memory in the SWIZZLE_128B image
+// (pixel row = 128 bytes; 16-byte chunk q of row r at chunk q ^ (r & 7): conflict-free 128-bit shared stores) and one thread
+// hands it to TMA: full 128-byte lines leave the SM instead of one 32-byte sector per lane and request.  Two staging buffers
+// (the accumulator stage picks one), so the store of tile t is read out of shared memory while tile t + 1 is computed.
+__global__ void __launch_bounds__(384, 2) k_conv_stem(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOh,
+                                                      const __grid_constant__ CUtensorMap tmOl, const TcParams p, const StemParams sp) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t afull_bar[STEM_STAGES], aempty_bar[STEM_STAGES], bfull_bar, tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ uint32_t lut[3][256];                                    // hi | lo << 16
+    __shared__ __align__(16) float s_scale[64], s_bias[64];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int BK = 32;
     constexpr int A_BYTES = BM * BK * 2;                                // 8 KB per (hi or lo) tile
-    const int B_BYTES = p.BN * BK * 2;
+    const int B_BYTES = p.BN * BK * 2;                                  // BN = 64: 4 KB
     uint8_t* sB = smem + (size_t)STEM_STAGES * 2 * A_BYTES;
+    uint8_t* sOut = sB + 8192;                                          // [2 buffers][hi | lo][128 rows x 128 B]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t ncols = 32;
     while ((int)ncols < 2 * p.BN) ncols <<= 1;
-    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
-        const int c = i >> 8, v = i & 255;
-        const float f = __fdiv_rn(__fsub_rn((float)v, sp.mean[c]), sp.sd[c]);
-        const __nv_bfloat16 hb = __float2bfloat16_rn(f);
-        const __nv_bfloat16 lb = __float2bfloat16_rn(f - __bfloat162float(hb));
-        lut[c][v] = (uint32_t)*reinterpret_cast<const uint16_t*>(&hb) | ((uint32_t)*reinterpret_cast<const uint16_t*>(&lb) << 16);
+    if (threadIdx.x < 64) {
+        s_scale[threadIdx.x] = p.scale[threadIdx.x];
+        s_bias[threadIdx.x] = p.bias[threadIdx.x];
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < STEM_STAGES; ++s) { mbar_init(&afull_bar[s], 128); mbar_init(&aempty_bar[s], 1); }
@@ -624,6 +656,8 @@ __global__ void __launch_bounds__(384, 2) k_conv_stem(const __grid_constant__ CU
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOl) : "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols)
@@ -666,53 +700,108 @@ __global__ void __launch_bounds__(384, 2) k_conv_stem(const __grid_constant__ CU
             umma_commit(&tfull_bar[as]);
         }
     } else if (warp >= 4 && warp < 8) {
-        tc_epilogue<false>(p, tmem_base, warp, lane, tfull_bar, tempty_bar);
+        // ---------------- epilogue: TMEM -> scale / bias / ReLU -> hi | lo -> staged tile -> TMA store ----------------
+        const int wq = warp & 3, r = wq * 32 + lane;
+        const bool leader = threadIdx.x == 128;
+        const int rsw = r & 7;
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+            const int as = ti & 1;
+            mbar_wait(&tfull_bar[as], (ti >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (ti >= 2) {                   // staging buffer `as`: the store issued two tiles ago has been read out of it
+                if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            uint8_t* sh = sOut + (size_t)as * 2 * STEM_OUT_TILE + (size_t)r * 128;
+            uint8_t* sl = sh + STEM_OUT_TILE;
+            const uint32_t trow = tmem_base + (uint32_t)(as * p.BN) + ((uint32_t)(wq * 32) << 16);
+            uint32_t vn[16];
+            tmem_ld16_nowait(trow, vn);
+#pragma unroll
+            for (int c = 0; c < 64; c += 16) {
+                uint32_t v[16];
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = vn[j];
+                if (c + 16 < 64) tmem_ld16_nowait(trow + c + 16, vn);
+                uint32_t wh[8], wl[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float f0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c + 2 * j], s_bias[c + 2 * j]);
+                    float f1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c + 2 * j + 1], s_bias[c + 2 * j + 1]);
+                    if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);       // hi = bf16(v)
+                    const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(f0 - __uint_as_float(hw << 16), f1 - __uint_as_float(hw & 0xffff0000u));
+                    wh[j] = hw;
+                    wl[j] = *reinterpret_cast<const uint32_t*>(&l2);                // lo = bf16(v - hi)
+                }
+                const int q = c >> 3;                                               // 16-byte chunks q, q + 1 of the 128-byte row
+                *reinterpret_cast<uint4*>(sh + ((q ^ rsw) << 4)) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                *reinterpret_cast<uint4*>(sh + (((q + 1) ^ rsw) << 4)) = make_uint4(wh[4], wh[5], wh[6], wh[7]);
+                *reinterpret_cast<uint4*>(sl + ((q ^ rsw) << 4)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                *reinterpret_cast<uint4*>(sl + (((q + 1) ^ rsw) << 4)) = make_uint4(wl[4], wl[5], wl[6], wl[7]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // staged rows -> visible to the TMA engine
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (leader) {
+                const int m0 = tile * BM;                                           // rows beyond M are clipped by the tensor map
+                const uint32_t s0 = smem_u32(sOut + (size_t)as * 2 * STEM_OUT_TILE);
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmOh), "r"(s0), "r"(0),
+                             "r"(m0)
+                             : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmOl),
+                             "r"(s0 + (uint32_t)STEM_OUT_TILE), "r"(0), "r"(m0)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all stores have landed before the CTA exits
     } else if (warp >= 8) {
         // ---------------- gather producers: thread r builds row r of the A tiles ----------------
         const int r = threadIdx.x - 256;
-        const int64_t plane = (int64_t)sp.H * sp.W;
+        const uint32_t plane = (uint32_t)(sp.H * sp.W), W = (uint32_t)sp.W;
+        const int sw = (r >> 1) & 3;
         int ti = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
             const int s = ti % STEM_STAGES;
-            mbar_wait(&aempty_bar[s], ((ti / STEM_STAGES) & 1) ^ 1);
-            const int64_t m = (int64_t)tile * BM + r;
+            const uint32_t m = (uint32_t)tile * BM + (uint32_t)r;      // M < 2^31 (checked by the host side)
             uint32_t v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0;
-            if (m < p.M) {
-                const int n_img = (int)(m / plane);
-                const int rem = (int)(m - (int64_t)n_img * plane);
-                const int y = rem / sp.W, x = rem - y * sp.W;
-                const uint8_t* img = sp.img[n_img];
+            for (int i = 27; i < 32; ++i) v[i] = 0;
+            const bool live = (int64_t)m < p.M;
+            const uint32_t n_img = m / plane, rem = m - n_img * plane;
+            const int y = (int)(rem / W), x = (int)(rem - (uint32_t)y * W);
+            const uint4* row = sp.norm + (size_t)n_img * plane + (size_t)y * W + x;
+            // the nine loads are issued before the stage is waited for: their latency overlaps the wait
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-                    const bool in_canvas = yy >= 0 && yy < sp.H && xx >= 0 && xx < sp.W;
-                    const bool in_img = in_canvas && yy < sp.th && xx < sp.tw;
-                    const uint8_t* px = img + ((int64_t)yy * sp.tw + xx) * 3;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int pv = in_img ? (int)__ldg(px + c) : 0;
-                        v[t * 3 + c] = in_canvas ? lut[c][pv] : 0u;
-                    }
-                }
+            for (int t = 0; t < 9; ++t) {
+                const int dy = t / 3 - 1, dx = t % 3 - 1;
+                const bool ok = live && y + dy >= 0 && y + dy < sp.H && x + dx >= 0 && x + dx < sp.W;
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) q = __ldg(row + dy * (int)W + dx);
+                v[t * 3] = q.x; v[t * 3 + 1] = q.y; v[t * 3 + 2] = q.z;
             }
+            mbar_wait(&aempty_bar[s], ((ti / STEM_STAGES) & 1) ^ 1);
             uint8_t* ahi = smem + (size_t)s * 2 * A_BYTES + (size_t)r * 64;
             uint8_t* alo = ahi + A_BYTES;
-            const int sw = (r >> 1) & 3;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {                              // 16-byte chunk c = channels 8c .. 8c+7
                 uint32_t wh[4], wl[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t a = v[8 * c + 2 * j], b = v[8 * c + 2 * j + 1];
-                    wh[j] = (a & 0xffffu) | (b << 16);
-                    wl[j] = (a >> 16) | (b & 0xffff0000u);
+                    wh[j] = __byte_perm(a, b, 0x5410);                 // (a & 0xffff) | (b << 16)
+                    wl[j] = __byte_perm(a, b, 0x7632);                 // (a >> 16) | (b & 0xffff0000)
                 }
                 *reinterpret_cast<uint4*>(ahi + ((c ^ sw) << 4)) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
                 *reinterpret_cast<uint4*>(alo + ((c ^ sw) << 4)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
             }
-            asm volatile("fence.proxy.async;" ::: "memory");            // generic-proxy writes -> visible to the tensor core
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
             mbar_arrive(&afull_bar[s]);
         }
     }
@@ -962,12 +1051,20 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
 
 // conv1_1 of the bf16x3 detector straight from the u8 images (k_conv_stem): out = split NHWC [nimg][H][W][64]
 bool conv_stem_supported(const ConvW& cw, const Act& out) {
-    return cw.w_split && cw.cin == 32 && cw.cout_pad == 64 && cw.kh == 1 && cw.kw == 1 && out.lo != nullptr;
+    return cw.w_split && cw.cin == 32 && cw.cout == 64 && cw.cout_pad == 64 && cw.kh == 1 && cw.kw == 1 && out.lo != nullptr && out.C == 64;
 }
 
-void conv_stem_forward(Handle* h, cudaStream_t st, const ConvW& cw, const uint8_t* const* imgs, int nimg, int th, int tw, Act& out,
-                       const float* mean, const float* sd, int flags) {
-    ARG_CHECK(conv_stem_supported(cw, out) && nimg >= 1 && nimg <= 16, "conv_stem: unsupported layer");
+// normalised canvas of one image for k_conv_stem: dst = [H][W] uint4
+void stem_norm_forward(Handle* h, cudaStream_t st, const uint8_t* img, int th, int tw, void* dst, int H, int W, const float* mean,
+                       const float* sd) {
+    k_stem_norm<<<dim3(cdiv(W, 256), H), 256, 0, st>>>(img, th, tw, reinterpret_cast<uint4*>(dst), H, W, mean[0], mean[1], mean[2], sd[0],
+                                                        sd[1], sd[2]);
+    count_launch(h);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void conv_stem_forward(Handle* h, cudaStream_t st, const ConvW& cw, const void* norm, Act& out, int flags) {
+    ARG_CHECK(conv_stem_supported(cw, out), "conv_stem: unsupported layer");
     TcParams p{};
     p.C1 = 32; p.C2 = 0;
     p.w_lo_off = cw.cin;
@@ -976,6 +1073,7 @@ void conv_stem_forward(Handle* h, cudaStream_t st, const ConvW& cw, const uint8_
     p.taps_w = 1; p.taps = 1; p.pad = 0; p.dil = 1;
     p.OH = out.H; p.OW = out.W; p.NIMG = out.N;
     p.M = (int64_t)out.N * out.H * out.W;
+    ARG_CHECK(p.M < (int64_t)1 << 31, "conv_stem: batch of %lld pixels", (long long)p.M);
     p.flat = 1;
     p.cout = cw.cout; p.BN = cw.cout_pad; p.n_tiles = 1;
     p.relu = (flags & CONV_RELU) ? 1 : 0;
@@ -986,27 +1084,28 @@ void conv_stem_forward(Handle* h, cudaStream_t st, const ConvW& cw, const uint8_
     p.total_tiles = p.m_tiles;
     p.stages = STEM_STAGES; p.p_stages = 0; p.patch_al = 0; p.ncat = 0;
     StemParams sp{};
-    for (int i = 0; i < nimg; ++i) sp.img[i] = imgs[i];
-    sp.th = th; sp.tw = tw; sp.H = out.H; sp.W = out.W; sp.nimg = nimg;
-    for (int c = 0; c < 3; ++c) { sp.mean[c] = mean[c]; sp.sd[c] = sd[c]; }
+    sp.norm = reinterpret_cast<const uint4*>(norm);
+    sp.H = out.H; sp.W = out.W;
     const uint64_t wcin = (uint64_t)cw.cin * 2;
     uint64_t wd[3] = {wcin, (uint64_t)cw.cout_pad, 1};
     uint64_t ws[2] = {wcin * 2, (uint64_t)cw.cout_pad * wcin * 2};
     uint32_t wb[3] = {32, (uint32_t)p.BN, 1};
     CUtensorMap mB = make_map(cw.w_split, 3, wd, ws, wb, 32);
-    const size_t smem = (size_t)STEM_STAGES * 2 * BM * 32 * 2 + (size_t)2 * p.BN * 32 * 2 + 1024;
-    static std::once_flag once;
-    static std::mutex mu;
+    // output maps: [M pixels][64 channels] bf16, one 128-pixel x 128-byte box per tile (SWIZZLE_128B staging image)
+    uint64_t od[2] = {64, (uint64_t)p.M};
+    uint64_t os[1] = {128};
+    uint32_t ob[2] = {64, (uint32_t)BM};
+    CUtensorMap mOh = make_map(out.p, 2, od, os, ob, 64), mOl = make_map(out.lo, 2, od, os, ob, 64);
+    const size_t smem = (size_t)STEM_STAGES * 2 * BM * 32 * 2 + 8192 + (size_t)4 * STEM_OUT_TILE + 1024;
     {
-        std::lock_guard<std::mutex> g(mu);
+        std::lock_guard<std::mutex> g(h->stat_mu);
         if (!h->stem_attr_set) {
             CUDA_CHECK(cudaFuncSetAttribute(k_conv_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             h->stem_attr_set = true;
         }
     }
-    (void)once;
     const unsigned grid = (unsigned)std::min<int64_t>(p.total_tiles, (int64_t)h->sm_count * 2);
-    k_conv_stem<<<grid, 384, smem, st>>>(mB, p, sp);
+    k_conv_stem<<<grid, 384, smem, st>>>(mB, mOh, mOl, p, sp);
     count_launch(h);
     CUDA_CHECK(cudaGetLastError());
 }

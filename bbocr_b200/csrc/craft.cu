@@ -175,18 +175,23 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     const bool gather = tc_first && (!split || !stem_direct_x3);
     const size_t canvas_px_bytes = gather ? 64 : 16;
     const size_t canvas_plane = (((size_t)nimg * H * W * canvas_px_bytes) + 255) & ~(size_t)255;
-    // bf16x3: gather + conv1_1 fused (k_conv_stem builds the A tiles in shared memory; no 32-channel stem tensor in HBM).
-    // BBOCR_STEM_FUSED=0: the two-kernel path (k_im2col_rgb_split + k_conv_tc), A/B switch
+    // bf16x3: gather + conv1_1 fused (k_conv_stem builds the A tiles in shared memory from a 16-byte-per-pixel normalised canvas;
+    // no 32-channel stem tensor in HBM).  BBOCR_STEM_FUSED=0: the two-kernel path (k_im2col_rgb_split + k_conv_tc), A/B switch
     static const bool stem_fused_on = !(getenv("BBOCR_STEM_FUSED") && atoi(getenv("BBOCR_STEM_FUSED")) == 0);
     const bool need_resize = g.th != g.H || g.tw != g.W;
-    const bool stem_fused = stem_fused_on && split && gather && !need_resize;
-    DevBuf canvas(stem_fused ? 16 : canvas_plane * (split && gather ? 2 : 1), st), resized;
+    const bool stem_fused = stem_fused_on && split && gather;
+    const float mean3[3] = {m0, m1, m2}, sd3[3] = {s0, s1, s2};
+    DevBuf canvas(stem_fused ? (size_t)nimg * H * W * 16 : canvas_plane * (split && gather ? 2 : 1), st), resized;
     if (need_resize) resized.alloc((size_t)g.th * g.tw * 3, st);
-    for (int i = 0; i < nimg && !stem_fused; ++i) {
+    for (int i = 0; i < nimg; ++i) {
         const uint8_t* src = imgs_dev[i];
         if (need_resize) {
             resize_bilinear_u8(h, st, imgs_dev[i], g.H, g.W, g.W * 3, 3, resized.as<uint8_t>(), g.th, g.tw);
             src = resized.as<uint8_t>();
+        }
+        if (stem_fused) {
+            stem_norm_forward(h, st, src, g.th, g.tw, canvas.as<uint8_t>() + (size_t)i * H * W * 16, H, W, mean3, sd3);
+            continue;
         }
         uint8_t* dst = canvas.as<uint8_t>() + (size_t)i * H * W * canvas_px_bytes;
         if (split && gather)
@@ -230,8 +235,20 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     // slice1
     Act a = alloc(b0, nimg, H, W, 64);
     if (stem_fused && conv_stem_supported(w.c1_1_tc, a)) {
-        const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
-        conv_stem_forward(h, st, w.c1_1_tc, imgs_dev, nimg, g.th, g.tw, a, mean, sd, R);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (h->conv_timing) {                           // same instrumentation as conv_forward (bench.py roofline)
+            CUDA_CHECK(cudaEventCreate(&e0));
+            CUDA_CHECK(cudaEventCreate(&e1));
+            CUDA_CHECK(cudaEventRecord(e0, st));
+        }
+        conv_stem_forward(h, st, w.c1_1_tc, canvas.p, a, R);
+        if (h->conv_timing) {
+            CUDA_CHECK(cudaEventRecord(e1, st));
+            std::lock_guard<std::mutex> lk(h->stat_mu);
+            h->conv_events.emplace_back(e0, e1);
+            h->conv_flops += 2.0 * (double)a.N * a.H * a.W * w.c1_1_tc.cout * w.c1_1_tc.cin;
+            h->conv_launches += 1;
+        }
     } else if (gather) {
         ARG_CHECK(!stem_fused, "conv_stem: layer shape not supported");
         Act x32;

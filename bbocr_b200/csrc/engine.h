@@ -150,8 +150,9 @@ Act act_alloc(Handle*, cudaStream_t, DevBuf& buf, int N, int H, int W, int C, bo
 // ---- conv_tc.cu : tcgen05 implicit GEMM ------------------------------------------------------------------------------
 bool conv_tc_supported(const ConvW&, const Act& in1, const Act& in2);
 bool conv_stem_supported(const ConvW&, const Act& out);
-void conv_stem_forward(Handle*, cudaStream_t, const ConvW&, const uint8_t* const* imgs, int nimg, int th, int tw, Act& out,
-                       const float* mean, const float* sd, int flags);
+void stem_norm_forward(Handle*, cudaStream_t, const uint8_t* img, int th, int tw, void* dst, int H, int W, const float* mean,
+                       const float* sd);
+void conv_stem_forward(Handle*, cudaStream_t, const ConvW&, const void* norm, Act& out, int flags);
 void conv_tc_forward(Handle*, cudaStream_t, const ConvW&, const Act& in1, const Act& in2, Act& out, int flags, Act* pooled,
                      const uint8_t* colmask = nullptr);
 

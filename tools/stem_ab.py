@@ -26,6 +26,8 @@ def main():
         img = (synth.title_page if kind == "title" else synth.book_cover)(seed, w, h)
         t, l, _ = reader.score_maps(img)
         out[f"t{i}"], out[f"l{i}"] = t, l
+    # the canvas-resize branch (INTER_LINEAR u8 resize in front of the stem, image smaller than the 32-aligned canvas)
+    out["t_resized"], out["l_resized"], _ = reader.score_maps(synth.title_page(35, 700, 500), canvas_size=480)
     # a batch of pages of one geometry through the batched detector (NIMG > 1 inside one launch)
     pages = [synth.title_page(40 + k, 640, 480) for k in range(3)]
     res = reader.readtext_batched(pages)
