@@ -227,7 +227,7 @@ __device__ __forceinline__ void store_split(void* hi_base, void* lo_base, int64_
 // TW in {8, 16} the 2x2 (2x1) pooling window lives in lanes {l, l^1, l^TW, l^TW^1} ({l, l^TW}).
 template <bool NCAT>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, int warp, int lane, uint64_t* tfull_bar,
-                                            uint64_t* tempty_bar) {
+                                            uint64_t* tempty_bar, const float* s_sb /* shared [scale 256 | bias 256] or nullptr */) {
         const int wq = warp & 3;
         const int r = wq * 32 + lane;
         int ti = 0;
@@ -269,11 +269,26 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                     for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
                 }
                 if (c + 16 < p.BN) tmem_ld16_nowait(trow + c + 16, vn);     // in flight while this group is scaled, split and stored
-                float f[16];
+                float f[16], sc[16], bi[16];
+                if (s_sb) {                         // one N tile: the layer's scale / bias sit in shared memory (8 LDS.128 per group
+                                                    // instead of 32 uniform global loads: those were ~40 % of the epilogue's stalls)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(s_sb + c + 4 * q);
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_sb + 256 + c + 4 * q);
+                        sc[4 * q] = a4.x; sc[4 * q + 1] = a4.y; sc[4 * q + 2] = a4.z; sc[4 * q + 3] = a4.w;
+                        bi[4 * q] = b4.x; bi[4 * q + 1] = b4.y; bi[4 * q + 2] = b4.z; bi[4 * q + 3] = b4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        sc[j] = __ldg(p.scale + tc.n0 + c + j);                     // padded to cout_pad
+                        bi[j] = __ldg(p.bias + tc.n0 + c + j);
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int n = tc.n0 + c + j;
-                    float a = fmaf(__uint_as_float(v[j]), __ldg(p.scale + n), __ldg(p.bias + n));   // padded to cout_pad
+                    float a = fmaf(__uint_as_float(v[j]), sc[j], bi[j]);
                     f[j] = p.relu ? fmaxf(a, 0.f) : a;
                     if (!colvalid) f[j] = 0.f;
                 }
@@ -318,6 +333,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc(const __grid_constant__ CUte
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_sb[512];            // scale[256] | bias[256] of a layer with one N tile
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int A_BYTES = BM * BK * 2;
     const int B_BYTES = p.BN * BK * 2;
@@ -327,6 +343,9 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc(const __grid_constant__ CUte
     const int kiters = p.taps * (kb1 + kb2);
     uint32_t ncols = 32;
     while ((int)ncols < (NCAT ? 4 : 2) * p.BN) ncols <<= 1;
+    const bool sb_res = p.n_tiles == 1;                  // BN = cout_pad <= 256
+    if (sb_res)
+        for (int i = threadIdx.x; i < p.BN; i += blockDim.x) { s_sb[i] = p.scale[i]; s_sb[256 + i] = p.bias[i]; }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -429,7 +448,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc(const __grid_constant__ CUte
             umma_commit(&tfull_bar[as]);
         }
     } else if (warp >= 4) {
-        tc_epilogue<NCAT>(p, tmem_base, warp, lane, tfull_bar, tempty_bar);
+        tc_epilogue<NCAT>(p, tmem_base, warp, lane, tfull_bar, tempty_bar, sb_res ? s_sb : nullptr);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -460,6 +479,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc_patch(const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[8], empty_bar[8], pfull_bar[4], pempty_bar[4], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_sb[512];            // scale[256] | bias[256] of a layer with one N tile
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int PIX = BK * 2;                              // bytes per pixel row of the operand tiles
     constexpr int PW = 10, PH = 18;                          // patch: 8 x 16 output pixels + halo
@@ -473,6 +493,9 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc_patch(const __grid_constant_
     const int kb1 = p.C1 / BK, kb2 = p.C2 / BK;
     uint32_t ncols = 32;
     while ((int)ncols < (NCAT ? 4 : 2) * p.BN) ncols <<= 1;
+    const bool sb_res = p.n_tiles == 1;                  // BN = cout_pad <= 256
+    if (sb_res)
+        for (int i = threadIdx.x; i < p.BN; i += blockDim.x) { s_sb[i] = p.scale[i]; s_sb[256 + i] = p.bias[i]; }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -574,7 +597,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc_patch(const __grid_constant_
             umma_commit(&tfull_bar[as]);
         }
     } else if (warp >= 4) {
-        tc_epilogue<NCAT>(p, tmem_base, warp, lane, tfull_bar, tempty_bar);
+        tc_epilogue<NCAT>(p, tmem_base, warp, lane, tfull_bar, tempty_bar, sb_res ? s_sb : nullptr);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
