@@ -225,11 +225,18 @@ __device__ __forceinline__ void store_split(void* hi_base, void* lo_base, int64_
 // Epilogue warps (4..7) of both kernels: tcgen05.ld 32x32b -> folded-BN scale/bias (+ReLU) -> optional fused 2x2 / 2x1 max-pool
 // by warp shuffles -> bf16 / fp32 / split NHWC stores -> tempty[acc].  TMEM lane r = pixel (r / TW, r % TW) of the tile; with
 // TW in {8, 16} the 2x2 (2x1) pooling window lives in lanes {l, l^1, l^TW, l^TW^1} ({l, l^TW}).
-template <bool NCAT>
+// EW = 8 (kernels that run one CTA per SM with BN = 128): two warps per TMEM lane quarter, each takes half of the columns.
+template <bool NCAT, int EW = 4>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, int warp, int lane, uint64_t* tfull_bar,
-                                            uint64_t* tempty_bar, const float* s_sb /* shared [scale 256 | bias 256] or nullptr */) {
+                                            uint64_t* tempty_bar, const float* s_sb /* shared [scale 256 | bias 256] or nullptr */,
+                                            float* s_pool = nullptr /* shared, 512 floats per epilogue warp, or nullptr */) {
         const int wq = warp & 3;
         const int r = wq * 32 + lane;
+        // 2x2 pooling through shared memory (s_pool): lane = (window w, column quad q).  Window w of the warp's 32 pixels =
+        // lanes {b, b^1, b^TW, b^TW^1} with b = w's bits spread around bit 0 and bit log2(TW)
+        float* my_pool = s_pool ? s_pool + (warp - 4) * 512 : nullptr;
+        const int pw = lane >> 2, pq = lane & 3;
+        const int pb = ((pw << 1) & (p.TW - 1)) | ((((pw << 1) & ~(p.TW - 1))) << 1);
         int ti = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
             const TileCoord tc = tile_coord(p, tile);
@@ -254,21 +261,25 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                     if (writer && py < POH && px < POW) pix2 = ((int64_t)tc.img * POH + py) * POW + px;
                 }
             }
+            // pooled pixel of the window this lane serves on the shared-memory pooling path (the window's base lane computed it)
+            const int64_t pix2w = (p.pool == 1 && my_pool) ? __shfl_sync(0xffffffffu, pix2, pb) : -1;
             const uint32_t trow = tmem_base + (uint32_t)(as * (NCAT ? 2 * p.BN : p.BN)) + ((uint32_t)(wq * 32) << 16);
             uint32_t vn[16];
-            tmem_ld16_nowait(trow, vn);
-            for (int c = 0; c < p.BN; c += 16) {
+            const int cw = p.BN / (EW / 4), c_lo = ((warp - 4) >> 2) * cw, c_hi = c_lo + cw;      // this warp's column range
+            tmem_ld16_nowait(trow + c_lo, vn);
+            for (int c = c_lo; c < c_hi; c += 16) {
                 uint32_t v[16];
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = vn[j];
                 if (NCAT) {                         // x_hi * w_lo accumulated in the second half of the stage
+                    // (loading this half one group ahead like the first one was tried: 120 registers, conv2_2 497 -> 535 us)
                     uint32_t v2[16];
                     tmem_ld16(trow + p.BN + c, v2);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
                 }
-                if (c + 16 < p.BN) tmem_ld16_nowait(trow + c + 16, vn);     // in flight while this group is scaled, split and stored
+                if (c + 16 < c_hi) tmem_ld16_nowait(trow + c + 16, vn);     // in flight while this group is scaled, split and stored
                 float f[16], sc[16], bi[16];
                 if (s_sb) {                         // one N tile: the layer's scale / bias sit in shared memory (8 LDS.128 per group
                                                     // instead of 32 uniform global loads: those were ~40 % of the epilogue's stalls)
@@ -298,7 +309,65 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                     else if (p.out_f32) store16(reinterpret_cast<float*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
                     else store16(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
                 }
-                if (p.pool) {
+                if (p.pool == 1 && my_pool) {
+                    // the warp's 32 x 16 activations go through shared memory (row = lane, 64 bytes, 16-byte chunk k at
+                    // k ^ ((lane >> 1) & 3)); lane (w, q) reads columns 4q .. 4q+3 of its window's four pixels: 4 + 4 128-bit
+                    // shared accesses and 12 max instead of 32 shuffles and 32 max, and every lane splits / stores 4 pooled
+                    // values instead of a quarter of the lanes 16 (the others computing theirs for nothing)
+                    const int sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        *reinterpret_cast<float4*>(my_pool + lane * 16 + ((k ^ sw) << 2)) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+                    __syncwarp();
+                    float4 m4;
+                    {
+                        const int r0 = pb, r1 = pb ^ 1, r2 = pb ^ p.TW, r3 = pb ^ p.TW ^ 1;
+                        const float4 a0 = *reinterpret_cast<const float4*>(my_pool + r0 * 16 + ((pq ^ ((r0 >> 1) & 3)) << 2));
+                        const float4 a1 = *reinterpret_cast<const float4*>(my_pool + r1 * 16 + ((pq ^ ((r1 >> 1) & 3)) << 2));
+                        const float4 a2 = *reinterpret_cast<const float4*>(my_pool + r2 * 16 + ((pq ^ ((r2 >> 1) & 3)) << 2));
+                        const float4 a3 = *reinterpret_cast<const float4*>(my_pool + r3 * 16 + ((pq ^ ((r3 >> 1) & 3)) << 2));
+                        m4.x = fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x));
+                        m4.y = fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y));
+                        m4.z = fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z));
+                        m4.w = fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w));
+                    }
+                    __syncwarp();                                   // the next group overwrites the staging rows
+                    if (pix2w >= 0) {
+                        const float m[4] = {m4.x, m4.y, m4.z, m4.w};
+                        const int nb = nbase + 4 * pq;
+                        const int64_t off = pix2w * p.cout + nb;
+                        if ((p.cout & 3) == 0 && nb + 4 <= p.cout) {
+                            if (p.split_out) {
+                                const __nv_bfloat162 h01 = __floats2bfloat162_rn(m[0], m[1]), h23 = __floats2bfloat162_rn(m[2], m[3]);
+                                const uint32_t w01 = *reinterpret_cast<const uint32_t*>(&h01), w23 = *reinterpret_cast<const uint32_t*>(&h23);
+                                const __nv_bfloat162 l01 = __floats2bfloat162_rn(m[0] - __uint_as_float(w01 << 16), m[1] - __uint_as_float(w01 & 0xffff0000u));
+                                const __nv_bfloat162 l23 = __floats2bfloat162_rn(m[2] - __uint_as_float(w23 << 16), m[3] - __uint_as_float(w23 & 0xffff0000u));
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + off) = make_uint2(w01, w23);
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2_lo) + off) =
+                                    make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+                            } else if (p.out_f32) {
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out2) + off) = m4;
+                            } else {
+                                const __nv_bfloat162 h01 = __floats2bfloat162_rn(m[0], m[1]), h23 = __floats2bfloat162_rn(m[2], m[3]);
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + off) =
+                                    make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+                            }
+                        } else {
+                            for (int j = 0; j < 4; ++j) {
+                                if (nb + j >= p.cout) break;
+                                if (p.split_out) {
+                                    const __nv_bfloat16 hb = __float2bfloat16_rn(m[j]);
+                                    reinterpret_cast<__nv_bfloat16*>(p.out2)[off + j] = hb;
+                                    reinterpret_cast<__nv_bfloat16*>(p.out2_lo)[off + j] = __float2bfloat16_rn(m[j] - __bfloat162float(hb));
+                                } else if (p.out_f32) {
+                                    reinterpret_cast<float*>(p.out2)[off + j] = m[j];
+                                } else {
+                                    reinterpret_cast<__nv_bfloat16*>(p.out2)[off + j] = __float2bfloat16_rn(m[j]);
+                                }
+                            }
+                        }
+                    }
+                } else if (p.pool) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         float m = f[j];
@@ -470,8 +539,8 @@ __device__ __forceinline__ uint64_t desc_kmajor_sbo(uint32_t saddr, uint32_t sbo
     return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
-template <int BK, bool NCAT>
-__global__ void __launch_bounds__(256, 2) k_conv_tc_patch(const __grid_constant__ CUtensorMap tmA1,
+template <int BK, bool NCAT, int EW = 4>
+__global__ void __launch_bounds__(128 + 32 * EW, EW == 4 ? 2 : 1) k_conv_tc_patch(const __grid_constant__ CUtensorMap tmA1,
                                                        const __grid_constant__ CUtensorMap tmA2,
                                                        const __grid_constant__ CUtensorMap tmA3,
                                                        const __grid_constant__ CUtensorMap tmA4,
@@ -480,6 +549,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc_patch(const __grid_constant_
     __shared__ uint64_t full_bar[8], empty_bar[8], pfull_bar[4], pempty_bar[4], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_sb[512];            // scale[256] | bias[256] of a layer with one N tile
+    __shared__ __align__(16) float s_pool[EW * 512];     // 2x2 pooling: 32 pixels x 16 columns per epilogue warp
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int PIX = BK * 2;                              // bytes per pixel row of the operand tiles
     constexpr int PW = 10, PH = 18;                          // patch: 8 x 16 output pixels + halo
@@ -500,7 +570,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc_patch(const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < p.p_stages; ++s) { mbar_init(&pfull_bar[s], 1); mbar_init(&pempty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -597,7 +667,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc_patch(const __grid_constant_
             umma_commit(&tfull_bar[as]);
         }
     } else if (warp >= 4) {
-        tc_epilogue<NCAT>(p, tmem_base, warp, lane, tfull_bar, tempty_bar, sb_res ? s_sb : nullptr);
+        tc_epilogue<NCAT, EW>(p, tmem_base, warp, lane, tfull_bar, tempty_bar, sb_res ? s_sb : nullptr, s_pool);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -1043,16 +1113,40 @@ void conv_tc_forward(Handle* h, cudaStream_t st, const ConvW& cw, const Act& in1
     // persistent grid: a multiple of the SM count (148 on B200), never more CTAs than tiles
     const unsigned grid = (unsigned)std::min<int64_t>(p.total_tiles, (int64_t)h->sm_count * ctas);
     if (!h->tc_attr_set) {          // per device (one handle = one device)
-#define TC_SMEM(...) CUDA_CHECK(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024))
+        // dynamic limit = the device's opt-in maximum per block minus the kernel's static shared memory (the patch kernels hold
+        // 10-18 KB of pooling / scale-bias staging statically)
+        int dev = 0, optin = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        auto set_smem = [&](const void* fn) {
+            cudaFuncAttributes fa;
+            CUDA_CHECK(cudaFuncGetAttributes(&fa, fn));
+            CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+        };
+#define TC_SMEM(...) set_smem(reinterpret_cast<const void*>(&__VA_ARGS__))
         TC_SMEM(k_conv_tc<64, 0, false>); TC_SMEM(k_conv_tc<32, 0, false>);
         TC_SMEM(k_conv_tc<64, 1, false>); TC_SMEM(k_conv_tc<32, 1, false>);
         TC_SMEM(k_conv_tc<64, 1, true>); TC_SMEM(k_conv_tc<32, 1, true>);
         TC_SMEM(k_conv_tc_patch<64, false>); TC_SMEM(k_conv_tc_patch<32, false>);
         TC_SMEM(k_conv_tc_patch<64, true>); TC_SMEM(k_conv_tc_patch<32, true>);
+        TC_SMEM(k_conv_tc_patch<64, false, 8>); TC_SMEM(k_conv_tc_patch<32, false, 8>);
+        TC_SMEM(k_conv_tc_patch<64, true, 8>); TC_SMEM(k_conv_tc_patch<32, true, 8>);
 #undef TC_SMEM
         h->tc_attr_set = true;
     }
-    if (patch && p.ncat) {
+    // one CTA per SM and BN = 128 (conv2_x, up2b): the four epilogue warps of the single resident CTA -- one per scheduler, ~0.2
+    // instructions per cycle each -- are the layer's critical path; eight warps split the columns.  (Layers with BN = 256 are
+    // tensor-bound, layers with BN <= 64 run two CTAs per SM.)  BBOCR_TC_EW8=0: A/B switch
+    static const bool ew8_on = !(getenv("BBOCR_TC_EW8") && atoi(getenv("BBOCR_TC_EW8")) == 0);
+    if (patch && ew8_on && ctas == 1 && p.BN == 128) {
+        if (p.ncat) {
+            if (bk == 64) k_conv_tc_patch<64, true, 8><<<grid, 384, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+            else k_conv_tc_patch<32, true, 8><<<grid, 384, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        } else {
+            if (bk == 64) k_conv_tc_patch<64, false, 8><<<grid, 384, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+            else k_conv_tc_patch<32, false, 8><<<grid, 384, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
+        }
+    } else if (patch && p.ncat) {
         if (bk == 64) k_conv_tc_patch<64, true><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
         else k_conv_tc_patch<32, true><<<grid, 256, smem, st>>>(mA1, mA2, mA3, mA4, mB, p);
     } else if (patch) {
