@@ -210,16 +210,39 @@ __device__ __forceinline__ void store16<__nv_bfloat16>(__nv_bfloat16* o, const f
     }
 }
 
-// split-precision store: hi = bf16(v), lo = bf16(v - hi)
-__device__ __forceinline__ void store_split(void* hi_base, void* lo_base, int64_t off, const float* f, int nbase, int cout) {
-    float hi[16], lo[16];
+// split-precision store: hi = bf16(v), lo = bf16(v - hi).  Packed conversions (cvt.rn.bf16x2.f32: 8 + 8 per group instead of 16 scalar
+// conversions and 16 packs); al32 = every 16-channel group of both tensors starts on a 32-byte boundary (a property of the layer,
+// uniform over the grid: the 256-bit store needs no per-thread alignment branch)
+__device__ __forceinline__ void store_split(void* hi_base, void* lo_base, int64_t off, const float* f, int nbase, int cout, bool al32) {
+    __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(hi_base) + off;
+    __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(lo_base) + off;
+    if ((cout & 7) == 0 && nbase + 16 <= cout) {
+        uint32_t wh[8], wl[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        hi[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
-        lo[j] = f[j] - hi[j];
+        for (int j = 0; j < 8; ++j) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h2);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(f[2 * j] - __uint_as_float(hw << 16), f[2 * j + 1] - __uint_as_float(hw & 0xffff0000u));
+            wh[j] = hw;
+            wl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        if (al32) {
+            st_global_256(oh, wh);
+            st_global_256(ol, wl);
+        } else {
+            *reinterpret_cast<uint4*>(oh) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            *reinterpret_cast<uint4*>(oh + 8) = make_uint4(wh[4], wh[5], wh[6], wh[7]);
+            *reinterpret_cast<uint4*>(ol) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+            *reinterpret_cast<uint4*>(ol + 8) = make_uint4(wl[4], wl[5], wl[6], wl[7]);
+        }
+    } else {
+        for (int j = 0; j < 16; ++j)
+            if (nbase + j < cout) {
+                const __nv_bfloat16 hb = __float2bfloat16_rn(f[j]);
+                oh[j] = hb;
+                ol[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hb));
+            }
     }
-    store16(reinterpret_cast<__nv_bfloat16*>(hi_base) + off, hi, nbase, cout);
-    store16(reinterpret_cast<__nv_bfloat16*>(lo_base) + off, lo, nbase, cout);
 }
 
 // Epilogue warps (4..7) of both kernels: tcgen05.ld 32x32b -> folded-BN scale/bias (+ReLU) -> optional fused 2x2 / 2x1 max-pool
@@ -235,6 +258,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
         // 2x2 pooling through shared memory (s_pool): lane = (window w, column quad q).  Window w of the warp's 32 pixels =
         // lanes {b, b^1, b^TW, b^TW^1} with b = w's bits spread around bit 0 and bit log2(TW)
         float* my_pool = s_pool ? s_pool + (warp - 4) * 512 : nullptr;
+        const bool al32 = (p.cout & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.out_lo) |
+                                                  reinterpret_cast<uintptr_t>(p.out2) | reinterpret_cast<uintptr_t>(p.out2_lo)) & 31) == 0;
         const int pw = lane >> 2, pq = lane & 3;
         const int pb = ((pw << 1) & (p.TW - 1)) | ((((pw << 1) & ~(p.TW - 1))) << 1);
         int ti = 0;
@@ -301,11 +326,14 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                 for (int j = 0; j < 16; ++j) {
                     float a = fmaf(__uint_as_float(v[j]), sc[j], bi[j]);
                     f[j] = p.relu ? fmaxf(a, 0.f) : a;
-                    if (!colvalid) f[j] = 0.f;
+                }
+                if (p.colmask && !colvalid) {       // recogniser strips only: gaps between concatenated crops
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = 0.f;
                 }
                 const int nbase = tc.n0 + c;
                 if (pix >= 0 && (!p.pool || p.write_full)) {
-                    if (p.split_out) store_split(p.out, p.out_lo, pix * p.cout + nbase, f, nbase, p.cout);
+                    if (p.split_out) store_split(p.out, p.out_lo, pix * p.cout + nbase, f, nbase, p.cout, al32);
                     else if (p.out_f32) store16(reinterpret_cast<float*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
                     else store16(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout + nbase, f, nbase, p.cout);
                 }
@@ -376,7 +404,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                         f[j] = m;
                     }
                     if (pix2 >= 0) {
-                        if (p.split_out) store_split(p.out2, p.out2_lo, pix2 * p.cout + nbase, f, nbase, p.cout);
+                        if (p.split_out) store_split(p.out2, p.out2_lo, pix2 * p.cout + nbase, f, nbase, p.cout, al32);
                         else if (p.out_f32) store16(reinterpret_cast<float*>(p.out2) + pix2 * p.cout + nbase, f, nbase, p.cout);
                         else store16(reinterpret_cast<__nv_bfloat16*>(p.out2) + pix2 * p.cout + nbase, f, nbase, p.cout);
                     }
