@@ -481,7 +481,7 @@ def main():
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
                          "frac": achieved / peak_burst if peak_burst else None, "traffic": traffic,
-                         "kernel": "k_conv_tc (+ k_conv_res in bf16 mode): the tcgen05 implicit-GEMM convolutions of the detector (CRAFT), "
+                         "kernel": "k_conv_stem + k_conv_tc / k_conv_tc_patch (+ k_conv_res in bf16 mode): the tcgen05 implicit-GEMM convolutions of the detector (CRAFT), "
                                    f"{int(iso_n // max(iso_pages, 1))} launches per page",
                          "launches": int(iso_n), "avg_launch_ms": iso_ms / iso_n if iso_n else None,
                          "peak_source": peak_src,

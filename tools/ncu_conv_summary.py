@@ -10,7 +10,7 @@ import json
 import re
 import sys
 
-LAYERS = [("conv1_1 (1x1 over the gathered 32-ch stem) 32->64 @1/1", 32, 64, 1, 1.0), ("conv1_2 64->64 @1/1 (+pool)", 64, 64, 9, 1.0),
+LAYERS = [("conv1_1 (k_conv_stem: K = 32 stem gathered in shared memory, TMA-store epilogue) 32->64 @1/1", 32, 64, 1, 1.0), ("conv1_2 64->64 @1/1 (+pool)", 64, 64, 9, 1.0),
           ("conv2_1 64->128 @1/2", 64, 128, 9, 0.25), ("conv2_2 128->128 @1/2 (+pool, skip)", 128, 128, 9, 0.25),
           ("conv3_1 128->256 @1/4", 128, 256, 9, 1 / 16), ("conv3_2 256->256 @1/4", 256, 256, 9, 1 / 16),
           ("conv3_3 256->256 @1/4 (+pool)", 256, 256, 9, 1 / 16), ("conv4_1 256->512 @1/8", 256, 512, 9, 1 / 64),
