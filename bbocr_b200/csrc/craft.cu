@@ -179,7 +179,9 @@ void craft_forward_batch_dev(Handle* h, cudaStream_t st, const uint8_t* const* i
     // no 32-channel stem tensor in HBM).  BBOCR_STEM_FUSED=0: the two-kernel path (k_im2col_rgb_split + k_conv_tc), A/B switch
     static const bool stem_fused_on = !(getenv("BBOCR_STEM_FUSED") && atoi(getenv("BBOCR_STEM_FUSED")) == 0);
     const bool need_resize = g.th != g.H || g.tw != g.W;
-    const bool stem_fused = stem_fused_on && split && gather;
+    const ConvW& c11 = w.c1_1_tc;                        // the fused stem is written for CRAFT's conv1_1 (27 -> 32 gathered channels, 64 outputs)
+    const bool stem_fused = stem_fused_on && split && gather && c11.w_split && c11.cin == 32 && c11.cout == 64 && c11.cout_pad == 64 &&
+                            c11.kh == 1 && c11.kw == 1;
     const float mean3[3] = {m0, m1, m2}, sd3[3] = {s0, s1, s2};
     DevBuf canvas(stem_fused ? (size_t)nimg * H * W * 16 : canvas_plane * (split && gather ? 2 : 1), st), resized;
     if (need_resize) resized.alloc((size_t)g.th * g.tw * 3, st);
