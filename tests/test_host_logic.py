@@ -272,3 +272,37 @@ def test_beam_decoders_match_the_restated_upstream(lib_built):
     assert greedy == "".join(chars[c - 1] for c in (30, 31, 32, space, 50))
     for dec in (1, 2):
         assert "".join(chars[i - 1] for i in lib_built.ctc_beam_decode(probs, dec, 5, space)) == greedy
+
+
+def test_epilogue_shared_memory_layouts_are_what_the_kernels_assume():
+    """Index arithmetic the conv_tc.cu epilogues rely on, restated (no GPU needed).
+    (1) 2x2 pooling through shared memory: window w (0..7) of a warp's 32 pixels has its base lane at w's bits spread around bit 0
+        and bit log2(TW); {b, b^1, b^TW, b^TW^1} over the eight windows partition the 32 lanes, and b is the lane the shuffle
+        path calls the writer ((lane & TW) == 0 and (lane & 1) == 0).
+    (2) staging swizzles: a quarter warp's 128-bit shared stores hit 8 distinct 16-byte bank groups
+        (pool tile: 64-byte rows, chunk k at k ^ ((lane >> 1) & 3); stem output tile: 128-byte rows, chunk q at q ^ (row & 7)).
+    (3) k_conv_stem's A rows: SWIZZLE_64B places 16-byte chunk c of 64-byte row r at chunk c ^ ((r >> 1) & 3), i.e. address bits
+        [4:5] ^= address bits [7:8]."""
+    for TW in (8, 16):
+        seen = set()
+        for w in range(8):
+            t = w << 1
+            b = (t & (TW - 1)) | ((t & ~(TW - 1)) << 1)
+            assert (b & TW) == 0 and (b & 1) == 0
+            lanes = {b, b ^ 1, b ^ TW, b ^ TW ^ 1}
+            assert len(lanes) == 4 and not (lanes & seen) and max(lanes) < 32
+            seen |= lanes
+        assert seen == set(range(32))
+    for quarter in range(4):
+        lanes = range(8 * quarter, 8 * quarter + 8)
+        for k in range(4):                                   # pool tile: byte offset lane * 64 + ((k ^ sw) << 4)
+            groups = {((lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) % 128) // 16 for lane in lanes}
+            assert len(groups) == 8
+        for q in range(8):                                   # stem output tile: byte offset row * 128 + ((q ^ (row & 7)) << 4)
+            groups = {((row * 128 + ((q ^ (row & 7)) << 4)) % 128) // 16 for row in lanes}
+            assert len(groups) == 8
+    for r in range(128):
+        for c in range(4):
+            addr = r * 64 + c * 16
+            swz = addr ^ (((addr >> 7) & 3) << 4)
+            assert swz == r * 64 + ((c ^ ((r >> 1) & 3)) << 4)
